@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures by running the REAL reference modules (CPU, fp32).
+
+Run in the build container only (``/root/reference`` is not present on the GPU box):
+
+    python tests/golden/make_golden.py
+
+What it does
+  * imports the reference's own classes -- UNetModel / SpatialTransformer (openaimodel.py, attention.py),
+    VAE Encoder / Decoder (model.py), DDIMSampler (ddim.py), i-DDPM create_model (script_util.py) and
+    DDPMDDIMWrapper (ddpm_ddim_wrapper.py) -- through the three shims of SURVEY.md section 8c
+    (omegaconf stub, DDIMSampler.register_buffer override, LatentDiffusion stand-in);
+  * loads the synthetic state_dict from ``cycle_diffusion_b200.specs`` with ``strict=True`` (this also
+    pins our parameter inventories against the reference's module trees);
+  * writes inputs + reference outputs to ``tests/golden/*.npz``.
+Nothing from the reference is copied into the repo; only numeric outputs are stored.
+"""
+import contextlib
+import io
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = '/root/reference'
+
+from cycle_diffusion_b200 import specs  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def _shim_omegaconf():
+    oc = types.ModuleType('omegaconf')
+    lc = types.ModuleType('omegaconf.listconfig')
+
+    class ListConfig(list):
+        pass
+    lc.ListConfig = ListConfig
+    oc.listconfig = lc
+    oc.ListConfig = ListConfig
+    sys.modules['omegaconf'] = oc
+    sys.modules['omegaconf.listconfig'] = lc
+
+
+def _quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def save(name, **arrs):
+    out = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()}
+    path = os.path.join(HERE, name + '.npz')
+    np.savez(path, **out)
+    print(f'wrote {name}.npz  ({os.path.getsize(path) / 1024:.0f} KiB)')
+
+
+def sd_checksum(sd):
+    """Detects drift of the synthetic-weight generator between machines / torch builds."""
+    s = 0.0
+    a = 0.0
+    for v in sd.values():
+        s += float(v.double().sum())
+        a += float(v.double().abs().sum())
+    return np.asarray([s, a])
+
+
+# ----------------------------------------------------------------------------------------------
+NARROW = dict(in_channels=4, out_channels=4, model_channels=32, attention_resolutions=(4, 2, 1), num_res_blocks=2,
+              channel_mult=(1, 2, 4, 4), num_heads=2, context_dim=48)
+WIDE = dict(in_channels=4, out_channels=4, model_channels=320, attention_resolutions=(1, 2), num_res_blocks=1,
+            channel_mult=(1, 2), num_heads=8, context_dim=768)
+VAE_SMALL = dict(ch=32, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, out_ch=3, z_channels=4, embed_dim=4)
+
+
+def build_ref_unet(cfg):
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    with _quiet():
+        m = UNetModel(image_size=32, in_channels=cfg['in_channels'], out_channels=cfg['out_channels'],
+                      model_channels=cfg['model_channels'], attention_resolutions=list(cfg['attention_resolutions']),
+                      num_res_blocks=cfg['num_res_blocks'], channel_mult=list(cfg['channel_mult']),
+                      num_heads=cfg['num_heads'], use_spatial_transformer=True, transformer_depth=1,
+                      context_dim=cfg['context_dim'], use_checkpoint=False, legacy=False)
+    return m.eval()
+
+
+def golden_unets():
+    for name, cfg, seed, B, hw in (('unet_sd_narrow', NARROW, 11, 2, 16), ('unet_sd_wide', WIDE, 12, 1, 16)):
+        sd = specs.synth_state_dict(specs.openai_unet_params(cfg), seed)
+        m = build_ref_unet(cfg)
+        m.load_state_dict(sd, strict=True)
+        g = torch.Generator().manual_seed(100 + seed)
+        x = torch.randn(B, cfg['in_channels'], hw, hw, generator=g)
+        ctx = torch.randn(B, 77, cfg['context_dim'], generator=g)
+        t = torch.tensor([901, 21][:B], dtype=torch.long)
+        with torch.no_grad():
+            y = m(x, t, context=ctx)
+        save(name, x=x, t=t, ctx=ctx, y=y, seed=seed, wsum=sd_checksum(sd))
+
+
+def golden_vae():
+    from ldm.modules.diffusionmodules.model import Encoder, Decoder
+    cfg = VAE_SMALL
+    sd = specs.synth_state_dict(specs.kl_vae_params(cfg), 21)
+    dd = dict(double_z=True, z_channels=cfg['z_channels'], resolution=64, in_channels=3, out_ch=3, ch=cfg['ch'],
+              ch_mult=list(cfg['ch_mult']), num_res_blocks=cfg['num_res_blocks'], attn_resolutions=[], dropout=0.0)
+    with _quiet():
+        enc, dec = Encoder(**dd).eval(), Decoder(**dd).eval()
+    enc.load_state_dict({k[len('encoder.'):]: v for k, v in sd.items() if k.startswith('encoder.')}, strict=True)
+    dec.load_state_dict({k[len('decoder.'):]: v for k, v in sd.items() if k.startswith('decoder.')}, strict=True)
+    quant = torch.nn.Conv2d(2 * cfg['z_channels'], 2 * cfg['embed_dim'], 1)
+    post = torch.nn.Conv2d(cfg['embed_dim'], cfg['z_channels'], 1)
+    quant.load_state_dict({'weight': sd['quant_conv.weight'], 'bias': sd['quant_conv.bias']})
+    post.load_state_dict({'weight': sd['post_quant_conv.weight'], 'bias': sd['post_quant_conv.bias']})
+    g = torch.Generator().manual_seed(121)
+    img = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    z = torch.randn(2, 4, 8, 8, generator=g)
+    with torch.no_grad():
+        moments = quant(enc(img))           # AutoencoderKL.encode, autoencoder.py:324-328
+        rec = dec(post(z))                  # AutoencoderKL.decode, autoencoder.py:330-333
+    save('vae_small', img=img, z=z, moments=moments, rec=rec, seed=21, wsum=sd_checksum(sd))
+
+
+def golden_iddpm():
+    sys.path.insert(0, os.path.join(REF, 'model/lib/ddpm_ddim'))
+    from models.improved_ddpm.script_util import create_model, AFHQ_DICT
+    cfg = specs.iddpm_config(64)
+    sd = specs.synth_state_dict(specs.iddpm_unet_params(cfg), 31)
+    with _quiet():
+        m = create_model(**{**AFHQ_DICT, 'image_size': 64}).eval()
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(131)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    t = torch.tensor([500., 3.])
+    with torch.no_grad():
+        y = m(x, t)
+    save('unet_iddpm64', x=x, t=t, y=y, seed=31, wsum=sd_checksum(sd))
+    # also pin the 256 inventory (no forward: just strict key/shape check)
+    cfg256 = specs.iddpm_config(256)
+    with _quiet():
+        m256 = create_model(**AFHQ_DICT)
+    ref_keys = {k: tuple(v.shape) for k, v in m256.state_dict().items()}
+    ours = {k: tuple(s) for k, s, _ in specs.iddpm_unet_params(cfg256)}
+    assert ref_keys == ours, 'i-DDPM 256 inventory mismatch'
+    print('i-DDPM 256 inventory matches the reference module tree')
+
+
+def golden_inventories():
+    """Full-size SD / LDM U-Net and KL-f8 VAE inventories against the reference module trees (meta device)."""
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from ldm.modules.diffusionmodules.model import Encoder, Decoder
+    for ctx in (768, 1280):
+        cfg = specs.sd_unet_config(ctx)
+        with torch.device('meta'), _quiet():
+            m = UNetModel(image_size=32, in_channels=4, out_channels=4, model_channels=320,
+                          attention_resolutions=[4, 2, 1], num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_heads=8,
+                          use_spatial_transformer=True, transformer_depth=1, context_dim=ctx, use_checkpoint=True,
+                          legacy=False)
+        ref = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        ours = {k: tuple(s) for k, s, _ in specs.openai_unet_params(cfg)}
+        assert ref == ours, f'SD U-Net inventory mismatch (ctx {ctx})'
+    cfg = specs.kl_f8_config()
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    with torch.device('meta'), _quiet():
+        enc, dec = Encoder(**dd), Decoder(**dd)
+    ref = {'encoder.' + k: tuple(v.shape) for k, v in enc.state_dict().items()}
+    ref.update({'decoder.' + k: tuple(v.shape) for k, v in dec.state_dict().items()})
+    ours = {k: tuple(s) for k, s, _ in specs.kl_vae_params(cfg) if not k.startswith(('quant', 'post_quant'))}
+    assert ref == ours, 'KL-f8 inventory mismatch'
+    print('SD/LDM U-Net and KL-f8 VAE inventories match the reference module trees')
+
+
+# ----------------------------------------------------------------------------------------------
+def golden_schedule():
+    from ldm.modules.diffusionmodules.util import make_beta_schedule, make_ddim_timesteps, make_ddim_sampling_parameters
+    betas = make_beta_schedule('linear', 1000, linear_start=0.00085, linear_end=0.012)
+    ac = torch.tensor(np.cumprod(1. - betas, axis=0), dtype=torch.float32)   # register_schedule, ddpm.py:124-135
+    out = {'alphas_cumprod': ac}
+    for S in (10, 50, 99, 100):
+        ts = make_ddim_timesteps('uniform', S, 1000, verbose=False)
+        sig, a, ap = make_ddim_sampling_parameters(ac.cpu(), ts, 0.1, verbose=False)
+        # what the step functions finally consume: torch.full((b,1,1,1), table[index]) -> fp32
+        f32 = lambda tab: torch.stack([torch.full((1,), tab[i]) for i in range(S)]).flatten()
+        out[f'ts_{S}'] = ts
+        out[f'a_{S}'] = f32(a)
+        out[f'aprev_{S}'] = f32(ap)
+        out[f'sigma_{S}'] = f32(sig)
+        out[f'sqrt1ma_{S}'] = f32(np.sqrt(1. - a))
+    save('schedule_ldm', **out)
+
+
+class _LatentStandIn:
+    """What DDIMSampler touches on ``self.model`` (ddpm.py:117-145, 882-983, 1386-1394)."""
+
+    def __init__(self, unet):
+        from ldm.modules.diffusionmodules.util import make_beta_schedule
+        betas = make_beta_schedule('linear', 1000, linear_start=0.00085, linear_end=0.012)
+        ac = np.cumprod(1. - betas, axis=0)
+        self.num_timesteps = 1000
+        self.betas = torch.tensor(betas, dtype=torch.float32)
+        self.alphas_cumprod = torch.tensor(ac, dtype=torch.float32)
+        self.alphas_cumprod_prev = torch.tensor(np.append(1., ac[:-1]), dtype=torch.float32)
+        self.device = torch.device('cpu')
+        self.parameterization = 'eps'
+        self.unet = unet
+
+    def apply_model(self, x, t, c):
+        return self.unet(x, t, context=c)
+
+
+def golden_ddim_cycle():
+    from ldm.models.diffusion.ddim import DDIMSampler
+
+    class CPUSampler(DDIMSampler):
+        def register_buffer(self, name, attr):      # stock one forces .to("cuda"), ddim.py:19-23
+            setattr(self, name, attr)
+
+    cfg = NARROW
+    sd = specs.synth_state_dict(specs.openai_unet_params(cfg), 11)
+    unet = build_ref_unet(cfg)
+    unet.load_state_dict(sd, strict=True)
+    model = _LatentStandIn(unet)
+    g = torch.Generator().manual_seed(141)
+    B = 2
+    x0 = torch.randn(B, 4, 16, 16, generator=g) * 0.8
+    c_src = torch.randn(B, 77, 48, generator=g)
+    c_tgt = torch.randn(B, 77, 48, generator=g)
+    uc = torch.randn(B, 77, 48, generator=g)
+    out = dict(x0=x0, c_src=c_src, c_tgt=c_tgt, uc=uc)
+    for tag, S, skip, wb, enc_scale, dec_scale in (('a', 10, 3, 11, 1.0, 3.0), ('b', 8, 0, 9, 2.0, 1.0)):
+        torch.manual_seed(1000 + S)
+        with torch.no_grad(), _quiet():
+            z_list = CPUSampler(model).ddpm_ddim_encoding(S, conditioning=c_src, batch_size=B, shape=(4, 16, 16), eta=0.1,
+                                                          white_box_steps=wb, skip_steps=skip, verbose=False, x0=x0,
+                                                          unconditional_guidance_scale=enc_scale,
+                                                          unconditional_conditioning=uc)
+            z = torch.stack(z_list, dim=1).view(B, -1)                       # SDW:203
+            eps_list = z.view(B, wb - skip, 4, 16, 16)                         # SDW:150
+            x_T, eps = eps_list[:, 0], eps_list[:, 1:]
+            same, _ = CPUSampler(model).sample_with_eps(S, eps, conditioning=c_src, batch_size=B, shape=(4, 16, 16),
+                                                        eta=0.1, verbose=False, x_T=x_T, skip_steps=skip,
+                                                        unconditional_guidance_scale=enc_scale,
+                                                        unconditional_conditioning=uc)
+            tgt, _ = CPUSampler(model).sample_with_eps(S, eps, conditioning=c_tgt, batch_size=B, shape=(4, 16, 16),
+                                                       eta=0.1, verbose=False, x_T=x_T, skip_steps=skip,
+                                                       unconditional_guidance_scale=dec_scale,
+                                                       unconditional_conditioning=uc)
+        print(f'ddim_cycle[{tag}]: same-condition reconstruction max|x0_hat-x0| = {(same - x0).abs().max():.3e}, '
+              f'|z|max = {z.abs().max():.2f}')
+        out.update({f'z_{tag}': z, f'same_{tag}': same, f'tgt_{tag}': tgt,
+                    f'cfg_{tag}': np.asarray([S, skip, wb, enc_scale, dec_scale, 1000 + S], dtype=np.float64)})
+    save('ddim_cycle_narrow', **out)
+
+
+def golden_pixel_cycle():
+    """cfg1: DDPMDDIMWrapper as-is on a 64x64 i-DDPM U-Net, 10 encode + 10 decode steps, B=1, plus a ddpm-type run."""
+    cfg = specs.iddpm_config(64)
+    sd = specs.synth_state_dict(specs.iddpm_unet_params(cfg), 31)
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp()
+    os.makedirs(os.path.join(tmp, 'ckpts/ddpm/configs'))
+    with open(os.path.join(tmp, 'ckpts/ddpm/configs/afhq.yml'), 'w') as f:
+        f.write('data:\n  dataset: AFHQ\n  image_size: 64\n  channels: 3\n'
+                'diffusion:\n  beta_start: 0.0001\n  beta_end: 0.02\n  num_diffusion_timesteps: 1000\n')
+    torch.save(sd, os.path.join(tmp, 'ckpts/ddpm/afhq64.pt'))
+    sys.path.insert(0, REF)
+    os.chdir(tmp)
+    try:
+        with _quiet():
+            import model.gan_wrapper.ddpm_ddim_wrapper as W
+        from model.lib.ddpm_ddim.models.improved_ddpm.script_util import create_model, AFHQ_DICT
+        W.i_DDPM = lambda name='AFHQ': create_model(**{**AFHQ_DICT, 'image_size': 64})
+        out = {}
+        g = torch.Generator().manual_seed(151)
+        image = torch.rand(1, 3, 64, 64, generator=g)
+        out['image'] = image
+        for tag, kw in (('ddim', dict(sample_type='ddim', eta=0.1, custom_steps=10, es_steps=10)),
+                        ('ddpm', dict(sample_type='ddpm', eta=None, custom_steps=20, es_steps=6))):
+            with _quiet():
+                w = W.DDPMDDIMWrapper(source_model_type='afhqcat256', source_model_path='ckpts/ddpm/afhq64.pt',
+                                      refine_steps=0, **kw)
+            torch.manual_seed(2000)
+            with torch.no_grad(), _quiet():
+                z = w.encode(image)
+                img = w(z)
+            out[f'z_{tag}'] = z
+            out[f'img_{tag}'] = img
+            print(f'pixel_cycle[{tag}]: z {tuple(z.shape)} |z|max {z.abs().max():.2f}  recon max|img-image| '
+                  f'{(img - image).abs().max():.3e}')
+        save('pixel_cycle_iddpm64', **out)
+    finally:
+        os.chdir(cwd)
+
+
+if __name__ == '__main__':
+    _shim_omegaconf()
+    sys.path.insert(0, os.path.join(REF, 'model/lib/stable_diffusion'))
+    golden_inventories()
+    golden_schedule()
+    golden_unets()
+    golden_vae()
+    golden_ddim_cycle()
+    golden_iddpm()
+    golden_pixel_cycle()

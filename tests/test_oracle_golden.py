@@ -1,0 +1,102 @@
+"""The oracle restatement against fixtures produced by the real reference modules (tests/golden/make_golden.py).
+
+CPU only.  Tolerances: the oracle calls the same ATen CPU kernels as the reference modules, in the same
+order, so single forwards agree to fp32 round-off (<= 2e-5 abs on O(1) outputs); recovered noise ``z`` is
+amplified by 1/sigma_t, so it is compared relative to its own magnitude.
+"""
+import numpy as np
+import pytest
+import torch
+
+from cycle_diffusion_b200 import specs
+from oracle import dpm_encoder, schedules, unet_iddpm, unet_openai, vae_kl
+from tests.common import NARROW, VAE_SMALL, WIDE, golden, maxdiff, wsum
+
+torch.set_num_threads(8)
+
+
+def test_schedule_tables_bit_exact():
+    g = golden('schedule_ldm')
+    ac = schedules.ldm_alphas_cumprod()
+    assert torch.equal(ac, g['alphas_cumprod'])
+    for S in (10, 50, 99, 100):
+        tab = schedules.DDIMTables(S, 0.1)
+        assert np.array_equal(tab.timesteps, g[f'ts_{S}'].numpy())
+        f32 = lambda t: torch.stack([torch.full((1,), t[i]) for i in range(S)]).flatten()
+        assert torch.equal(f32(tab.alphas), g[f'a_{S}'])
+        assert torch.equal(f32(tab.alphas_prev), g[f'aprev_{S}'])
+        assert torch.equal(f32(tab.sigmas), g[f'sigma_{S}'])
+        assert torch.equal(f32(tab.sqrt_one_minus_alphas), g[f'sqrt1ma_{S}'])
+    assert list(schedules.ddim_timesteps(10)) == [1, 101, 201, 301, 401, 501, 601, 701, 801, 901]
+
+
+@pytest.mark.parametrize('name,cfg', [('unet_sd_narrow', NARROW), ('unet_sd_wide', WIDE)])
+def test_openai_unet(name, cfg):
+    g = golden(name)
+    sd = specs.synth_state_dict(specs.openai_unet_params(cfg), int(g['seed']))
+    assert np.allclose(wsum(sd), g['wsum'], rtol=1e-12), 'synthetic weight generator drifted'
+    with torch.no_grad():
+        y = unet_openai.unet_forward(sd, cfg, g['x'], g['t'], g['ctx'])
+    assert maxdiff(y, g['y']) <= 2e-5 * max(1.0, float(g['y'].abs().max()))
+
+
+def test_vae():
+    g = golden('vae_small')
+    sd = specs.synth_state_dict(specs.kl_vae_params(VAE_SMALL), int(g['seed']))
+    assert np.allclose(wsum(sd), g['wsum'], rtol=1e-12)
+    with torch.no_grad():
+        m = vae_kl.encode_moments(sd, VAE_SMALL, g['img'])
+        r = vae_kl.decode(sd, VAE_SMALL, g['z'])
+    assert maxdiff(m, g['moments']) <= 2e-5 * max(1.0, float(g['moments'].abs().max()))
+    assert maxdiff(r, g['rec']) <= 2e-5 * max(1.0, float(g['rec'].abs().max()))
+
+
+def test_iddpm_unet():
+    g = golden('unet_iddpm64')
+    cfg = specs.iddpm_config(64)
+    sd = specs.synth_state_dict(specs.iddpm_unet_params(cfg), int(g['seed']))
+    assert np.allclose(wsum(sd), g['wsum'], rtol=1e-12)
+    with torch.no_grad():
+        y = unet_iddpm.unet_forward(sd, cfg, g['x'], g['t'])
+    assert maxdiff(y, g['y']) <= 2e-5 * max(1.0, float(g['y'].abs().max()))
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_ddim_cycle(tag):
+    g = golden('ddim_cycle_narrow')
+    S, skip, wb, enc_scale, dec_scale, seed = [float(v) for v in g[f'cfg_{tag}']]
+    S, skip, wb, seed = int(S), int(skip), int(wb), int(seed)
+    sd = specs.synth_state_dict(specs.openai_unet_params(NARROW), 11)
+    unet = lambda x, t, c: unet_openai.unet_forward(sd, NARROW, x, t, c)
+    B = g['x0'].shape[0]
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        z_list = dpm_encoder.latent_encode(unet, g['x0'], g['c_src'], g['uc'], S, 0.1, skip, wb, enc_scale)
+        z = torch.stack(z_list, dim=1).view(B, -1)
+        zref = g[f'z_{tag}']
+        assert z.shape == zref.shape
+        assert maxdiff(z, zref) <= 1e-4 * float(zref.abs().max())
+        eps_list = zref.view(B, wb - skip, 4, 16, 16)
+        same = dpm_encoder.latent_decode(unet, eps_list[:, 0], eps_list[:, 1:], g['c_src'], g['uc'], S, 0.1, skip, enc_scale)
+        tgt = dpm_encoder.latent_decode(unet, eps_list[:, 0], eps_list[:, 1:], g['c_tgt'], g['uc'], S, 0.1, skip, dec_scale)
+    assert maxdiff(same, g[f'same_{tag}']) <= 1e-4
+    assert maxdiff(tgt, g[f'tgt_{tag}']) <= 1e-4
+    # built-in known-answer property: same-condition cycle reconstructs x0
+    assert maxdiff(same, g['x0']) <= 1e-4
+
+
+@pytest.mark.parametrize('tag,kw', [('ddim', dict(sample_type='ddim', eta=0.1, custom_steps=10, es_steps=10)),
+                                    ('ddpm', dict(sample_type='ddpm', eta=None, custom_steps=20, es_steps=6))])
+def test_pixel_cycle(tag, kw):
+    g = golden('pixel_cycle_iddpm64')
+    cfg = specs.iddpm_config(64)
+    sd = specs.synth_state_dict(specs.iddpm_unet_params(cfg), 31)
+    model = lambda x, t: unet_iddpm.unet_forward(sd, cfg, x, t)
+    cyc = dpm_encoder.PixelCycle(model, resolution=64, **kw)
+    torch.manual_seed(2000)
+    with torch.no_grad():
+        z = cyc.encode(g['image'])
+        zref = g[f'z_{tag}']
+        assert maxdiff(z, zref) <= 2e-4 * float(zref.abs().max())
+        img = cyc.forward(zref)
+    assert maxdiff(img, g[f'img_{tag}']) <= 1e-3
