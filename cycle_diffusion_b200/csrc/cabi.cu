@@ -1,0 +1,500 @@
+// cabi.cu -- the extern "C" surface declared in include/cdx.h, plus the in-library loop drivers
+// (DPM-Encoder inversion and decode-with-recovered-noise) so that a whole chain is enqueued without
+// returning to the host language between steps.
+#include <string.h>
+
+#include <algorithm>
+
+#include "nets.cuh"
+
+struct cdx_engine { cdx::Engine e; };
+struct cdx_net { cdx::Net* n; cdx_engine* owner; };
+
+namespace cdx {
+const std::string& last_error();
+
+namespace {
+
+template <class F>
+int guard(F&& f) {
+  try {
+    f();
+    return CDX_OK;
+  } catch (const Error& err) {
+    set_last_error(err.what());
+    return err.code;
+  } catch (const std::exception& err) {
+    set_last_error(std::string("internal error: ") + err.what());
+    return CDX_E_INVALID;
+  }
+}
+
+// run `f` once in sizing mode, grow the arena, then for real
+template <class F>
+void with_arena(Engine& e, F&& f) {
+  CDX_CUDA(cudaSetDevice(e.device));
+  e.arena.begin_dry();
+  try {
+    f();
+  } catch (...) {
+    e.arena.dry = false;
+    e.arena.off = 0;
+    throw;
+  }
+  e.arena.end_dry();
+  f();
+  e.arena.off = 0;
+}
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// fill a device float vector with one value per row, repeated `rep` times (timestep vector for [x;x] CFG batches)
+void upload_timesteps(Engine& e, const float* t_host, int n_steps, int reps, float* dev, cudaStream_t s) {
+  if (e.dry()) return;
+  std::vector<float> h((size_t)n_steps * reps);
+  for (int i = 0; i < n_steps; ++i)
+    for (int r = 0; r < reps; ++r) h[(size_t)i * reps + r] = t_host[i];
+  // pageable source: the runtime stages the copy before returning, so `h` may die afterwards
+  CDX_CUDA(cudaMemcpyAsync(dev, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+}
+
+// dst[b, slot, :] = src[b, :]  for a [B, n_slots, chw] tensor
+void scatter_slot(Engine& e, const float* src, float* dst, int B, int chw, int n_slots, int slot, cudaStream_t s) {
+  if (e.dry()) return;
+  CDX_CUDA(cudaMemcpy2DAsync(dst + (size_t)slot * chw, (size_t)n_slots * chw * sizeof(float), src, (size_t)chw * sizeof(float),
+                             (size_t)chw * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+}
+void gather_slot(Engine& e, const float* src, float* dst, int B, int chw, int n_slots, int slot, cudaStream_t s) {
+  if (e.dry()) return;
+  CDX_CUDA(cudaMemcpy2DAsync(dst, (size_t)chw * sizeof(float), src + (size_t)slot * chw, (size_t)n_slots * chw * sizeof(float),
+                             (size_t)chw * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+}
+void copy_dd(Engine& e, const float* src, float* dst, size_t n, cudaStream_t s) {
+  if (e.dry()) return;
+  CDX_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+}
+
+// One guided eps-prediction: fills e_c / e_uc pointers (e_uc = nullptr when no CFG batch ran).  ddim.py:550-559
+struct Guided {
+  Net& unet;
+  Engine& e;
+  int B, C, h, w, L;
+  float scale;
+  const float* c;
+  const float* uc;
+  float* x_in = nullptr;     // [2B, C,h,w]
+  float* ctx_in = nullptr;   // [2B, L, D]
+  float* eout = nullptr;     // [2B, C,h,w]
+  bool cfg;
+  Guided(Net& u, int B_, int C_, int h_, int w_, int L_, float scale_, const float* c_, const float* uc_, cudaStream_t s)
+      : unet(u), e(*u.eng), B(B_), C(C_), h(h_), w(w_), L(L_), scale(scale_), c(c_), uc(uc_) {
+    cfg = (uc != nullptr) && scale != 1.0f && scale != 0.0f;
+    const size_t n = (size_t)B * C * h * w;
+    const int D = unet.ucfg.context_dim;
+    eout = (float*)e.arena.alloc((cfg ? 2 : 1) * n * sizeof(float));
+    if (cfg) {
+      x_in = (float*)e.arena.alloc(2 * n * sizeof(float));
+      ctx_in = (float*)e.arena.alloc((size_t)2 * B * L * D * sizeof(float));
+      copy_dd(e, uc, ctx_in, (size_t)B * L * D, s);                          // cat([uc, c]): uncond first
+      copy_dd(e, c, ctx_in + (size_t)B * L * D, (size_t)B * L * D, s);
+    }
+  }
+  // t_dev2: device vector holding the timestep 2B times
+  void run(const float* x, const float* t_dev2, const float** e_c, const float** e_uc, cudaStream_t s) {
+    const size_t n = (size_t)B * C * h * w;
+    if (cfg) {
+      copy_dd(e, x, x_in, n, s);
+      copy_dd(e, x, x_in + n, n, s);
+      unet_forward(unet, x_in, t_dev2, ctx_in, L, eout, 2 * B, h, w, s);
+      *e_uc = eout;
+      *e_c = eout + n;
+    } else {
+      const float* cond = (uc != nullptr && scale == 0.0f) ? uc : c;
+      unet_forward(unet, x, t_dev2, cond, L, eout, B, h, w, s);
+      *e_c = eout;
+      *e_uc = nullptr;
+    }
+  }
+};
+
+}  // namespace
+}  // namespace cdx
+
+using namespace cdx;
+
+static inline cdx::Engine& engine_of(cdx_engine* h) { return h->e; }
+
+extern "C" {
+
+int cdx_abi_version(void) { return CDX_ABI_VERSION; }
+const char* cdx_last_error(void) { return cdx::last_error().c_str(); }
+
+int cdx_engine_create(int device, cdx_engine** out) {
+  return guard([&] {
+    CDX_CHECK(out != nullptr, "engine_create: null out");
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count <= 0)
+      throw Error(CDX_E_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(err));
+    CDX_CHECK(device >= 0 && device < count, "engine_create: device %d out of range (count %d)", device, count);
+    CDX_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CDX_CUDA(cudaGetDeviceProperties(&prop, device));
+    cdx_engine* eng = new cdx_engine();
+    eng->e.device = device;
+    eng->e.num_sms = prop.multiProcessorCount;
+    *out = eng;
+  });
+}
+void cdx_engine_destroy(cdx_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->e.device);
+  cudaDeviceSynchronize();
+  e->e.arena.destroy();
+  delete e;
+}
+size_t cdx_engine_workspace_bytes(const cdx_engine* e) { return e ? e->e.arena.cap : 0; }
+uint64_t cdx_engine_launch_count(const cdx_engine* e) { return e ? e->e.launches : 0; }
+int cdx_engine_set_mma_mode(cdx_engine* e, int mode) {
+  return guard([&] {
+    CDX_CHECK(e != nullptr && (mode == 0 || mode == 1), "set_mma_mode: bad arguments");
+    e->e.mma_mode = mode;
+  });
+}
+
+// ---------------------------------------------------------------- networks
+int cdx_unet_create(cdx_engine* e, const cdx_unet_config* cfg, cdx_net** out) {
+  return guard([&] {
+    CDX_CHECK(cfg && out, "unet_create: null argument");
+    cdx_net* h = new cdx_net();
+    h->owner = e;
+    static Engine host_only;   // inventory-only nets (e == NULL) can be built without a GPU
+    h->n = make_unet(e ? &e->e : &host_only, *cfg);
+    *out = h;
+  });
+}
+int cdx_vae_create(cdx_engine* e, const cdx_vae_config* cfg, cdx_net** out) {
+  return guard([&] {
+    CDX_CHECK(cfg && out, "vae_create: null argument");
+    cdx_net* h = new cdx_net();
+    h->owner = e;
+    static Engine host_only;
+    h->n = make_vae(e ? &e->e : &host_only, *cfg);
+    *out = h;
+  });
+}
+void cdx_net_destroy(cdx_net* n) {
+  if (!n) return;
+  destroy_net(n->n);
+  delete n;
+}
+int cdx_net_num_params(const cdx_net* n) { return n ? (int)n->n->params.size() : 0; }
+const char* cdx_net_param_name(const cdx_net* n, int i) {
+  if (!n || i < 0 || i >= (int)n->n->params.size()) return nullptr;
+  return n->n->params[i].name.c_str();
+}
+int cdx_net_param_shape(const cdx_net* n, int i, int64_t dims[4]) {
+  if (!n || i < 0 || i >= (int)n->n->params.size()) return CDX_E_INVALID;
+  const Param& p = n->n->params[i];
+  for (int k = 0; k < 4; ++k) dims[k] = k < p.rank ? p.dims[k] : 1;
+  return p.rank;
+}
+int cdx_net_load_param(cdx_net* n, const char* name, const float* data, int on_device, const int64_t* dims, int rank) {
+  return guard([&] {
+    CDX_CHECK(n && n->owner && name && data && dims, "load_param: null argument (nets created without an engine are inventory-only)");
+    net_load_param(*n->n, name, data, on_device != 0, dims, rank);
+  });
+}
+int cdx_net_finalize(cdx_net* n) {
+  return guard([&] {
+    CDX_CHECK(n && n->owner, "finalize: null / inventory-only net");
+    net_finalize(*n->n);
+  });
+}
+int cdx_net_weight_blob(cdx_net* n, void** dev_ptr, size_t* bytes) {
+  return guard([&] {
+    CDX_CHECK(n && n->owner && dev_ptr && bytes, "weight_blob: null argument");
+    net_ensure_blob(*n->n);
+    *dev_ptr = n->n->blob;
+    *bytes = n->n->blob_floats * sizeof(float);
+  });
+}
+int cdx_net_adopt_blob(cdx_net* n) {
+  return guard([&] {
+    CDX_CHECK(n && n->owner, "adopt_blob: null / inventory-only net");
+    net_ensure_blob(*n->n);
+    for (Param& p : n->n->params) p.loaded = true;
+    net_finalize(*n->n);
+  });
+}
+int cdx_unet_set_time_freqs(cdx_net* n, const float* freqs, int half) {
+  return guard([&] {
+    CDX_CHECK(n && freqs, "set_time_freqs: null argument");
+    CDX_CHECK(n->n->kind != NET_VAE, "set_time_freqs on a VAE");
+    CDX_CHECK(half == n->n->ucfg.model_channels / 2, "set_time_freqs: half=%d, expected %d", half, n->n->ucfg.model_channels / 2);
+    n->n->freqs_host.assign(freqs, freqs + half);
+    if (n->n->finalized) net_finalize(*n->n);
+  });
+}
+
+int cdx_unet_forward(cdx_net* n, const float* x, const float* t_dev, const float* ctx, int ctx_len, float* out, int B, int H, int W,
+                     void* stream) {
+  return guard([&] {
+    CDX_CHECK(n && n->owner && x && t_dev && out && B > 0, "unet_forward: bad arguments");
+    with_arena(n->owner->e, [&] { unet_forward(*n->n, x, t_dev, ctx, ctx_len, out, B, H, W, S(stream)); });
+  });
+}
+int cdx_vae_encode(cdx_net* n, const float* img, float* moments, int B, int R, void* stream) {
+  return guard([&] {
+    CDX_CHECK(n && n->owner && img && moments && B > 0, "vae_encode: bad arguments");
+    with_arena(n->owner->e, [&] { vae_encode(*n->n, img, moments, B, R, S(stream)); });
+  });
+}
+int cdx_vae_decode(cdx_net* n, const float* z, float* img, int B, int h, void* stream) {
+  return guard([&] {
+    CDX_CHECK(n && n->owner && z && img && B > 0, "vae_decode: bad arguments");
+    with_arena(n->owner->e, [&] { vae_decode(*n->n, z, img, B, h, S(stream)); });
+  });
+}
+
+// ---------------------------------------------------------------- per-step kernels
+#define ENG_CALL(EH_, ...)                                 \
+  return guard([&] {                                       \
+    CDX_CHECK((EH_) != nullptr, "null engine");            \
+    CDX_CUDA(cudaSetDevice(engine_of(EH_).device));        \
+    __VA_ARGS__;                                           \
+  })
+
+int cdx_affine(cdx_engine* e, const float* x, float a, float b, float* out, size_t n, void* s) { ENG_CALL(e, affine(e->e, x, a, b, out, n, S(s))); }
+int cdx_shift_scale(cdx_engine* e, const float* x, float b, float a, float* out, size_t n, void* s) { ENG_CALL(e, shift_scale(e->e, x, b, a, out, n, S(s))); }
+int cdx_q_sample(cdx_engine* e, const float* x0, const float* nz, float sa, float s1, float* out, size_t n, void* s) {
+  ENG_CALL(e, q_sample(e->e, x0, nz, sa, s1, out, n, S(s)));
+}
+int cdx_vae_posterior(cdx_engine* e, const float* mom, const float* nz, float sf, float* out, int B, int C, int hw, void* s) {
+  ENG_CALL(e, vae_posterior(e->e, mom, nz, sf, out, B, C, hw, S(s)));
+}
+int cdx_ddim_posterior_sample(cdx_engine* e, const float* x0, const float* xt, const float* nz, const cdx_ddim_coef* c, float* o, size_t n, void* s) {
+  ENG_CALL(e, CDX_CHECK(c, "null coef"); ddim_posterior_sample(e->e, x0, xt, nz, *c, o, n, S(s)));
+}
+int cdx_ddim_compute_eps(cdx_engine* e, const float* xt, const float* xn, const float* e_c, const float* e_uc, float scale, const cdx_ddim_coef* c,
+                         float* o, size_t n, void* s) {
+  ENG_CALL(e, CDX_CHECK(c, "null coef"); ddim_compute_eps(e->e, xt, xn, e_c, e_uc, scale, *c, o, n, S(s)));
+}
+int cdx_ddim_step_with_eps(cdx_engine* e, const float* x, const float* e_c, const float* e_uc, float scale, const float* eps, const cdx_ddim_coef* c,
+                           float* o, size_t n, void* s) {
+  ENG_CALL(e, CDX_CHECK(c, "null coef"); ddim_step_with_eps(e->e, x, e_c, e_uc, scale, eps, *c, o, n, S(s)));
+}
+int cdx_pixel_posterior_sample(cdx_engine* e, const float* x0, const float* xt, const float* nz, const cdx_pixel_coef* c, float* o, size_t n, void* s) {
+  ENG_CALL(e, CDX_CHECK(c, "null coef"); pixel_posterior_sample(e->e, x0, xt, nz, *c, o, n, S(s)));
+}
+int cdx_pixel_compute_eps(cdx_engine* e, const float* xt, const float* xn, const float* et, const cdx_pixel_coef* c, float* o, int B, int chw,
+                          int net_chw, void* s) {
+  ENG_CALL(e, CDX_CHECK(c, "null coef"); pixel_compute_eps(e->e, xt, xn, et, *c, o, B, chw, net_chw, S(s)));
+}
+int cdx_pixel_step_with_eps(cdx_engine* e, const float* xt, const float* et, const float* eps, const cdx_pixel_coef* c, float* o, int B, int chw,
+                            int net_chw, void* s) {
+  ENG_CALL(e, CDX_CHECK(c, "null coef"); pixel_step_with_eps(e->e, xt, et, eps, *c, o, B, chw, net_chw, S(s)));
+}
+
+// ---------------------------------------------------------------- loop drivers
+int cdx_latent_encode(cdx_net* un, const float* x0, const float* c, const float* uc, int L, float scale, const cdx_ddim_coef* coef,
+                      const float* t_host, int n_steps, int n_rec, const float* noise, float sqrt_a_T, float sqrt_1ma_T, float* z_out, int B,
+                      int C, int h, int w, void* stream) {
+  return guard([&] {
+    CDX_CHECK(un && un->owner && x0 && c && coef && t_host && noise && z_out, "latent_encode: null argument");
+    CDX_CHECK(n_steps >= 1 && n_rec >= 0 && n_rec <= n_steps, "latent_encode: n_steps=%d n_rec=%d", n_steps, n_rec);
+    for (int i = 0; i < n_rec; ++i) CDX_CHECK(coef[i].sigma > 0.f, "latent_encode: eta must be > 0 (sigma[%d] == 0), ddim.py:268", i);
+    Engine& e = un->owner->e;
+    Net& unet = *un->n;
+    cudaStream_t s = S(stream);
+    const int chw = C * h * w;
+    const size_t n = (size_t)B * chw;
+    with_arena(e, [&] {
+      Scope sc(e.arena);
+      float* xt = (float*)e.arena.alloc(n * sizeof(float));
+      float* xn = (float*)e.arena.alloc(n * sizeof(float));
+      float* eps = (float*)e.arena.alloc(n * sizeof(float));
+      float* tdev = (float*)e.arena.alloc((size_t)n_steps * 2 * B * sizeof(float));
+      upload_timesteps(e, t_host, n_steps, 2 * B, tdev, s);
+      Guided g(unet, B, C, h, w, L, scale, c, uc, s);
+      q_sample(e, x0, noise, sqrt_a_T, sqrt_1ma_T, xt, n, s);                         // ddim.py:477-479
+      scatter_slot(e, xt, z_out, B, chw, n_rec + 1, 0, s);
+      const int iters = e.dry() ? std::min(n_rec, 1) : n_rec;
+      for (int i = 0; i < iters; ++i) {
+        const int index = n_steps - 1 - i;
+        const float* xt_next = xn;
+        if (index == 0) xt_next = x0;                                                 // ddim.py:583-584
+        else ddim_posterior_sample(e, x0, xt, noise + (size_t)(1 + i) * n, coef[i], xn, n, s);
+        const float *e_c, *e_uc;
+        g.run(xt, tdev + (size_t)i * 2 * B, &e_c, &e_uc, s);
+        ddim_compute_eps(e, xt, xt_next, e_c, e_uc, scale, coef[i], eps, n, s);
+        scatter_slot(e, eps, z_out, B, chw, n_rec + 1, 1 + i, s);
+        if (index != 0) std::swap(xt, xn);
+      }
+    });
+  });
+}
+
+int cdx_latent_decode(cdx_net* un, const float* z, int n_eps, const float* c, const float* uc, int L, float scale, const cdx_ddim_coef* coef,
+                      const float* t_host, int n_steps, const float* extra_noise, float* x_out, int B, int C, int h, int w, void* stream) {
+  return guard([&] {
+    CDX_CHECK(un && un->owner && z && c && coef && t_host && x_out, "latent_decode: null argument");
+    CDX_CHECK(n_steps >= 1 && n_eps >= 0, "latent_decode: n_steps=%d n_eps=%d", n_steps, n_eps);
+    CDX_CHECK(n_eps >= n_steps || extra_noise != nullptr, "latent_decode: %d steps but only %d recovered noises and no extra noise", n_steps, n_eps);
+    Engine& e = un->owner->e;
+    Net& unet = *un->n;
+    cudaStream_t s = S(stream);
+    const int chw = C * h * w;
+    const size_t n = (size_t)B * chw;
+    with_arena(e, [&] {
+      Scope sc(e.arena);
+      float* xa = (float*)e.arena.alloc(n * sizeof(float));
+      float* xb = (float*)e.arena.alloc(n * sizeof(float));
+      float* eps = (float*)e.arena.alloc(n * sizeof(float));
+      float* tdev = (float*)e.arena.alloc((size_t)n_steps * 2 * B * sizeof(float));
+      upload_timesteps(e, t_host, n_steps, 2 * B, tdev, s);
+      Guided g(unet, B, C, h, w, L, scale, c, uc, s);
+      gather_slot(e, z, xa, B, chw, n_eps + 1, 0, s);                                  // x_T = eps_list[:, 0], SDW:153
+      const int iters = e.dry() ? 1 : n_steps;
+      for (int i = 0; i < iters; ++i) {
+        const float *e_c, *e_uc;
+        g.run(xa, tdev + (size_t)i * 2 * B, &e_c, &e_uc, s);
+        const float* nz;
+        if (i < n_eps) { gather_slot(e, z, eps, B, chw, n_eps + 1, 1 + i, s); nz = eps; }
+        else nz = extra_noise + (size_t)(i - n_eps) * n;
+        float* dst = (i == n_steps - 1) ? x_out : xb;
+        ddim_step_with_eps(e, xa, e_c, e_uc, scale, nz, coef[i], dst, n, s);
+        std::swap(xa, xb);
+      }
+    });
+  });
+}
+
+int cdx_pixel_encode(cdx_net* un, const float* x0, const cdx_pixel_coef* coef, const float* t_host, int n_rec, const float* noise,
+                     float sqrt_a_T, float sqrt_1ma_T, float* z_out, int B, int C, int R, void* stream) {
+  return guard([&] {
+    CDX_CHECK(un && un->owner && x0 && noise && z_out, "pixel_encode: null argument");
+    CDX_CHECK(n_rec >= 0 && (n_rec == 0 || (coef && t_host)), "pixel_encode: n_rec=%d", n_rec);
+    Engine& e = un->owner->e;
+    Net& unet = *un->n;
+    cudaStream_t s = S(stream);
+    const int chw = C * R * R;
+    const int net_chw = unet.ucfg.out_channels * R * R;
+    const size_t n = (size_t)B * chw;
+    with_arena(e, [&] {
+      Scope sc(e.arena);
+      float* xt = (float*)e.arena.alloc(n * sizeof(float));
+      float* xn = (float*)e.arena.alloc(n * sizeof(float));
+      float* eps = (float*)e.arena.alloc(n * sizeof(float));
+      float* et = (float*)e.arena.alloc((size_t)B * net_chw * sizeof(float));
+      float* tdev = (float*)e.arena.alloc((size_t)std::max(n_rec, 1) * B * sizeof(float));
+      upload_timesteps(e, t_host, n_rec, B, tdev, s);
+      q_sample(e, x0, noise, sqrt_a_T, sqrt_1ma_T, xt, n, s);                          // sample_xt, DW:310-314 (incl. the DW:483 index quirk)
+      scatter_slot(e, xt, z_out, B, chw, n_rec + 1, 0, s);
+      const int iters = e.dry() ? std::min(n_rec, 1) : n_rec;
+      for (int i = 0; i < iters; ++i) {
+        pixel_posterior_sample(e, x0, xt, noise + (size_t)(1 + i) * n, coef[i], xn, n, s);
+        unet_forward(unet, xt, tdev + (size_t)i * B, nullptr, 0, et, B, R, R, s);
+        pixel_compute_eps(e, xt, xn, et, coef[i], eps, B, chw, net_chw, s);
+        scatter_slot(e, eps, z_out, B, chw, n_rec + 1, 1 + i, s);
+        std::swap(xt, xn);
+      }
+    });
+  });
+}
+
+int cdx_pixel_decode(cdx_net* un, const float* z, int n_eps, const cdx_pixel_coef* coef, const float* t_host, int n_steps,
+                     const float* last_noise, float* x_out, int B, int C, int R, void* stream) {
+  return guard([&] {
+    CDX_CHECK(un && un->owner && z && coef && t_host && x_out, "pixel_decode: null argument");
+    CDX_CHECK(n_steps >= 1 && n_eps >= 0 && n_eps <= n_steps, "pixel_decode: n_steps=%d n_eps=%d", n_steps, n_eps);
+    Engine& e = un->owner->e;
+    Net& unet = *un->n;
+    cudaStream_t s = S(stream);
+    const int chw = C * R * R;
+    const int net_chw = unet.ucfg.out_channels * R * R;
+    const size_t n = (size_t)B * chw;
+    with_arena(e, [&] {
+      Scope sc(e.arena);
+      float* xa = (float*)e.arena.alloc(n * sizeof(float));
+      float* xb = (float*)e.arena.alloc(n * sizeof(float));
+      float* eps = (float*)e.arena.alloc(n * sizeof(float));
+      float* et = (float*)e.arena.alloc((size_t)B * net_chw * sizeof(float));
+      float* tdev = (float*)e.arena.alloc((size_t)n_steps * B * sizeof(float));
+      upload_timesteps(e, t_host, n_steps, B, tdev, s);
+      gather_slot(e, z, xa, B, chw, n_eps + 1, 0, s);
+      const int iters = e.dry() ? 1 : n_steps;
+      for (int i = 0; i < iters; ++i) {
+        unet_forward(unet, xa, tdev + (size_t)i * B, nullptr, 0, et, B, R, R, s);
+        const float* nz = nullptr;
+        if (i < n_eps) { gather_slot(e, z, eps, B, chw, n_eps + 1, 1 + i, s); nz = eps; }
+        else if (last_noise) nz = last_noise + (size_t)(i - n_eps) * n;
+        float* dst = (i == n_steps - 1) ? x_out : xb;
+        pixel_step_with_eps(e, xa, et, nz, coef[i], dst, B, chw, net_chw, s);
+        std::swap(xa, xb);
+      }
+    });
+  });
+}
+
+// ---------------------------------------------------------------- unit-test hooks
+int cdx_op_conv3x3(cdx_engine* eh, const float* x, const float* w_oihw, const float* bias, float* y, int B, int H, int W, int Cin, int Cout,
+                   int stride, int pad_lo, int upsample, void* stream) {
+  return guard([&] {
+    CDX_CHECK(eh && x && w_oihw && y, "op_conv3x3: null argument");
+    Engine& e = eh->e;
+    cudaStream_t s = S(stream);
+    with_arena(e, [&] {
+      Scope sc(e.arena);
+      float* wr = (float*)e.arena.alloc((size_t)Cout * Cin * 9 * sizeof(float));
+      repack_conv3x3(e, w_oihw, wr, Cout, Cin, s);
+      const int Hl = H * upsample, Wl = W * upsample;
+      GemmArgs g;
+      g.mode = 1;
+      g.Hout = stride == 1 ? Hl : Hl / 2;
+      g.Wout = stride == 1 ? Wl : Wl / 2;
+      g.M = B * g.Hout * g.Wout; g.N = Cout; g.K = 9 * Cin;
+      g.A = x; g.lda = Cin; g.C1 = Cin;
+      g.Hin = H; g.Win = W; g.stride = stride; g.pad = pad_lo; g.up = upsample;
+      g.Bw = wr; g.ldb = 9 * Cin;
+      g.Cout = y; g.ldc = Cout;
+      g.bias = bias;
+      gemm(e, g, s);
+    });
+  });
+}
+int cdx_op_linear(cdx_engine* eh, const float* x, const float* w, const float* bias, float* y, int M, int K, int N, void* stream) {
+  return guard([&] {
+    CDX_CHECK(eh && x && w && y, "op_linear: null argument");
+    CDX_CUDA(cudaSetDevice(eh->e.device));
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K;
+    g.A = x; g.lda = K; g.C1 = K;
+    g.Bw = w; g.ldb = K;
+    g.Cout = y; g.ldc = N;
+    g.bias = bias;
+    gemm(eh->e, g, S(stream));
+  });
+}
+int cdx_op_groupnorm(cdx_engine* eh, const float* x, const float* gamma, const float* beta, float eps, int silu_, float* y, int B, int HW, int C,
+                     void* stream) {
+  return guard([&] {
+    CDX_CHECK(eh && x && gamma && beta && y, "op_groupnorm: null argument");
+    with_arena(eh->e, [&] { groupnorm(eh->e, x, C, nullptr, 0, gamma, beta, eps, silu_ != 0, nullptr, nullptr, 0, y, B, HW, S(stream)); });
+  });
+}
+int cdx_op_layernorm(cdx_engine* eh, const float* x, const float* gamma, const float* beta, float* y, int M, int C, void* stream) {
+  ENG_CALL(eh, layernorm(eh->e, x, gamma, beta, y, M, C, S(stream)));
+}
+int cdx_op_attention(cdx_engine* eh, const float* q, const float* k, const float* v, float* out, int B, int Nq, int Nk, int heads, int d, float scale,
+                     void* stream) {
+  return guard([&] {
+    CDX_CHECK(eh && q && k && v && out, "op_attention: null argument");
+    const int C = heads * d;
+    with_arena(eh->e, [&] { attention(eh->e, q, C, k, C, v, C, out, C, B, Nq, Nk, heads, d, d, scale, S(stream)); });
+  });
+}
+int cdx_op_nchw_to_nhwc(cdx_engine* eh, const float* x, float* y, int B, int C, int HW, void* stream) { ENG_CALL(eh, nchw_to_nhwc(eh->e, x, y, B, C, HW, S(stream))); }
+int cdx_op_nhwc_to_nchw(cdx_engine* eh, const float* x, float* y, int B, int C, int HW, void* stream) { ENG_CALL(eh, nhwc_to_nchw(eh->e, x, y, B, C, HW, S(stream))); }
+
+}  // extern "C"

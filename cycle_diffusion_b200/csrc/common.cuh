@@ -1,0 +1,158 @@
+// common.cuh -- engine-wide declarations: error plumbing, workspace arena, tensor views, op prototypes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+#include "../../include/cdx.h"
+
+namespace cdx {
+
+// ------------------------------------------------------------------------------------------------
+// errors: C++ exceptions inside the library, translated to CDX_E_* + thread-local message at the ABI
+// ------------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+void set_last_error(const std::string& m);
+
+#define CDX_CHECK(cond, ...)                                                     \
+  do {                                                                           \
+    if (!(cond)) {                                                               \
+      char _b[512];                                                              \
+      snprintf(_b, sizeof(_b), __VA_ARGS__);                                     \
+      throw ::cdx::Error(CDX_E_INVALID, std::string(_b) + " [" #cond "]");       \
+    }                                                                            \
+  } while (0)
+
+#define CDX_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      char _b[512];                                                                            \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      throw ::cdx::Error(CDX_E_CUDA, _b);                                                      \
+    }                                                                                          \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// workspace arena: stack (mark/release) allocator over one device slab, sized by a dry run of the call.
+// All work of an engine is enqueued on a single stream, so memory released to the stack can be reused
+// by later launches without extra synchronisation.
+// ------------------------------------------------------------------------------------------------
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, high = 0;
+  bool dry = false;
+  void* alloc(size_t bytes);
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+  void begin_dry();   // start a sizing pass: allocations only advance the offset
+  void end_dry();     // grow the slab to the recorded high-water mark, rewind
+  void destroy();
+};
+
+struct Engine {
+  int device = 0;
+  int num_sms = 148;
+  int mma_mode = 0;              // 0 SIMT FFMA, 1 tcgen05 3xTF32
+  Arena arena;
+  uint64_t launches = 0;
+  bool dry() const { return arena.dry; }
+};
+
+struct Scope {   // RAII arena scope
+  Arena& a;
+  size_t m;
+  explicit Scope(Arena& ar) : a(ar), m(ar.mark()) {}
+  ~Scope() { a.release(m); }
+};
+
+// NHWC activation view: p[((b*H + y)*W + x)*C + c]; a [M,C] token matrix is H=M/B, W=1.
+struct Tensor {
+  float* p = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  size_t numel() const { return (size_t)B * H * W * C; }
+  int rows() const { return B * H * W; }
+};
+inline Tensor alloc_tensor(Engine& e, int B, int H, int W, int C) {
+  Tensor t;
+  t.B = B; t.H = H; t.W = W; t.C = C;
+  t.p = (float*)e.arena.alloc(t.numel() * sizeof(float));
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense contraction (implicit GEMM) arguments, shared by the SIMT and tcgen05 back ends
+//   C[m,n] = alpha * sum_k A(m,k) * W(n,k)  (+ bias[n]) (+ rowvec[m / rows_per_batch, n]) (+ residual[m,n])
+// A is either a dense row matrix (two channel-concatenated sources allowed) or the implicit im2col of
+// a 3x3 convolution over an NHWC tensor (k = tap*Cin + c).
+// ------------------------------------------------------------------------------------------------
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  int mode = 0;                       // 0 dense rows, 1 conv3x3 gather
+  const float* A = nullptr;  int lda = 0;  int C1 = 0;   // first source: C1 channels, row/pixel stride lda
+  const float* A2 = nullptr; int lda2 = 0; int C2 = 0;   // optional second source (channel concat)
+  // conv geometry (mode 1): stored input [B,Hin,Win,*], logical input is up x larger (nearest)
+  int Hin = 0, Win = 0, Hout = 0, Wout = 0, stride = 1, pad = 1, up = 1;
+  const float* Bw = nullptr; int ldb = 0; int b_kn = 0;   // weights [N][K] (b_kn=0) or [K][N] (b_kn=1)
+  float* Cout = nullptr; int ldc = 0;
+  const float* bias = nullptr;
+  const float* rowvec = nullptr; int ld_rowvec = 0; int rows_per_batch = 1;
+  const float* residual = nullptr; int ldr = 0;
+  float alpha = 1.f;
+  int out_nchw = 0;                  // store C as [B, N, rows_per_img] instead of [M, N]
+  int rows_per_img = 0;
+  // batching over blockIdx.z = zb*heads + zh
+  int batch = 1, heads = 1;
+  long long sA_b = 0, sA_h = 0, sB_b = 0, sB_h = 0, sC_b = 0, sC_h = 0;
+};
+void gemm(Engine& e, const GemmArgs& a, cudaStream_t s);
+// tcgen05 back end (kernels_tc.cu); returns false when the shape is not eligible
+bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------
+// normalisation / softmax / elementwise ops (kernels_norm.cu, kernels_elem.cu)
+// ------------------------------------------------------------------------------------------------
+// GroupNorm(32) over NHWC, optionally over the channel-concat of two sources; y = [silu]( gn(x)*(1+scale)+shift )
+void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, const float* gamma, const float* beta,
+               float eps, bool silu, const float* scale, const float* shift, int ld_ss, float* y, int B, int HW,
+               cudaStream_t s);
+void layernorm(Engine& e, const float* x, const float* gamma, const float* beta, float* y, int M, int C, cudaStream_t s);
+void softmax_rows(Engine& e, float* x, long long rows, int L, int ld, cudaStream_t s);   // in place
+void silu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s);
+void geglu(Engine& e, const float* x, float* y, int M, int C, cudaStream_t s);   // x [M,2C] -> y [M,C] = x[:, :C]*gelu(x[:, C:])
+void add(Engine& e, const float* a, const float* b, float* y, size_t n, cudaStream_t s);
+void avgpool2(Engine& e, const float* x, float* y, int B, int H, int W, int C, cudaStream_t s);      // -> [B,H/2,W/2,C]
+void upsample2(Engine& e, const float* x, float* y, int B, int H, int W, int C, cudaStream_t s);     // -> [B,2H,2W,C]
+void nchw_to_nhwc(Engine& e, const float* x, float* y, int B, int C, int HW, cudaStream_t s);
+void nhwc_to_nchw(Engine& e, const float* x, float* y, int B, int C, int HW, cudaStream_t s);
+void timestep_embedding(Engine& e, const float* t, const float* freqs, float* emb, int B, int half, cudaStream_t s);
+void repack_conv3x3(Engine& e, const float* w_oihw, float* w_ohwi, int O, int I, cudaStream_t s);
+void copy_rows(Engine& e, const float* src, float* dst, size_t n, cudaStream_t s);
+void attention(Engine& e, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+               int B, int Nq, int Nk, int heads, int d, int head_stride, float scale, cudaStream_t s);
+
+// scheduler kernels (kernels_elem.cu)
+void affine(Engine& e, const float* x, float a, float b, float* out, size_t n, cudaStream_t s);
+void shift_scale(Engine& e, const float* x, float b, float a, float* out, size_t n, cudaStream_t s);
+void q_sample(Engine& e, const float* x0, const float* noise, float sa, float s1ma, float* out, size_t n, cudaStream_t s);
+void vae_posterior(Engine& e, const float* moments, const float* noise, float sf, float* out, int B, int C, int hw, cudaStream_t s);
+void ddim_posterior_sample(Engine& e, const float* x0, const float* xt, const float* noise, const cdx_ddim_coef& c, float* out, size_t n, cudaStream_t s);
+void ddim_compute_eps(Engine& e, const float* xt, const float* xt_next, const float* e_c, const float* e_uc, float scale,
+                      const cdx_ddim_coef& c, float* out, size_t n, cudaStream_t s);
+void ddim_step_with_eps(Engine& e, const float* x, const float* e_c, const float* e_uc, float scale, const float* eps,
+                        const cdx_ddim_coef& c, float* out, size_t n, cudaStream_t s);
+void pixel_posterior_sample(Engine& e, const float* x0, const float* xt, const float* noise, const cdx_pixel_coef& c, float* out, size_t n, cudaStream_t s);
+void pixel_compute_eps(Engine& e, const float* xt, const float* xt_next, const float* et, const cdx_pixel_coef& c, float* out,
+                       int B, int chw, int net_chw, cudaStream_t s);
+void pixel_step_with_eps(Engine& e, const float* xt, const float* et, const float* eps, const cdx_pixel_coef& c, float* out,
+                         int B, int chw, int net_chw, cudaStream_t s);
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace cdx

@@ -1,0 +1,50 @@
+// engine.cu -- per-device context: workspace arena, error state.
+#include "common.cuh"
+
+namespace cdx {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+const std::string& last_error() { return g_last_error; }
+
+// Stack allocator over one device slab.  Every top-level ABI call first replays its op sequence in `dry` mode
+// (no launches, no memory touched) to learn the high-water mark, grows the slab if needed, then runs for real --
+// so steady-state calls never touch cudaMalloc and the slab size is exact.
+void* Arena::alloc(size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  void* p = nullptr;
+  if (dry) {
+    p = reinterpret_cast<void*>((uintptr_t)0x1000 + off);   // never dereferenced
+  } else {
+    if (off + bytes > cap) throw Error(CDX_E_NOMEM, "arena: allocation beyond the dry-run high-water mark (engine bug)");
+    p = base + off;
+  }
+  off += bytes;
+  if (off > high) high = off;
+  return p;
+}
+
+void Arena::begin_dry() { dry = true; off = 0; high = 0; }
+
+void Arena::end_dry() {
+  dry = false;
+  off = 0;
+  if (high > cap) {
+    cudaDeviceSynchronize();   // earlier calls may still be using the old slab
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    const size_t want = high + (1u << 20);
+    cudaError_t err = cudaMalloc(&base, want);
+    if (err != cudaSuccess) throw Error(CDX_E_NOMEM, std::string("arena cudaMalloc(") + std::to_string(want) + ") failed: " + cudaGetErrorString(err));
+    cap = want;
+  }
+}
+
+void Arena::destroy() {
+  if (base) cudaFree(base);
+  base = nullptr;
+  cap = off = high = 0;
+}
+
+}  // namespace cdx

@@ -1,0 +1,320 @@
+// kernels_elem.cu -- elementwise / layout kernels and the fused per-step scheduler kernels.
+//
+// Scheduler kernels restate, op for op and with round-to-nearest intrinsics (no FMA contraction), the reference's
+// per-step tensor arithmetic so that they are bit-exact against the reference CPU path:
+//   ddim_posterior_sample   DDIMSampler.sample_xt_next          ddim.py:582-601
+//   ddim_compute_eps        CFG combine + compute_eps tail      ddim.py:555-559, 575-579
+//   ddim_step_with_eps      CFG combine + p_sample_ddim_with_eps tail   ddim.py:613-617, 634-645
+//   pixel_*                 sample_xt_next / compute_eps / denoising_step_with_eps   ddpm_ddim_wrapper.py:114-307
+//   vae_posterior           DiagonalGaussianDistribution.sample * scale_factor      distributions.py:24-37, ddpm.py:536-543
+// Each is one launch instead of the reference's ~8-10 elementwise launches per step.
+#include "common.cuh"
+
+namespace cdx {
+namespace {
+
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define SUB(a, b) __fsub_rn((a), (b))
+#define DIV(a, b) __fdiv_rn((a), (b))
+
+inline int grid_for(size_t n, int num_sms) {
+  size_t b = (n + 255) / 256;
+  size_t cap = (size_t)num_sms * 16;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+#define GRID_STRIDE(i, n) for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (size_t)gridDim.x * blockDim.x)
+
+__global__ void affine_kernel(const float* __restrict__ x, float a, float b, float* __restrict__ y, size_t n) {
+  GRID_STRIDE(i, n) y[i] = ADD(MUL(a, x[i]), b);
+}
+__global__ void shift_scale_kernel(const float* __restrict__ x, float b, float a, float* __restrict__ y, size_t n) {
+  GRID_STRIDE(i, n) y[i] = MUL(ADD(x[i], b), a);
+}
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ nz, float sa, float s1, float* __restrict__ y, size_t n) {
+  GRID_STRIDE(i, n) y[i] = ADD(MUL(sa, x0[i]), MUL(s1, nz[i]));
+}
+__global__ void silu_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  GRID_STRIDE(i, n) { const float v = x[i]; y[i] = v / (1.f + expf(-v)); }
+}
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, size_t n) {
+  GRID_STRIDE(i, n) y[i] = a[i] + b[i];
+}
+__global__ void copy_kernel(const float* __restrict__ a, float* __restrict__ y, size_t n) {
+  GRID_STRIDE(i, n) y[i] = a[i];
+}
+// x [M,2C] -> y [M,C] = x[:, :C] * gelu_erf(x[:, C:])   (attention.py:42-44)
+__global__ void geglu_kernel(const float* __restrict__ x, float* __restrict__ y, size_t M, int C) {
+  const size_t n = M * (size_t)C;
+  GRID_STRIDE(i, n) {
+    const size_t m = i / C;
+    const int c = (int)(i - m * C);
+    const float v = x[m * 2 * C + c];
+    const float g = x[m * 2 * C + C + c];
+    y[i] = v * (0.5f * g * (1.f + erff(g * 0.70710678118654752440f)));
+  }
+}
+__global__ void avgpool2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t n = (size_t)B * Ho * Wo * C;
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const float* p = x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + c;
+    // ATen avg_pool2d sums the window then divides
+    y[i] = (p[0] + p[C] + p[(size_t)W * C] + p[(size_t)W * C + C]) * 0.25f;
+  }
+}
+__global__ void upsample2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = H * 2, Wo = W * 2;
+  const size_t n = (size_t)B * Ho * Wo * C;
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    y[i] = x[(((size_t)b * H + (oy >> 1)) * W + (ox >> 1)) * C + c];
+  }
+}
+// tiled transposes between [B,C,HW] and [B,HW,C]
+__global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int Cc) {
+  // x: [b][R][Cc] -> y: [b][Cc][R]
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float* xb = x + (size_t)b * R * Cc;
+  float* yb = y + (size_t)b * R * Cc;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[j][threadIdx.x] = xb[(size_t)r * Cc + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) yb[(size_t)c * R + r] = tile[threadIdx.x][j];
+  }
+}
+__global__ void temb_kernel(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ emb, int B, int half) {
+  const int n = B * half;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int b = i / half, j = i - b * half;
+    const float a = MUL(t[b], freqs[j]);
+    emb[(size_t)b * 2 * half + j] = cosf(a);
+    emb[(size_t)b * 2 * half + half + j] = sinf(a);
+  }
+}
+// OIHW (3x3) -> O,kh,kw,I
+__global__ void repack_conv_kernel(const float* __restrict__ w, float* __restrict__ o, int O, int I) {
+  const size_t n = (size_t)O * I * 9;
+  GRID_STRIDE(idx, n) {
+    const int i = (int)(idx % I);
+    size_t r = idx / I;
+    const int tap = (int)(r % 9);
+    const int oc = (int)(r / 9);
+    o[idx] = w[((size_t)oc * I + i) * 9 + tap];
+  }
+}
+
+__global__ void vae_posterior_kernel(const float* __restrict__ mom, const float* __restrict__ nz, float sf, float* __restrict__ out,
+                                     int B, int C, int hw) {
+  const size_t n = (size_t)B * C * hw;
+  GRID_STRIDE(i, n) {
+    const size_t b = i / ((size_t)C * hw);
+    const size_t r = i - b * (size_t)C * hw;
+    const float mean = mom[b * 2 * C * hw + r];
+    float z = mean;
+    if (nz) {
+      float lv = mom[b * 2 * C * hw + (size_t)C * hw + r];
+      lv = fminf(fmaxf(lv, -30.0f), 20.0f);
+      const float sd = expf(MUL(0.5f, lv));
+      z = ADD(mean, MUL(sd, nz[i]));
+    }
+    out[i] = MUL(sf, z);
+  }
+}
+
+__device__ __forceinline__ float cfg_combine(const float* e_c, const float* e_uc, float scale, size_t i) {
+  const float ec = e_c[i];
+  if (e_uc == nullptr) return ec;
+  const float eu = e_uc[i];
+  return ADD(eu, MUL(scale, SUB(ec, eu)));      // e_t_uncond + s * (e_t - e_t_uncond), ddim.py:559
+}
+
+__global__ void ddim_posterior_kernel(const float* __restrict__ x0, const float* __restrict__ xt, const float* __restrict__ nz,
+                                      cdx_ddim_coef c, float* __restrict__ out, size_t n) {
+  GRID_STRIDE(i, n) {
+    const float e_t = DIV(SUB(xt[i], MUL(c.sqrt_at, x0[i])), c.sqrt_1m_at);       // ddim.py:597
+    const float dir = MUL(c.dir_coef, e_t);                                       // :598
+    const float noise = MUL(c.sigma, nz[i]);                                      // :599
+    out[i] = ADD(ADD(MUL(c.sqrt_aprev, x0[i]), dir), noise);                      // :600
+  }
+}
+__global__ void ddim_compute_eps_kernel(const float* __restrict__ xt, const float* __restrict__ xn, const float* __restrict__ e_c,
+                                        const float* __restrict__ e_uc, float scale, cdx_ddim_coef c, float* __restrict__ out, size_t n) {
+  GRID_STRIDE(i, n) {
+    const float e_t = cfg_combine(e_c, e_uc, scale, i);
+    const float pred_x0 = DIV(SUB(xt[i], MUL(c.sqrt_1m_at_tab, e_t)), c.sqrt_at);          // ddim.py:576
+    const float dir = MUL(c.dir_coef, e_t);                                                // :578
+    out[i] = DIV(DIV(SUB(SUB(xn[i], MUL(c.sqrt_aprev, pred_x0)), dir), c.sigma), 1.0f);    // :579 (temperature 1)
+  }
+}
+__global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ e_c, const float* __restrict__ e_uc, float scale,
+                                 const float* __restrict__ eps, cdx_ddim_coef c, float* __restrict__ out, size_t n) {
+  GRID_STRIDE(i, n) {
+    const float e_t = cfg_combine(e_c, e_uc, scale, i);
+    const float pred_x0 = DIV(SUB(x[i], MUL(c.sqrt_1m_at_tab, e_t)), c.sqrt_at);           // ddim.py:634
+    const float dir = MUL(c.dir_coef, e_t);                                                // :638
+    const float noise = MUL(MUL(c.sigma, eps[i]), 1.0f);                                   // :642
+    out[i] = ADD(ADD(MUL(c.sqrt_aprev, pred_x0), dir), noise);                             // :645
+  }
+}
+
+__global__ void pixel_posterior_kernel(const float* __restrict__ x0, const float* __restrict__ xt, const float* __restrict__ nz,
+                                       cdx_pixel_coef c, float* __restrict__ out, size_t n) {
+  GRID_STRIDE(i, n) {
+    if (c.ddpm) {
+      const float mean = ADD(MUL(c.w0, x0[i]), MUL(c.wt, xt[i]));                           // DW:293
+      out[i] = ADD(mean, MUL(c.post_std, nz[i]));                                           // DW:297
+    } else {
+      const float et = DIV(SUB(xt[i], MUL(c.sqrt_at, x0[i])), c.sqrt_1m_at);                // DW:299
+      out[i] = ADD(ADD(MUL(c.sqrt_at_next, x0[i]), MUL(c.c2, et)), MUL(c.c1, nz[i]));       // DW:302
+    }
+  }
+}
+__global__ void pixel_compute_eps_kernel(const float* __restrict__ xt, const float* __restrict__ xn, const float* __restrict__ et_,
+                                         cdx_pixel_coef c, float* __restrict__ out, int B, int chw, int net_chw) {
+  const size_t n = (size_t)B * chw;
+  GRID_STRIDE(i, n) {
+    const size_t b = i / chw;
+    const float et = et_[b * net_chw + (i - b * chw)];
+    if (c.ddpm) {
+      const float mean = MUL(c.inv_sqrt_1m_bt, SUB(xt[i], MUL(c.weight, et)));             // DW:266
+      out[i] = DIV(SUB(xn[i], mean), c.std_model);                                          // DW:268
+    } else {
+      const float x0_t = DIV(SUB(xt[i], MUL(et, c.sqrt_1m_at)), c.sqrt_at);                 // DW:271
+      out[i] = DIV(SUB(SUB(xn[i], MUL(c.sqrt_at_next, x0_t)), MUL(c.c2, et)), c.c1);        // DW:275
+    }
+  }
+}
+__global__ void pixel_step_kernel(const float* __restrict__ xt, const float* __restrict__ et_, const float* __restrict__ eps,
+                                  cdx_pixel_coef c, float* __restrict__ out, int B, int chw, int net_chw) {
+  const size_t n = (size_t)B * chw;
+  GRID_STRIDE(i, n) {
+    const size_t b = i / chw;
+    const float et = et_[b * net_chw + (i - b * chw)];
+    const float nz = eps ? eps[i] : 0.f;
+    if (c.ddpm) {
+      const float mean = MUL(c.inv_sqrt_1m_bt, SUB(xt[i], MUL(c.weight, et)));             // DW:204
+      out[i] = ADD(mean, MUL(MUL(c.mask, c.std_model), nz));                                // DW:208
+    } else {
+      const float x0_t = DIV(SUB(xt[i], MUL(et, c.sqrt_1m_at)), c.sqrt_at);                 // DW:213
+      out[i] = ADD(ADD(MUL(c.sqrt_at_next, x0_t), MUL(c.c2, et)), MUL(c.c1, nz));           // DW:222
+    }
+  }
+}
+
+}  // namespace
+
+#define LAUNCH1(kernel, n, ...)                                   \
+  do {                                                            \
+    if (e.dry()) break;                                           \
+    kernel<<<grid_for((n), e.num_sms), 256, 0, s>>>(__VA_ARGS__); \
+    CDX_CUDA(cudaGetLastError());                                 \
+    e.launches++;                                                 \
+  } while (0)
+
+void affine(Engine& e, const float* x, float a, float b, float* out, size_t n, cudaStream_t s) { LAUNCH1(affine_kernel, n, x, a, b, out, n); }
+void shift_scale(Engine& e, const float* x, float b, float a, float* out, size_t n, cudaStream_t s) { LAUNCH1(shift_scale_kernel, n, x, b, a, out, n); }
+void q_sample(Engine& e, const float* x0, const float* nz, float sa, float s1, float* out, size_t n, cudaStream_t s) { LAUNCH1(q_sample_kernel, n, x0, nz, sa, s1, out, n); }
+void silu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s) { LAUNCH1(silu_kernel, n, x, y, n); }
+void add(Engine& e, const float* a, const float* b, float* y, size_t n, cudaStream_t s) { LAUNCH1(add_kernel, n, a, b, y, n); }
+void copy_rows(Engine& e, const float* a, float* y, size_t n, cudaStream_t s) { LAUNCH1(copy_kernel, n, a, y, n); }
+void geglu(Engine& e, const float* x, float* y, int M, int C, cudaStream_t s) { LAUNCH1(geglu_kernel, (size_t)M * C, x, y, (size_t)M, C); }
+void avgpool2(Engine& e, const float* x, float* y, int B, int H, int W, int C, cudaStream_t s) {
+  CDX_CHECK(H % 2 == 0 && W % 2 == 0, "avgpool2: odd size %dx%d", H, W);
+  LAUNCH1(avgpool2_kernel, (size_t)B * (H / 2) * (W / 2) * C, x, y, B, H, W, C);
+}
+void upsample2(Engine& e, const float* x, float* y, int B, int H, int W, int C, cudaStream_t s) {
+  LAUNCH1(upsample2_kernel, (size_t)B * H * W * 4 * C, x, y, B, H, W, C);
+}
+void nchw_to_nhwc(Engine& e, const float* x, float* y, int B, int C, int HW, cudaStream_t s) {
+  if (e.dry()) return;
+  // x [b][C][HW] -> y [b][HW][C]
+  transpose_kernel<<<dim3(cdiv(HW, 32), cdiv(C, 32), B), dim3(32, 8), 0, s>>>(x, y, C, HW);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+void nhwc_to_nchw(Engine& e, const float* x, float* y, int B, int C, int HW, cudaStream_t s) {
+  if (e.dry()) return;
+  transpose_kernel<<<dim3(cdiv(C, 32), cdiv(HW, 32), B), dim3(32, 8), 0, s>>>(x, y, HW, C);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+void timestep_embedding(Engine& e, const float* t, const float* freqs, float* emb, int B, int half, cudaStream_t s) {
+  if (e.dry()) return;
+  temb_kernel<<<cdiv(B * half, 256), 256, 0, s>>>(t, freqs, emb, B, half);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+void repack_conv3x3(Engine& e, const float* w, float* o, int O, int I, cudaStream_t s) { LAUNCH1(repack_conv_kernel, (size_t)O * I * 9, w, o, O, I); }
+void vae_posterior(Engine& e, const float* mom, const float* nz, float sf, float* out, int B, int C, int hw, cudaStream_t s) {
+  LAUNCH1(vae_posterior_kernel, (size_t)B * C * hw, mom, nz, sf, out, B, C, hw);
+}
+void ddim_posterior_sample(Engine& e, const float* x0, const float* xt, const float* nz, const cdx_ddim_coef& c, float* out, size_t n, cudaStream_t s) {
+  LAUNCH1(ddim_posterior_kernel, n, x0, xt, nz, c, out, n);
+}
+void ddim_compute_eps(Engine& e, const float* xt, const float* xn, const float* e_c, const float* e_uc, float scale, const cdx_ddim_coef& c,
+                      float* out, size_t n, cudaStream_t s) {
+  LAUNCH1(ddim_compute_eps_kernel, n, xt, xn, e_c, e_uc, scale, c, out, n);
+}
+void ddim_step_with_eps(Engine& e, const float* x, const float* e_c, const float* e_uc, float scale, const float* eps, const cdx_ddim_coef& c,
+                        float* out, size_t n, cudaStream_t s) {
+  LAUNCH1(ddim_step_kernel, n, x, e_c, e_uc, scale, eps, c, out, n);
+}
+void pixel_posterior_sample(Engine& e, const float* x0, const float* xt, const float* nz, const cdx_pixel_coef& c, float* out, size_t n, cudaStream_t s) {
+  LAUNCH1(pixel_posterior_kernel, n, x0, xt, nz, c, out, n);
+}
+void pixel_compute_eps(Engine& e, const float* xt, const float* xn, const float* et, const cdx_pixel_coef& c, float* out, int B, int chw,
+                       int net_chw, cudaStream_t s) {
+  LAUNCH1(pixel_compute_eps_kernel, (size_t)B * chw, xt, xn, et, c, out, B, chw, net_chw);
+}
+void pixel_step_with_eps(Engine& e, const float* xt, const float* et, const float* eps, const cdx_pixel_coef& c, float* out, int B, int chw,
+                         int net_chw, cudaStream_t s) {
+  LAUNCH1(pixel_step_kernel, (size_t)B * chw, xt, et, eps, c, out, B, chw, net_chw);
+}
+
+// softmax(q k^T * scale) v through two batched contractions and a row softmax.  Scores live in the arena
+// ([B*heads, Nq, ldS]); the fused tcgen05 flash kernel supersedes this when eligible.
+void attention(Engine& e, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo, int B, int Nq,
+               int Nk, int heads, int d, int head_stride, float scale, cudaStream_t s) {
+  Scope sc(e.arena);
+  const int ldS = (Nk + 3) & ~3;
+  float* S = (float*)e.arena.alloc((size_t)B * heads * Nq * ldS * sizeof(float));
+  GemmArgs g;
+  g.M = Nq; g.N = Nk; g.K = d; g.mode = 0;
+  g.A = q; g.lda = ldq; g.C1 = d;
+  g.Bw = k; g.ldb = ldk; g.b_kn = 0;
+  g.Cout = S; g.ldc = ldS; g.alpha = scale;
+  g.batch = B; g.heads = heads;
+  g.sA_b = (long long)Nq * ldq; g.sA_h = head_stride;
+  g.sB_b = (long long)Nk * ldk; g.sB_h = head_stride;
+  g.sC_b = (long long)heads * Nq * ldS; g.sC_h = (long long)Nq * ldS;
+  gemm(e, g, s);
+  softmax_rows(e, S, (long long)B * heads * Nq, Nk, ldS, s);
+  GemmArgs h;
+  h.M = Nq; h.N = d; h.K = Nk; h.mode = 0;
+  h.A = S; h.lda = ldS; h.C1 = Nk;
+  h.Bw = v; h.ldb = ldv; h.b_kn = 1;
+  h.Cout = out; h.ldc = ldo;
+  h.batch = B; h.heads = heads;
+  h.sA_b = (long long)heads * Nq * ldS; h.sA_h = (long long)Nq * ldS;
+  h.sB_b = (long long)Nk * ldv; h.sB_h = head_stride;
+  h.sC_b = (long long)Nq * ldo; h.sC_h = d;
+  gemm(e, h, s);
+}
+
+}  // namespace cdx

@@ -1,0 +1,218 @@
+// kernels_norm.cu -- HBM-bound normalisation kernels: GroupNorm(32)(+scale-shift)(+SiLU), LayerNorm, row softmax.
+//
+// GroupNorm follows GroupNorm32 / Normalize (util.py:215-217 eps 1e-5; attention.py:76-77 and model.py:38-39 eps 1e-6)
+// on NHWC activations, optionally over the channel concatenation of two tensors (the U-Net skip `th.cat`, OAI:736)
+// so that the concat is never materialised before the norm.  Statistics are accumulated in fp64 (one read),
+// then one read + one write applies  y = (x - mean) * rstd * gamma + beta  [ * (1+scale) + shift ] [ SiLU ].
+// Algorithmic HBM bytes: 2 reads + 1 write of the activation (stats pass + apply pass).
+#include "common.cuh"
+
+namespace cdx {
+namespace {
+
+constexpr int GN_GROUPS = 32;
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + expf(-v)); }
+
+// partial sums: part[((b*nchunk + chunk)*32 + g)*2 + {0,1}]
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
+                                                       int C2, int HW, int rows_per_chunk, double* __restrict__ part) {
+  const int C = C1 + C2;
+  const int cpg = C / GN_GROUPS;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  __shared__ double ssum[GN_GROUPS], ssq[GN_GROUPS];
+  if (threadIdx.x < GN_GROUPS) { ssum[threadIdx.x] = 0.0; ssq[threadIdx.x] = 0.0; }
+  __syncthreads();
+  const int r0 = chunk * rows_per_chunk;
+  const int r1 = min(HW, r0 + rows_per_chunk);
+  // thread (tr, tc): tc owns float4 channel slots tc, tc+ncol, ...; tr strides over the rows of the chunk.  A float4 may
+  // straddle two groups when cpg % 4 != 0 (C=320 -> cpg=10), so each of its 4 lanes accumulates separately and is
+  // flushed to its own group's shared accumulator once per slot.
+  const int C4 = C >> 2;
+  const int ncol = min(C4, (int)blockDim.x);
+  const int nrow_par = blockDim.x / ncol;
+  const int tr = threadIdx.x / ncol, tc = threadIdx.x - tr * ncol;
+  if (tr < nrow_par) {
+    for (int c4 = tc; c4 < C4; c4 += ncol) {
+      const int c = c4 * 4;
+      double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+      const float* base = (c < C1) ? (x1 + (long long)b * HW * C1 + c) : (x2 + (long long)b * HW * C2 + (c - C1));
+      const int ldx = (c < C1) ? C1 : C2;
+      for (int r = r0 + tr; r < r1; r += nrow_par) {
+        const float4 v = *reinterpret_cast<const float4*>(base + (long long)r * ldx);
+        const double d0 = v.x, d1 = v.y, d2 = v.z, d3 = v.w;
+        s[0] += d0; q[0] += d0 * d0;
+        s[1] += d1; q[1] += d1 * d1;
+        s[2] += d2; q[2] += d2 * d2;
+        s[3] += d3; q[3] += d3 * d3;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = (c + j) / cpg;
+        atomicAdd(&ssum[g], s[j]);
+        atomicAdd(&ssq[g], q[j]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {
+    double* o = part + (((long long)b * gridDim.x + chunk) * GN_GROUPS + threadIdx.x) * 2;
+    o[0] = ssum[threadIdx.x];
+    o[1] = ssq[threadIdx.x];
+  }
+}
+
+// mean_rstd[(b*32+g)*2 + {0,1}]
+__global__ void gn_finalize_kernel(const double* __restrict__ part, int nchunk, double inv_count, float eps,
+                                   float* __restrict__ mean_rstd) {
+  const int b = blockIdx.x, g = threadIdx.x;
+  double s = 0.0, q = 0.0;
+  for (int c = 0; c < nchunk; ++c) {
+    const double* o = part + (((long long)b * nchunk + c) * GN_GROUPS + g) * 2;
+    s += o[0];
+    q += o[1];
+  }
+  const double mean = s * inv_count;
+  double var = q * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mean_rstd[(b * GN_GROUPS + g) * 2 + 0] = (float)mean;
+  mean_rstd[(b * GN_GROUPS + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ mean_rstd, int silu,
+                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       int ld_ss, float* __restrict__ y, int HW, long long total4) {
+  const int C = C1 + C2;
+  const int cpg = C / GN_GROUPS;
+  const int C4 = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / C4;           // b*HW + r
+    const int c = (int)(i % C4) * 4;
+    const int b = (int)(row / HW);
+    const float4 v = (c < C1) ? *reinterpret_cast<const float4*>(x1 + row * C1 + c)
+                              : *reinterpret_cast<const float4*>(x2 + row * C2 + (c - C1));
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    const float e[4] = {v.x, v.y, v.z, v.w};
+    const float gg[4] = {ga.x, ga.y, ga.z, ga.w};
+    const float bb[4] = {be.x, be.y, be.z, be.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cpg;
+      const float mean = mean_rstd[(b * GN_GROUPS + g) * 2 + 0];
+      const float rstd = mean_rstd[(b * GN_GROUPS + g) * 2 + 1];
+      float t = (e[j] - mean) * rstd * gg[j] + bb[j];
+      if (scale) t = t * (1.f + scale[(long long)b * ld_ss + c + j]) + shift[(long long)b * ld_ss + c + j];
+      if (silu) t = silu_f(t);
+      o[j] = t;
+    }
+    *reinterpret_cast<float4*>(y + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// one warp per row
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* __restrict__ y, int M, int C,
+                                                        float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float* xr = x + (long long)warp * C;
+  float* yr = y + (long long)warp * C;
+  const int C4 = C >> 2;
+  float s = 0.f;
+  for (int i = lane; i < C4; i += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + i * 4);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+  for (int i = lane; i < C4; i += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + i * 4);
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.f / sqrtf(q / (float)C + eps);
+  for (int i = lane; i < C4; i += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + i * 4);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + i * 4);
+    const float4 b = *reinterpret_cast<const float4*>(beta + i * 4);
+    float4 o;
+    o.x = (v.x - mean) * rstd * g.x + b.x;
+    o.y = (v.y - mean) * rstd * g.y + b.y;
+    o.z = (v.z - mean) * rstd * g.z + b.z;
+    o.w = (v.w - mean) * rstd * g.w + b.w;
+    *reinterpret_cast<float4*>(yr + i * 4) = o;
+  }
+}
+
+// in-place softmax over rows of length L (row stride ld); one warp per row, three passes (row stays in L1/L2)
+__global__ void __launch_bounds__(256) softmax_kernel(float* __restrict__ x, long long rows, int L, int ld) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float* r = x + warp * ld;
+  float mx = -INFINITY;
+  for (int i = lane; i < L; i += 32) mx = fmaxf(mx, r[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float s = 0.f;
+  for (int i = lane; i < L; i += 32) {
+    const float ev = expf(r[i] - mx);
+    r[i] = ev;
+    s += ev;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv = 1.f / s;
+  for (int i = lane; i < L; i += 32) r[i] = r[i] * inv;
+}
+
+}  // namespace
+
+void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, const float* gamma, const float* beta, float eps,
+               bool silu, const float* scale, const float* shift, int ld_ss, float* y, int B, int HW, cudaStream_t s) {
+  const int C = C1 + C2;
+  CDX_CHECK(C % GN_GROUPS == 0, "groupnorm: C=%d not divisible by 32", C);
+  CDX_CHECK(C1 % 4 == 0 && C2 % 4 == 0, "groupnorm: channel counts must be multiples of 4 (C1=%d C2=%d)", C1, C2);
+  Scope sc(e.arena);
+  int nchunk = cdiv(4LL * e.num_sms, B);
+  if (nchunk > HW) nchunk = HW;
+  if (nchunk < 1) nchunk = 1;
+  const int rows_per_chunk = cdiv(HW, nchunk);
+  nchunk = cdiv(HW, rows_per_chunk);
+  double* part = (double*)e.arena.alloc((size_t)B * nchunk * GN_GROUPS * 2 * sizeof(double));
+  float* mr = (float*)e.arena.alloc((size_t)B * GN_GROUPS * 2 * sizeof(float));
+  if (e.dry()) return;
+  gn_stats_kernel<<<dim3(nchunk, B), 256, 0, s>>>(x1, C1, x2, C2, HW, rows_per_chunk, part);
+  gn_finalize_kernel<<<B, GN_GROUPS, 0, s>>>(part, nchunk, 1.0 / ((double)HW * (C / GN_GROUPS)), eps, mr);
+  const long long total4 = (long long)B * HW * (C / 4);
+  int blocks = (int)std::min<long long>((total4 + 255) / 256, (long long)e.num_sms * 16);
+  gn_apply_kernel<<<blocks, 256, 0, s>>>(x1, C1, x2, C2, gamma, beta, mr, silu ? 1 : 0, scale, shift, ld_ss, y, HW, total4);
+  CDX_CUDA(cudaGetLastError());
+  e.launches += 3;
+}
+
+void layernorm(Engine& e, const float* x, const float* gamma, const float* beta, float* y, int M, int C, cudaStream_t s) {
+  CDX_CHECK(C % 4 == 0, "layernorm: C=%d must be a multiple of 4", C);
+  if (e.dry()) return;
+  layernorm_kernel<<<cdiv((long long)M * 32, 256), 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+
+void softmax_rows(Engine& e, float* x, long long rows, int L, int ld, cudaStream_t s) {
+  if (e.dry()) return;
+  softmax_kernel<<<cdiv(rows * 32, 256), 256, 0, s>>>(x, rows, L, ld);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+
+}  // namespace cdx

@@ -1,0 +1,710 @@
+// nets.cu -- graph executors for the three network families on the path.
+//
+//   SD v1 / LDM text2img U-Net   UNetModel.forward      ref ldm/modules/diffusionmodules/openaimodel.py:710-742 (built :506-686)
+//                                ResBlock._forward      ref openaimodel.py:255-275
+//                                SpatialTransformer     ref ldm/modules/attention.py:196-261
+//   improved-DDPM pixel U-Net    UNetModel.forward      ref model/lib/ddpm_ddim/models/improved_ddpm/unet.py:639-668 (built :476-626)
+//                                ResBlock / AttentionBlock / QKVAttentionLegacy   ref unet.py:241-261, 304-310, 342-363
+//   KL-f8 VAE                    Encoder / Decoder      ref ldm/modules/diffusionmodules/model.py:434-459, 535-568
+//                                ResnetBlock / AttnBlock / Downsample / Upsample   ref model.py:42-202
+//
+// B200-first design decisions (DESIGN.md has the full rationale):
+//   * activations are NHWC, so a [B,H,W,C] feature map *is* the [B*HW, C] token matrix: the reference's
+//     'b c h w -> b (h w) c' rearranges disappear and every conv / Linear is one implicit-GEMM family;
+//   * skip-connection concatenation (th.cat, OAI:736) is never materialised: GroupNorm and the 1x1 skip conv read
+//     two sources;
+//   * nearest-2x upsampling is folded into the following conv's gather; bias, timestep-embedding add and the
+//     residual add are GEMM epilogues; all 22 ResBlock emb projections run as ONE GEMM per U-Net call;
+//   * q/k/v (self) and k/v (cross) projections are single fused GEMMs over weights stored adjacently in the blob.
+#include <math.h>
+#include <string.h>
+
+#include "nets.cuh"
+
+namespace cdx {
+
+// ================================================================================================ inventory
+namespace {
+
+struct Inv {
+  Net& n;
+  explicit Inv(Net& net) : n(net) {}
+  void add(const std::string& name, std::initializer_list<int64_t> dims, int segment = 0, bool conv3 = false) {
+    Param p;
+    p.name = name;
+    p.rank = (int)dims.size();
+    size_t ne = 1;
+    int i = 0;
+    for (int64_t d : dims) { p.dims[i++] = d; ne *= (size_t)d; }
+    p.numel = ne;
+    p.segment = segment;
+    p.conv3 = conv3;
+    n.index[name] = (int)n.params.size();
+    n.params.push_back(p);
+  }
+  void conv(const std::string& name, int cin, int cout, int k) {
+    add(name + ".weight", {cout, cin, k, k}, 0, k == 3);
+    add(name + ".bias", {cout});
+  }
+  void lin(const std::string& name, int cin, int cout, bool bias = true, int seg = 0) {
+    add(name + ".weight", {cout, cin}, seg ? 1 : 0);
+    if (bias) add(name + ".bias", {cout}, seg ? 2 : 0);
+  }
+  void norm(const std::string& name, int c) {
+    add(name + ".weight", {c});
+    add(name + ".bias", {c});
+  }
+};
+
+bool contains(const int* arr, int n, int v) {
+  for (int i = 0; i < n; ++i)
+    if (arr[i] == v) return true;
+  return false;
+}
+
+std::string S(const std::string& a, int i) { return a + std::to_string(i); }
+
+void build_unet_inventory(Net& n) {
+  const cdx_unet_config& c = n.ucfg;
+  const bool oai = c.kind == CDX_UNET_OPENAI;
+  Inv v(n);
+  const int mc = c.model_channels, ted = 4 * mc;
+  n.ted = ted;
+  int emb_rows = 0;
+  auto res = [&](const std::string& p, int cin, int cout) {
+    v.norm(p + ".in_layers.0", cin);
+    v.conv(p + ".in_layers.2", cin, cout, 3);
+    const int erows = oai ? cout : 2 * cout;
+    v.lin(p + ".emb_layers.1", ted, erows, true, 1);
+    n.emb_off[p] = emb_rows;
+    emb_rows += erows;
+    v.norm(p + ".out_layers.0", cout);
+    v.conv(p + ".out_layers.3", cout, cout, 3);
+    if (cin != cout) v.conv(p + ".skip_connection", cin, cout, 1);
+  };
+  auto st = [&](const std::string& p, int ch) {
+    v.norm(p + ".norm", ch);
+    v.conv(p + ".proj_in", ch, ch, 1);
+    const std::string t = p + ".transformer_blocks.0";
+    for (int a = 1; a <= 2; ++a) {
+      const std::string ap = t + ".attn" + std::to_string(a);
+      const int kd = (a == 1) ? ch : c.context_dim;
+      v.lin(ap + ".to_q", ch, ch, false);
+      v.lin(ap + ".to_k", kd, ch, false);
+      v.lin(ap + ".to_v", kd, ch, false);
+      v.lin(ap + ".to_out.0", ch, ch);
+    }
+    v.lin(t + ".ff.net.0.proj", ch, 8 * ch);
+    v.lin(t + ".ff.net.2", 4 * ch, ch);
+    v.norm(t + ".norm1", ch);
+    v.norm(t + ".norm2", ch);
+    v.norm(t + ".norm3", ch);
+    v.conv(p + ".proj_out", ch, ch, 1);
+  };
+  auto attn = [&](const std::string& p, int ch) {   // i-DDPM AttentionBlock
+    v.norm(p + ".norm", ch);
+    v.add(p + ".qkv.weight", {3 * ch, ch, 1});
+    v.add(p + ".qkv.bias", {3 * ch});
+    v.add(p + ".proj_out.weight", {ch, ch, 1});
+    v.add(p + ".proj_out.bias", {ch});
+  };
+  auto attention_layer = [&](const std::string& p, int ch) { oai ? st(p, ch) : attn(p, ch); };
+
+  v.lin("time_embed.0", mc, ted);
+  v.lin("time_embed.2", ted, ted);
+  int ch = c.channel_mult[0] * mc;
+  if (oai) ch = mc;
+  v.conv("input_blocks.0.0", c.in_channels, ch, 3);
+  std::vector<int> chans{ch};
+  int ds = 1, bi = 1;
+  for (int level = 0; level < c.n_mult; ++level) {
+    const int m = c.channel_mult[level];
+    for (int r = 0; r < c.num_res_blocks; ++r) {
+      const std::string bp = S("input_blocks.", bi);
+      res(bp + ".0", ch, m * mc);
+      ch = m * mc;
+      if (contains(c.attention_ds, c.n_attn, ds)) attention_layer(bp + ".1", ch);
+      chans.push_back(ch);
+      ++bi;
+    }
+    if (level != c.n_mult - 1) {
+      const std::string bp = S("input_blocks.", bi);
+      if (oai) v.conv(bp + ".0.op", ch, ch, 3);
+      else res(bp + ".0", ch, ch);
+      chans.push_back(ch);
+      ++bi;
+      ds *= 2;
+    }
+  }
+  res("middle_block.0", ch, ch);
+  attention_layer("middle_block.1", ch);
+  res("middle_block.2", ch, ch);
+  int bo = 0;
+  for (int level = c.n_mult - 1; level >= 0; --level) {
+    const int m = c.channel_mult[level];
+    for (int i = 0; i <= c.num_res_blocks; ++i) {
+      const int ich = chans.back();
+      chans.pop_back();
+      const std::string bp = S("output_blocks.", bo);
+      res(bp + ".0", ch + ich, mc * m);
+      ch = mc * m;
+      int li = 1;
+      if (contains(c.attention_ds, c.n_attn, ds)) { attention_layer(bp + "." + std::to_string(li), ch); ++li; }
+      if (level && i == c.num_res_blocks) {
+        if (oai) v.conv(bp + "." + std::to_string(li) + ".conv", ch, ch, 3);
+        else res(bp + "." + std::to_string(li), ch, ch);
+        ds /= 2;
+      }
+      ++bo;
+    }
+  }
+  v.norm("out.0", ch);
+  v.conv("out.2", oai ? mc : c.channel_mult[0] * mc, c.out_channels, 3);
+  n.emb_rows = emb_rows;
+}
+
+void build_vae_inventory(Net& n) {
+  const cdx_vae_config& c = n.vcfg;
+  Inv v(n);
+  auto res = [&](const std::string& p, int cin, int cout) {
+    v.norm(p + ".norm1", cin);
+    v.conv(p + ".conv1", cin, cout, 3);
+    v.norm(p + ".norm2", cout);
+    v.conv(p + ".conv2", cout, cout, 3);
+    if (cin != cout) v.conv(p + ".nin_shortcut", cin, cout, 1);
+  };
+  auto attn = [&](const std::string& p, int ch) {
+    v.norm(p + ".norm", ch);
+    v.conv(p + ".q", ch, ch, 1);
+    v.conv(p + ".k", ch, ch, 1);
+    v.conv(p + ".v", ch, ch, 1);
+    v.conv(p + ".proj_out", ch, ch, 1);
+  };
+  const int ch = c.ch, L = c.n_mult;
+  const std::string E = "encoder.", D = "decoder.";
+  v.conv(E + "conv_in", c.in_channels, ch, 3);
+  int block_in = ch;
+  for (int lvl = 0; lvl < L; ++lvl) {
+    block_in = ch * (lvl == 0 ? 1 : c.ch_mult[lvl - 1]);
+    const int block_out = ch * c.ch_mult[lvl];
+    for (int b = 0; b < c.num_res_blocks; ++b) {
+      res(E + "down." + std::to_string(lvl) + ".block." + std::to_string(b), block_in, block_out);
+      block_in = block_out;
+    }
+    if (lvl != L - 1) v.conv(E + "down." + std::to_string(lvl) + ".downsample.conv", block_in, block_in, 3);
+  }
+  res(E + "mid.block_1", block_in, block_in);
+  attn(E + "mid.attn_1", block_in);
+  res(E + "mid.block_2", block_in, block_in);
+  v.norm(E + "norm_out", block_in);
+  v.conv(E + "conv_out", block_in, 2 * c.z_channels, 3);
+
+  block_in = ch * c.ch_mult[L - 1];
+  v.conv(D + "conv_in", c.z_channels, block_in, 3);
+  res(D + "mid.block_1", block_in, block_in);
+  attn(D + "mid.attn_1", block_in);
+  res(D + "mid.block_2", block_in, block_in);
+  for (int lvl = L - 1; lvl >= 0; --lvl) {
+    const int block_out = ch * c.ch_mult[lvl];
+    for (int b = 0; b <= c.num_res_blocks; ++b) {
+      res(D + "up." + std::to_string(lvl) + ".block." + std::to_string(b), block_in, block_out);
+      block_in = block_out;
+    }
+    if (lvl != 0) v.conv(D + "up." + std::to_string(lvl) + ".upsample.conv", block_in, block_in, 3);
+  }
+  v.norm(D + "norm_out", block_in);
+  v.conv(D + "conv_out", block_in, c.out_ch, 3);
+  v.conv("quant_conv", 2 * c.z_channels, 2 * c.embed_dim, 1);
+  v.conv("post_quant_conv", c.embed_dim, c.z_channels, 1);
+}
+
+void assign_offsets(Net& n) {
+  size_t off = 0;
+  auto align = [&](size_t a) { off = (off + a - 1) / a * a; };
+  // general segment: inventory order, 16-byte aligned starts (adjacent q/k/v weights stay contiguous)
+  for (Param& p : n.params)
+    if (p.segment == 0) { align(4); p.off = off; off += p.numel; }
+  align(64);
+  n.emb_w_off = off;
+  for (Param& p : n.params)
+    if (p.segment == 1) { p.off = off; off += p.numel; }
+  align(64);
+  n.emb_b_off = off;
+  for (Param& p : n.params)
+    if (p.segment == 2) { p.off = off; off += p.numel; }
+  align(64);
+  n.blob_floats = off;
+}
+
+}  // namespace
+
+const Param& Net::param(const std::string& name) const {
+  auto it = index.find(name);
+  if (it == index.end()) throw Error(CDX_E_INVALID, "unknown parameter '" + name + "'");
+  return params[it->second];
+}
+
+Net* make_unet(Engine* e, const cdx_unet_config& cfg) {
+  CDX_CHECK(cfg.kind == CDX_UNET_OPENAI || cfg.kind == CDX_UNET_IDDPM, "unet: bad kind %d", cfg.kind);
+  CDX_CHECK(cfg.n_mult >= 1 && cfg.n_mult <= 8 && cfg.n_attn >= 0 && cfg.n_attn <= 8, "unet: bad level counts");
+  CDX_CHECK(cfg.model_channels % 32 == 0, "unet: model_channels must be a multiple of 32 (GroupNorm32)");
+  if (cfg.kind == CDX_UNET_OPENAI) CDX_CHECK(cfg.num_heads > 0 && cfg.context_dim > 0, "unet: heads/context_dim");
+  else CDX_CHECK(cfg.num_head_channels > 0, "unet: num_head_channels");
+  Net* n = new Net();
+  n->eng = e;
+  n->kind = cfg.kind == CDX_UNET_OPENAI ? NET_UNET_OPENAI : NET_UNET_IDDPM;
+  n->ucfg = cfg;
+  build_unet_inventory(*n);
+  assign_offsets(*n);
+  // default sinusoid frequencies (util.py:161-163); the host normally overrides them with torch's own values
+  const int half = cfg.model_channels / 2;
+  n->freqs_host.resize(half);
+  const float sc = (float)(-log(10000.0));
+  for (int i = 0; i < half; ++i) n->freqs_host[i] = expf(sc * (float)i / (float)half);
+  return n;
+}
+
+Net* make_vae(Engine* e, const cdx_vae_config& cfg) {
+  CDX_CHECK(cfg.n_mult >= 1 && cfg.n_mult <= 8, "vae: bad level count");
+  CDX_CHECK(cfg.ch % 32 == 0, "vae: ch must be a multiple of 32");
+  Net* n = new Net();
+  n->eng = e;
+  n->kind = NET_VAE;
+  n->vcfg = cfg;
+  build_vae_inventory(*n);
+  assign_offsets(*n);
+  return n;
+}
+
+void destroy_net(Net* n) {
+  if (!n) return;
+  if (n->blob) cudaFree(n->blob);
+  if (n->freqs_dev) cudaFree(n->freqs_dev);
+  delete n;
+}
+
+void net_ensure_blob(Net& n) {
+  if (n.blob) return;
+  CDX_CUDA(cudaSetDevice(n.eng->device));
+  CDX_CUDA(cudaMalloc(&n.blob, n.blob_floats * sizeof(float)));
+  CDX_CUDA(cudaMemset(n.blob, 0, n.blob_floats * sizeof(float)));
+}
+
+void net_load_param(Net& n, const char* name, const float* data, bool on_device, const int64_t* dims, int rank) {
+  auto it = n.index.find(name);
+  CDX_CHECK(it != n.index.end(), "load_param: unknown parameter '%s'", name);
+  Param& p = n.params[it->second];
+  CDX_CHECK(rank == p.rank, "load_param %s: rank %d != %d", name, rank, p.rank);
+  for (int i = 0; i < rank; ++i) CDX_CHECK(dims[i] == p.dims[i], "load_param %s: dim %d is %lld, expected %lld", name, i, (long long)dims[i], (long long)p.dims[i]);
+  net_ensure_blob(n);
+  Engine& e = *n.eng;
+  float* dst = n.blob + p.off;
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (p.conv3) {
+    float* tmp = nullptr;
+    CDX_CUDA(cudaMalloc(&tmp, p.numel * sizeof(float)));
+    CDX_CUDA(cudaMemcpy(tmp, data, p.numel * sizeof(float), kind));
+    repack_conv3x3(e, tmp, dst, (int)p.dims[0], (int)p.dims[1], 0);
+    CDX_CUDA(cudaDeviceSynchronize());
+    CDX_CUDA(cudaFree(tmp));
+  } else {
+    CDX_CUDA(cudaMemcpy(dst, data, p.numel * sizeof(float), kind));
+  }
+  p.loaded = true;
+  n.finalized = false;
+}
+
+void net_finalize(Net& n) {
+  for (const Param& p : n.params) CDX_CHECK(p.loaded, "finalize: parameter '%s' was never loaded", p.name.c_str());
+  if (n.kind != NET_VAE) {
+    if (!n.freqs_dev) CDX_CUDA(cudaMalloc(&n.freqs_dev, n.freqs_host.size() * sizeof(float)));
+    CDX_CUDA(cudaMemcpy(n.freqs_dev, n.freqs_host.data(), n.freqs_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  n.finalized = true;
+}
+
+// ================================================================================================ executors
+namespace {
+
+struct Exec {
+  Net& n;
+  Engine& e;
+  cudaStream_t s;
+  Exec(Net& net, cudaStream_t st) : n(net), e(*net.eng), s(st) {}
+
+  Tensor alloc(int B, int H, int W, int C) { return alloc_tensor(e, B, H, W, C); }
+
+  // y = conv3x3(x [, x2 concat]) + bias (+ rowvec per sample) (+ residual); up: nearest-2x folded into the gather
+  Tensor conv3(const Tensor& x, const std::string& name, int stride = 1, int pad = 1, int up = 1, const float* rowvec = nullptr,
+               int ld_rowvec = 0, const float* residual = nullptr, float* out_nchw = nullptr) {
+    const Param& w = n.param(name + ".weight");
+    const int Cout = (int)w.dims[0], Cin = (int)w.dims[1];
+    CDX_CHECK(Cin == x.C, "conv %s: input has %d channels, weight expects %d", name.c_str(), x.C, Cin);
+    const int Hl = x.H * up, Wl = x.W * up;
+    int Ho, Wo;
+    if (stride == 1) { Ho = Hl; Wo = Wl; }
+    else { Ho = Hl / 2; Wo = Wl / 2; }
+    Tensor y;
+    if (out_nchw) { y.p = out_nchw; y.B = x.B; y.H = Ho; y.W = Wo; y.C = Cout; }
+    else y = alloc(x.B, Ho, Wo, Cout);
+    GemmArgs g;
+    g.mode = 1;
+    g.M = x.B * Ho * Wo; g.N = Cout; g.K = 9 * Cin;
+    g.A = x.p; g.lda = x.C; g.C1 = x.C;
+    g.Hin = x.H; g.Win = x.W; g.Hout = Ho; g.Wout = Wo; g.stride = stride; g.pad = pad; g.up = up;
+    g.Bw = n.blob + w.off; g.ldb = 9 * Cin;
+    g.Cout = y.p; g.ldc = Cout;
+    g.bias = n.P(name + ".bias");
+    g.rowvec = rowvec; g.ld_rowvec = ld_rowvec; g.rows_per_batch = Ho * Wo;
+    g.residual = residual; g.ldr = Cout;
+    if (out_nchw) { g.out_nchw = 1; g.rows_per_img = Ho * Wo; }
+    gemm(e, g, s);
+    return y;
+  }
+
+  // y[M,N] = x[M,K] (optionally [x | x2]) @ W[N,K]^T (+bias) (+residual)
+  void linear_into(const float* x, int lda, int C1, const float* x2, int lda2, int C2, int M, const float* W, int N, const float* bias,
+                   const float* residual, int ldr, float* y, int ldc) {
+    GemmArgs g;
+    g.mode = 0;
+    g.M = M; g.N = N; g.K = C1 + C2;
+    g.A = x; g.lda = lda; g.C1 = C1;
+    g.A2 = x2; g.lda2 = lda2; g.C2 = C2;
+    g.Bw = W; g.ldb = C1 + C2;
+    g.Cout = y; g.ldc = ldc;
+    g.bias = bias;
+    g.residual = residual; g.ldr = ldr;
+    gemm(e, g, s);
+  }
+  // single-source convenience: named weight [N,K(,1,1)], optional named bias
+  Tensor linear(const Tensor& x, const std::string& name, bool bias, const float* residual = nullptr) {
+    const Param& w = n.param(name + ".weight");
+    const int N = (int)w.dims[0], K = (int)w.dims[1];
+    CDX_CHECK(K == x.C, "linear %s: input width %d, weight expects %d", name.c_str(), x.C, K);
+    Tensor y = alloc(x.B, x.H, x.W, N);
+    linear_into(x.p, x.C, x.C, nullptr, 0, 0, x.rows(), n.blob + w.off, N, bias ? n.P(name + ".bias") : nullptr, residual, N, y.p, N);
+    return y;
+  }
+
+  Tensor gn(const Tensor& x, const Tensor* x2, const std::string& name, float eps, bool act, const float* scale = nullptr,
+            const float* shift = nullptr, int ld_ss = 0) {
+    const int C = x.C + (x2 ? x2->C : 0);
+    Tensor y = alloc(x.B, x.H, x.W, C);
+    groupnorm(e, x.p, x.C, x2 ? x2->p : nullptr, x2 ? x2->C : 0, n.P(name + ".weight"), n.P(name + ".bias"), eps, act, scale, shift, ld_ss,
+              y.p, x.B, x.H * x.W, s);
+    return y;
+  }
+  Tensor ln(const Tensor& x, const std::string& name) {
+    Tensor y = alloc(x.B, x.H, x.W, x.C);
+    layernorm(e, x.p, n.P(name + ".weight"), n.P(name + ".bias"), y.p, x.rows(), x.C, s);
+    return y;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ U-Nets
+struct UNetExec : Exec {
+  const float* E = nullptr;   // [B, emb_rows] all ResBlock emb projections
+  const float* ctx = nullptr;
+  int ctx_len = 0;
+  bool oai;
+  UNetExec(Net& net, cudaStream_t st) : Exec(net, st), oai(net.kind == NET_UNET_OPENAI) {}
+
+  // ResBlock (OAI:255-275 / IU:241-261).  updown: 0 none, 1 down (avg-pool), 2 up (nearest)
+  Tensor resblock(const Tensor& x, const Tensor* x2, const std::string& p, int updown = 0) {
+    const int Cout = n.dim0(p + ".in_layers.2.weight");
+    const int eoff = n.emb_off.at(p);
+    const int oH = updown == 1 ? x.H / 2 : (updown == 2 ? x.H * 2 : x.H);
+    const int oW = updown == 1 ? x.W / 2 : (updown == 2 ? x.W * 2 : x.W);
+    Tensor out = alloc(x.B, oH, oW, Cout);
+    Scope sc(e.arena);
+    Tensor h1 = gn(x, x2, p + ".in_layers.0", 1e-5f, true);
+    Tensor xs = x;    // skip-path input after x_upd
+    Tensor h2;
+    if (updown == 1) {
+      CDX_CHECK(!x2, "res down with concat input");
+      Tensor hp = alloc(x.B, oH, oW, x.C);
+      avgpool2(e, h1.p, hp.p, x.B, x.H, x.W, x.C, s);
+      xs = alloc(x.B, oH, oW, x.C);
+      avgpool2(e, x.p, xs.p, x.B, x.H, x.W, x.C, s);
+      h2 = conv3(hp, p + ".in_layers.2");
+    } else if (updown == 2) {
+      CDX_CHECK(!x2, "res up with concat input");
+      xs = alloc(x.B, oH, oW, x.C);
+      upsample2(e, x.p, xs.p, x.B, x.H, x.W, x.C, s);
+      h2 = conv3(h1, p + ".in_layers.2", 1, 1, 2);
+    } else if (oai) {
+      h2 = conv3(h1, p + ".in_layers.2", 1, 1, 1, E + eoff, n.emb_rows);     // + emb_out (OAI:273)
+    } else {
+      h2 = conv3(h1, p + ".in_layers.2");
+    }
+    if (!oai && updown == 0) { /* nothing: scale-shift handled in the norm below */ }
+    Tensor h3 = oai ? gn(h2, nullptr, p + ".out_layers.0", 1e-5f, true)
+                    : gn(h2, nullptr, p + ".out_layers.0", 1e-5f, true, E + eoff, E + eoff + Cout, n.emb_rows);   // IU:253-257
+    const float* residual;
+    if (n.has(p + ".skip_connection.weight")) {
+      Tensor sk = alloc(x.B, oH, oW, Cout);
+      linear_into(xs.p, xs.C, xs.C, x2 ? x2->p : nullptr, x2 ? x2->C : 0, x2 ? x2->C : 0, xs.rows(), n.P(p + ".skip_connection.weight"), Cout,
+                  n.P(p + ".skip_connection.bias"), nullptr, 0, sk.p, Cout);
+      residual = sk.p;
+    } else {
+      CDX_CHECK(!x2 && xs.C == Cout, "resblock %s: identity skip with mismatching channels", p.c_str());
+      residual = xs.p;
+    }
+    // conv3 allocates its own output on the arena; write into `out` by running the GEMM directly
+    {
+      const Param& w = n.param(p + ".out_layers.3.weight");
+      GemmArgs g;
+      g.mode = 1;
+      g.M = h3.rows(); g.N = Cout; g.K = 9 * h3.C;
+      g.A = h3.p; g.lda = h3.C; g.C1 = h3.C;
+      g.Hin = h3.H; g.Win = h3.W; g.Hout = h3.H; g.Wout = h3.W; g.stride = 1; g.pad = 1; g.up = 1;
+      g.Bw = n.blob + w.off; g.ldb = 9 * h3.C;
+      g.Cout = out.p; g.ldc = Cout;
+      g.bias = n.P(p + ".out_layers.3.bias");
+      g.residual = residual; g.ldr = Cout;
+      gemm(e, g, s);
+    }
+    return out;
+  }
+
+  // SpatialTransformer (ATT:250-261) with one BasicTransformerBlock (ATT:211-215)
+  Tensor spatial_transformer(const Tensor& x, const std::string& p) {
+    const int C = x.C, heads = n.ucfg.num_heads, d = C / heads;
+    const int M = x.rows(), HW = x.H * x.W, B = x.B;
+    Tensor out = alloc(B, x.H, x.W, C);
+    Scope sc(e.arena);
+    const float scale = (float)pow((double)d, -0.5);
+    const std::string t = p + ".transformer_blocks.0";
+    Tensor xn = gn(x, nullptr, p + ".norm", 1e-6f, false);
+    Tensor h = linear(xn, p + ".proj_in", true);
+    // --- self-attention: fused q|k|v projection (weights adjacent in the blob)
+    Tensor h2;
+    {
+      Tensor n1 = ln(h, t + ".norm1");
+      Tensor qkv = alloc(B, x.H, x.W, 3 * C);
+      linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 3 * C, nullptr, nullptr, 0, qkv.p, 3 * C);
+      Tensor a = alloc(B, x.H, x.W, C);
+      attention(e, qkv.p, 3 * C, qkv.p + C, 3 * C, qkv.p + 2 * C, 3 * C, a.p, C, B, HW, HW, heads, d, d, scale, s);
+      h2 = linear(a, t + ".attn1.to_out.0", true, h.p);
+    }
+    // --- cross-attention: q from tokens, fused k|v projection of the context
+    Tensor h3;
+    {
+      Tensor n2 = ln(h2, t + ".norm2");
+      Tensor q = linear(n2, t + ".attn2.to_q", false);
+      const int D = n.ucfg.context_dim;
+      Tensor kv = alloc(B, ctx_len, 1, 2 * C);
+      linear_into(ctx, D, D, nullptr, 0, 0, B * ctx_len, n.P(t + ".attn2.to_k.weight"), 2 * C, nullptr, nullptr, 0, kv.p, 2 * C);
+      Tensor a = alloc(B, x.H, x.W, C);
+      attention(e, q.p, C, kv.p, 2 * C, kv.p + C, 2 * C, a.p, C, B, HW, ctx_len, heads, d, d, scale, s);
+      h3 = linear(a, t + ".attn2.to_out.0", true, h2.p);
+    }
+    // --- GEGLU feed-forward (ATT:37-64)
+    Tensor h4;
+    {
+      Tensor n3 = ln(h3, t + ".norm3");
+      Tensor f = linear(n3, t + ".ff.net.0.proj", true);
+      Tensor g = alloc(B, x.H, x.W, 4 * C);
+      geglu(e, f.p, g.p, M, 4 * C, s);
+      h4 = linear(g, t + ".ff.net.2", true, h3.p);
+    }
+    linear_into(h4.p, C, C, nullptr, 0, 0, M, n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C);
+    return out;
+  }
+
+  // i-DDPM AttentionBlock + QKVAttentionLegacy (IU:304-310, 342-363): qkv channels are [head][q|k|v][d]
+  Tensor attention_block(const Tensor& x, const std::string& p) {
+    const int C = x.C, d = n.ucfg.num_head_channels, heads = C / d;
+    const int M = x.rows(), HW = x.H * x.W, B = x.B;
+    Tensor out = alloc(B, x.H, x.W, C);
+    Scope sc(e.arena);
+    Tensor xn = gn(x, nullptr, p + ".norm", 1e-5f, false);
+    Tensor qkv = alloc(B, x.H, x.W, 3 * C);
+    linear_into(xn.p, C, C, nullptr, 0, 0, M, n.P(p + ".qkv.weight"), 3 * C, n.P(p + ".qkv.bias"), nullptr, 0, qkv.p, 3 * C);
+    const float sq = (float)(1.0 / sqrt(sqrt((double)d)));
+    Tensor a = alloc(B, x.H, x.W, C);
+    attention(e, qkv.p, 3 * C, qkv.p + d, 3 * C, qkv.p + 2 * d, 3 * C, a.p, C, B, HW, HW, heads, d, 3 * d, sq * sq, s);
+    linear_into(a.p, C, C, nullptr, 0, 0, M, n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C);
+    return out;
+  }
+
+  Tensor attn_layer(const Tensor& x, const std::string& p) { return oai ? spatial_transformer(x, p) : attention_block(x, p); }
+
+  void forward(const float* x_nchw, const float* t_dev, const float* context, int L, float* out_nchw, int B, int H, int W) {
+    const cdx_unet_config& c = n.ucfg;
+    ctx = context;
+    ctx_len = L;
+    const int mc = c.model_channels, half = mc / 2, ted = n.ted;
+    Scope top(e.arena);
+    // --- timestep embedding MLP + all ResBlock emb projections in one GEMM
+    Tensor temb = alloc(B, 1, 1, mc);
+    timestep_embedding(e, t_dev, n.freqs_dev, temb.p, B, half, s);
+    Tensor e1 = linear(temb, "time_embed.0", true);
+    silu(e, e1.p, e1.p, e1.numel(), s);
+    Tensor emb = linear(e1, "time_embed.2", true);
+    silu(e, emb.p, emb.p, emb.numel(), s);   // every consumer applies SiLU first (OAI:219, IU:205)
+    Tensor Eall = alloc(B, 1, 1, n.emb_rows);
+    linear_into(emb.p, ted, ted, nullptr, 0, 0, B, n.blob + n.emb_w_off, n.emb_rows, n.blob + n.emb_b_off, nullptr, 0, Eall.p, n.emb_rows);
+    E = Eall.p;
+
+    Tensor xin = alloc(B, H, W, c.in_channels);
+    nchw_to_nhwc(e, x_nchw, xin.p, B, c.in_channels, H * W, s);
+
+    std::vector<Tensor> hs;
+    Tensor h = conv3(xin, "input_blocks.0.0");
+    hs.push_back(h);
+    int ds = 1, bi = 1;
+    for (int level = 0; level < c.n_mult; ++level) {
+      for (int r = 0; r < c.num_res_blocks; ++r) {
+        const std::string bp = S("input_blocks.", bi);
+        h = resblock(h, nullptr, bp + ".0");
+        if (contains(c.attention_ds, c.n_attn, ds)) h = attn_layer(h, bp + ".1");
+        hs.push_back(h);
+        ++bi;
+      }
+      if (level != c.n_mult - 1) {
+        const std::string bp = S("input_blocks.", bi);
+        if (oai) h = conv3(h, bp + ".0.op", 2, 1);
+        else h = resblock(h, nullptr, bp + ".0", 1);
+        hs.push_back(h);
+        ++bi;
+        ds *= 2;
+      }
+    }
+    h = resblock(h, nullptr, "middle_block.0");
+    h = attn_layer(h, "middle_block.1");
+    h = resblock(h, nullptr, "middle_block.2");
+    int bo = 0;
+    for (int level = c.n_mult - 1; level >= 0; --level) {
+      for (int i = 0; i <= c.num_res_blocks; ++i) {
+        const Tensor skip = hs.back();
+        hs.pop_back();
+        const std::string bp = S("output_blocks.", bo);
+        h = resblock(h, &skip, bp + ".0");
+        int li = 1;
+        if (contains(c.attention_ds, c.n_attn, ds)) { h = attn_layer(h, bp + "." + std::to_string(li)); ++li; }
+        if (level && i == c.num_res_blocks) {
+          if (oai) h = conv3(h, bp + "." + std::to_string(li) + ".conv", 1, 1, 2);
+          else h = resblock(h, nullptr, bp + "." + std::to_string(li), 2);
+          ds /= 2;
+        }
+        ++bo;
+      }
+    }
+    Tensor ho = gn(h, nullptr, "out.0", 1e-5f, true);
+    conv3(ho, "out.2", 1, 1, 1, nullptr, 0, nullptr, out_nchw);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ VAE
+struct VaeExec : Exec {
+  VaeExec(Net& net, cudaStream_t st) : Exec(net, st) {}
+
+  Tensor resnet(const Tensor& x, const std::string& p) {
+    const int Cout = n.dim0(p + ".conv1.weight");
+    Tensor out = alloc(x.B, x.H, x.W, Cout);
+    Scope sc(e.arena);
+    Tensor h1 = gn(x, nullptr, p + ".norm1", 1e-6f, true);
+    Tensor h2 = conv3(h1, p + ".conv1");
+    Tensor h3 = gn(h2, nullptr, p + ".norm2", 1e-6f, true);
+    const float* residual = x.p;
+    if (n.has(p + ".nin_shortcut.weight")) {
+      Tensor sk = linear(x, p + ".nin_shortcut", true);
+      residual = sk.p;
+    }
+    const Param& w = n.param(p + ".conv2.weight");
+    GemmArgs g;
+    g.mode = 1;
+    g.M = h3.rows(); g.N = Cout; g.K = 9 * h3.C;
+    g.A = h3.p; g.lda = h3.C; g.C1 = h3.C;
+    g.Hin = h3.H; g.Win = h3.W; g.Hout = h3.H; g.Wout = h3.W;
+    g.Bw = n.blob + w.off; g.ldb = 9 * h3.C;
+    g.Cout = out.p; g.ldc = Cout;
+    g.bias = n.P(p + ".conv2.bias");
+    g.residual = residual; g.ldr = Cout;
+    gemm(e, g, s);
+    return out;
+  }
+
+  // AttnBlock (AEM:178-202): single head, d = C, scale C^-1/2
+  Tensor attn(const Tensor& x, const std::string& p) {
+    const int C = x.C, HW = x.H * x.W;
+    Tensor out = alloc(x.B, x.H, x.W, C);
+    Scope sc(e.arena);
+    Tensor xn = gn(x, nullptr, p + ".norm", 1e-6f, false);
+    Tensor q = linear(xn, p + ".q", true);
+    Tensor k = linear(xn, p + ".k", true);
+    Tensor v = linear(xn, p + ".v", true);
+    Tensor a = alloc(x.B, x.H, x.W, C);
+    attention(e, q.p, C, k.p, C, v.p, C, a.p, C, x.B, HW, HW, 1, C, C, (float)pow((double)C, -0.5), s);
+    linear_into(a.p, C, C, nullptr, 0, 0, x.rows(), n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C);
+    return out;
+  }
+
+  void encode(const float* img_nchw, float* moments_nchw, int B, int R) {
+    const cdx_vae_config& c = n.vcfg;
+    Scope top(e.arena);
+    const std::string E = "encoder.";
+    Tensor xin = alloc(B, R, R, c.in_channels);
+    nchw_to_nhwc(e, img_nchw, xin.p, B, c.in_channels, R * R, s);
+    Tensor h = conv3(xin, E + "conv_in");
+    for (int lvl = 0; lvl < c.n_mult; ++lvl) {
+      for (int b = 0; b < c.num_res_blocks; ++b) h = resnet(h, E + "down." + std::to_string(lvl) + ".block." + std::to_string(b));
+      if (lvl != c.n_mult - 1) h = conv3(h, E + "down." + std::to_string(lvl) + ".downsample.conv", 2, 0);   // pad (0,1,0,1), AEM:72-76
+    }
+    h = resnet(h, E + "mid.block_1");
+    h = attn(h, E + "mid.attn_1");
+    h = resnet(h, E + "mid.block_2");
+    Tensor ho = gn(h, nullptr, E + "norm_out", 1e-6f, true);
+    Tensor m = conv3(ho, E + "conv_out");
+    Tensor q = linear(m, "quant_conv", true);
+    nhwc_to_nchw(e, q.p, moments_nchw, B, q.C, q.H * q.W, s);
+  }
+
+  void decode(const float* z_nchw, float* img_nchw, int B, int hsz) {
+    const cdx_vae_config& c = n.vcfg;
+    Scope top(e.arena);
+    const std::string D = "decoder.";
+    Tensor zin = alloc(B, hsz, hsz, c.embed_dim);
+    nchw_to_nhwc(e, z_nchw, zin.p, B, c.embed_dim, hsz * hsz, s);
+    Tensor h = linear(zin, "post_quant_conv", true);
+    h = conv3(h, D + "conv_in");
+    h = resnet(h, D + "mid.block_1");
+    h = attn(h, D + "mid.attn_1");
+    h = resnet(h, D + "mid.block_2");
+    for (int lvl = c.n_mult - 1; lvl >= 0; --lvl) {
+      for (int b = 0; b <= c.num_res_blocks; ++b) h = resnet(h, D + "up." + std::to_string(lvl) + ".block." + std::to_string(b));
+      if (lvl != 0) h = conv3(h, D + "up." + std::to_string(lvl) + ".upsample.conv", 1, 1, 2);
+    }
+    Tensor ho = gn(h, nullptr, D + "norm_out", 1e-6f, true);
+    conv3(ho, D + "conv_out", 1, 1, 1, nullptr, 0, nullptr, img_nchw);
+  }
+};
+
+}  // namespace
+
+void unet_forward(Net& n, const float* x_nchw, const float* t_dev, const float* ctx, int ctx_len, float* out_nchw, int B, int H, int W,
+                  cudaStream_t s) {
+  CDX_CHECK(n.kind == NET_UNET_OPENAI || n.kind == NET_UNET_IDDPM, "unet_forward on a non-U-Net");
+  CDX_CHECK(n.finalized, "unet_forward before finalize");
+  if (n.kind == NET_UNET_OPENAI) CDX_CHECK(ctx != nullptr && ctx_len > 0, "unet_forward: the SD/LDM U-Net needs a context");
+  const int down = 1 << (n.ucfg.n_mult - 1);
+  CDX_CHECK(H % down == 0 && W % down == 0, "unet_forward: %dx%d not divisible by %d", H, W, down);
+  UNetExec ex(n, s);
+  ex.forward(x_nchw, t_dev, ctx, ctx_len, out_nchw, B, H, W);
+}
+
+void vae_encode(Net& n, const float* img, float* moments, int B, int R, cudaStream_t s) {
+  CDX_CHECK(n.kind == NET_VAE && n.finalized, "vae_encode: not a finalized VAE");
+  CDX_CHECK(R % (1 << (n.vcfg.n_mult - 1)) == 0, "vae_encode: resolution %d", R);
+  VaeExec ex(n, s);
+  ex.encode(img, moments, B, R);
+}
+
+void vae_decode(Net& n, const float* z, float* img, int B, int h, cudaStream_t s) {
+  CDX_CHECK(n.kind == NET_VAE && n.finalized, "vae_decode: not a finalized VAE");
+  VaeExec ex(n, s);
+  ex.decode(z, img, B, h);
+}
+
+}  // namespace cdx

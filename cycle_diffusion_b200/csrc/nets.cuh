@@ -1,0 +1,61 @@
+// nets.cuh -- network objects: parameter inventory, packed weight blob, forward executors.
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cdx {
+
+struct Param {
+  std::string name;
+  int64_t dims[4] = {0, 0, 0, 0};
+  int rank = 0;
+  size_t numel = 0;
+  size_t off = 0;        // float offset into the blob
+  int segment = 0;       // 0 general, 1 emb-proj weights (concatenated), 2 emb-proj biases (concatenated)
+  bool conv3 = false;    // stored repacked O,kh,kw,I
+  bool loaded = false;
+};
+
+enum NetKind { NET_UNET_OPENAI = 1, NET_UNET_IDDPM = 2, NET_VAE = 3 };
+
+struct Net {
+  Engine* eng = nullptr;
+  int kind = 0;
+  cdx_unet_config ucfg{};
+  cdx_vae_config vcfg{};
+  std::vector<Param> params;
+  std::unordered_map<std::string, int> index;
+  float* blob = nullptr;
+  size_t blob_floats = 0;
+  bool finalized = false;
+  // timestep embedding
+  std::vector<float> freqs_host;
+  float* freqs_dev = nullptr;
+  // concatenated ResBlock emb projections: weights [emb_rows][ted] at emb_w_off, biases at emb_b_off
+  size_t emb_w_off = 0, emb_b_off = 0;
+  int emb_rows = 0, ted = 0;
+  std::unordered_map<std::string, int> emb_off;   // ResBlock prefix -> row offset
+
+  const Param& param(const std::string& name) const;
+  float* P(const std::string& name) const { return blob + param(name).off; }
+  bool has(const std::string& name) const { return index.find(name) != index.end(); }
+  int dim0(const std::string& name) const { return (int)param(name).dims[0]; }
+};
+
+Net* make_unet(Engine* e, const cdx_unet_config& cfg);
+Net* make_vae(Engine* e, const cdx_vae_config& cfg);
+void destroy_net(Net* n);
+void net_load_param(Net& n, const char* name, const float* data, bool on_device, const int64_t* dims, int rank);
+void net_finalize(Net& n);
+void net_ensure_blob(Net& n);
+
+// forward executors (enqueue only; caller handles arena dry-run)
+void unet_forward(Net& n, const float* x_nchw, const float* t_dev, const float* ctx, int ctx_len, float* out_nchw, int B, int H,
+                  int W, cudaStream_t s);
+void vae_encode(Net& n, const float* img_nchw, float* moments_nchw, int B, int R, cudaStream_t s);
+void vae_decode(Net& n, const float* z_nchw, float* img_nchw, int B, int h, cudaStream_t s);
+
+}  // namespace cdx

@@ -1,0 +1,325 @@
+"""Drop-in `gan_wrapper` classes: the reference's plugin surface for the hot path, backed by libcdx.
+
+Mirrors (same constructor kwargs, method names, argument meaning, return layouts and precondition checks):
+  SDStochasticTextWrapper            ref model/gan_wrapper/stable_diffusion_stochastic_text_wrapper.py:100-253
+  LatentDiffStochasticTextWrapper    ref model/gan_wrapper/latentdiff_stochastic_text_wrapper.py:102-252
+  DDPMDDIMWrapper                    ref model/gan_wrapper/ddpm_ddim_wrapper.py:317-538
+  get_gan_wrapper                    ref model/gan_wrapper/get_gan_wrapper.py:3-31
+
+Differences that are deliberate and documented in INTEGRATION.md:
+  * weights come from a reference-format ``state_dict`` / checkpoint path given by keyword (or ``'synthetic'``);
+    the packed blob can be shared between wrappers and broadcast across ranks;
+  * the text encoder is an injected callable ``cond_stage(list[str]) -> [B,77,D]`` (CLIP / BERT text towers are
+    out of scope for this engine); a deterministic stand-in is provided for tests and benchmarks;
+  * random draws are taken from the torch CPU generator in the reference's order and uploaded, so a run is
+    reproducible against the reference CPU path under the same ``torch.manual_seed``;
+  * Directional-CLIP ranking of the ensemble is an injected callable; with a single ensemble
+    member no ranking is needed.
+"""
+import hashlib
+import os
+
+import numpy as np
+import torch
+
+from . import specs
+from .engine import Engine, UNet, VAE
+from .schedule import DDIMSchedule, PixelSchedule
+
+
+class SyntheticTextEncoder:
+    """Deterministic stand-in for FrozenCLIPEmbedder / BERTEmbedder: prompt string -> N(0,1) tokens [77, dim].
+
+    Same interface as ``model.get_learned_conditioning`` (ddpm.py:545-556).  Not a language model: it only gives
+    distinct, reproducible conditioning tensors so the sampling path can be exercised without checkpoints.
+    """
+
+    def __init__(self, dim, n_tokens=77, device='cpu'):
+        self.dim, self.n_tokens, self.device = dim, n_tokens, device
+
+    def __call__(self, texts):
+        assert isinstance(texts, list) and isinstance(texts[0], str)       # SDW:29-30
+        out = []
+        for t in texts:
+            seed = int.from_bytes(hashlib.sha256(t.encode('utf-8')).digest()[:4], 'little')
+            g = torch.Generator().manual_seed(seed)
+            out.append(torch.randn(self.n_tokens, self.dim, generator=g))
+        return torch.stack(out).to(self.device)
+
+
+def _load_sd(state_dict, ckpt_default, synth_params, seed):
+    if isinstance(state_dict, dict):
+        return state_dict
+    if state_dict == 'synthetic':
+        return specs.synth_state_dict(synth_params, seed)
+    path = state_dict if isinstance(state_dict, str) else ckpt_default
+    if not os.path.exists(path):
+        raise FileNotFoundError(f'checkpoint {path} not found; pass state_dict=<dict>, a path, or "synthetic"')
+    sd = torch.load(path, map_location='cpu')
+    return sd['state_dict'] if 'state_dict' in sd else sd       # txt2img.py:27-32 / DW:378-379
+
+
+class _LatentGenerator:
+    """What the text wrappers call ``self.generator`` (LatentDiffusion): U-Net + first stage + cond stage."""
+
+    def __init__(self, engine, unet, vae, cond_stage, channels, image_size, scale_factor, sample_posterior):
+        self.engine, self.unet, self.vae, self.cond_stage = engine, unet, vae, cond_stage
+        self.channels, self.image_size, self.scale_factor = channels, image_size, scale_factor
+        self.sample_posterior = sample_posterior
+        self.alphas_cumprod = None      # default LDM linear schedule (v1-inference.yaml:5-9)
+
+    def get_learned_conditioning(self, c):
+        return self.cond_stage(c)
+
+    def encode_first_stage(self, image):
+        return self.vae.encode_moments(image)                              # moments of the DiagonalGaussianDistribution
+
+    def get_first_stage_encoding(self, moments):
+        noise = None
+        if self.sample_posterior:                                          # ddpm.py:536-543; distributions.py:36 draws on the CPU
+            B, C2, h, w = moments.shape
+            noise = torch.randn(B, C2 // 2, h, w)
+        return self.engine.vae_posterior(moments, noise, self.scale_factor)
+
+    def decode_first_stage(self, z):
+        return self.vae.decode(self.engine.affine(z, 1. / self.scale_factor, 0.0))     # ddpm.py:705
+
+
+class _StochasticTextWrapperBase(torch.nn.Module):
+    RESOLUTION = 512
+    LATENT = 64
+    CONTEXT_DIM = 768
+    SAMPLE_POSTERIOR = True
+    CKPT_DIR = 'ckpts/stable_diffusion'
+
+    def __init__(self, source_model_type, custom_steps, eta, white_box_steps, skip_steps,
+                 encoder_unconditional_guidance_scales=None, decoder_unconditional_guidance_scales=None, n_trials=None, *,
+                 engine=None, device=0, state_dict=None, cond_stage=None, ranker=None, unet_config=None, vae_config=None,
+                 latent_size=None, resolution=None, generator=None, seed=1234):
+        super().__init__()
+        self.encoder_unconditional_guidance_scales = encoder_unconditional_guidance_scales
+        self.decoder_unconditional_guidance_scales = decoder_unconditional_guidance_scales
+        self.n_trials = n_trials
+        self.eta, self.custom_steps, self.white_box_steps, self.skip_steps = eta, custom_steps, white_box_steps, skip_steps
+        self.resolution = resolution or self.RESOLUTION
+        self.precision = "full"
+        self.directional_clip = ranker
+        if generator is not None:
+            self.generator = generator
+            self.engine = generator.engine
+        else:
+            self.engine = engine or Engine(device)
+            ucfg = unet_config or specs.sd_unet_config(self.CONTEXT_DIM)
+            vcfg = vae_config or specs.kl_f8_config()
+            unet, vae = UNet(self.engine, ucfg, 'openai'), VAE(self.engine, vcfg)
+            ckpt = os.path.join(self.CKPT_DIR, str(source_model_type))
+            if state_dict == 'synthetic':
+                unet.load_state_dict(specs.synth_state_dict(specs.openai_unet_params(ucfg), seed))
+                vae.load_state_dict(specs.synth_state_dict(specs.kl_vae_params(vcfg), seed + 1))
+            else:
+                sd = _load_sd(state_dict, ckpt, None, seed)
+                unet.load_state_dict(sd, prefix='model.diffusion_model.', strict=False)
+                vae.load_state_dict(sd, prefix='first_stage_model.', strict=False)
+            cond = cond_stage or SyntheticTextEncoder(ucfg['context_dim'])
+            self.generator = _LatentGenerator(self.engine, unet, vae, cond, ucfg['in_channels'], latent_size or self.LATENT, 0.18215,
+                                              self.SAMPLE_POSTERIOR)
+        self._dummy = torch.nn.Parameter(torch.zeros(1, device=self.engine.device), requires_grad=False)
+
+    # -- helpers mirroring the module-level functions of the reference wrapper
+    def _get_condition(self, text, bs):
+        assert isinstance(text, list)
+        assert isinstance(text[0], str)
+        uc = self.generator.get_learned_conditioning(bs * [""])
+        c = self.generator.get_learned_conditioning(text)
+        return c, uc
+
+    def _encode_noise(self, sched, n_rec, shape):
+        """Draws of _ddpm_ddim_encoding in order: x_T (ddim.py:479), then one per step except index==0 (ddim.py:583-584, 599)."""
+        noise = torch.zeros((n_rec + 1,) + tuple(shape))
+        noise[0] = torch.randn(shape)
+        for i in range(n_rec):
+            if sched.refine_steps - 1 - i != 0:
+                noise[1 + i] = torch.randn(shape)
+        return noise
+
+    def generate(self, z_ensemble, decode_text):
+        g = self.generator
+        img_ensemble = []
+        for i, z in enumerate(z_ensemble):
+            skip_steps = self.skip_steps[i % len(self.skip_steps)]
+            bsz = z.shape[0]
+            if self.white_box_steps != -1:
+                eps_list = z.view(bsz, (self.white_box_steps - skip_steps), g.channels, g.image_size, g.image_size)
+            else:
+                eps_list = z.view(bsz, 1, g.channels, g.image_size, g.image_size)
+            for scale in self.decoder_unconditional_guidance_scales:
+                c, uc = self._get_condition(decode_text, bsz)
+                sched = DDIMSchedule(self.custom_steps, self.eta, skip_steps, g.alphas_cumprod)
+                n_extra = sched.refine_steps - (eps_list.shape[1] - 1)
+                extra = None
+                if n_extra > 0:                                                   # ddim.py:640: fresh noise where none was recovered
+                    extra = torch.stack([torch.randn(eps_list[:, 0].shape) for _ in range(n_extra)])
+                sample = g.unet.latent_decode(eps_list, c, uc, scale, sched, extra)
+                img_ensemble.append(g.decode_first_stage(sample))
+        return img_ensemble
+
+    def encode(self, image, encode_text):
+        g, e = self.generator, self.engine
+        image = e.shift_scale(image, -0.5, 2.0)                                   # (image - 0.5) * 2.0
+        assert image.shape[2] == image.shape[3] == self.resolution
+        x0 = g.get_first_stage_encoding(g.encode_first_stage(image))
+        bsz = image.shape[0]
+        z_ensemble = []
+        for _trial in range(self.n_trials):
+            for enc_scale in self.encoder_unconditional_guidance_scales:
+                for skip_steps in self.skip_steps:
+                    c, uc = self._get_condition(encode_text, bsz)
+                    assert self.eta > 0                                           # ddim.py:268
+                    sched = DDIMSchedule(self.custom_steps, self.eta, skip_steps, g.alphas_cumprod)
+                    n_rec = max(0, min(sched.refine_steps, self.white_box_steps - skip_steps - 1))
+                    noise = self._encode_noise(sched, n_rec, x0.shape)
+                    z = g.unet.latent_encode(x0, c, uc, enc_scale, sched, n_rec, noise)
+                    z_ensemble.append(z.view(bsz, -1))
+        return z_ensemble
+
+    def forward(self, z_ensemble, original_img, encode_text, decode_text):
+        img_ensemble = self.generate(z_ensemble, decode_text)
+        assert len(img_ensemble) == len(self.decoder_unconditional_guidance_scales) * len(
+            self.encoder_unconditional_guidance_scales) * len(self.skip_steps) * self.n_trials
+        img_ensemble = [self.engine.shift_scale(img, 1.0, 0.5) for img in img_ensemble]     # Normalize(mean=-1, std=2)
+        if len(img_ensemble) == 1:
+            return img_ensemble[0]
+        if self.directional_clip is None:
+            raise NotImplementedError('ranking an ensemble needs ranker=<callable(img, original_img, encode_text, decode_text) '
+                                      '-> (_, score[B])> (DirectionalCLIP is outside the engine, SURVEY.md 8f-3)')
+        scores = []
+        for img in img_ensemble:
+            _, s = self.directional_clip(img, original_img, encode_text, decode_text)
+            assert s.shape == (img.shape[0],)
+            scores.append(s)
+        best_idx = torch.argmax(torch.stack(scores, dim=1), dim=1)
+        return torch.stack([img_ensemble[best_idx[b].item()][b] for b in range(best_idx.shape[0])], dim=0)
+
+    @property
+    def device(self):
+        return self.engine.device
+
+
+class SDStochasticTextWrapper(_StochasticTextWrapperBase):
+    """Stable Diffusion v1 (512 px, latent 64, CLIP context 768, posterior *sample*)."""
+
+
+class LatentDiffStochasticTextWrapper(_StochasticTextWrapperBase):
+    """LDM text2img-large (256 px, latent 32, BERT context 1280, posterior *mean*: latentdiff/.../ddpm.py:537-538)."""
+    RESOLUTION = 256
+    LATENT = 32
+    CONTEXT_DIM = 1280
+    SAMPLE_POSTERIOR = False
+    CKPT_DIR = 'ckpts/text2img-large'
+
+
+class DDPMDDIMWrapper(torch.nn.Module):
+    """Pixel-space DPM-Encoder / decoder (improved-DDPM U-Net for AFHQ / FFHQ)."""
+
+    def __init__(self, source_model_type, sample_type, custom_steps, es_steps, source_model_path=None, refine_steps=0,
+                 refine_iterations=1, eta=None, t_0=None, enforce_class_input=None, *, engine=None, device=0, state_dict=None,
+                 image_size=None, unet=None, seed=4321):
+        super().__init__()
+        self.enforce_class_input = enforce_class_input
+        self.custom_steps, self.refine_steps, self.refine_iterations = custom_steps, refine_steps, refine_iterations
+        self.sample_type, self.eta = sample_type, eta
+        self.t_0 = t_0 if t_0 is not None else 999
+        self.es_steps = es_steps
+        if self.sample_type == 'ddim':
+            assert self.eta > 0
+        elif self.sample_type == 'ddpm':
+            assert self.eta is None
+        else:
+            raise ValueError()
+        if image_size is None:
+            digits = ''.join(ch for ch in str(source_model_type) if ch.isdigit())
+            image_size = int(digits) if digits else 256
+        self.learn_sigma = False
+        if unet is not None:
+            self.generator, self.engine = unet, unet.engine
+        else:
+            self.engine = engine or Engine(device)
+            cfg = specs.iddpm_config(image_size)
+            self.generator = UNet(self.engine, cfg, 'iddpm')
+            sd = _load_sd(state_dict if state_dict is not None else source_model_path, source_model_path or '', specs.iddpm_unet_params(cfg), seed)
+            self.generator.load_state_dict(sd)
+        self.resolution = image_size
+        self.channels = 3
+        self.latent_dim = self.resolution ** 2 * self.channels * self.es_steps
+        self.sched = PixelSchedule(sample_type, custom_steps, es_steps, eta, self.t_0)
+        self._dummy = torch.nn.Parameter(torch.zeros(1, device=self.engine.device), requires_grad=False)
+
+    def generate(self, z, class_label):
+        bsz = z.shape[0]
+        eps_list = z.view(bsz, self.es_steps, self.channels, self.resolution, self.resolution)
+        if self.enforce_class_input:
+            assert class_label is not None
+            raise NotImplementedError()
+        shape = eps_list[:, 0].shape
+        last = torch.randn(shape).unsqueeze(0)       # denoising_step draws once more; the draw is multiplied by 0 (DU:115,131)
+        x = self.generator.pixel_decode(eps_list, self.sched, last_noise=last)
+        if self.refine_steps != 0:
+            assert self.refine_steps < self.custom_steps
+            ref = PixelSchedule(self.sample_type, self.custom_steps, self.es_steps, 1 if self.sample_type == 'ddim' else None, self.t_0)
+            pairs = self.sched.pairs[-self.refine_steps:] if self.refine_steps <= len(self.sched.pairs) else self.sched.pairs
+            coefs = [ref.step_coef(i, j, 1 if self.sample_type == 'ddim' else None) for i, j in pairs]
+            t_loop = [float(i) for i, _ in pairs]
+            at = PixelSchedule._extract(self.sched.cumprod, self.refine_steps - 1)               # DW:436-437
+            for _ in range(self.refine_iterations):
+                xt = self.engine.q_sample(x, torch.randn(shape), at.sqrt().item(), (1 - at).sqrt().item())
+                noises = torch.stack([torch.randn(shape) for _ in pairs])
+                x = self.generator.pixel_decode(xt.view(bsz, 1, *shape[1:]), ref, coefs=coefs, t_loop=t_loop, last_noise=noises)
+        return x
+
+    def encode(self, image, class_label=None):
+        e = self.engine
+        image = e.shift_scale(image, -0.5, 2.0)
+        assert image.shape[2] == image.shape[3] == self.resolution
+        if self.enforce_class_input:
+            assert class_label is not None
+            raise NotImplementedError()
+        bsz = image.shape[0]
+        n_rec = self.es_steps - 1
+        noise = torch.stack([torch.randn(image.shape) for _ in range(n_rec + 1)])     # sample_xt, then one per sample_xt_next
+        z = self.generator.pixel_encode(image, self.sched, noise).view(bsz, -1)
+        assert z.shape[1] == self.latent_dim
+        return z
+
+    def forward(self, z, class_label=None):
+        img = self.generate(z, class_label)
+        return self.engine.shift_scale(img, 1.0, 0.5)
+
+    @property
+    def device(self):
+        return self.engine.device
+
+
+def get_gan_wrapper(args, target=False, **extra):
+    """Same kwarg plumbing as the reference factory: every ``[gan]`` key but ``gan_type`` becomes a kwarg;
+    ``target_*`` keys are renamed ``source_*`` for the target model.  ``extra`` carries engine/state_dict/... ."""
+    items = list(args.items()) if isinstance(args, dict) else list(args)
+    gan_type = args['gan_type'] if isinstance(args, dict) else args.gan_type
+    kwargs = {}
+    for kw, arg in items:
+        if kw != 'gan_type':
+            if (not kw.startswith('source_')) and (not kw.startswith('target_')):
+                kwargs[kw] = arg
+            else:
+                if target and kw.startswith('target_'):
+                    kwargs['source_' + kw[len('target_'):]] = arg
+                elif (not target) and kw.startswith('source_'):
+                    kwargs[kw] = arg
+    kwargs.update(extra)
+    if gan_type == "DDPM_DDIM":
+        return DDPMDDIMWrapper(**kwargs)
+    elif gan_type == "LatentDiffStochasticText":
+        return LatentDiffStochasticTextWrapper(**kwargs)
+    elif gan_type == "SDStochasticText":
+        return SDStochasticTextWrapper(**kwargs)
+    else:
+        raise ValueError()

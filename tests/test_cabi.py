@@ -1,0 +1,62 @@
+"""CPU-only checks of the C ABI: the library loads, exports every symbol include/cdx.h declares, fails loudly
+without a GPU, and its parameter inventories agree with cycle_diffusion_b200.specs (which make_golden.py pins
+against the reference module trees with load_state_dict(strict=True))."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from cycle_diffusion_b200 import _cabi, specs
+from cycle_diffusion_b200.engine import UNet, VAE
+from tests.common import NARROW, VAE_SMALL, WIDE
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, 'include', 'cdx.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(cdx_[a-z0-9_]+)\s*\(', txt)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    syms = header_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(_cabi.lib, s), f'{s} declared in cdx.h but not exported by libcdx.so'
+        assert s in _cabi.SIGNATURES, f'{s} has no ctypes signature'
+    assert sorted(_cabi.SIGNATURES) == syms
+    assert _cabi.lib.cdx_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='needs a box without CUDA')
+def test_engine_creation_fails_loudly_without_gpu():
+    h = C.c_void_p()
+    rc = _cabi.lib.cdx_engine_create(0, C.byref(h))
+    assert rc == -2 and b'no usable CUDA device' in _cabi.lib.cdx_last_error()
+    from cycle_diffusion_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine(0)
+
+
+@pytest.mark.parametrize('cfg,kind,ref', [
+    (specs.sd_unet_config(768), 'openai', specs.openai_unet_params), (specs.sd_unet_config(1280), 'openai', specs.openai_unet_params),
+    (NARROW, 'openai', specs.openai_unet_params), (WIDE, 'openai', specs.openai_unet_params),
+    (specs.iddpm_config(256), 'iddpm', specs.iddpm_unet_params), (specs.iddpm_config(64), 'iddpm', specs.iddpm_unet_params)])
+def test_unet_inventory_matches_specs(cfg, kind, ref):
+    net = UNet(None, cfg, kind)       # inventory-only (no engine, no GPU)
+    assert net.inventory() == [(n, tuple(s)) for n, s, _ in ref(cfg)]
+
+
+@pytest.mark.parametrize('cfg', [specs.kl_f8_config(), VAE_SMALL])
+def test_vae_inventory_matches_specs(cfg):
+    net = VAE(None, cfg)
+    assert net.inventory() == [(n, tuple(s)) for n, s, _ in specs.kl_vae_params(cfg)]
+
+
+def test_inventory_only_net_rejects_compute():
+    net = UNet(None, NARROW, 'openai')
+    with pytest.raises(AssertionError):
+        net.finalize()

@@ -1,0 +1,132 @@
+"""Path-level parity on the GPU: DPM-Encoder inversion + decode loops and the drop-in wrappers, against the
+reference-generated fixtures and the CPU oracle under the same torch.manual_seed.
+
+The recovered noise z is amplified by 1/sigma_t (|z| reaches 1e2-1e3 with synthetic weights), so z is compared
+relative to its own max; decoded latents / images use the north-star bar |delta| <= 1e-3 (fp32 latents)."""
+import pytest
+import torch
+
+from cycle_diffusion_b200 import specs
+from tests.common import NARROW, VAE_SMALL, golden, maxdiff
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from cycle_diffusion_b200.engine import Engine
+    return Engine(0)
+
+
+def _encode_noise(sched, n_rec, shape):
+    noise = torch.zeros((n_rec + 1,) + tuple(shape))
+    noise[0] = torch.randn(shape)
+    for i in range(n_rec):
+        if sched.refine_steps - 1 - i != 0:
+            noise[1 + i] = torch.randn(shape)
+    return noise
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_latent_cycle_vs_reference_fixture(eng, tag):
+    from cycle_diffusion_b200.engine import UNet
+    from cycle_diffusion_b200.schedule import DDIMSchedule
+    g = golden('ddim_cycle_narrow')
+    S, skip, wb, enc_scale, dec_scale, seed = [float(v) for v in g[f'cfg_{tag}']]
+    S, skip, wb, seed = int(S), int(skip), int(wb), int(seed)
+    sd = specs.synth_state_dict(specs.openai_unet_params(NARROW), 11)
+    unet = UNet(eng, NARROW, 'openai').load_state_dict(sd)
+    sched = DDIMSchedule(S, 0.1, skip)
+    n_rec = min(sched.refine_steps, wb - skip - 1)
+    torch.manual_seed(seed)
+    noise = _encode_noise(sched, n_rec, g['x0'].shape)
+    z = unet.latent_encode(g['x0'], g['c_src'], g['uc'], enc_scale, sched, n_rec, noise)
+    zref = g[f'z_{tag}'].view(z.shape)
+    rz = maxdiff(z.cpu(), zref) / float(zref.abs().max())
+    same = unet.latent_decode(zref, g['c_src'], g['uc'], enc_scale, sched).cpu()
+    tgt = unet.latent_decode(zref, g['c_tgt'], g['uc'], dec_scale, sched).cpu()
+    own = unet.latent_decode(z, g['c_src'], g['uc'], enc_scale, sched).cpu()       # engine encode -> engine decode
+    print(f'cycle[{tag}]: rel|dz| {rz:.2e}  |d same| {maxdiff(same, g[f"same_{tag}"]):.2e}  |d tgt| {maxdiff(tgt, g[f"tgt_{tag}"]):.2e}'
+          f'  own-cycle |x0_hat - x0| {maxdiff(own, g["x0"]):.2e}')
+    assert rz < 2e-4
+    assert maxdiff(same, g[f'same_{tag}']) < 1e-3
+    assert maxdiff(tgt, g[f'tgt_{tag}']) < 1e-3
+    assert maxdiff(own, g['x0']) < 1e-3
+
+
+@pytest.mark.parametrize('tag,kw', [('ddim', dict(sample_type='ddim', eta=0.1, custom_steps=10, es_steps=10)),
+                                    ('ddpm', dict(sample_type='ddpm', eta=None, custom_steps=20, es_steps=6))])
+def test_pixel_wrapper_vs_reference_fixture(eng, tag, kw):
+    """BASELINE config 1: DDPMDDIMWrapper on the 64x64 i-DDPM U-Net, fixture from the unmodified reference wrapper."""
+    from cycle_diffusion_b200.wrappers import DDPMDDIMWrapper
+    g = golden('pixel_cycle_iddpm64')
+    cfg = specs.iddpm_config(64)
+    sd = specs.synth_state_dict(specs.iddpm_unet_params(cfg), 31)
+    w = DDPMDDIMWrapper('afhqcat64', source_model_path=None, state_dict=sd, image_size=64, engine=eng, **kw)
+    assert (w.resolution, w.channels, w.latent_dim) == (64, 3, 64 * 64 * 3 * kw['es_steps'])
+    torch.manual_seed(2000)
+    z = w.encode(g['image'])
+    zref = g[f'z_{tag}']
+    rz = maxdiff(z.cpu(), zref) / float(zref.abs().max())
+    img = w(zref).cpu()
+    print(f'pixel[{tag}]: rel|dz| {rz:.2e}  |d img| {maxdiff(img, g[f"img_{tag}"]):.2e}')
+    assert z.shape == zref.shape
+    assert rz < 5e-4
+    assert maxdiff(img, g[f'img_{tag}']) < 1e-3
+    with pytest.raises(AssertionError):
+        w.encode(torch.rand(1, 3, 32, 32))                 # DW:472 resolution check
+
+
+def test_sd_wrapper_vs_oracle_end_to_end(eng):
+    """SDStochasticTextWrapper surface (encode -> forward) on a small SD-topology model against the CPU oracle's
+    restatement of the same wrapper, same seeds: VAE encode + posterior sample + DPM-Encoder + CFG decode + VAE decode."""
+    from cycle_diffusion_b200.wrappers import SDStochasticTextWrapper, SyntheticTextEncoder
+    from oracle import dpm_encoder, unet_openai, vae_kl
+    usd = specs.synth_state_dict(specs.openai_unet_params(NARROW), 11)
+    vsd = specs.synth_state_dict(specs.kl_vae_params(VAE_SMALL), 21)
+    sd = {'model.diffusion_model.' + k: v for k, v in usd.items()}
+    sd.update({'first_stage_model.' + k: v for k, v in vsd.items()})
+    cond = SyntheticTextEncoder(48)
+    kw = dict(custom_steps=6, eta=0.1, white_box_steps=7, skip_steps=[2], encoder_unconditional_guidance_scales=[1.0],
+              decoder_unconditional_guidance_scales=[3.0], n_trials=1)
+    w = SDStochasticTextWrapper('synthetic', engine=eng, state_dict=sd, cond_stage=cond, unet_config=NARROW, vae_config=VAE_SMALL,
+                                latent_size=16, resolution=128, **kw)
+    image = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(0))
+    src, tgt = ['a photo of a cat', 'a tree'], ['a photo of a dog', 'a tree in winter']
+    torch.manual_seed(123)
+    z_ens = w.encode(image, src)
+    img = w(z_ens, image, src, tgt).cpu()
+    ora = dpm_encoder.LatentCycle(lambda x, t, c: unet_openai.unet_forward(usd, NARROW, x, t, c),
+                                  lambda im: vae_kl.encode_moments(vsd, VAE_SMALL, im), lambda zz: vae_kl.decode(vsd, VAE_SMALL, zz), cond,
+                                  channels=4, latent_size=16, resolution=128, **kw)
+    torch.manual_seed(123)
+    with torch.no_grad():
+        z_ref = ora.encode(image, src)
+        img_ref = ora.forward_all(z_ref, tgt)[0]
+        img_x = ora.forward_all([z_ens[0].cpu()], tgt)[0]          # oracle decode of the engine's z
+    rz = maxdiff(z_ens[0].cpu(), z_ref[0]) / float(z_ref[0].abs().max())
+    print(f'sd wrapper: z {tuple(z_ens[0].shape)} rel|dz| {rz:.2e}  |d img| {maxdiff(img, img_ref):.2e}  cross |d img| {maxdiff(img, img_x):.2e}')
+    assert len(z_ens) == 1 and z_ens[0].shape == z_ref[0].shape
+    assert rz < 2e-4
+    assert maxdiff(img, img_ref) < 1e-3
+    assert maxdiff(img, img_x) < 1e-3
+    with pytest.raises(AssertionError):
+        w.encode(torch.rand(1, 3, 64, 64), ['x'])          # SDW:178 resolution check
+
+
+def test_model_api_and_factory(eng):
+    """TextUnsupervisedTranslation.forward keeps the reference signature and return tuple (text_unsupervised_translation.py:24-40)."""
+    from cycle_diffusion_b200.models import TextUnsupervisedTranslation
+    from cycle_diffusion_b200.wrappers import SyntheticTextEncoder
+    usd = specs.synth_state_dict(specs.openai_unet_params(NARROW), 11)
+    vsd = specs.synth_state_dict(specs.kl_vae_params(VAE_SMALL), 21)
+    sd = {'model.diffusion_model.' + k: v for k, v in usd.items()}
+    sd.update({'first_stage_model.' + k: v for k, v in vsd.items()})
+    gan = dict(gan_type='SDStochasticText', source_model_type='synthetic', custom_steps=4, eta=0.1, white_box_steps=5, skip_steps=[1],
+               encoder_unconditional_guidance_scales=[1], decoder_unconditional_guidance_scales=[2.0], n_trials=1)
+    m = TextUnsupervisedTranslation(dict(gan=gan), engine=eng, state_dict=sd, cond_stage=SyntheticTextEncoder(48), unet_config=NARROW,
+                                    vae_config=VAE_SMALL, latent_size=16, resolution=128).eval()
+    image = torch.rand(1, 3, 128, 128)
+    (orig, img), loss, losses = m(torch.tensor([0]), image, ['a'], ['b'])
+    assert orig is image and img.shape == (1, 3, 128, 128) and loss.shape == (1,) and losses == {}
+    assert torch.isfinite(img).all()
