@@ -50,6 +50,8 @@ SIGNATURES = {
     'cdx_engine_workspace_bytes': (_S, [_P]),
     'cdx_engine_launch_count': (C.c_uint64, [_P]),
     'cdx_engine_set_mma_mode': (_I, [_P, _I]),
+    'cdx_engine_profile': (_I, [_P, _I]),
+    'cdx_engine_profile_read': (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     'cdx_unet_create': (_I, [_P, C.POINTER(UnetConfig), C.POINTER(_P)]),
     'cdx_vae_create': (_I, [_P, C.POINTER(VaeConfig), C.POINTER(_P)]),
     'cdx_net_destroy': (None, [_P]),

@@ -162,6 +162,31 @@ int cdx_engine_set_mma_mode(cdx_engine* e, int mode) {
   });
 }
 
+int cdx_engine_profile(cdx_engine* e, int enable) {
+  return guard([&] {
+    CDX_CHECK(e != nullptr, "profile: null engine");
+    CDX_CUDA(cudaSetDevice(e->e.device));
+    CDX_CUDA(cudaDeviceSynchronize());
+    for (ProfRec& r : e->e.prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    e->e.prof.recs.clear();
+    e->e.prof.on = enable != 0;
+  });
+}
+int cdx_engine_profile_read(cdx_engine* e, int tag, double* ms, double* flops, double* bytes, uint64_t* launches) {
+  return guard([&] {
+    CDX_CHECK(e && ms && flops && bytes && launches && tag >= 0 && tag < PROF_NTAGS, "profile_read: bad arguments");
+    CDX_CUDA(cudaSetDevice(e->e.device));
+    CDX_CUDA(cudaDeviceSynchronize());
+    *ms = 0; *flops = 0; *bytes = 0; *launches = 0;
+    for (const ProfRec& r : e->e.prof.recs) {
+      if (r.tag != tag) continue;
+      float t = 0.f;
+      CDX_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+      *ms += t; *flops += r.flops; *bytes += r.bytes; *launches += (uint64_t)r.launches;
+    }
+  });
+}
+
 // ---------------------------------------------------------------- networks
 int cdx_unet_create(cdx_engine* e, const cdx_unet_config* cfg, cdx_net** out) {
   return guard([&] {

@@ -56,13 +56,35 @@ struct Arena {
   void destroy();
 };
 
+// per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline numbers)
+enum ProfTag {
+  PROF_CONV_FFMA = 0, PROF_DENSE_FFMA = 1, PROF_BATCHED_FFMA = 2, PROF_CONV_TC = 3, PROF_DENSE_TC = 4, PROF_BATCHED_TC = 5,
+  PROF_GROUPNORM = 6, PROF_LAYERNORM = 7, PROF_SOFTMAX = 8, PROF_ELEMENTWISE = 9, PROF_NTAGS = 10
+};
+struct ProfRec { cudaEvent_t a, b; int tag; double flops, bytes; int launches; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+};
+
 struct Engine {
+  Profiler prof;
   int device = 0;
   int num_sms = 148;
   int mma_mode = 0;              // 0 SIMT FFMA, 1 tcgen05 3xTF32
   Arena arena;
   uint64_t launches = 0;
   bool dry() const { return arena.dry; }
+};
+
+// RAII: time everything enqueued between construction and destruction under one tag (no-op unless profiling)
+struct ProfScope {
+  Engine& e;
+  cudaStream_t s;
+  int idx = -1;
+  ProfScope(Engine& eng, cudaStream_t st, int tag, double flops, double bytes, int launches);
+  ~ProfScope();
 };
 
 struct Scope {   // RAII arena scope

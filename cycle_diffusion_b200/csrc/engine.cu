@@ -41,6 +41,20 @@ void Arena::end_dry() {
   }
 }
 
+ProfScope::ProfScope(Engine& eng, cudaStream_t st, int tag, double flops, double bytes, int launches) : e(eng), s(st) {
+  if (!e.prof.on || e.dry()) return;
+  ProfRec r;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  r.tag = tag; r.flops = flops; r.bytes = bytes; r.launches = launches;
+  cudaEventRecord(r.a, s);
+  idx = (int)e.prof.recs.size();
+  e.prof.recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(e.prof.recs[idx].b, s);
+}
+
 void Arena::destroy() {
   if (base) cudaFree(base);
   base = nullptr;

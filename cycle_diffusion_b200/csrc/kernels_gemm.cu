@@ -307,6 +307,9 @@ void gemm(Engine& e, const GemmArgs& a, cudaStream_t s) {
   if (a.mode == 0) CDX_CHECK(a.K == a.C1 + a.C2, "dense: K != C1+C2");
   if (e.dry()) return;
   if (e.mma_mode == 1 && gemm_tc(e, a, s)) return;
+  const double zz = (double)a.batch * a.heads;
+  ProfScope ps(e, s, a.batch * a.heads > 1 ? PROF_BATCHED_FFMA : (a.mode == 1 ? PROF_CONV_FFMA : PROF_DENSE_FFMA),
+               2.0 * a.M * a.N * a.K * zz, 4.0 * zz * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
 
   // 128-bit path eligibility: every float4 must be 16B aligned and must not straddle sources / taps
   bool vec = aligned16(a.A) && (a.lda % 4 == 0) && (a.C1 % 4 == 0) && aligned16(a.Bw) && (a.ldb % 4 == 0);

@@ -191,6 +191,7 @@ void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, cons
   double* part = (double*)e.arena.alloc((size_t)B * nchunk * GN_GROUPS * 2 * sizeof(double));
   float* mr = (float*)e.arena.alloc((size_t)B * GN_GROUPS * 2 * sizeof(float));
   if (e.dry()) return;
+  ProfScope ps(e, s, PROF_GROUPNORM, 0.0, 2.0 * 4.0 * B * (double)HW * C, 3);   // algorithmic: one read + one write
   gn_stats_kernel<<<dim3(nchunk, B), 256, 0, s>>>(x1, C1, x2, C2, HW, rows_per_chunk, part);
   gn_finalize_kernel<<<B, GN_GROUPS, 0, s>>>(part, nchunk, 1.0 / ((double)HW * (C / GN_GROUPS)), eps, mr);
   const long long total4 = (long long)B * HW * (C / 4);
@@ -203,6 +204,7 @@ void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, cons
 void layernorm(Engine& e, const float* x, const float* gamma, const float* beta, float* y, int M, int C, cudaStream_t s) {
   CDX_CHECK(C % 4 == 0, "layernorm: C=%d must be a multiple of 4", C);
   if (e.dry()) return;
+  ProfScope ps(e, s, PROF_LAYERNORM, 0.0, 2.0 * 4.0 * (double)M * C, 1);
   layernorm_kernel<<<cdiv((long long)M * 32, 256), 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
@@ -210,6 +212,7 @@ void layernorm(Engine& e, const float* x, const float* gamma, const float* beta,
 
 void softmax_rows(Engine& e, float* x, long long rows, int L, int ld, cudaStream_t s) {
   if (e.dry()) return;
+  ProfScope ps(e, s, PROF_SOFTMAX, 0.0, 2.0 * 4.0 * (double)rows * L, 1);
   softmax_kernel<<<cdiv(rows * 32, 256), 256, 0, s>>>(x, rows, L, ld);
   CDX_CUDA(cudaGetLastError());
   e.launches++;

@@ -62,6 +62,22 @@ class Engine:
     def set_mma_mode(self, mode):
         check(lib.cdx_engine_set_mma_mode(self.h, int(mode)))
 
+    PROF_TAGS = ['conv3x3_ffma', 'dense_ffma', 'batched_ffma', 'conv3x3_tc', 'dense_tc', 'batched_tc', 'groupnorm', 'layernorm',
+                 'softmax', 'other']
+
+    def profile(self, enable):
+        check(lib.cdx_engine_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """{tag: dict(ms, flops, bytes, launches)} of everything recorded since profile(True)."""
+        out = {}
+        for i, name in enumerate(self.PROF_TAGS):
+            ms, fl, by, n = C.c_double(), C.c_double(), C.c_double(), C.c_uint64()
+            check(lib.cdx_engine_profile_read(self.h, i, C.byref(ms), C.byref(fl), C.byref(by), C.byref(n)))
+            if n.value:
+                out[name] = dict(ms=ms.value, flops=fl.value, bytes=by.value, launches=int(n.value))
+        return out
+
     def empty(self, *shape):
         return torch.empty(*shape, dtype=torch.float32, device=self.device)
 

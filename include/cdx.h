@@ -54,6 +54,14 @@ void cdx_engine_destroy(cdx_engine* e);
 size_t cdx_engine_workspace_bytes(const cdx_engine* e);
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 uint64_t cdx_engine_launch_count(const cdx_engine* e);
+/* Per-kernel-family timing with CUDA events on the launching stream (off by default; bench.py turns it on for a
+ * separate, untimed pass).  Tags: 0 conv3x3 FFMA, 1 dense FFMA, 2 batched (attention) FFMA, 3 conv3x3 tcgen05,
+ * 4 dense tcgen05, 5 batched tcgen05, 6 GroupNorm, 7 LayerNorm, 8 softmax, 9 other.  profile_read synchronises the
+ * device, sums the records of `tag` (ms, algorithmic flops / bytes, launches) and keeps them until profile(e, 1/0)
+ * is called again. */
+#define CDX_PROF_NTAGS 10
+int cdx_engine_profile(cdx_engine* e, int enable);
+int cdx_engine_profile_read(cdx_engine* e, int tag, double* ms, double* flops, double* bytes, uint64_t* launches);
 /* select the dense-contraction path: 0 = SIMT fp32 FFMA tiles, 1 = tcgen05 3xTF32 split (fp32-faithful) */
 int cdx_engine_set_mma_mode(cdx_engine* e, int mode);
 
