@@ -1,7 +1,441 @@
-// kernels_tc.cu -- tcgen05 / TMEM / TMA back end for the dense contractions (3xTF32 split, fp32-faithful).
-// Placeholder until the kernel lands: reports "not eligible" so that every contraction takes the FFMA path.
+// kernels_tc.cu -- tcgen05 / TMEM / TMA back end for the dense contractions: fp32-faithful 3xTF32.
+//
+// Why 3xTF32: the path's acceptance bar is parity with the reference's fp32 CPU path (|d pixel| <= 1e-3 through
+// 50-250 sequential U-Net calls with a 1/sigma_t amplification), which plain TF32/BF16 tensor-core math cannot hold
+// (SURVEY.md section 7).  Every fp32 operand x is split as  hi = x & 0xFFFFE000 (exactly representable in TF32) and
+// lo = x - hi (exact in fp32), and the product is accumulated as  hi*hi + lo*hi + hi*lo  in the fp32 TMEM accumulator
+// (the dropped lo*lo term is < 2^-22 relative).  Three tcgen05.mma.kind::tf32 per K-chunk.
+//
+// Kernel shape (one 128 x 128 output tile per CTA, K walked in 32-float = 128-byte blocks):
+//   warp 0      TMA producer: cp.async.bulk.tensor loads of the raw fp32 A and B blocks into 128B-swizzled smem.
+//               A is either a 2D [M,K] row matrix (dense / 1x1 conv / Linear, optionally two channel-concatenated
+//               sources) or -- for conv3x3 -- a 4D box {32 ch, bw, bh, bn} of the NHWC activation shifted by the
+//               tap (dy-1, dx-1): TMA's out-of-bounds zero fill *is* the conv's zero padding, so im2col is never
+//               materialised and the halo costs nothing.
+//   warps 2-9   split: read each landed block once, write hi in place and lo to a twin buffer (same swizzle),
+//               fence.proxy.async, signal the MMA warp.  The same warps run the epilogue.
+//   warp 1      MMA issuer: one lane issues 12 tcgen05.mma (4 K-chunks x 3 products) per block into a 128-column
+//               fp32 TMEM accumulator, tcgen05.commit releases the smem stage back to the producer.
+//   epilogue    tcgen05.ld 32x32b.x32 -> registers -> alpha, +bias, +per-sample row vector (timestep embedding),
+//               +residual -> 128-bit global stores.
+// 3 stages x 64 KB (A hi/lo + B hi/lo) = 192 KB dynamic smem, 1 CTA / SM.
+#include <cuda.h>
+
+#include <map>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace cdx {
-bool gemm_tc(Engine&, const GemmArgs&, cudaStream_t) { return false; }
+namespace {
+
+constexpr int TBM = 128, TBN = 128, TBK = 32;
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = TBM * TBK * 4;          // 16 KB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi, A_lo, B_hi, B_lo
+constexpr int NUM_SPLIT_WARPS = 8;
+constexpr int TC_THREADS = 64 + NUM_SPLIT_WARPS * 32;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+
+struct TcParams {
+  int M, N, K;
+  int mode;                 // 0 dense, 1 conv3x3 (stride 1, pad 1)
+  int C1, C2;               // dense: channels of source 1 / 2 (k-blocks never straddle: C1 % 32 == 0 when C2 > 0)
+  int Cin;                  // conv: input channels (multiple of 32)
+  int H, W, B;              // conv: spatial size (in == out) and batch
+  int bw, bh, bn;           // conv: pixel box of one M tile (bw*bh*bn == 128)
+  int tiles_x, tiles_y;     // conv: tiles per row / column
+  float* C; int ldc;
+  const float* bias;
+  const float* rowvec; int ld_rowvec; int rows_per_batch;
+  const float* residual; int ldr;
+  float alpha;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// bounded wait: a protocol bug traps (error returned to the host) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, 128-byte-swizzled smem operand descriptor (rows of 128 B, 8-row atoms of 1024 B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address
+  d |= (uint64_t)0 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
+               const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 1024-byte aligned (swizzle atoms)
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  // barrier layout (8 B each): full_raw[S], full_split[S], empty[S], acc_full, then the TMEM base address word
+  auto bar_full_raw = [&](int s) { return bars + 8u * s; };
+  auto bar_full_split = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto bar_empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  const uint32_t bar_acc = bars + 8u * (3 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (p.K + TBK - 1) / TBK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full_raw(s), 1);
+      mbar_init(bar_full_split(s), NUM_SPLIT_WARPS);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // ---- tile coordinates
+  const int n0 = blockIdx.y * TBN;
+  int m0 = 0, x0 = 0, y0 = 0, b0 = 0;
+  if (p.mode == 0) {
+    m0 = blockIdx.x * TBM;
+  } else {
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y; t /= p.tiles_y;
+    x0 = tx * p.bw; y0 = ty * p.bh; b0 = t * p.bn;
+  }
+
+  if (warp == 0) {
+    // =========================================================================== TMA producer
+    if (lane == 0) {
+      const int cblocks = p.mode == 1 ? p.Cin / TBK : 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES, it = kb / STAGES;
+        mbar_wait(bar_empty(s), (it & 1) ^ 1);
+        const uint32_t sa = base + s * STAGE_BYTES;              // A raw -> becomes A_hi
+        const uint32_t sb = sa + 2 * TILE_BYTES;                 // B raw -> becomes B_hi
+        mbar_expect_tx(bar_full_raw(s), 2 * TILE_BYTES);
+        if (p.mode == 0) {
+          const int k0 = kb * TBK;
+          if (k0 < p.C1) tma_load_2d(sa, &mapA, k0, m0, bar_full_raw(s));
+          else tma_load_2d(sa, &mapA2, k0 - p.C1, m0, bar_full_raw(s));
+        } else {
+          const int tap = kb / cblocks, cb = kb - tap * cblocks;
+          const int dy = tap / 3, dx = tap - dy * 3;
+          tma_load_4d(sa, &mapA, cb * TBK, x0 + dx - 1, y0 + dy - 1, b0, bar_full_raw(s));   // OOB -> zeros = padding
+        }
+        tma_load_2d(sb, &mapB, kb * TBK, n0, bar_full_raw(s));
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES, it = kb / STAGES;
+        mbar_wait(bar_full_split(s), it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * STAGE_BYTES;
+        const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_BYTES);
+        const uint64_t b_hi = make_desc(sa + 2 * TILE_BYTES), b_lo = make_desc(sa + 3 * TILE_BYTES);
+#pragma unroll
+        for (int j = 0; j < TBK / 8; ++j) {
+          const uint64_t adv = (uint64_t)((j * 8 * 4) >> 4);      // 32 bytes per K-chunk of 8 tf32
+          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+        }
+        umma_commit(bar_empty(s));          // smem stage reusable once these MMAs have read it
+      }
+      umma_commit(bar_acc);                 // accumulator complete
+    }
+  } else {
+    // =========================================================================== split warps (+ epilogue)
+    const int st = threadIdx.x - 64;        // 0..255
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES, it = kb / STAGES;
+      mbar_wait(bar_full_raw(s), it & 1);
+      const uint32_t sa = base + s * STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < (2 * TILE_BYTES / 16) / (NUM_SPLIT_WARPS * 32); ++i) {
+        const int idx = st + i * NUM_SPLIT_WARPS * 32;            // float4 index over [A | B]
+        const uint32_t off = (uint32_t)idx * 16u;
+        const uint32_t src = off < (uint32_t)TILE_BYTES ? sa + off : sa + 2 * TILE_BYTES + (off - TILE_BYTES);
+        uint32_t v0, v1, v2, v3;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(src));
+        const uint32_t h0 = v0 & 0xFFFFE000u, h1 = v1 & 0xFFFFE000u, h2 = v2 & 0xFFFFE000u, h3 = v3 & 0xFFFFE000u;
+        const float l0 = __uint_as_float(v0) - __uint_as_float(h0), l1 = __uint_as_float(v1) - __uint_as_float(h1);
+        const float l2 = __uint_as_float(v2) - __uint_as_float(h2), l3 = __uint_as_float(v3) - __uint_as_float(h3);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(src), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(src + TILE_BYTES), "r"(__float_as_uint(l0)), "r"(__float_as_uint(l1)),
+                     "r"(__float_as_uint(l2)), "r"(__float_as_uint(l3))
+                     : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full_split(s));
+    }
+
+    // ---- epilogue: TMEM -> registers -> global
+    mbar_wait(bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;              // column half: 0 -> cols 0..63, 1 -> cols 64..127
+    const int r = q * 32 + lane;                   // tile row owned by this thread
+    long long m;
+    bool row_ok;
+    if (p.mode == 0) {
+      m = (long long)m0 + r;
+      row_ok = m < p.M;
+    } else {
+      const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+      const int b = b0 + nl;
+      row_ok = b < p.B;
+      m = ((long long)b * p.H + (y0 + yl)) * p.W + (x0 + xl);
+    }
+    const float* rv = (p.rowvec && row_ok) ? p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec : nullptr;
+    const float* rs = (p.residual && row_ok) ? p.residual + m * p.ldr : nullptr;
+    float* crow = p.C + m * p.ldc;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col0 = half * 64 + cc * 32;
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + col0 + j;
+          if (n >= p.N) break;                     // N % 4 == 0 is an eligibility condition
+          float4 o;
+          o.x = p.alpha * __uint_as_float(v[j + 0]);
+          o.y = p.alpha * __uint_as_float(v[j + 1]);
+          o.z = p.alpha * __uint_as_float(v[j + 2]);
+          o.w = p.alpha * __uint_as_float(v[j + 3]);
+          if (p.bias) { const float4 t = *reinterpret_cast<const float4*>(p.bias + n); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+          if (rv) { const float4 t = *reinterpret_cast<const float4*>(rv + n); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+          if (rs) { const float4 t = *reinterpret_cast<const float4*>(rs + n); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+          *reinterpret_cast<float4*>(crow + n) = o;
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t dims[4], strides[3];
+  uint32_t box[4];
+  int rank;
+  bool operator<(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
+};
+
+// fp32, 128B swizzle, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
+const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
+  static std::map<MapKey, CUtensorMap> cache;
+  MapKey k;
+  memset(&k, 0, sizeof(k));
+  k.ptr = ptr;
+  k.rank = rank;
+  for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+  for (int i = 0; i < rank - 1; ++i) k.strides[i] = strides[i];
+  auto it = cache.find(k);
+  if (it != cache.end()) return it->second;
+  if (cache.size() > 65536) cache.clear();
+  CUtensorMap m;
+  cuuint64_t gd[4];
+  cuuint64_t gs[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides[i];
+  EncodeTiledFn enc = get_encode();
+  if (!enc) throw Error(CDX_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[256];
+    snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u", (int)r, rank,
+             (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0), (unsigned long long)(rank > 2 ? gd[2] : 0),
+             (unsigned long long)(rank > 3 ? gd[3] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0);
+    throw Error(CDX_E_CUDA, b);
+  }
+  return cache.emplace(k, m).first->second;
+}
+
+inline bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace
+
+bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
+  // ---- eligibility (everything else takes the FFMA tiles)
+  if (a.batch * a.heads != 1 || a.b_kn || a.out_nchw) return false;
+  if ((a.N & 3) || (a.ldc & 3) || !a16(a.Cout) || !a16(a.Bw) || (a.ldb & 3)) return false;
+  if (a.bias && !a16(a.bias)) return false;
+  if (a.rowvec && (!a16(a.rowvec) || (a.ld_rowvec & 3))) return false;
+  if (a.residual && (!a16(a.residual) || (a.ldr & 3))) return false;
+  if (!a16(a.A) || (a.lda & 3)) return false;
+  if (a.M < 64 || a.N < 32) return false;           // tiny problems: tile quantisation loses to the FFMA 64x64 tiles
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.C = a.Cout; p.ldc = a.ldc;
+  p.bias = a.bias;
+  p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec; p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
+  p.residual = a.residual; p.ldr = a.ldr;
+  p.alpha = a.alpha;
+  const CUtensorMap *mA, *mA2, *mB;
+  dim3 grid;
+  if (a.mode == 0) {
+    if (a.K & 3) return false;
+    if (a.A2) {
+      if ((a.C1 % TBK) || !a16(a.A2) || (a.lda2 & 3) || (a.C2 & 3)) return false;
+    }
+    p.mode = 0; p.C1 = a.C1; p.C2 = a.C2;
+    {
+      uint64_t d[2] = {(uint64_t)a.C1, (uint64_t)a.M}, st[1] = {(uint64_t)a.lda * 4};
+      uint32_t bx[2] = {TBK, TBM};
+      mA = &get_map(a.A, 2, d, st, bx);
+    }
+    if (a.A2) {
+      uint64_t d[2] = {(uint64_t)a.C2, (uint64_t)a.M}, st[1] = {(uint64_t)a.lda2 * 4};
+      uint32_t bx[2] = {TBK, TBM};
+      mA2 = &get_map(a.A2, 2, d, st, bx);
+    } else {
+      mA2 = mA;
+    }
+    grid = dim3(cdiv(a.M, TBM), cdiv(a.N, TBN), 1);
+  } else {
+    const int Cin = a.C1;
+    if (a.A2 || a.stride != 1 || a.pad != 1 || a.up != 1) return false;
+    if (Cin % TBK) return false;
+    if (a.Hin != a.Hout || a.Win != a.Wout || !pow2(a.Hin) || !pow2(a.Win)) return false;
+    const int B = a.M / (a.Hout * a.Wout);
+    int bw = a.Win < 16 ? a.Win : 16;
+    int bh = a.Hin < TBM / bw ? a.Hin : TBM / bw;
+    int bn = TBM / (bw * bh);
+    if (bn > 256) return false;
+    p.mode = 1; p.Cin = Cin; p.H = a.Hin; p.W = a.Win; p.B = B;
+    p.bw = bw; p.bh = bh; p.bn = bn;
+    p.tiles_x = a.Win / bw; p.tiles_y = a.Hin / bh;
+    uint64_t d[4] = {(uint64_t)Cin, (uint64_t)a.Win, (uint64_t)a.Hin, (uint64_t)B};
+    uint64_t st[3] = {(uint64_t)a.lda * 4, (uint64_t)a.lda * 4 * a.Win, (uint64_t)a.lda * 4 * a.Win * a.Hin};
+    uint32_t bx[4] = {TBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    mA = &get_map(a.A, 4, d, st, bx);
+    mA2 = mA;
+    grid = dim3(p.tiles_x * p.tiles_y * cdiv(B, bn), cdiv(a.N, TBN), 1);
+  }
+  {
+    uint64_t d[2] = {(uint64_t)a.K, (uint64_t)a.N}, st[1] = {(uint64_t)a.ldb * 4};
+    uint32_t bx[2] = {TBK, TBN};
+    mB = &get_map(a.Bw, 2, d, st, bx);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  ProfScope ps(e, s, a.mode == 1 ? PROF_CONV_TC : PROF_DENSE_TC, 2.0 * a.M * a.N * a.K,
+               4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
+  tc_gemm_kernel<<<grid, TC_THREADS, SMEM_BYTES, s>>>(*mA, *mA2, *mB, p);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+  return true;
+}
+
 }  // namespace cdx

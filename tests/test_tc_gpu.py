@@ -1,0 +1,109 @@
+"""tcgen05 3xTF32 back end (mma_mode 1): per-op and network-level parity against fp32 references.
+
+3xTF32 keeps ~2^-21 relative error per product (hi*hi + lo*hi + hi*lo with fp32 TMEM accumulation), so the same
+fp32 round-off budgets as the FFMA path apply (2e-5 relative per op, 2e-4 through a whole U-Net)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cycle_diffusion_b200 import specs
+from tests.common import NARROW, VAE_SMALL, WIDE, golden, maxdiff
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from cycle_diffusion_b200.engine import Engine
+    e = Engine(0)
+    e.set_mma_mode(1)
+    return e
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / max(1e-30, float(b.double().abs().max())))
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize('M,K,N', [(128, 32, 128), (128, 64, 128), (256, 320, 128), (4096, 320, 2560), (1000, 96, 100), (300, 1280, 36),
+                                   (20000, 640, 640), (308, 768, 640)])
+def test_linear_tc(eng, M, K, N):
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    l0 = eng.profile(True)
+    y = eng.op_linear(x.cuda(), w.cuda(), b.cuda()).cpu()
+    fam = eng.profile_read()
+    eng.profile(False)
+    assert 'dense_tc' in fam, f'tcgen05 path was not taken: {fam}'
+    r = rel(y, F.linear(x, w, b))
+    print(f'linear_tc {M}x{K}x{N}: rel {r:.2e}')
+    assert r < 2e-5
+
+
+@pytest.mark.parametrize('B,Cin,Cout,H', [(1, 32, 128, 16), (2, 64, 64, 16), (1, 320, 320, 32), (4, 128, 256, 64), (3, 96, 160, 8), (8, 64, 32, 4),
+                                           (2, 1280, 1280, 8)])
+def test_conv3x3_tc(eng, B, Cin, Cout, H):
+    g = torch.Generator().manual_seed(Cin * 1000 + Cout + H)
+    x = torch.randn(B, Cin, H, H, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)
+    b = torch.randn(Cout, generator=g)
+    eng.profile(True)
+    y = nchw(eng.op_conv3x3(nhwc(x).cuda(), w.cuda(), b.cuda(), 1, 1, 1).cpu())
+    fam = eng.profile_read()
+    eng.profile(False)
+    assert 'conv3x3_tc' in fam, f'tcgen05 path was not taken: {fam}'
+    r = rel(y, F.conv2d(x, w, b, padding=1))
+    print(f'conv_tc B{B} {Cin}->{Cout} @{H}: rel {r:.2e}')
+    assert r < 2e-5
+
+
+@pytest.mark.parametrize('name,cfg', [('unet_sd_narrow', NARROW), ('unet_sd_wide', WIDE)])
+def test_unet_tc_vs_reference_fixture(eng, name, cfg):
+    from cycle_diffusion_b200.engine import UNet
+    g = golden(name)
+    sd = specs.synth_state_dict(specs.openai_unet_params(cfg), int(g['seed']))
+    net = UNet(eng, cfg, 'openai').load_state_dict(sd)
+    eng.profile(True)
+    y = net(g['x'], g['t'], g['ctx']).cpu()
+    fam = eng.profile_read()
+    eng.profile(False)
+    r = float((y.double() - g['y'].double()).abs().max() / max(1.0, float(g['y'].abs().max())))
+    print(f'{name} (tcgen05): rel max err {r:.3e}; families {{k: v["launches"] for k, v in fam.items()}}')
+    assert 'conv3x3_tc' in fam or 'dense_tc' in fam
+    assert r < 2e-4
+
+
+def test_cycle_tc_vs_reference_fixture(eng):
+    from cycle_diffusion_b200.engine import UNet
+    from cycle_diffusion_b200.schedule import DDIMSchedule
+    g = golden('ddim_cycle_narrow')
+    S, skip, wb, enc_scale, dec_scale, seed = [float(v) for v in g['cfg_a']]
+    S, skip, wb, seed = int(S), int(skip), int(wb), int(seed)
+    sd = specs.synth_state_dict(specs.openai_unet_params(NARROW), 11)
+    unet = UNet(eng, NARROW, 'openai').load_state_dict(sd)
+    sched = DDIMSchedule(S, 0.1, skip)
+    n_rec = min(sched.refine_steps, wb - skip - 1)
+    torch.manual_seed(seed)
+    noise = torch.zeros((n_rec + 1,) + tuple(g['x0'].shape))
+    noise[0] = torch.randn(g['x0'].shape)
+    for i in range(n_rec):
+        if sched.refine_steps - 1 - i != 0:
+            noise[1 + i] = torch.randn(g['x0'].shape)
+    z = unet.latent_encode(g['x0'], g['c_src'], g['uc'], enc_scale, sched, n_rec, noise)
+    zref = g['z_a'].view(z.shape)
+    rz = maxdiff(z.cpu(), zref) / float(zref.abs().max())
+    tgt = unet.latent_decode(zref, g['c_tgt'], g['uc'], dec_scale, sched).cpu()
+    own = unet.latent_decode(z, g['c_src'], g['uc'], enc_scale, sched).cpu()
+    print(f'cycle (tcgen05): rel|dz| {rz:.2e} |d tgt| {maxdiff(tgt, g["tgt_a"]):.2e} own-cycle {maxdiff(own, g["x0"]):.2e}')
+    assert rz < 2e-4 and maxdiff(tgt, g['tgt_a']) < 1e-3 and maxdiff(own, g['x0']) < 1e-3
