@@ -5,6 +5,12 @@
 // (SURVEY.md section 7).  Every fp32 operand x is split as  hi = x & 0xFFFFE000 (exactly representable in TF32) and
 // lo = x - hi (exact in fp32), and the product is accumulated as  hi*hi + lo*hi + hi*lo  in the fp32 TMEM accumulator
 // (the dropped lo*lo term is < 2^-22 relative).  Three tcgen05.mma.kind::tf32 per K-chunk.
+// Both parts are rounded to nearest (hi = rn_tf32(x), lo = rn_tf32(x - hi)) so that no systematic bias is introduced.
+//
+// Tensor-core accumulation truncates (measured: the error of a single long accumulation grows linearly with K,
+// 5.8e-5 relative at K = 11520), so the K loop is cut into chunks of 8 blocks (256 elements): each chunk accumulates
+// in one of two TMEM buffers and is then drained by the epilogue warps into fp32 registers with round-to-nearest adds
+// while the next chunk is already running in the other buffer.
 //
 // Kernel shape (one 128 x 128 output tile per CTA, K walked in 32-float = 128-byte blocks):
 //   warp 0      TMA producer: cp.async.bulk.tensor loads of the raw fp32 A and B blocks into 128B-swizzled smem.
@@ -12,12 +18,12 @@
 //               sources) or -- for conv3x3 -- a 4D box {32 ch, bw, bh, bn} of the NHWC activation shifted by the
 //               tap (dy-1, dx-1): TMA's out-of-bounds zero fill *is* the conv's zero padding, so im2col is never
 //               materialised and the halo costs nothing.
-//   warps 2-9   split: read each landed block once, write hi in place and lo to a twin buffer (same swizzle),
-//               fence.proxy.async, signal the MMA warp.  The same warps run the epilogue.
+//   warps 2-5   split: read each landed block once, write hi in place and lo to a twin buffer (same swizzle),
+//               fence.proxy.async, signal the MMA warp.
 //   warp 1      MMA issuer: one lane issues 12 tcgen05.mma (4 K-chunks x 3 products) per block into a 128-column
-//               fp32 TMEM accumulator, tcgen05.commit releases the smem stage back to the producer.
-//   epilogue    tcgen05.ld 32x32b.x32 -> registers -> alpha, +bias, +per-sample row vector (timestep embedding),
-//               +residual -> 128-bit global stores.
+//               fp32 TMEM accumulator (two buffers), tcgen05.commit releases the smem stage back to the producer.
+//   warps 6-9   drain + epilogue: per chunk tcgen05.ld 32x32b.x32 -> RN add into 128 fp32 registers per thread;
+//               at the end alpha, +bias, +per-sample row vector (timestep embedding), +residual -> 128-bit stores.
 // 3 stages x 64 KB (A hi/lo + B hi/lo) = 192 KB dynamic smem, 1 CTA / SM.
 #include <cuda.h>
 
@@ -33,8 +39,11 @@ constexpr int TBM = 128, TBN = 128, TBK = 32;
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = TBM * TBK * 4;          // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi, A_lo, B_hi, B_lo
-constexpr int NUM_SPLIT_WARPS = 8;
-constexpr int TC_THREADS = 64 + NUM_SPLIT_WARPS * 32;
+constexpr int NUM_SPLIT_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int KCHUNK = 8;                          // k-blocks per TMEM accumulation chunk (256 K elements)
+constexpr int TMEM_COLS = 2 * TBN;                 // two accumulator buffers
+constexpr int TC_THREADS = 64 + (NUM_SPLIT_WARPS + NUM_EPI_WARPS) * 32;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
 
 struct TcParams {
@@ -133,12 +142,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 1024-byte aligned (swizzle atoms)
   const uint32_t bars = base + STAGES * STAGE_BYTES;
-  // barrier layout (8 B each): full_raw[S], full_split[S], empty[S], acc_full, then the TMEM base address word
+  // barrier layout (8 B each): full_raw[S], full_split[S], empty[S], acc_full[2], acc_empty[2], then the TMEM base word
   auto bar_full_raw = [&](int s) { return bars + 8u * s; };
   auto bar_full_split = [&](int s) { return bars + 8u * (STAGES + s); };
   auto bar_empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  const uint32_t bar_acc = bars + 8u * (3 * STAGES);
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
+  auto bar_acc_full = [&](int b) { return bars + 8u * (3 * STAGES + b); };
+  auto bar_acc_empty = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + TBK - 1) / TBK;
@@ -149,11 +159,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_init(bar_full_split(s), NUM_SPLIT_WARPS);
       mbar_init(bar_empty(s), 1);
     }
-    mbar_init(bar_acc, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full(b), 1);
+      mbar_init(bar_acc_empty(b), NUM_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -202,55 +215,81 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES, it = kb / STAGES;
+        const int chunk = kb / KCHUNK, buf = chunk & 1, kin = kb - chunk * KCHUNK;
+        if (kin == 0 && chunk >= 2) {       // the buffer's previous chunk must have been drained
+          mbar_wait(bar_acc_empty(buf), ((chunk >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         mbar_wait(bar_full_split(s), it & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = base + s * STAGE_BYTES;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * TBN);
         const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_BYTES);
         const uint64_t b_hi = make_desc(sa + 2 * TILE_BYTES), b_lo = make_desc(sa + 3 * TILE_BYTES);
 #pragma unroll
         for (int j = 0; j < TBK / 8; ++j) {
           const uint64_t adv = (uint64_t)((j * 8 * 4) >> 4);      // 32 bytes per K-chunk of 8 tf32
-          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
-          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_tf32(acc, a_lo + adv, b_hi + adv, idesc, (kin > 0 || j > 0) ? 1u : 0u);     // small terms first
+          umma_tf32(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, 1u);
         }
         umma_commit(bar_empty(s));          // smem stage reusable once these MMAs have read it
+        if (kin == KCHUNK - 1 || kb == num_kb - 1) umma_commit(bar_acc_full(buf));   // chunk complete
       }
-      umma_commit(bar_acc);                 // accumulator complete
     }
-  } else {
-    // =========================================================================== split warps (+ epilogue)
-    const int st = threadIdx.x - 64;        // 0..255
+  } else if (warp < 2 + NUM_SPLIT_WARPS) {
+    // =========================================================================== split warps
+    const int st = threadIdx.x - 64;        // 0..127
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES, it = kb / STAGES;
       mbar_wait(bar_full_raw(s), it & 1);
       const uint32_t sa = base + s * STAGE_BYTES;
-#pragma unroll
+#pragma unroll 4
       for (int i = 0; i < (2 * TILE_BYTES / 16) / (NUM_SPLIT_WARPS * 32); ++i) {
         const int idx = st + i * NUM_SPLIT_WARPS * 32;            // float4 index over [A | B]
         const uint32_t off = (uint32_t)idx * 16u;
         const uint32_t src = off < (uint32_t)TILE_BYTES ? sa + off : sa + 2 * TILE_BYTES + (off - TILE_BYTES);
-        uint32_t v0, v1, v2, v3;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(src));
-        const uint32_t h0 = v0 & 0xFFFFE000u, h1 = v1 & 0xFFFFE000u, h2 = v2 & 0xFFFFE000u, h3 = v3 & 0xFFFFE000u;
-        const float l0 = __uint_as_float(v0) - __uint_as_float(h0), l1 = __uint_as_float(v1) - __uint_as_float(h1);
-        const float l2 = __uint_as_float(v2) - __uint_as_float(h2), l3 = __uint_as_float(v3) - __uint_as_float(h3);
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(src), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(src + TILE_BYTES), "r"(__float_as_uint(l0)), "r"(__float_as_uint(l1)),
-                     "r"(__float_as_uint(l2)), "r"(__float_as_uint(l3))
-                     : "memory");
+        uint32_t v[4], h[4], l[4];
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(src));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          h[c] = (v[c] + 0x1000u) & 0xFFFFE000u;                                       // hi = rn_tf32(x)
+          const float lo = __uint_as_float(v[c]) - __uint_as_float(h[c]);              // exact
+          l[c] = (__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u;                        // lo = rn_tf32(x - hi)
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(src), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(src + TILE_BYTES), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full_split(s));
     }
-
-    // ---- epilogue: TMEM -> registers -> global
-    mbar_wait(bar_acc, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;              // column half: 0 -> cols 0..63, 1 -> cols 64..127
+  } else {
+    // =========================================================================== drain + epilogue warps
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may access (warps 6..9 -> 2,3,0,1)
     const int r = q * 32 + lane;                   // tile row owned by this thread
+    float acc[TBN];
+#pragma unroll
+    for (int j = 0; j < TBN; ++j) acc[j] = 0.f;
+    const int num_chunks = (num_kb + KCHUNK - 1) / KCHUNK;
+    for (int chunk = 0; chunk < num_chunks; ++chunk) {
+      const int buf = chunk & 1;
+      mbar_wait(bar_acc_full(buf), (chunk >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TBN);
+#pragma unroll
+      for (int part = 0; part < TBN / 32; ++part) {
+        uint32_t v[32];
+        tmem_ld32(taddr + part * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[part * 32 + j] += __uint_as_float(v[j]);     // round-to-nearest fp32 add
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+    }
+
     long long m;
     bool row_ok;
     if (p.mode == 0) {
@@ -262,25 +301,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       row_ok = b < p.B;
       m = ((long long)b * p.H + (y0 + yl)) * p.W + (x0 + xl);
     }
-    const float* rv = (p.rowvec && row_ok) ? p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec : nullptr;
-    const float* rs = (p.residual && row_ok) ? p.residual + m * p.ldr : nullptr;
-    float* crow = p.C + m * p.ldc;
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col0 = half * 64 + cc * 32;
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row_ok) {
+    if (row_ok) {
+      const float* rv = p.rowvec ? p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec : nullptr;
+      const float* rs = p.residual ? p.residual + m * p.ldr : nullptr;
+      float* crow = p.C + m * p.ldc;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + col0 + j;
-          if (n >= p.N) break;                     // N % 4 == 0 is an eligibility condition
+      for (int j = 0; j < TBN; j += 4) {
+        const int n = n0 + j;
+        if (n < p.N) {                               // N % 4 == 0 is an eligibility condition
           float4 o;
-          o.x = p.alpha * __uint_as_float(v[j + 0]);
-          o.y = p.alpha * __uint_as_float(v[j + 1]);
-          o.z = p.alpha * __uint_as_float(v[j + 2]);
-          o.w = p.alpha * __uint_as_float(v[j + 3]);
+          o.x = p.alpha * acc[j + 0];
+          o.y = p.alpha * acc[j + 1];
+          o.z = p.alpha * acc[j + 2];
+          o.w = p.alpha * acc[j + 3];
           if (p.bias) { const float4 t = *reinterpret_cast<const float4*>(p.bias + n); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
           if (rv) { const float4 t = *reinterpret_cast<const float4*>(rv + n); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
           if (rs) { const float4 t = *reinterpret_cast<const float4*>(rs + n); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
@@ -294,7 +327,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
