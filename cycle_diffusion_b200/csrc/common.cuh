@@ -136,6 +136,8 @@ struct GemmArgs {
 void gemm(Engine& e, const GemmArgs& a, cudaStream_t s);
 // tcgen05 back end (kernels_tc.cu); returns false when the shape is not eligible
 bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s);
+bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, int head_stride, const float* vt, float* out, int ldo, int B,
+                  int Nq, int Nk, int heads, int d, float scale, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
 // normalisation / softmax / elementwise ops (kernels_norm.cu, kernels_elem.cu)

@@ -2,7 +2,7 @@
 //
 // Why 3xTF32: the path's acceptance bar is parity with the reference's fp32 CPU path (|d pixel| <= 1e-3 through
 // 50-250 sequential U-Net calls with a 1/sigma_t amplification), which plain TF32/BF16 tensor-core math cannot hold
-// (SURVEY.md section 7).  Every fp32 operand x is split as  hi = x & 0xFFFFE000 (exactly representable in TF32) and
+// (SURVEY.md section 7).  Every fp32 operand x is split as  hi = rn_tf32(x) (exactly representable in TF32) and
 // lo = x - hi (exact in fp32), and the product is accumulated as  hi*hi + lo*hi + hi*lo  in the fp32 TMEM accumulator
 // (the dropped lo*lo term is < 2^-22 relative).  Three tcgen05.mma.kind::tf32 per K-chunk.
 // Both parts are rounded to nearest (hi = rn_tf32(x), lo = rn_tf32(x - hi)) so that no systematic bias is introduced.
@@ -59,6 +59,11 @@ struct TcParams {
   const float* rowvec; int ld_rowvec; int rows_per_batch;
   const float* residual; int ldr;
   float alpha;
+  // mode 2 (batched dense, blockIdx.z = zb*heads + zh): 4D maps, coordinate recipe per operand
+  int heads;
+  int a_code[4], b_code[4];   // per map dim: 0 -> k0, 1 -> row0, 2 -> zh, 3 -> zb, 4 -> 0
+  int a_rowoff_h, b_rowoff_h; // row0 += zh * rowoff (heads packed along the row dimension)
+  long long sC_b, sC_h;       // output offsets per zb / zh
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -177,9 +182,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   // ---- tile coordinates
   const int n0 = blockIdx.y * TBN;
-  int m0 = 0, x0 = 0, y0 = 0, b0 = 0;
+  int m0 = 0, x0 = 0, y0 = 0, b0 = 0, zb = 0, zh = 0;
   if (p.mode == 0) {
     m0 = blockIdx.x * TBM;
+  } else if (p.mode == 2) {
+    m0 = blockIdx.x * TBM;
+    zb = blockIdx.z / p.heads;
+    zh = blockIdx.z - zb * p.heads;
   } else {
     int t = blockIdx.x;
     const int tx = t % p.tiles_x; t /= p.tiles_x;
@@ -201,6 +210,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int k0 = kb * TBK;
           if (k0 < p.C1) tma_load_2d(sa, &mapA, k0, m0, bar_full_raw(s));
           else tma_load_2d(sa, &mapA2, k0 - p.C1, m0, bar_full_raw(s));
+        } else if (p.mode == 2) {
+          const int k0 = kb * TBK;
+          int ca[4], cb4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int ac = p.a_code[i], bc = p.b_code[i];
+            ca[i] = ac == 0 ? k0 : ac == 1 ? m0 + zh * p.a_rowoff_h : ac == 2 ? zh : ac == 3 ? zb : 0;
+            cb4[i] = bc == 0 ? k0 : bc == 1 ? n0 + zh * p.b_rowoff_h : bc == 2 ? zh : bc == 3 ? zb : 0;
+          }
+          tma_load_4d(sa, &mapA, ca[0], ca[1], ca[2], ca[3], bar_full_raw(s));
+          tma_load_4d(sb, &mapB, cb4[0], cb4[1], cb4[2], cb4[3], bar_full_raw(s));
+          continue;
         } else {
           const int tap = kb / cblocks, cb = kb - tap * cblocks;
           const int dy = tap / 3, dx = tap - dy * 3;
@@ -292,7 +313,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     long long m;
     bool row_ok;
-    if (p.mode == 0) {
+    if (p.mode != 1) {
       m = (long long)m0 + r;
       row_ok = m < p.M;
     } else {
@@ -304,7 +325,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (row_ok) {
       const float* rv = p.rowvec ? p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec : nullptr;
       const float* rs = p.residual ? p.residual + m * p.ldr : nullptr;
-      float* crow = p.C + m * p.ldc;
+      float* crow = p.C + zb * p.sC_b + zh * p.sC_h + m * p.ldc;
 #pragma unroll
       for (int j = 0; j < TBN; j += 4) {
         const int n = n0 + j;
@@ -392,7 +413,77 @@ const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dims, cons
 inline bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+void ensure_attr() {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+}
+
 }  // namespace
+
+// softmax(q k^T * scale) v on the tensor cores: two batched 3xTF32 contractions around the row-softmax kernel.
+//   q, k : [B, N*, heads*head_stride-ish] token matrices (row strides ldq / ldk, head h at column h*head_stride)
+//   vt   : V transposed, [heads*d, B*Nk] (row c = channel, column b*Nk + j), produced by a swapped-role GEMM
+//   out  : [B, Nq, ldo], head h at column h*d
+// Requires Nk % 32 == 0 (a K block must not run into the next sample's columns of vt), d % 4 == 0.
+bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, int head_stride, const float* vt, float* out, int ldo, int B,
+                  int Nq, int Nk, int heads, int d, float scale, cudaStream_t s) {
+  if ((Nk % TBK) || (d & 3) || (ldq & 3) || (ldk & 3) || (head_stride & 3) || (ldo & 3) || Nq < 64) return false;
+  if (!a16(q) || !a16(k) || !a16(vt) || !a16(out)) return false;
+  Scope sc(e.arena);
+  const int ldS = Nk;
+  float* S = (float*)e.arena.alloc((size_t)B * heads * Nq * ldS * sizeof(float));
+  if (e.dry()) return true;
+  ensure_attr();
+  TcParams p;
+  // ---- S = scale * Q K^T
+  {
+    memset(&p, 0, sizeof(p));
+    p.mode = 2; p.M = Nq; p.N = Nk; p.K = d; p.heads = heads; p.alpha = scale;
+    p.C = S; p.ldc = ldS; p.sC_b = (long long)heads * Nq * ldS; p.sC_h = (long long)Nq * ldS;
+    p.rows_per_batch = 1;
+    const int code[4] = {0, 2, 1, 3};      // dims {d, heads, rows, B}
+    for (int i = 0; i < 4; ++i) { p.a_code[i] = code[i]; p.b_code[i] = code[i]; }
+    uint64_t da[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)Nq, (uint64_t)B};
+    uint64_t sa[3] = {(uint64_t)head_stride * 4, (uint64_t)ldq * 4, (uint64_t)Nq * ldq * 4};
+    uint64_t db[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)Nk, (uint64_t)B};
+    uint64_t sb[3] = {(uint64_t)head_stride * 4, (uint64_t)ldk * 4, (uint64_t)Nk * ldk * 4};
+    uint32_t bx[4] = {TBK, 1, TBM, 1};
+    const CUtensorMap& mA = get_map(q, 4, da, sa, bx);
+    const CUtensorMap& mB = get_map(k, 4, db, sb, bx);
+    ProfScope ps(e, s, PROF_BATCHED_TC, 2.0 * Nq * Nk * d * B * heads, 4.0 * B * heads * ((double)Nq * d + (double)Nk * d + (double)Nq * Nk), 1);
+    tc_gemm_kernel<<<dim3(cdiv(Nq, TBM), cdiv(Nk, TBN), B * heads), TC_THREADS, SMEM_BYTES, s>>>(mA, mA, mB, p);
+    CDX_CUDA(cudaGetLastError());
+    e.launches++;
+  }
+  softmax_rows(e, S, (long long)B * heads * Nq, Nk, ldS, s);
+  // ---- O = P V   (B operand = V^T rows h*d .. h*d+d-1, K along the sample's Nk columns)
+  {
+    memset(&p, 0, sizeof(p));
+    p.mode = 2; p.M = Nq; p.N = d; p.K = Nk; p.heads = heads; p.alpha = 1.f;
+    p.C = out; p.ldc = ldo; p.sC_b = (long long)Nq * ldo; p.sC_h = d;
+    p.rows_per_batch = 1;
+    const int ac[4] = {0, 1, 2, 3};        // P dims {Nk, Nq, heads, B}
+    const int bc[4] = {0, 3, 1, 4};        // V^T dims {Nk, B, heads*d, 1}
+    for (int i = 0; i < 4; ++i) { p.a_code[i] = ac[i]; p.b_code[i] = bc[i]; }
+    p.b_rowoff_h = d;
+    uint64_t da[4] = {(uint64_t)Nk, (uint64_t)Nq, (uint64_t)heads, (uint64_t)B};
+    uint64_t sa[3] = {(uint64_t)ldS * 4, (uint64_t)Nq * ldS * 4, (uint64_t)heads * Nq * ldS * 4};
+    uint32_t bxa[4] = {TBK, TBM, 1, 1};
+    uint64_t db[4] = {(uint64_t)Nk, (uint64_t)B, (uint64_t)heads * d, 1};
+    uint64_t sb[3] = {(uint64_t)Nk * 4, (uint64_t)B * Nk * 4, (uint64_t)B * Nk * 4 * heads * d};
+    uint32_t bxb[4] = {TBK, 1, TBN, 1};
+    const CUtensorMap& mA = get_map(S, 4, da, sa, bxa);
+    const CUtensorMap& mB = get_map(vt, 4, db, sb, bxb);
+    ProfScope ps(e, s, PROF_BATCHED_TC, 2.0 * Nq * Nk * d * B * heads, 4.0 * B * heads * ((double)Nq * Nk + (double)Nk * d + (double)Nq * d), 1);
+    tc_gemm_kernel<<<dim3(cdiv(Nq, TBM), cdiv(d, TBN), B * heads), TC_THREADS, SMEM_BYTES, s>>>(mA, mA, mB, p);
+    CDX_CUDA(cudaGetLastError());
+    e.launches++;
+  }
+  return true;
+}
 
 bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   // ---- eligibility (everything else takes the FFMA tiles)
@@ -458,11 +549,8 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
     uint32_t bx[2] = {TBK, TBN};
     mB = &get_map(a.Bw, 2, d, st, bx);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  ensure_attr();
+  p.heads = 1;
   ProfScope ps(e, s, a.mode == 1 ? PROF_CONV_TC : PROF_DENSE_TC, 2.0 * a.M * a.N * a.K,
                4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
   tc_gemm_kernel<<<grid, TC_THREADS, SMEM_BYTES, s>>>(*mA, *mA2, *mB, p);

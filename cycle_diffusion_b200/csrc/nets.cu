@@ -340,6 +340,13 @@ struct Exec {
     const Param& w = n.param(name + ".weight");
     const int Cout = (int)w.dims[0], Cin = (int)w.dims[1];
     CDX_CHECK(Cin == x.C, "conv %s: input has %d channels, weight expects %d", name.c_str(), x.C, Cin);
+    if (up == 2 && e.mma_mode == 1 && (Cin % 32) == 0 && !out_nchw) {
+      // tcgen05 path: the TMA box gather cannot express the >>1 source index, so materialise the nearest-2x upsample
+      // (one extra write+read of the activation, <2% of the conv's time) and run the plain tensor-core conv on it
+      Tensor xu = alloc(x.B, x.H * 2, x.W * 2, x.C);
+      upsample2(e, x.p, xu.p, x.B, x.H, x.W, x.C, s);
+      return conv3(xu, name, stride, pad, 1, rowvec, ld_rowvec, residual, out_nchw);
+    }
     const int Hl = x.H * up, Wl = x.W * up;
     int Ho, Wo;
     if (stride == 1) { Ho = Hl; Wo = Wl; }
@@ -481,10 +488,24 @@ struct UNetExec : Exec {
     Tensor h2;
     {
       Tensor n1 = ln(h, t + ".norm1");
-      Tensor qkv = alloc(B, x.H, x.W, 3 * C);
-      linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 3 * C, nullptr, nullptr, 0, qkv.p, 3 * C);
       Tensor a = alloc(B, x.H, x.W, C);
-      attention(e, qkv.p, 3 * C, qkv.p + C, 3 * C, qkv.p + 2 * C, 3 * C, a.p, C, B, HW, HW, heads, d, d, scale, s);
+      bool done = false;
+      if (e.mma_mode == 1 && (HW % 32) == 0 && HW >= 128 && (d % 4) == 0) {
+        // tensor-core attention: fused q|k projection, V produced transposed (V^T = Wv . X^T, a swapped-role GEMM)
+        // so that both P.V operands are K-major for tcgen05
+        Scope sa(e.arena);
+        Tensor qk = alloc(B, x.H, x.W, 2 * C);
+        linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 2 * C, nullptr, nullptr, 0, qk.p, 2 * C);
+        float* vt = (float*)e.arena.alloc((size_t)C * M * sizeof(float));
+        linear_into(n.P(t + ".attn1.to_v.weight"), C, C, nullptr, 0, 0, C, n1.p, M, nullptr, nullptr, 0, vt, M);
+        done = attention_tc(e, qk.p, 2 * C, qk.p + C, 2 * C, d, vt, a.p, C, B, HW, HW, heads, d, scale, s);
+      }
+      if (!done) {
+        Scope sa(e.arena);
+        Tensor qkv = alloc(B, x.H, x.W, 3 * C);
+        linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 3 * C, nullptr, nullptr, 0, qkv.p, 3 * C);
+        attention(e, qkv.p, 3 * C, qkv.p + C, 3 * C, qkv.p + 2 * C, 3 * C, a.p, C, B, HW, HW, heads, d, d, scale, s);
+      }
       h2 = linear(a, t + ".attn1.to_out.0", true, h.p);
     }
     // --- cross-attention: q from tokens, fused k|v projection of the context
