@@ -484,6 +484,12 @@ int cdx_op_conv3x3(cdx_engine* eh, const float* x, const float* w_oihw, const fl
       g.Bw = wr; g.ldb = 9 * Cin;
       g.Cout = y; g.ldc = Cout;
       g.bias = bias;
+      if (e.mma_mode == 1) {   // exercise the TS kernel: build the TF32 planes of the (repacked) weight on the fly
+        float* hi = (float*)e.arena.alloc((size_t)Cout * Cin * 9 * sizeof(float));
+        float* lo = (float*)e.arena.alloc((size_t)Cout * Cin * 9 * sizeof(float));
+        split_planes(e, wr, hi, lo, (size_t)Cout * Cin * 9, s);
+        g.Bw_hi = hi; g.Bw_lo = lo;
+      }
       gemm(e, g, s);
     });
   });
@@ -491,14 +497,23 @@ int cdx_op_conv3x3(cdx_engine* eh, const float* x, const float* w_oihw, const fl
 int cdx_op_linear(cdx_engine* eh, const float* x, const float* w, const float* bias, float* y, int M, int K, int N, void* stream) {
   return guard([&] {
     CDX_CHECK(eh && x && w && y, "op_linear: null argument");
-    CDX_CUDA(cudaSetDevice(eh->e.device));
-    GemmArgs g;
-    g.M = M; g.N = N; g.K = K;
-    g.A = x; g.lda = K; g.C1 = K;
-    g.Bw = w; g.ldb = K;
-    g.Cout = y; g.ldc = N;
-    g.bias = bias;
-    gemm(eh->e, g, S(stream));
+    Engine& e = eh->e;
+    with_arena(e, [&] {
+      Scope sc(e.arena);
+      GemmArgs g;
+      g.M = M; g.N = N; g.K = K;
+      g.A = x; g.lda = K; g.C1 = K;
+      g.Bw = w; g.ldb = K;
+      g.Cout = y; g.ldc = N;
+      g.bias = bias;
+      if (e.mma_mode == 1) {
+        float* hi = (float*)e.arena.alloc((size_t)N * K * sizeof(float));
+        float* lo = (float*)e.arena.alloc((size_t)N * K * sizeof(float));
+        split_planes(e, w, hi, lo, (size_t)N * K, S(stream));
+        g.Bw_hi = hi; g.Bw_lo = lo;
+      }
+      gemm(e, g, S(stream));
+    });
   });
 }
 int cdx_op_groupnorm(cdx_engine* eh, const float* x, const float* gamma, const float* beta, float eps, int silu_, float* y, int B, int HW, int C,

@@ -122,6 +122,7 @@ struct GemmArgs {
   // conv geometry (mode 1): stored input [B,Hin,Win,*], logical input is up x larger (nearest)
   int Hin = 0, Win = 0, Hout = 0, Wout = 0, stride = 1, pad = 1, up = 1;
   const float* Bw = nullptr; int ldb = 0; int b_kn = 0;   // weights [N][K] (b_kn=0) or [K][N] (b_kn=1)
+  const float* Bw_hi = nullptr; const float* Bw_lo = nullptr;   // optional pre-split TF32 planes of Bw (same geometry)
   float* Cout = nullptr; int ldc = 0;
   const float* bias = nullptr;
   const float* rowvec = nullptr; int ld_rowvec = 0; int rows_per_batch = 1;
@@ -136,6 +137,7 @@ struct GemmArgs {
 void gemm(Engine& e, const GemmArgs& a, cudaStream_t s);
 // tcgen05 back end (kernels_tc.cu); returns false when the shape is not eligible
 bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s);
+void split_planes(Engine& e, const float* w, float* hi, float* lo, size_t n, cudaStream_t s);   // hi = rn_tf32(w), lo = rn_tf32(w - hi)
 bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, int head_stride, const float* vt, float* out, int ldo, int B,
                   int Nq, int Nk, int heads, int d, float scale, cudaStream_t s);
 

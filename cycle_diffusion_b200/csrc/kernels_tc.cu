@@ -2,29 +2,35 @@
 //
 // Why 3xTF32: the path's acceptance bar is parity with the reference's fp32 CPU path (|d pixel| <= 1e-3 through
 // 50-250 sequential U-Net calls with a 1/sigma_t amplification), which plain TF32/BF16 tensor-core math cannot hold
-// (SURVEY.md section 7).  Every fp32 operand x is split as  hi = rn_tf32(x) (exactly representable in TF32) and
-// lo = x - hi (exact in fp32), and the product is accumulated as  hi*hi + lo*hi + hi*lo  in the fp32 TMEM accumulator
-// (the dropped lo*lo term is < 2^-22 relative).  Three tcgen05.mma.kind::tf32 per K-chunk.
-// Both parts are rounded to nearest (hi = rn_tf32(x), lo = rn_tf32(x - hi)) so that no systematic bias is introduced.
+// (SURVEY.md section 7).  Every fp32 operand x is split as  hi = rn_tf32(x)  and  lo = rn_tf32(x - hi)  (x - hi is
+// exact in fp32) and the product is accumulated as  lo*hi + hi*lo + hi*hi  in the fp32 TMEM accumulator (the dropped
+// lo*lo term is < 2^-22 relative).  Three tcgen05.mma.kind::tf32 per 8-wide K chunk.
 //
-// Tensor-core accumulation truncates (measured: the error of a single long accumulation grows linearly with K,
-// 5.8e-5 relative at K = 11520), so the K loop is cut into chunks of 8 blocks (256 elements): each chunk accumulates
-// in one of two TMEM buffers and is then drained by the epilogue warps into fp32 registers with round-to-nearest adds
-// while the next chunk is already running in the other buffer.
+// Tensor-core accumulation truncates (measured: the error of one long accumulation grows linearly with K, 5.8e-5
+// relative at K = 11520), so the K loop is cut into chunks of 8 blocks (256 elements): each chunk accumulates in one of
+// two TMEM buffers and is drained by the epilogue warps into fp32 registers with round-to-nearest adds while the next
+// chunk already runs in the other buffer.  Measured error after both fixes: ~1.3e-6 relative, independent of K.
 //
-// Kernel shape (one 128 x 128 output tile per CTA, K walked in 32-float = 128-byte blocks):
-//   warp 0      TMA producer: cp.async.bulk.tensor loads of the raw fp32 A and B blocks into 128B-swizzled smem.
-//               A is either a 2D [M,K] row matrix (dense / 1x1 conv / Linear, optionally two channel-concatenated
-//               sources) or -- for conv3x3 -- a 4D box {32 ch, bw, bh, bn} of the NHWC activation shifted by the
-//               tap (dy-1, dx-1): TMA's out-of-bounds zero fill *is* the conv's zero padding, so im2col is never
-//               materialised and the halo costs nothing.
-//   warps 2-5   split: read each landed block once, write hi in place and lo to a twin buffer (same swizzle),
-//               fence.proxy.async, signal the MMA warp.
-//   warp 1      MMA issuer: one lane issues 12 tcgen05.mma (4 K-chunks x 3 products) per block into a 128-column
-//               fp32 TMEM accumulator (two buffers), tcgen05.commit releases the smem stage back to the producer.
-//   warps 6-9   drain + epilogue: per chunk tcgen05.ld 32x32b.x32 -> RN add into 128 fp32 registers per thread;
-//               at the end alpha, +bias, +per-sample row vector (timestep embedding), +residual -> 128-bit stores.
-// 3 stages x 64 KB (A hi/lo + B hi/lo) = 192 KB dynamic smem, 1 CTA / SM.
+// One 128 x 128 output tile per CTA, K walked in 32-float (128-byte) blocks, 320 threads:
+//   warp 0      TMA producer (cp.async.bulk.tensor, 128B-swizzled smem).  A is a 2D [M,K] row matrix (dense / 1x1 conv /
+//               Linear, optionally two channel-concatenated sources), or for conv3x3 a 4D box {32 ch, bw, bh, bn} of
+//               the NHWC activation shifted by the tap (dy-1, dx-1): TMA's out-of-bounds zero fill *is* the conv's
+//               zero padding, so im2col is never materialised and the halo costs nothing; or (batched mode) 4D maps
+//               over (k, head, row, batch) for the attention contractions.
+//   warp 1      MMA issuer: one lane issues 12 tcgen05.mma per K block, tcgen05.commit hands the stage back.
+//   warps 2-5   split warps.
+//   warps 6-9   drain + epilogue: tcgen05.ld 32x32b.x32 per chunk -> RN add into 128 fp32 registers per thread; at the
+//               end alpha, +bias, +per-sample row vector (timestep embedding), +residual -> 128-bit global stores.
+//
+// Two variants of the operand path (template parameter TS):
+//   TS = false  "SS": A and B raw tiles land in smem, the split warps rewrite both as hi (in place) + lo (twin buffer),
+//               both operands are read from smem by the MMA.  3 stages x 64 KB.  Generic (B may be an activation).
+//   TS = true   "TS": weights are pre-split once at load time into hi / lo planes in HBM, so B_hi and B_lo arrive
+//               straight from TMA; the split warps read the raw A row from smem, and store hi / lo with tcgen05.st into
+//               TMEM, from where the MMA takes the A operand.  No smem writes by the SM and no smem reads of A by the
+//               tensor core: the ncu profile of the SS variant showed shared-memory bandwidth (LSU split traffic +
+//               tensor-core operand fetch ~ 84 % of smem cycles, tensor pipe 33 % active) as the limiter.
+//               4 stages x 48 KB; TMEM: 2 x 128 accumulator columns + 4 x 64 A columns = 512.
 #include <cuda.h>
 
 #include <map>
@@ -36,19 +42,24 @@ namespace cdx {
 namespace {
 
 constexpr int TBM = 128, TBN = 128, TBK = 32;
-constexpr int STAGES = 3;
 constexpr int TILE_BYTES = TBM * TBK * 4;          // 16 KB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi, A_lo, B_hi, B_lo
 constexpr int NUM_SPLIT_WARPS = 4;
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int KCHUNK = 8;                          // k-blocks per TMEM accumulation chunk (256 K elements)
-constexpr int TMEM_COLS = 2 * TBN;                 // two accumulator buffers
 constexpr int TC_THREADS = 64 + (NUM_SPLIT_WARPS + NUM_EPI_WARPS) * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+
+template <bool TS>
+struct Cfg {
+  static constexpr int STAGES = TS ? 4 : 3;
+  static constexpr int STAGE_BYTES = TS ? 3 * TILE_BYTES : 4 * TILE_BYTES;   // TS: A_raw, B_hi, B_lo ; SS: A_hi, A_lo, B_hi, B_lo
+  static constexpr int TMEM_COLS = TS ? 512 : 256;
+  static constexpr int A_COL0 = 256;               // TS: A stage s lives at columns A_COL0 + 64 s (hi) / + 32 (lo)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+};
 
 struct TcParams {
   int M, N, K;
-  int mode;                 // 0 dense, 1 conv3x3 (stride 1, pad 1)
+  int mode;                 // 0 dense, 1 conv3x3 (stride 1, pad 1), 2 batched dense
   int C1, C2;               // dense: channels of source 1 / 2 (k-blocks never straddle: C1 % 32 == 0 when C2 > 0)
   int Cin;                  // conv: input channels (multiple of 32)
   int H, W, B;              // conv: spatial size (in == out) and batch
@@ -59,7 +70,7 @@ struct TcParams {
   const float* rowvec; int ld_rowvec; int rows_per_batch;
   const float* residual; int ldr;
   float alpha;
-  // mode 2 (batched dense, blockIdx.z = zb*heads + zh): 4D maps, coordinate recipe per operand
+  // mode 2 (blockIdx.z = zb*heads + zh): 4D maps, coordinate recipe per operand
   int heads;
   int a_code[4], b_code[4];   // per map dim: 0 -> k0, 1 -> row0, 2 -> zh, 3 -> zb, 4 -> 0
   int a_rowoff_h, b_rowoff_h; // row0 += zh * rowoff (heads packed along the row dimension)
@@ -106,12 +117,22 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
                "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] . B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -129,6 +150,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 
 // K-major, 128-byte-swizzled smem operand descriptor (rows of 128 B, 8-row atoms of 1024 B)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -141,9 +172,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
+__device__ __forceinline__ uint32_t rn_tf32(uint32_t bits) { return (bits + 0x1000u) & 0xFFFFE000u; }
+
+template <bool TS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
-               const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
+  constexpr int STAGES = Cfg<TS>::STAGES;
+  constexpr int STAGE_BYTES = Cfg<TS>::STAGE_BYTES;
+  constexpr int TMEM_COLS = Cfg<TS>::TMEM_COLS;
+  // smem offsets inside a stage
+  constexpr int OFF_A = 0;                                   // SS: A_hi (raw in place) ; TS: A_raw
+  constexpr int OFF_ALO = TILE_BYTES;                        // SS only
+  constexpr int OFF_BHI = TS ? TILE_BYTES : 2 * TILE_BYTES;
+  constexpr int OFF_BLO = TS ? 2 * TILE_BYTES : 3 * TILE_BYTES;
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 1024-byte aligned (swizzle atoms)
   const uint32_t bars = base + STAGES * STAGE_BYTES;
@@ -203,15 +246,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES, it = kb / STAGES;
         mbar_wait(bar_empty(s), (it & 1) ^ 1);
-        const uint32_t sa = base + s * STAGE_BYTES;              // A raw -> becomes A_hi
-        const uint32_t sb = sa + 2 * TILE_BYTES;                 // B raw -> becomes B_hi
-        mbar_expect_tx(bar_full_raw(s), 2 * TILE_BYTES);
+        const uint32_t st = base + s * STAGE_BYTES;
+        const uint32_t sa = st + OFF_A, sb = st + OFF_BHI;
+        mbar_expect_tx(bar_full_raw(s), (TS ? 3 : 2) * TILE_BYTES);
+        const int k0 = kb * TBK;
         if (p.mode == 0) {
-          const int k0 = kb * TBK;
           if (k0 < p.C1) tma_load_2d(sa, &mapA, k0, m0, bar_full_raw(s));
           else tma_load_2d(sa, &mapA2, k0 - p.C1, m0, bar_full_raw(s));
         } else if (p.mode == 2) {
-          const int k0 = kb * TBK;
           int ca[4], cb4[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -221,13 +263,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           tma_load_4d(sa, &mapA, ca[0], ca[1], ca[2], ca[3], bar_full_raw(s));
           tma_load_4d(sb, &mapB, cb4[0], cb4[1], cb4[2], cb4[3], bar_full_raw(s));
-          continue;
+          continue;                                               // (batched mode is SS only)
         } else {
           const int tap = kb / cblocks, cb = kb - tap * cblocks;
           const int dy = tap / 3, dx = tap - dy * 3;
           tma_load_4d(sa, &mapA, cb * TBK, x0 + dx - 1, y0 + dy - 1, b0, bar_full_raw(s));   // OOB -> zeros = padding
         }
-        tma_load_2d(sb, &mapB, kb * TBK, n0, bar_full_raw(s));
+        tma_load_2d(sb, &mapB, k0, n0, bar_full_raw(s));
+        if (TS) tma_load_2d(st + OFF_BLO, &mapBlo, k0, n0, bar_full_raw(s));
       }
     }
   } else if (warp == 1) {
@@ -243,47 +286,89 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         mbar_wait(bar_full_split(s), it & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = base + s * STAGE_BYTES;
+        const uint32_t st = base + s * STAGE_BYTES;
         const uint32_t acc = tmem_base + (uint32_t)(buf * TBN);
-        const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_BYTES);
-        const uint64_t b_hi = make_desc(sa + 2 * TILE_BYTES), b_lo = make_desc(sa + 3 * TILE_BYTES);
+        const uint64_t b_hi = make_desc(st + OFF_BHI), b_lo = make_desc(st + OFF_BLO);
+        if (TS) {
+          const uint32_t a_hi = tmem_base + (uint32_t)(Cfg<TS>::A_COL0 + s * 64), a_lo = a_hi + 32;
 #pragma unroll
-        for (int j = 0; j < TBK / 8; ++j) {
-          const uint64_t adv = (uint64_t)((j * 8 * 4) >> 4);      // 32 bytes per K-chunk of 8 tf32
-          umma_tf32(acc, a_lo + adv, b_hi + adv, idesc, (kin > 0 || j > 0) ? 1u : 0u);     // small terms first
-          umma_tf32(acc, a_hi + adv, b_lo + adv, idesc, 1u);
-          umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, 1u);
+          for (int j = 0; j < TBK / 8; ++j) {
+            const uint64_t adv = (uint64_t)((j * 8 * 4) >> 4);    // 32 bytes per K chunk of 8 tf32 in smem; 8 columns in TMEM
+            umma_ts(acc, a_lo + j * 8, b_hi + adv, idesc, (kin > 0 || j > 0) ? 1u : 0u);      // small terms first
+            umma_ts(acc, a_hi + j * 8, b_lo + adv, idesc, 1u);
+            umma_ts(acc, a_hi + j * 8, b_hi + adv, idesc, 1u);
+          }
+        } else {
+          const uint64_t a_hi = make_desc(st + OFF_A), a_lo = make_desc(st + OFF_ALO);
+#pragma unroll
+          for (int j = 0; j < TBK / 8; ++j) {
+            const uint64_t adv = (uint64_t)((j * 8 * 4) >> 4);
+            umma_ss(acc, a_lo + adv, b_hi + adv, idesc, (kin > 0 || j > 0) ? 1u : 0u);
+            umma_ss(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_ss(acc, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
         }
-        umma_commit(bar_empty(s));          // smem stage reusable once these MMAs have read it
+        umma_commit(bar_empty(s));          // stage (smem and, for TS, its TMEM A columns) reusable once these MMAs are done
         if (kin == KCHUNK - 1 || kb == num_kb - 1) umma_commit(bar_acc_full(buf));   // chunk complete
       }
     }
   } else if (warp < 2 + NUM_SPLIT_WARPS) {
     // =========================================================================== split warps
-    const int st = threadIdx.x - 64;        // 0..127
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
-      mbar_wait(bar_full_raw(s), it & 1);
-      const uint32_t sa = base + s * STAGE_BYTES;
-#pragma unroll 4
-      for (int i = 0; i < (2 * TILE_BYTES / 16) / (NUM_SPLIT_WARPS * 32); ++i) {
-        const int idx = st + i * NUM_SPLIT_WARPS * 32;            // float4 index over [A | B]
-        const uint32_t off = (uint32_t)idx * 16u;
-        const uint32_t src = off < (uint32_t)TILE_BYTES ? sa + off : sa + 2 * TILE_BYTES + (off - TILE_BYTES);
-        uint32_t v[4], h[4], l[4];
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(src));
+    if (TS) {
+      // thread = one tile row: read its 128 raw bytes (8 swizzled 16-byte chunks), store hi / lo into TMEM lane `row`
+      const int q = warp & 3;                    // TMEM lane quadrant (warps 2..5 -> 2,3,0,1)
+      const int row = q * 32 + lane;
+      const uint32_t rbase = (uint32_t)row * 128u;
+      const uint32_t rx = (uint32_t)(row & 7);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES, it = kb / STAGES;
+        mbar_wait(bar_full_raw(s), it & 1);
+        const uint32_t sa = base + s * STAGE_BYTES + OFF_A + rbase;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          h[c] = (v[c] + 0x1000u) & 0xFFFFE000u;                                       // hi = rn_tf32(x)
-          const float lo = __uint_as_float(v[c]) - __uint_as_float(h[c]);              // exact
-          l[c] = (__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u;                        // lo = rn_tf32(x - hi)
+        for (int c = 0; c < 8; ++c) {
+          uint32_t v[4];
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(sa + (((uint32_t)c ^ rx) << 4)));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t h = rn_tf32(v[e]);
+            hi[c * 4 + e] = h;
+            lo[c * 4 + e] = rn_tf32(__float_as_uint(__uint_as_float(v[e]) - __uint_as_float(h)));
+          }
         }
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(src), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(src + TILE_BYTES), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<TS>::A_COL0 + s * 64);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full_split(s));
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full_split(s));
+    } else {
+      const int st_ = threadIdx.x - 64;        // 0..127
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES, it = kb / STAGES;
+        mbar_wait(bar_full_raw(s), it & 1);
+        const uint32_t sa = base + s * STAGE_BYTES;
+#pragma unroll 4
+        for (int i = 0; i < (2 * TILE_BYTES / 16) / (NUM_SPLIT_WARPS * 32); ++i) {
+          const int idx = st_ + i * NUM_SPLIT_WARPS * 32;            // float4 index over [A | B]
+          const uint32_t off = (uint32_t)idx * 16u;
+          const uint32_t src = off < (uint32_t)TILE_BYTES ? sa + off : sa + 2 * TILE_BYTES + (off - TILE_BYTES);
+          uint32_t v[4], h[4], l[4];
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(src));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            h[c] = rn_tf32(v[c]);                                                           // hi = rn_tf32(x)
+            l[c] = rn_tf32(__float_as_uint(__uint_as_float(v[c]) - __uint_as_float(h[c])));   // lo = rn_tf32(x - hi)
+          }
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(src), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(src + TILE_BYTES), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full_split(s));
+      }
     }
   } else {
     // =========================================================================== drain + epilogue warps
@@ -352,6 +437,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
+// x -> (rn_tf32(x), rn_tf32(x - rn_tf32(x)))  : one-time preparation of the weight planes for the TS variant
+__global__ void split_planes_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t b = __float_as_uint(w[i]);
+    const uint32_t h = rn_tf32(b);
+    hi[i] = __uint_as_float(h);
+    lo[i] = __uint_as_float(rn_tf32(__float_as_uint(w[i] - __uint_as_float(h))));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -416,15 +511,25 @@ inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 void ensure_attr() {
   static bool attr_set = false;
   if (!attr_set) {
-    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
     attr_set = true;
   }
 }
 
 }  // namespace
 
+void split_planes(Engine& e, const float* w, float* hi, float* lo, size_t n, cudaStream_t s) {
+  if (e.dry()) return;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)e.num_sms * 16) blocks = (size_t)e.num_sms * 16;
+  split_planes_kernel<<<(unsigned)(blocks ? blocks : 1), 256, 0, s>>>(w, hi, lo, n);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+
 // softmax(q k^T * scale) v on the tensor cores: two batched 3xTF32 contractions around the row-softmax kernel.
-//   q, k : [B, N*, heads*head_stride-ish] token matrices (row strides ldq / ldk, head h at column h*head_stride)
+//   q, k : [B, N*, ...] token matrices (row strides ldq / ldk, head h at column h*head_stride)
 //   vt   : V transposed, [heads*d, B*Nk] (row c = channel, column b*Nk + j), produced by a swapped-role GEMM
 //   out  : [B, Nq, ldo], head h at column h*d
 // Requires Nk % 32 == 0 (a K block must not run into the next sample's columns of vt), d % 4 == 0.
@@ -454,7 +559,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     const CUtensorMap& mA = get_map(q, 4, da, sa, bx);
     const CUtensorMap& mB = get_map(k, 4, db, sb, bx);
     ProfScope ps(e, s, PROF_BATCHED_TC, 2.0 * Nq * Nk * d * B * heads, 4.0 * B * heads * ((double)Nq * d + (double)Nk * d + (double)Nq * Nk), 1);
-    tc_gemm_kernel<<<dim3(cdiv(Nq, TBM), cdiv(Nk, TBN), B * heads), TC_THREADS, SMEM_BYTES, s>>>(mA, mA, mB, p);
+    tc_gemm_kernel<false><<<dim3(cdiv(Nq, TBM), cdiv(Nk, TBN), B * heads), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -478,7 +583,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     const CUtensorMap& mA = get_map(S, 4, da, sa, bxa);
     const CUtensorMap& mB = get_map(vt, 4, db, sb, bxb);
     ProfScope ps(e, s, PROF_BATCHED_TC, 2.0 * Nq * Nk * d * B * heads, 4.0 * B * heads * ((double)Nq * Nk + (double)Nk * d + (double)Nq * d), 1);
-    tc_gemm_kernel<<<dim3(cdiv(Nq, TBM), cdiv(d, TBN), B * heads), TC_THREADS, SMEM_BYTES, s>>>(mA, mA, mB, p);
+    tc_gemm_kernel<false><<<dim3(cdiv(Nq, TBM), cdiv(d, TBN), B * heads), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -503,7 +608,8 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec; p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
   p.residual = a.residual; p.ldr = a.ldr;
   p.alpha = a.alpha;
-  const CUtensorMap *mA, *mA2, *mB;
+  p.heads = 1;
+  const CUtensorMap *mA, *mA2, *mB, *mBlo;
   dim3 grid;
   if (a.mode == 0) {
     if (a.K & 3) return false;
@@ -544,16 +650,18 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
     mA2 = mA;
     grid = dim3(p.tiles_x * p.tiles_y * cdiv(B, bn), cdiv(a.N, TBN), 1);
   }
+  const bool ts = a.Bw_hi != nullptr && a.Bw_lo != nullptr && a16(a.Bw_hi) && a16(a.Bw_lo);
   {
     uint64_t d[2] = {(uint64_t)a.K, (uint64_t)a.N}, st[1] = {(uint64_t)a.ldb * 4};
     uint32_t bx[2] = {TBK, TBN};
-    mB = &get_map(a.Bw, 2, d, st, bx);
+    mB = &get_map(ts ? a.Bw_hi : a.Bw, 2, d, st, bx);
+    mBlo = ts ? &get_map(a.Bw_lo, 2, d, st, bx) : mB;
   }
   ensure_attr();
-  p.heads = 1;
   ProfScope ps(e, s, a.mode == 1 ? PROF_CONV_TC : PROF_DENSE_TC, 2.0 * a.M * a.N * a.K,
                4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
-  tc_gemm_kernel<<<grid, TC_THREADS, SMEM_BYTES, s>>>(*mA, *mA2, *mB, p);
+  if (ts) tc_gemm_kernel<true><<<grid, TC_THREADS, Cfg<true>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
+  else tc_gemm_kernel<false><<<grid, TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
   return true;

@@ -279,6 +279,8 @@ Net* make_vae(Engine* e, const cdx_vae_config& cfg) {
 void destroy_net(Net* n) {
   if (!n) return;
   if (n->blob) cudaFree(n->blob);
+  if (n->blob_hi) cudaFree(n->blob_hi);
+  if (n->blob_lo) cudaFree(n->blob_lo);
   if (n->freqs_dev) cudaFree(n->freqs_dev);
   delete n;
 }
@@ -312,6 +314,7 @@ void net_load_param(Net& n, const char* name, const float* data, bool on_device,
   }
   p.loaded = true;
   n.finalized = false;
+  n.planes_valid = false;
 }
 
 void net_finalize(Net& n) {
@@ -319,6 +322,14 @@ void net_finalize(Net& n) {
   if (n.kind != NET_VAE) {
     if (!n.freqs_dev) CDX_CUDA(cudaMalloc(&n.freqs_dev, n.freqs_host.size() * sizeof(float)));
     CDX_CUDA(cudaMemcpy(n.freqs_dev, n.freqs_host.data(), n.freqs_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (!n.planes_valid) {
+    // TF32 hi / lo planes of every weight for the tcgen05 TS kernel (3x the weight memory: 10.3 GB for SD v1-4 of 180 GB)
+    if (!n.blob_hi) CDX_CUDA(cudaMalloc(&n.blob_hi, n.blob_floats * sizeof(float)));
+    if (!n.blob_lo) CDX_CUDA(cudaMalloc(&n.blob_lo, n.blob_floats * sizeof(float)));
+    split_planes(*n.eng, n.blob, n.blob_hi, n.blob_lo, n.blob_floats, 0);
+    CDX_CUDA(cudaDeviceSynchronize());
+    n.planes_valid = true;
   }
   n.finalized = true;
 }
@@ -333,6 +344,16 @@ struct Exec {
   Exec(Net& net, cudaStream_t st) : n(net), e(*net.eng), s(st) {}
 
   Tensor alloc(int B, int H, int W, int C) { return alloc_tensor(e, B, H, W, C); }
+
+  // weights living in the blob have pre-split TF32 planes at the same offset
+  void run(GemmArgs& g) {
+    if (n.planes_valid && g.Bw >= n.blob && g.Bw < n.blob + n.blob_floats) {
+      const size_t off = (size_t)(g.Bw - n.blob);
+      g.Bw_hi = n.blob_hi + off;
+      g.Bw_lo = n.blob_lo + off;
+    }
+    gemm(e, g, s);
+  }
 
   // y = conv3x3(x [, x2 concat]) + bias (+ rowvec per sample) (+ residual); up: nearest-2x folded into the gather
   Tensor conv3(const Tensor& x, const std::string& name, int stride = 1, int pad = 1, int up = 1, const float* rowvec = nullptr,
@@ -365,7 +386,7 @@ struct Exec {
     g.rowvec = rowvec; g.ld_rowvec = ld_rowvec; g.rows_per_batch = Ho * Wo;
     g.residual = residual; g.ldr = Cout;
     if (out_nchw) { g.out_nchw = 1; g.rows_per_img = Ho * Wo; }
-    gemm(e, g, s);
+    run(g);
     return y;
   }
 
@@ -381,7 +402,7 @@ struct Exec {
     g.Cout = y; g.ldc = ldc;
     g.bias = bias;
     g.residual = residual; g.ldr = ldr;
-    gemm(e, g, s);
+    run(g);
   }
   // single-source convenience: named weight [N,K(,1,1)], optional named bias
   Tensor linear(const Tensor& x, const std::string& name, bool bias, const float* residual = nullptr) {
@@ -469,7 +490,7 @@ struct UNetExec : Exec {
       g.Cout = out.p; g.ldc = Cout;
       g.bias = n.P(p + ".out_layers.3.bias");
       g.residual = residual; g.ldr = Cout;
-      gemm(e, g, s);
+      run(g);
     }
     return out;
   }
@@ -643,7 +664,7 @@ struct VaeExec : Exec {
     g.Cout = out.p; g.ldc = Cout;
     g.bias = n.P(p + ".conv2.bias");
     g.residual = residual; g.ldr = Cout;
-    gemm(e, g, s);
+    run(g);
     return out;
   }
 

@@ -29,6 +29,9 @@ struct Net {
   std::vector<Param> params;
   std::unordered_map<std::string, int> index;
   float* blob = nullptr;
+  float* blob_hi = nullptr;     // rn_tf32(blob)            } pre-split planes for the tcgen05 TS kernel,
+  float* blob_lo = nullptr;     // rn_tf32(blob - blob_hi)  } same offsets as `blob`, derived at finalize
+  bool planes_valid = false;
   size_t blob_floats = 0;
   bool finalized = false;
   // timestep embedding
