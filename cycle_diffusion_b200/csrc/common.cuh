@@ -72,7 +72,7 @@ struct Engine {
   Profiler prof;
   int device = 0;
   int num_sms = 148;
-  int mma_mode = 0;              // 0 SIMT FFMA, 1 tcgen05 3xTF32
+  int mma_mode = 1;              // 0 SIMT FFMA (exact fp32), 1 tcgen05 3xTF32 (default)
   Arena arena;
   uint64_t launches = 0;
   bool dry() const { return arena.dry; }
