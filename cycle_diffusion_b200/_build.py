@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcdx.so')
 STAMP = os.path.join(HERE, '.libcdx.stamp')
 
-SOURCES = ['engine.cu', 'kernels_gemm.cu', 'kernels_tc.cu', 'kernels_norm.cu', 'kernels_elem.cu', 'nets.cu', 'cabi.cu']
+SOURCES = ['engine.cu', 'kernels_gemm.cu', 'kernels_tc.cu', 'kernels_attn.cu', 'kernels_norm.cu', 'kernels_elem.cu', 'nets.cu', 'cabi.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--use_fast_math=false',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '--expt-relaxed-constexpr', '-Xptxas', '-v']
 

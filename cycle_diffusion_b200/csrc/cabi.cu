@@ -157,8 +157,9 @@ size_t cdx_engine_workspace_bytes(const cdx_engine* e) { return e ? e->e.arena.c
 uint64_t cdx_engine_launch_count(const cdx_engine* e) { return e ? e->e.launches : 0; }
 int cdx_engine_set_mma_mode(cdx_engine* e, int mode) {
   return guard([&] {
-    CDX_CHECK(e != nullptr && (mode == 0 || mode == 1), "set_mma_mode: bad arguments");
-    e->e.mma_mode = mode;
+    CDX_CHECK(e != nullptr && (mode == 0 || mode == 1 || mode == 2), "set_mma_mode: bad arguments");
+    e->e.mma_mode = mode == 0 ? 0 : 1;       // 2 = tcgen05 contractions but unfused attention (A/B comparisons)
+    e->e.flash_attn = mode == 1;
   });
 }
 
@@ -531,7 +532,34 @@ int cdx_op_attention(cdx_engine* eh, const float* q, const float* k, const float
   return guard([&] {
     CDX_CHECK(eh && q && k && v && out, "op_attention: null argument");
     const int C = heads * d;
-    with_arena(eh->e, [&] { attention(eh->e, q, C, k, C, v, C, out, C, B, Nq, Nk, heads, d, d, scale, S(stream)); });
+    Engine& e = eh->e;
+    cudaStream_t s = S(stream);
+    with_arena(e, [&] {
+      Scope sc(e.arena);
+      bool done = false;
+      if (e.mma_mode == 1 && Nq == Nk && (Nq % 32) == 0 && Nq >= 128 && (d % 4) == 0) {
+        // same operand preparation as the SpatialTransformer: q|k side by side, V transposed, TF32 planes
+        const int M = B * Nq;
+        float* qk = (float*)e.arena.alloc((size_t)M * 2 * C * sizeof(float));
+        float* vt = (float*)e.arena.alloc((size_t)C * M * sizeof(float));
+        if (!e.dry()) {
+          CDX_CUDA(cudaMemcpy2DAsync(qk, (size_t)2 * C * 4, q, (size_t)C * 4, (size_t)C * 4, M, cudaMemcpyDeviceToDevice, s));
+          CDX_CUDA(cudaMemcpy2DAsync(qk + C, (size_t)2 * C * 4, k, (size_t)C * 4, (size_t)C * 4, M, cudaMemcpyDeviceToDevice, s));
+        }
+        nhwc_to_nchw(e, v, vt, 1, C, M, s);
+        if (e.flash_attn && (Nq % 128) == 0) {
+          float* qh = (float*)e.arena.alloc((size_t)M * 2 * C * sizeof(float));
+          float* ql = (float*)e.arena.alloc((size_t)M * 2 * C * sizeof(float));
+          float* vh = (float*)e.arena.alloc((size_t)C * M * sizeof(float));
+          float* vl = (float*)e.arena.alloc((size_t)C * M * sizeof(float));
+          split_planes(e, qk, qh, ql, (size_t)M * 2 * C, s);
+          split_planes(e, vt, vh, vl, (size_t)C * M, s);
+          done = flash_attention_tc(e, qh, ql, 2 * C, C, vh, vl, out, C, B, Nq, heads, d, scale, s);
+        }
+        if (!done) done = attention_tc(e, qk, 2 * C, qk + C, 2 * C, d, vt, out, C, B, Nq, Nk, heads, d, scale, s);
+      }
+      if (!done) attention(e, q, C, k, C, v, C, out, C, B, Nq, Nk, heads, d, d, scale, s);
+    });
   });
 }
 int cdx_op_nchw_to_nhwc(cdx_engine* eh, const float* x, float* y, int B, int C, int HW, void* stream) { ENG_CALL(eh, nchw_to_nhwc(eh->e, x, y, B, C, HW, S(stream))); }

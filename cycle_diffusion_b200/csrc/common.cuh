@@ -72,6 +72,7 @@ struct Engine {
   Profiler prof;
   int device = 0;
   int num_sms = 148;
+  bool flash_attn = true;        // fused tcgen05 attention kernel (kernels_attn.cu); false -> unfused QK^T / softmax / PV
   int mma_mode = 1;              // 0 SIMT FFMA (exact fp32), 1 tcgen05 3xTF32 (default)
   Arena arena;
   uint64_t launches = 0;
@@ -137,6 +138,8 @@ struct GemmArgs {
 void gemm(Engine& e, const GemmArgs& a, cudaStream_t s);
 // tcgen05 back end (kernels_tc.cu); returns false when the shape is not eligible
 bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s);
+bool flash_attention_tc(Engine& e, const float* qk_hi, const float* qk_lo, int ld, int k_off, const float* vt_hi, const float* vt_lo, float* out,
+                        int ldo, int B, int N, int heads, int d, float scale, cudaStream_t s);
 void split_planes(Engine& e, const float* w, float* hi, float* lo, size_t n, cudaStream_t s);   // hi = rn_tf32(w), lo = rn_tf32(w - hi)
 bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, int head_stride, const float* vt, float* out, int ldo, int B,
                   int Nq, int Nk, int heads, int d, float scale, cudaStream_t s);

@@ -1,0 +1,394 @@
+// kernels_attn.cu -- fused self-attention on tcgen05 (flash-style, fp32-faithful 3xTF32).
+//
+//   out[b, q, h*d + c] = sum_j softmax_j( scale * <Q[b,q,h,:], K[b,j,h,:]> ) * V[b,j,h,c]
+// replaces CrossAttention.forward's two einsums + softmax (ldm/modules/attention.py:178-192), which materialise a
+// [B*heads, N, N] fp32 score matrix (4.3 GB per layer at N=4096, B=8) -- here scores never leave the SM.
+//
+// Inputs are the TF32 hi / lo planes (rn_tf32(x), rn_tf32(x - hi)) of the fused q|k projection [B*N, 2C] and of the
+// transposed value projection V^T [C, B*N] (see nets.cu), so every operand tile arrives by TMA ready for the tensor core.
+//
+// One CTA = 128 queries of one (batch, head); keys are walked in blocks of 64.  192 threads:
+//   warp 0    TMA producer: Q planes once (through a staging buffer), then K / V^T hi+lo tiles into two 2-deep rings.
+//   warp 1    MMA issuer.  S_j = Q K_j^T as TS-mode MMAs (Q hi/lo live in TMEM, K tiles in smem): lo*hi + hi*lo + hi*hi,
+//             M=128, N=64, K=d.  O_j = P_j V_j with P hi/lo in TMEM and V^T tiles in smem, M=128, N=round16(d), K=64,
+//             written FRESH into TMEM for every key block.  S is double-buffered so S_{j+1} is computed while the
+//             softmax of block j runs.
+//   warps 2-5 softmax + accumulation, one thread per query row: tcgen05.ld S -> online max / exp2 / row sum in registers
+//             -> split P into hi/lo -> tcgen05.st into TMEM; O_total = O_total * corr + O_j with round-to-nearest fp32
+//             adds in registers (the tensor core's accumulation truncates, see kernels_tc.cu; accumulating per block in
+//             registers also makes the online-softmax rescale free).  Final O / l -> global.
+// TMEM columns: S0 0..63, S1 64..127, P_hi 128..191, P_lo 192..255, O 256..(256+NV), Q_hi 352.., Q_lo 352+d..  (<= 512).
+#include "tc_common.cuh"
+
+namespace cdx {
+namespace {
+
+using namespace tc;
+
+constexpr int AQ = 128;        // queries per CTA
+constexpr int AKV = 64;        // keys per block
+constexpr int ATTN_THREADS = 192;
+
+template <int D>
+struct ACfg {
+  static constexpr int KB2 = (D + 31) / 32;                 // 32-float k-blocks covering the head dim
+  static constexpr int NV = (D + 15) / 16 * 16;             // PV MMA N (rows of the V^T tile)
+  static constexpr int KTILE = AKV * 128;                   // one k-block tile of K: 64 rows x 128 B
+  static constexpr int K_STAGE = 2 * KB2 * KTILE;           // hi + lo
+  static constexpr int VTILE = NV * 128;                    // one 32-key block of V^T: NV rows x 128 B
+  static constexpr int V_STAGE = 2 * 2 * VTILE;             // (2 key sub-blocks) x (hi + lo)
+  static constexpr int Q_STAGE = KB2 * AQ * 128;            // one plane of Q
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = 2 * K_STAGE;
+  static constexpr int OFF_Q = OFF_V + 2 * V_STAGE;
+  static constexpr int OFF_BAR = OFF_Q + Q_STAGE;
+  static constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;
+  static constexpr int COL_S = 0, COL_PH = 128, COL_PL = 192, COL_O = 256, COL_QH = 352, COL_QL = 352 + D;
+  static_assert(D % 8 == 0 && D >= 16 && D <= 80, "head dim must be a multiple of 8 in [16, 80]");
+  static_assert(COL_QL + D <= 512, "TMEM overflow");
+  static_assert(SMEM_BYTES <= 232448, "smem overflow");
+};
+
+struct AttnParams {
+  int N, heads, d, B;
+  float scale_log2e;      // scale * log2(e): scores are kept in the log2 domain
+  float* out; int ldo;
+};
+
+#define TMEM_LD(NUM, ...) asm volatile("tcgen05.ld.sync.aligned.32x32b.x" #NUM ".b32 " __VA_ARGS__)
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
+flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_constant__ CUtensorMap mapQl,
+                  const __grid_constant__ CUtensorMap mapKh, const __grid_constant__ CUtensorMap mapKl,
+                  const __grid_constant__ CUtensorMap mapVh, const __grid_constant__ CUtensorMap mapVl, const AttnParams p) {
+  using C = ACfg<D>;
+  constexpr int KB2 = C::KB2, NV = C::NV;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + C::OFF_BAR;
+  // barriers (8 B each)
+  const uint32_t bar_q_full = bars + 0;          // TMA: a Q plane landed in the staging buffer (2 phases)
+  const uint32_t bar_q_free = bars + 8;          // softmax warps: staging buffer consumed (plane 0)
+  const uint32_t bar_q_ready = bars + 16;        // softmax warps: Q hi/lo complete in TMEM
+  auto bar_k_full = [&](int s) { return bars + 24u + 8u * s; };
+  auto bar_k_empty = [&](int s) { return bars + 40u + 8u * s; };
+  auto bar_v_full = [&](int s) { return bars + 56u + 8u * s; };
+  auto bar_v_empty = [&](int s) { return bars + 72u + 8u * s; };
+  auto bar_s_full = [&](int s) { return bars + 88u + 8u * s; };
+  auto bar_s_empty = [&](int s) { return bars + 104u + 8u * s; };
+  const uint32_t bar_p_full = bars + 120;
+  const uint32_t bar_pv_done = bars + 128;
+  const uint32_t bar_o_empty = bars + 136;
+  const uint32_t tmem_slot = bars + 144;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
+  const int nb = p.N / AKV;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar_q_full, 1);
+    mbar_init(bar_q_free, 4);
+    mbar_init(bar_q_ready, 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_k_full(s), 1);
+      mbar_init(bar_k_empty(s), 1);
+      mbar_init(bar_v_full(s), 1);
+      mbar_init(bar_v_empty(s), 1);
+      mbar_init(bar_s_full(s), 1);
+      mbar_init(bar_s_empty(s), 4);
+    }
+    mbar_init(bar_p_full, 4);
+    mbar_init(bar_pv_done, 1);
+    mbar_init(bar_o_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // =========================================================================== TMA producer
+    if (lane == 0) {
+      const uint32_t sq = base + C::OFF_Q;
+      // Q: hi plane, then (after the softmax warps moved it to TMEM) lo plane through the same staging buffer
+      mbar_expect_tx(bar_q_full, C::Q_STAGE);
+      for (int kb = 0; kb < KB2; ++kb) tma_load_4d(sq + kb * AQ * 128, &mapQh, kb * 32, h, q0, b, bar_q_full);
+      mbar_wait(bar_q_free, 0);
+      mbar_expect_tx(bar_q_full, C::Q_STAGE);
+      for (int kb = 0; kb < KB2; ++kb) tma_load_4d(sq + kb * AQ * 128, &mapQl, kb * 32, h, q0, b, bar_q_full);
+      for (int j = 0; j < nb; ++j) {
+        const int s = j & 1, it = j >> 1;
+        // K block j: [64 keys x d] hi + lo
+        mbar_wait(bar_k_empty(s), (it & 1) ^ 1);
+        const uint32_t sk = base + C::OFF_K + s * C::K_STAGE;
+        mbar_expect_tx(bar_k_full(s), C::K_STAGE);
+        for (int kb = 0; kb < KB2; ++kb) {
+          tma_load_4d(sk + kb * C::KTILE, &mapKh, kb * 32, h, j * AKV, b, bar_k_full(s));
+          tma_load_4d(sk + (KB2 + kb) * C::KTILE, &mapKl, kb * 32, h, j * AKV, b, bar_k_full(s));
+        }
+        // V^T block j: [NV channel rows x 64 keys] as two 32-key tiles, hi + lo
+        mbar_wait(bar_v_empty(s), (it & 1) ^ 1);
+        const uint32_t sv = base + C::OFF_V + s * C::V_STAGE;
+        mbar_expect_tx(bar_v_full(s), C::V_STAGE);
+        for (int kk = 0; kk < 2; ++kk) {
+          tma_load_4d(sv + kk * C::VTILE, &mapVh, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(s));
+          tma_load_4d(sv + (2 + kk) * C::VTILE, &mapVl, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_qk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AKV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
+      const uint32_t q_hi = tmem_base + C::COL_QH, q_lo = tmem_base + C::COL_QL;
+      const uint32_t p_hi = tmem_base + C::COL_PH, p_lo = tmem_base + C::COL_PL;
+      const uint32_t o_acc = tmem_base + C::COL_O;
+
+      auto issue_qk = [&](int j) {
+        const int s = j & 1;
+        const uint32_t sk = base + C::OFF_K + s * C::K_STAGE;
+        const uint32_t s_acc = tmem_base + C::COL_S + s * AKV;
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) {      // K chunks of 8 floats along the head dim
+          const int kb = c >> 2;
+          const uint64_t adv = (uint64_t)(((c & 3) * 32) >> 4);
+          const uint64_t k_hi = make_desc(sk + kb * C::KTILE) + adv;
+          const uint64_t k_lo = make_desc(sk + (KB2 + kb) * C::KTILE) + adv;
+          umma_ts(s_acc, q_lo + c * 8, k_hi, idesc_qk, c > 0 ? 1u : 0u);
+          umma_ts(s_acc, q_hi + c * 8, k_lo, idesc_qk, 1u);
+          umma_ts(s_acc, q_hi + c * 8, k_hi, idesc_qk, 1u);
+        }
+        umma_commit(bar_s_full(s));
+        umma_commit(bar_k_empty(s));
+      };
+
+      mbar_wait(bar_q_ready, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      mbar_wait(bar_k_full(0), 0);
+      issue_qk(0);
+      for (int j = 0; j < nb; ++j) {
+        if (j + 1 < nb) {
+          const int s1 = (j + 1) & 1;
+          mbar_wait(bar_k_full(s1), ((j + 1) >> 1) & 1);
+          if (j + 1 >= 2) mbar_wait(bar_s_empty(s1), (((j + 1) >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          issue_qk(j + 1);
+        }
+        const int s = j & 1;
+        mbar_wait(bar_p_full, j & 1);
+        mbar_wait(bar_v_full(s), (j >> 1) & 1);
+        if (j >= 1) mbar_wait(bar_o_empty, (j - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sv = base + C::OFF_V + s * C::V_STAGE;
+#pragma unroll
+        for (int c = 0; c < AKV / 8; ++c) {    // K chunks of 8 keys
+          const int kk = c >> 2;
+          const uint64_t adv = (uint64_t)(((c & 3) * 32) >> 4);
+          const uint64_t v_hi = make_desc(sv + kk * C::VTILE) + adv;
+          const uint64_t v_lo = make_desc(sv + (2 + kk) * C::VTILE) + adv;
+          umma_ts(o_acc, p_lo + c * 8, v_hi, idesc_pv, c > 0 ? 1u : 0u);
+          umma_ts(o_acc, p_hi + c * 8, v_lo, idesc_pv, 1u);
+          umma_ts(o_acc, p_hi + c * 8, v_hi, idesc_pv, 1u);
+        }
+        umma_commit(bar_pv_done);
+        umma_commit(bar_v_empty(s));
+      }
+    }
+  } else {
+    // =========================================================================== softmax + accumulation warps
+    const int qd = warp & 3;                       // TMEM lane quadrant (warps 2..5 -> 2,3,0,1)
+    const int row = qd * 32 + lane;                // query row of this thread
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    const uint32_t rbase = (uint32_t)row * 128u, rx = (uint32_t)(row & 7);
+
+    // ---- Q planes: staging smem -> TMEM (this thread's row)
+#pragma unroll 1
+    for (int plane = 0; plane < 2; ++plane) {
+      mbar_wait(bar_q_full, plane);
+      const uint32_t col = tmem_base + lane_base + (plane == 0 ? C::COL_QH : C::COL_QL);
+#pragma unroll
+      for (int c8 = 0; c8 < D / 8; ++c8) {         // 8 floats = two 16-byte chunks
+        const int kb = c8 >> 2, ch = (c8 & 3) * 2;
+        const uint32_t a = base + C::OFF_Q + kb * AQ * 128 + rbase;
+        uint32_t v[8];
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(a + (((uint32_t)ch ^ rx) << 4)));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(a + (((uint32_t)(ch + 1) ^ rx) << 4)));
+        tmem_st8(col + c8 * 8, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(plane == 0 ? bar_q_free : bar_q_ready);
+    }
+
+    float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+    float o[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) o[c] = 0.f;
+
+    auto accumulate_o = [&](int jdone) {          // O_total = O_total * corr + O_blk  (block jdone)
+      mbar_wait(bar_pv_done, jdone & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int part = 0; part < NV / 16; ++part) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + lane_base + C::COL_O + part * 16, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[part * 16 + c] = o[part * 16 + c] * corr_prev + __uint_as_float(v[c]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_o_empty);
+    };
+
+#pragma unroll 1
+    for (int j = 0; j < nb; ++j) {
+      const int s = j & 1;
+      mbar_wait(bar_s_full(s), (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float sc[AKV];
+#pragma unroll
+      for (int part = 0; part < AKV / 32; ++part) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_base + C::COL_S + s * AKV + part * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 32; ++c) sc[part * 32 + c] = __uint_as_float(v[c]) * p.scale_log2e;
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s_empty(s));
+
+      float mx = sc[0];
+#pragma unroll
+      for (int c = 1; c < AKV; ++c) mx = fmaxf(mx, sc[c]);
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = exp2f(m_run - m_new);           // 0 on the first block (m_run = -inf)
+      float psum = 0.f;
+#pragma unroll
+      for (int c = 0; c < AKV; ++c) {
+        sc[c] = exp2f(sc[c] - m_new);
+        psum += sc[c];
+      }
+      l_run = l_run * corr + psum;
+      m_run = m_new;
+
+      if (j >= 1) accumulate_o(j - 1);                   // also guarantees PV_{j-1} finished reading the P buffers
+
+      // P -> hi / lo planes in TMEM
+#pragma unroll
+      for (int c8 = 0; c8 < AKV / 8; ++c8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t bits = __float_as_uint(sc[c8 * 8 + e]);
+          hi[e] = rn_tf32(bits);
+          lo[e] = rn_tf32(__float_as_uint(sc[c8 * 8 + e] - __uint_as_float(hi[e])));
+        }
+        tmem_st8(tmem_base + lane_base + C::COL_PH + c8 * 8, hi);
+        tmem_st8(tmem_base + lane_base + C::COL_PL + c8 * 8, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p_full);
+      corr_prev = corr;
+      // note: corr of block j rescales everything accumulated before block j; it is applied when O_blk_j is added
+      if (j == 0) corr_prev = 1.f;                       // nothing accumulated yet (avoid 0 * 0 ambiguity with -inf)
+    }
+    // the rescale belonging to the last block, then its contribution
+    accumulate_o(nb - 1);
+
+    const float inv_l = 1.f / l_run;
+    float* dst = p.out + ((long long)b * p.N + q0 + row) * p.ldo + h * p.d;
+#pragma unroll
+    for (int c = 0; c < D; c += 4) {
+      float4 v;
+      v.x = o[c] * inv_l; v.y = o[c + 1] * inv_l; v.z = o[c + 2] * inv_l; v.w = o[c + 3] * inv_l;
+      *reinterpret_cast<float4*>(dst + c) = v;
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+template <int D>
+void launch_flash(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& kh, const CUtensorMap& kl, const CUtensorMap& vh,
+                  const CUtensorMap& vl, const AttnParams& p, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    CDX_CUDA(cudaFuncSetAttribute(flash_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<D>::SMEM_BYTES));
+    attr = true;
+  }
+  flash_attn_kernel<D><<<dim3(p.N / AQ, p.heads, p.B), ATTN_THREADS, ACfg<D>::SMEM_BYTES, s>>>(qh, ql, kh, kl, vh, vl, p);
+}
+
+}  // namespace
+
+// qk_hi / qk_lo: TF32 planes of the fused q|k projection [B*N, ld] (q at column 0, k at column k_off, head h at h*d);
+// vt_hi / vt_lo: planes of V^T [heads*d, B*N].  out [B, N, ldo], head h at column h*d.
+bool flash_attention_tc(Engine& e, const float* qk_hi, const float* qk_lo, int ld, int k_off, const float* vt_hi, const float* vt_lo, float* out,
+                        int ldo, int B, int N, int heads, int d, float scale, cudaStream_t s) {
+  if ((N % AQ) || (d % 8) || d < 16 || d > 80 || (ld & 3) || (k_off & 3) || (ldo & 3)) return false;
+  if (!(d == 16 || d == 32 || d == 40 || d == 64 || d == 80)) return false;
+  if (!a16(qk_hi) || !a16(qk_lo) || !a16(vt_hi) || !a16(vt_lo) || !a16(out)) return false;
+  if (e.dry()) return true;
+  const int NV = (d + 15) / 16 * 16;
+  uint64_t dq[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
+  uint64_t sq[3] = {(uint64_t)d * 4, (uint64_t)ld * 4, (uint64_t)N * ld * 4};
+  uint32_t bq[4] = {32, 1, AQ, 1}, bk[4] = {32, 1, AKV, 1};
+  uint64_t dv[4] = {(uint64_t)N, (uint64_t)B, (uint64_t)heads * d, 1};
+  uint64_t sv[3] = {(uint64_t)N * 4, (uint64_t)B * N * 4, (uint64_t)B * N * 4 * heads * d};
+  uint32_t bv[4] = {32, 1, (uint32_t)NV, 1};
+  const CUtensorMap& qh = get_map(qk_hi, 4, dq, sq, bq);
+  const CUtensorMap& ql = get_map(qk_lo, 4, dq, sq, bq);
+  const CUtensorMap& kh = get_map(qk_hi + k_off, 4, dq, sq, bk);
+  const CUtensorMap& kl = get_map(qk_lo + k_off, 4, dq, sq, bk);
+  const CUtensorMap& vh = get_map(vt_hi, 4, dv, sv, bv);
+  const CUtensorMap& vl = get_map(vt_lo, 4, dv, sv, bv);
+  AttnParams p;
+  p.N = N; p.heads = heads; p.d = d; p.B = B;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = out; p.ldo = ldo;
+  ProfScope ps(e, s, PROF_BATCHED_TC, 4.0 * N * (double)N * d * B * heads, 4.0 * B * heads * (3.0 * N * d + (double)N * d), 1);
+  switch (d) {
+    case 16: launch_flash<16>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 32: launch_flash<32>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 40: launch_flash<40>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 64: launch_flash<64>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 80: launch_flash<80>(qh, ql, kh, kl, vh, vl, p, s); break;
+    default: return false;
+  }
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+  return true;
+}
+
+}  // namespace cdx

@@ -519,7 +519,21 @@ struct UNetExec : Exec {
         linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 2 * C, nullptr, nullptr, 0, qk.p, 2 * C);
         float* vt = (float*)e.arena.alloc((size_t)C * M * sizeof(float));
         linear_into(n.P(t + ".attn1.to_v.weight"), C, C, nullptr, 0, 0, C, n1.p, M, nullptr, nullptr, 0, vt, M);
-        done = attention_tc(e, qk.p, 2 * C, qk.p + C, 2 * C, d, vt, a.p, C, B, HW, HW, heads, d, scale, s);
+        {
+          // fused flash attention needs the TF32 hi / lo planes of q|k and V^T (one read + two writes each)
+          Scope sf(e.arena);
+          const size_t nqk = (size_t)M * 2 * C, nvt = (size_t)C * M;
+          float* qk_hi = (float*)e.arena.alloc(nqk * sizeof(float));
+          float* qk_lo = (float*)e.arena.alloc(nqk * sizeof(float));
+          float* vt_hi = (float*)e.arena.alloc(nvt * sizeof(float));
+          float* vt_lo = (float*)e.arena.alloc(nvt * sizeof(float));
+          if (e.flash_attn && (HW % 128) == 0 && (d == 16 || d == 32 || d == 40 || d == 64 || d == 80)) {
+            split_planes(e, qk.p, qk_hi, qk_lo, nqk, s);
+            split_planes(e, vt, vt_hi, vt_lo, nvt, s);
+            done = flash_attention_tc(e, qk_hi, qk_lo, 2 * C, C, vt_hi, vt_lo, a.p, C, B, HW, heads, d, scale, s);
+          }
+        }
+        if (!done) done = attention_tc(e, qk.p, 2 * C, qk.p + C, 2 * C, d, vt, a.p, C, B, HW, HW, heads, d, scale, s);
       }
       if (!done) {
         Scope sa(e.arena);

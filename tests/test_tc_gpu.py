@@ -107,3 +107,28 @@ def test_cycle_tc_vs_reference_fixture(eng):
     own = unet.latent_decode(z, g['c_src'], g['uc'], enc_scale, sched).cpu()
     print(f'cycle (tcgen05): rel|dz| {rz:.2e} |d tgt| {maxdiff(tgt, g["tgt_a"]):.2e} own-cycle {maxdiff(own, g["x0"]):.2e}')
     assert rz < 2e-4 and maxdiff(tgt, g['tgt_a']) < 1e-3 and maxdiff(own, g['x0']) < 1e-3
+
+
+@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('B,N,heads,d', [(1, 4096, 8, 40), (2, 1024, 8, 80), (2, 256, 2, 16), (1, 128, 4, 64), (1, 256, 3, 32), (3, 384, 2, 40)])
+def test_attention_tc(B, N, heads, d, mode):
+    """mode 1: fused flash kernel (tcgen05, S/P never leave the SM); mode 2: unfused tcgen05 QK^T / softmax / PV^T."""
+    from cycle_diffusion_b200.engine import Engine
+    e = Engine(0)
+    e.set_mma_mode(mode)
+    g = torch.Generator().manual_seed(N + d)
+    C = heads * d
+    q, k, v = (torch.randn(B, N, C, generator=g) for _ in range(3))
+    q = q * 1.5
+    scale = d ** -0.5
+    sp = lambda t: t.reshape(B, -1, heads, d).permute(0, 2, 1, 3)
+    attn = (torch.einsum('bhid,bhjd->bhij', sp(q), sp(k)) * scale).softmax(-1)
+    ref = torch.einsum('bhij,bhjd->bhid', attn, sp(v)).permute(0, 2, 1, 3).reshape(B, N, C)
+    e.profile(True)
+    y = e.op_attention(q.cuda(), k.cuda(), v.cuda(), heads, scale).cpu()
+    fam = e.profile_read()
+    e.profile(False)
+    err = float((y - ref).abs().max())
+    print(f'attention mode {mode} B{B} N{N} h{heads} d{d}: max abs err {err:.2e}  ({ {k_: round(v_["ms"], 3) for k_, v_ in fam.items()} })')
+    assert 'batched_tc' in fam
+    assert err < 2e-5
