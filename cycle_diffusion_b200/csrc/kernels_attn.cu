@@ -7,13 +7,15 @@
 // Inputs are the TF32 hi / lo planes (rn_tf32(x), rn_tf32(x - hi)) of the fused q|k projection [B*N, 2C] and of the
 // transposed value projection V^T [C, B*N] (see nets.cu), so every operand tile arrives by TMA ready for the tensor core.
 //
-// One CTA = 128 queries of one (batch, head); keys are walked in blocks of 64.  192 threads:
+// One CTA = 128 queries of one (batch, head); keys are walked in blocks of 64.  320 threads:
 //   warp 0    TMA producer: Q planes once (through a staging buffer), then K / V^T hi+lo tiles into two 2-deep rings.
 //   warp 1    MMA issuer.  S_j = Q K_j^T as TS-mode MMAs (Q hi/lo live in TMEM, K tiles in smem): lo*hi + hi*lo + hi*hi,
 //             M=128, N=64, K=d.  O_j = P_j V_j with P hi/lo in TMEM and V^T tiles in smem, M=128, N=round16(d), K=64,
 //             written FRESH into TMEM for every key block.  S is double-buffered so S_{j+1} is computed while the
 //             softmax of block j runs.
-//   warps 2-5 softmax + accumulation, one thread per query row: tcgen05.ld S -> online max / exp2 / row sum in registers
+//   warps 2-9 softmax + accumulation, two threads per query row (32 key columns and half of the O columns each; the row
+//             max is exchanged through smem, a first profile showed 4 softmax warps issue-bound at 30 % tensor activity):
+//             tcgen05.ld S -> online max / exp2 / row sum in registers
 //             -> split P into hi/lo -> tcgen05.st into TMEM; O_total = O_total * corr + O_j with round-to-nearest fp32
 //             adds in registers (the tensor core's accumulation truncates, see kernels_tc.cu; accumulating per block in
 //             registers also makes the online-softmax rescale free).  Final O / l -> global.
@@ -27,7 +29,7 @@ using namespace tc;
 
 constexpr int AQ = 128;        // queries per CTA
 constexpr int AKV = 64;        // keys per block
-constexpr int ATTN_THREADS = 192;
+constexpr int ATTN_THREADS = 320;      // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quadrant)
 
 template <int D>
 struct ACfg {
@@ -42,11 +44,13 @@ struct ACfg {
   static constexpr int OFF_V = 2 * K_STAGE;
   static constexpr int OFF_Q = OFF_V + 2 * V_STAGE;
   static constexpr int OFF_BAR = OFF_Q + Q_STAGE;
-  static constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;
+  static constexpr int OFF_XCHG = OFF_BAR + 256;            // float xchg[2 buffers][2 halves][128 rows]
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 2048 + 512;   // 512 B slack: the dynamic window is declared __align__(1024)
   static constexpr int COL_S = 0, COL_PH = 128, COL_PL = 192, COL_O = 256, COL_QH = 352, COL_QL = 352 + D;
   static_assert(D % 8 == 0 && D >= 16 && D <= 80, "head dim must be a multiple of 8 in [16, 80]");
   static_assert(COL_QL + D <= 512, "TMEM overflow");
   static_assert(SMEM_BYTES <= 232448, "smem overflow");
+  static_assert(NV % 16 == 0, "NV");
 };
 
 struct AttnParams {
@@ -70,6 +74,18 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int D>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_constant__ CUtensorMap mapQl,
@@ -77,7 +93,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
                   const __grid_constant__ CUtensorMap mapVh, const __grid_constant__ CUtensorMap mapVl, const AttnParams p) {
   using C = ACfg<D>;
   constexpr int KB2 = C::KB2, NV = C::NV;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + C::OFF_BAR;
   // barriers (8 B each)
@@ -109,11 +125,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       mbar_init(bar_v_full(s), 1);
       mbar_init(bar_v_empty(s), 1);
       mbar_init(bar_s_full(s), 1);
-      mbar_init(bar_s_empty(s), 4);
+      mbar_init(bar_s_empty(s), 8);
     }
-    mbar_init(bar_p_full, 4);
+    mbar_init(bar_p_full, 8);
     mbar_init(bar_pv_done, 1);
-    mbar_init(bar_o_empty, 4);
+    mbar_init(bar_o_empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -217,46 +233,52 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
     }
   } else {
     // =========================================================================== softmax + accumulation warps
-    const int qd = warp & 3;                       // TMEM lane quadrant (warps 2..5 -> 2,3,0,1)
+    const int qd = warp & 3;                       // TMEM lane quadrant (warps 2..9 -> 2,3,0,1,2,3,0,1)
+    const int hf = (warp - 2) >> 2;                // 0: key columns 0..31 / O columns [0, NV/2), 1: the other halves
     const int row = qd * 32 + lane;                // query row of this thread
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     const uint32_t rbase = (uint32_t)row * 128u, rx = (uint32_t)(row & 7);
+    constexpr int HC = AKV / 2;                    // 32 score columns per thread
+    constexpr int HO = NV / 2;                     // O columns per thread (8, 16, 24, 32, 40)
+    const uint32_t xchg = base + C::OFF_XCHG;      // [buffer][half][row] floats
 
-    // ---- Q planes: staging smem -> TMEM (this thread's row)
+    // ---- Q planes: staging smem -> TMEM (this thread's row); done by the first four warps
+    if (hf == 0) {
 #pragma unroll 1
-    for (int plane = 0; plane < 2; ++plane) {
-      mbar_wait(bar_q_full, plane);
-      const uint32_t col = tmem_base + lane_base + (plane == 0 ? C::COL_QH : C::COL_QL);
+      for (int plane = 0; plane < 2; ++plane) {
+        mbar_wait(bar_q_full, plane);
+        const uint32_t col = tmem_base + lane_base + (plane == 0 ? C::COL_QH : C::COL_QL);
 #pragma unroll
-      for (int c8 = 0; c8 < D / 8; ++c8) {         // 8 floats = two 16-byte chunks
-        const int kb = c8 >> 2, ch = (c8 & 3) * 2;
-        const uint32_t a = base + C::OFF_Q + kb * AQ * 128 + rbase;
-        uint32_t v[8];
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(a + (((uint32_t)ch ^ rx) << 4)));
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(a + (((uint32_t)(ch + 1) ^ rx) << 4)));
-        tmem_st8(col + c8 * 8, v);
+        for (int c8 = 0; c8 < D / 8; ++c8) {         // 8 floats = two 16-byte chunks
+          const int kb = c8 >> 2, ch = (c8 & 3) * 2;
+          const uint32_t a = base + C::OFF_Q + kb * AQ * 128 + rbase;
+          uint32_t v[8];
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(a + (((uint32_t)ch ^ rx) << 4)));
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(a + (((uint32_t)(ch + 1) ^ rx) << 4)));
+          tmem_st8(col + c8 * 8, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(plane == 0 ? bar_q_free : bar_q_ready);
       }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(plane == 0 ? bar_q_free : bar_q_ready);
     }
 
     float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
-    float o[NV];
+    float o[HO];
 #pragma unroll
-    for (int c = 0; c < NV; ++c) o[c] = 0.f;
+    for (int c = 0; c < HO; ++c) o[c] = 0.f;
 
-    auto accumulate_o = [&](int jdone) {          // O_total = O_total * corr + O_blk  (block jdone)
+    auto accumulate_o = [&](int jdone) {          // O_total = O_total * corr + O_blk  (block jdone), this thread's columns
       mbar_wait(bar_pv_done, jdone & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int part = 0; part < NV / 16; ++part) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + lane_base + C::COL_O + part * 16, v);
+      for (int part = 0; part < HO / 8; ++part) {
+        uint32_t v[8];
+        tmem_ld8(tmem_base + lane_base + C::COL_O + hf * HO + part * 8, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int c = 0; c < 16; ++c) o[part * 16 + c] = o[part * 16 + c] * corr_prev + __uint_as_float(v[c]);
+        for (int c = 0; c < 8; ++c) o[part * 8 + c] = o[part * 8 + c] * corr_prev + __uint_as_float(v[c]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -268,28 +290,34 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       const int s = j & 1;
       mbar_wait(bar_s_full(s), (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float sc[AKV];
-#pragma unroll
-      for (int part = 0; part < AKV / 32; ++part) {
+      float sc[HC];
+      {
         uint32_t v[32];
-        tmem_ld32(tmem_base + lane_base + C::COL_S + s * AKV + part * 32, v);
+        tmem_ld32(tmem_base + lane_base + C::COL_S + s * AKV + hf * HC, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int c = 0; c < 32; ++c) sc[part * 32 + c] = __uint_as_float(v[c]) * p.scale_log2e;
+        for (int c = 0; c < HC; ++c) sc[c] = __uint_as_float(v[c]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_s_empty(s));
 
+      // row max over both halves (raw scores; the positive scale commutes with max)
       float mx = sc[0];
 #pragma unroll
-      for (int c = 1; c < AKV; ++c) mx = fmaxf(mx, sc[c]);
+      for (int c = 1; c < HC; ++c) mx = fmaxf(mx, sc[c]);
+      const uint32_t xa = xchg + (uint32_t)(((j & 1) * 2) * 128 + row) * 4u;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xa + (uint32_t)hf * 512u), "f"(mx) : "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      float other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xa + (uint32_t)(hf ^ 1) * 512u) : "memory");
+      mx = fmaxf(mx, other) * p.scale_log2e;
       const float m_new = fmaxf(m_run, mx);
-      const float corr = exp2f(m_run - m_new);           // 0 on the first block (m_run = -inf)
+      const float corr = ex2_approx(m_run - m_new);      // 0 on the first block (m_run = -inf)
       float psum = 0.f;
 #pragma unroll
-      for (int c = 0; c < AKV; ++c) {
-        sc[c] = exp2f(sc[c] - m_new);
+      for (int c = 0; c < HC; ++c) {
+        sc[c] = ex2_approx(fmaf(sc[c], p.scale_log2e, -m_new));
         psum += sc[c];
       }
       l_run = l_run * corr + psum;
@@ -297,37 +325,42 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
 
       if (j >= 1) accumulate_o(j - 1);                   // also guarantees PV_{j-1} finished reading the P buffers
 
-      // P -> hi / lo planes in TMEM
+      // P -> hi / lo planes in TMEM (hi rounded to nearest; lo is left to the tensor core's own truncation: |lo| <= 2^-12 p)
 #pragma unroll
-      for (int c8 = 0; c8 < AKV / 8; ++c8) {
+      for (int c8 = 0; c8 < HC / 8; ++c8) {
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const uint32_t bits = __float_as_uint(sc[c8 * 8 + e]);
-          hi[e] = rn_tf32(bits);
-          lo[e] = rn_tf32(__float_as_uint(sc[c8 * 8 + e] - __uint_as_float(hi[e])));
+          hi[e] = rn_tf32(__float_as_uint(sc[c8 * 8 + e]));
+          lo[e] = __float_as_uint(sc[c8 * 8 + e] - __uint_as_float(hi[e]));
         }
-        tmem_st8(tmem_base + lane_base + C::COL_PH + c8 * 8, hi);
-        tmem_st8(tmem_base + lane_base + C::COL_PL + c8 * 8, lo);
+        tmem_st8(tmem_base + lane_base + C::COL_PH + hf * HC + c8 * 8, hi);
+        tmem_st8(tmem_base + lane_base + C::COL_PL + hf * HC + c8 * 8, lo);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p_full);
-      corr_prev = corr;
-      // note: corr of block j rescales everything accumulated before block j; it is applied when O_blk_j is added
-      if (j == 0) corr_prev = 1.f;                       // nothing accumulated yet (avoid 0 * 0 ambiguity with -inf)
+      corr_prev = (j == 0) ? 1.f : corr;                 // corr_j rescales what was accumulated before block j
     }
-    // the rescale belonging to the last block, then its contribution
     accumulate_o(nb - 1);
 
-    const float inv_l = 1.f / l_run;
-    float* dst = p.out + ((long long)b * p.N + q0 + row) * p.ldo + h * p.d;
+    // total row sum = both halves; exchange through smem (buffer 0 of the max exchange is free again: nb >= 2 or resynced below)
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+    const uint32_t xl = xchg + (uint32_t)row * 4u;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xl + (uint32_t)hf * 512u), "f"(l_run) : "memory");
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+    float l_other;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(xl + (uint32_t)(hf ^ 1) * 512u) : "memory");
+    const float inv_l = 1.f / (l_run + l_other);
+    float* dst = p.out + ((long long)b * p.N + q0 + row) * p.ldo + h * p.d + hf * HO;
 #pragma unroll
-    for (int c = 0; c < D; c += 4) {
-      float4 v;
-      v.x = o[c] * inv_l; v.y = o[c + 1] * inv_l; v.z = o[c + 2] * inv_l; v.w = o[c + 3] * inv_l;
-      *reinterpret_cast<float4*>(dst + c) = v;
+    for (int c = 0; c < HO; c += 4) {
+      if (hf * HO + c < D) {
+        float4 v;
+        v.x = o[c] * inv_l; v.y = o[c + 1] * inv_l; v.z = o[c + 2] * inv_l; v.w = o[c + 3] * inv_l;
+        *reinterpret_cast<float4*>(dst + c) = v;
+      }
     }
   }
 
