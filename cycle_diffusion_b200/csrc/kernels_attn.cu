@@ -39,11 +39,16 @@ struct ACfg {
   static constexpr int K_STAGE = 2 * KB2 * KTILE;           // hi + lo
   static constexpr int VTILE = NV * 128;                    // one 32-key block of V^T: NV rows x 128 B
   static constexpr int V_STAGE = 2 * 2 * VTILE;             // (2 key sub-blocks) x (hi + lo)
-  static constexpr int Q_STAGE = KB2 * AQ * 128;            // one plane of Q
+  static constexpr int Q_STAGE = KB2 * AQ * 128;            // one plane of Q (== K_STAGE)
+  // ring depths: the prefetch distance must cover the TMA latency (a first profile with 2-deep rings had the MMA thread
+  // spinning on k_full); the Q staging buffer is the LAST K stage, which is first needed KS-1 blocks into the loop
+  static constexpr int KS = (D <= 64) ? 4 : 3;
+  static constexpr int VS = (D <= 64) ? 3 : 2;
   static constexpr int OFF_K = 0;
-  static constexpr int OFF_V = 2 * K_STAGE;
-  static constexpr int OFF_Q = OFF_V + 2 * V_STAGE;
-  static constexpr int OFF_BAR = OFF_Q + Q_STAGE;
+  static constexpr int OFF_V = KS * K_STAGE;
+  static constexpr int OFF_Q = (KS - 1) * K_STAGE;
+  static constexpr int OFF_BAR = OFF_V + VS * V_STAGE;
+  static_assert(Q_STAGE == K_STAGE, "Q staging aliases a K stage");
   static constexpr int OFF_XCHG = OFF_BAR + 256;            // float xchg[2 buffers][2 halves][128 rows]
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 2048 + 512;   // 512 B slack: the dynamic window is declared __align__(1024)
   static constexpr int COL_S = 0, COL_PH = 128, COL_PL = 192, COL_O = 256, COL_QH = 352, COL_QL = 352 + D;
@@ -100,16 +105,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
   const uint32_t bar_q_full = bars + 0;          // TMA: a Q plane landed in the staging buffer (2 phases)
   const uint32_t bar_q_free = bars + 8;          // softmax warps: staging buffer consumed (plane 0)
   const uint32_t bar_q_ready = bars + 16;        // softmax warps: Q hi/lo complete in TMEM
-  auto bar_k_full = [&](int s) { return bars + 24u + 8u * s; };
-  auto bar_k_empty = [&](int s) { return bars + 40u + 8u * s; };
-  auto bar_v_full = [&](int s) { return bars + 56u + 8u * s; };
-  auto bar_v_empty = [&](int s) { return bars + 72u + 8u * s; };
-  auto bar_s_full = [&](int s) { return bars + 88u + 8u * s; };
-  auto bar_s_empty = [&](int s) { return bars + 104u + 8u * s; };
-  const uint32_t bar_p_full = bars + 120;
-  const uint32_t bar_pv_done = bars + 128;
-  const uint32_t bar_o_empty = bars + 136;
-  const uint32_t tmem_slot = bars + 144;
+  constexpr int KS = C::KS, VS = C::VS;
+  auto bar_k_full = [&](int s) { return bars + 24u + 8u * s; };      // 4 slots
+  auto bar_k_empty = [&](int s) { return bars + 56u + 8u * s; };     // 4 slots
+  auto bar_v_full = [&](int s) { return bars + 88u + 8u * s; };      // 3 slots
+  auto bar_v_empty = [&](int s) { return bars + 112u + 8u * s; };    // 3 slots
+  auto bar_s_full = [&](int s) { return bars + 136u + 8u * s; };
+  auto bar_s_empty = [&](int s) { return bars + 152u + 8u * s; };
+  const uint32_t bar_p_full = bars + 168;
+  const uint32_t bar_pv_done = bars + 176;
+  const uint32_t bar_o_empty = bars + 184;
+  const uint32_t tmem_slot = bars + 192;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
@@ -119,11 +125,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
     mbar_init(bar_q_full, 1);
     mbar_init(bar_q_free, 4);
     mbar_init(bar_q_ready, 4);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < KS; ++s) {
       mbar_init(bar_k_full(s), 1);
       mbar_init(bar_k_empty(s), 1);
+    }
+    for (int s = 0; s < VS; ++s) {
       mbar_init(bar_v_full(s), 1);
       mbar_init(bar_v_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(bar_s_full(s), 1);
       mbar_init(bar_s_empty(s), 8);
     }
@@ -153,8 +163,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       mbar_expect_tx(bar_q_full, C::Q_STAGE);
       for (int kb = 0; kb < KB2; ++kb) tma_load_4d(sq + kb * AQ * 128, &mapQl, kb * 32, h, q0, b, bar_q_full);
       for (int j = 0; j < nb; ++j) {
-        const int s = j & 1, it = j >> 1;
+        const int s = j % KS, it = j / KS;
         // K block j: [64 keys x d] hi + lo
+        if (j == KS - 1) mbar_wait(bar_q_ready, 0);            // the last K stage doubles as the Q staging buffer
         mbar_wait(bar_k_empty(s), (it & 1) ^ 1);
         const uint32_t sk = base + C::OFF_K + s * C::K_STAGE;
         mbar_expect_tx(bar_k_full(s), C::K_STAGE);
@@ -163,12 +174,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           tma_load_4d(sk + (KB2 + kb) * C::KTILE, &mapKl, kb * 32, h, j * AKV, b, bar_k_full(s));
         }
         // V^T block j: [NV channel rows x 64 keys] as two 32-key tiles, hi + lo
-        mbar_wait(bar_v_empty(s), (it & 1) ^ 1);
-        const uint32_t sv = base + C::OFF_V + s * C::V_STAGE;
-        mbar_expect_tx(bar_v_full(s), C::V_STAGE);
+        const int sv_ = j % VS, itv = j / VS;
+        mbar_wait(bar_v_empty(sv_), (itv & 1) ^ 1);
+        const uint32_t sv = base + C::OFF_V + sv_ * C::V_STAGE;
+        mbar_expect_tx(bar_v_full(sv_), C::V_STAGE);
         for (int kk = 0; kk < 2; ++kk) {
-          tma_load_4d(sv + kk * C::VTILE, &mapVh, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(s));
-          tma_load_4d(sv + (2 + kk) * C::VTILE, &mapVl, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(s));
+          tma_load_4d(sv + kk * C::VTILE, &mapVh, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(sv_));
+          tma_load_4d(sv + (2 + kk) * C::VTILE, &mapVl, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(sv_));
         }
       }
     }
@@ -182,8 +194,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       const uint32_t o_acc = tmem_base + C::COL_O;
 
       auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        const uint32_t sk = base + C::OFF_K + s * C::K_STAGE;
+        const int s = j & 1, ks = j % KS;
+        const uint32_t sk = base + C::OFF_K + ks * C::K_STAGE;
         const uint32_t s_acc = tmem_base + C::COL_S + s * AKV;
 #pragma unroll
         for (int c = 0; c < D / 8; ++c) {      // K chunks of 8 floats along the head dim
@@ -196,7 +208,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           umma_ts(s_acc, q_hi + c * 8, k_hi, idesc_qk, 1u);
         }
         umma_commit(bar_s_full(s));
-        umma_commit(bar_k_empty(s));
+        umma_commit(bar_k_empty(ks));
       };
 
       mbar_wait(bar_q_ready, 0);
@@ -206,17 +218,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       for (int j = 0; j < nb; ++j) {
         if (j + 1 < nb) {
           const int s1 = (j + 1) & 1;
-          mbar_wait(bar_k_full(s1), ((j + 1) >> 1) & 1);
+          mbar_wait(bar_k_full((j + 1) % KS), ((j + 1) / KS) & 1);
           if (j + 1 >= 2) mbar_wait(bar_s_empty(s1), (((j + 1) >> 1) - 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           issue_qk(j + 1);
         }
-        const int s = j & 1;
+        const int vs = j % VS;
+        mbar_wait(bar_v_full(vs), (j / VS) & 1);
         mbar_wait(bar_p_full, j & 1);
-        mbar_wait(bar_v_full(s), (j >> 1) & 1);
         if (j >= 1) mbar_wait(bar_o_empty, (j - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sv = base + C::OFF_V + s * C::V_STAGE;
+        const uint32_t sv = base + C::OFF_V + vs * C::V_STAGE;
 #pragma unroll
         for (int c = 0; c < AKV / 8; ++c) {    // K chunks of 8 keys
           const int kk = c >> 2;
@@ -228,7 +240,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           umma_ts(o_acc, p_hi + c * 8, v_hi, idesc_pv, 1u);
         }
         umma_commit(bar_pv_done);
-        umma_commit(bar_v_empty(s));
+        umma_commit(bar_v_empty(vs));
       }
     }
   } else {
