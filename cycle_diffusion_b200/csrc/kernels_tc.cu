@@ -31,6 +31,8 @@
 //               tensor core: the ncu profile of the SS variant showed shared-memory bandwidth (LSU split traffic +
 //               tensor-core operand fetch ~ 84 % of smem cycles, tensor pipe 33 % active) as the limiter.
 //               4 stages x 48 KB; TMEM: 2 x 128 accumulator columns + 4 x 64 A columns = 512.
+#include <algorithm>
+
 #include "tc_common.cuh"
 
 namespace cdx {
@@ -72,7 +74,11 @@ struct TcParams {
   int a_code[4], b_code[4];   // per map dim: 0 -> k0, 1 -> row0, 2 -> zh, 3 -> zb, 4 -> 0
   int a_rowoff_h, b_rowoff_h; // row0 += zh * rowoff (heads packed along the row dimension)
   long long sC_b, sC_h;       // output offsets per zb / zh
+  // persistent tile scheduler: tile t -> (tm = t % tiles_m, tn = (t / tiles_m) % tiles_n, z = t / (tiles_m * tiles_n))
+  int tiles_m, tiles_n, total_tiles;
 };
+
+struct TileCoord { int n0, m0, x0, y0, b0, zb, zh; };
 
 template <bool TS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -123,28 +129,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // ---- tile coordinates
-  const int n0 = blockIdx.y * TBN;
-  int m0 = 0, x0 = 0, y0 = 0, b0 = 0, zb = 0, zh = 0;
-  if (p.mode == 0) {
-    m0 = blockIdx.x * TBM;
-  } else if (p.mode == 2) {
-    m0 = blockIdx.x * TBM;
-    zb = blockIdx.z / p.heads;
-    zh = blockIdx.z - zb * p.heads;
-  } else {
-    int t = blockIdx.x;
-    const int tx = t % p.tiles_x; t /= p.tiles_x;
-    const int ty = t % p.tiles_y; t /= p.tiles_y;
-    x0 = tx * p.bw; y0 = ty * p.bh; b0 = t * p.bn;
-  }
+  // ---- persistent tile loop: every role walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... with GLOBAL k-block and
+  // chunk counters, so the smem ring and the two TMEM accumulator buffers keep rolling across tiles and the MMAs of tile
+  // i+1 overlap the global stores of tile i
+  auto tile_coord = [&](int t) {
+    TileCoord c;
+    const int tm = t % p.tiles_m;
+    const int r = t / p.tiles_m;
+    const int tn = r % p.tiles_n, z = r / p.tiles_n;
+    c.n0 = tn * TBN;
+    c.m0 = 0; c.x0 = 0; c.y0 = 0; c.b0 = 0; c.zb = 0; c.zh = 0;
+    if (p.mode == 1) {
+      int u = tm;
+      const int tx = u % p.tiles_x; u /= p.tiles_x;
+      const int ty = u % p.tiles_y; u /= p.tiles_y;
+      c.x0 = tx * p.bw; c.y0 = ty * p.bh; c.b0 = u * p.bn;
+    } else {
+      c.m0 = tm * TBM;
+      c.zb = z / p.heads;
+      c.zh = z - c.zb * p.heads;
+    }
+    return c;
+  };
 
   if (warp == 0) {
     // =========================================================================== TMA producer
     if (lane == 0) {
       const int cblocks = p.mode == 1 ? p.Cin / TBK : 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES, it = kb / STAGES;
+      int gkb = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc_ = tile_coord(t);
+      const int n0 = tc_.n0, m0 = tc_.m0, x0 = tc_.x0, y0 = tc_.y0, b0 = tc_.b0, zb = tc_.zb, zh = tc_.zh;
+      for (int kb = 0; kb < num_kb; ++kb, ++gkb) {
+        const int s = gkb % STAGES, it = gkb / STAGES;
         mbar_wait(bar_empty(s), (it & 1) ^ 1);
         const uint32_t st = base + s * STAGE_BYTES;
         const uint32_t sa = st + OFF_A, sb = st + OFF_BHI;
@@ -172,14 +189,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tma_load_2d(sb, &mapB, k0, n0, bar_full_raw(s));
         if (TS) tma_load_2d(st + OFF_BLO, &mapBlo, k0, n0, bar_full_raw(s));
       }
+      }
     }
   } else if (warp == 1) {
     // =========================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES, it = kb / STAGES;
-        const int chunk = kb / KCHUNK, buf = chunk & 1, kin = kb - chunk * KCHUNK;
+      int gkb = 0, gchunk0 = 0;
+      const int chunks_per_tile = (num_kb + KCHUNK - 1) / KCHUNK;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, gchunk0 += chunks_per_tile)
+      for (int kb = 0; kb < num_kb; ++kb, ++gkb) {
+        const int s = gkb % STAGES, it = gkb / STAGES;
+        const int lchunk = kb / KCHUNK, kin = kb - lchunk * KCHUNK;
+        const int chunk = gchunk0 + lchunk, buf = chunk & 1;
         if (kin == 0 && chunk >= 2) {       // the buffer's previous chunk must have been drained
           mbar_wait(bar_acc_empty(buf), ((chunk >> 1) - 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -220,8 +242,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int row = q * 32 + lane;
       const uint32_t rbase = (uint32_t)row * 128u;
       const uint32_t rx = (uint32_t)(row & 7);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES, it = kb / STAGES;
+      int gkb = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x)
+      for (int kb = 0; kb < num_kb; ++kb, ++gkb) {
+        const int s = gkb % STAGES, it = gkb / STAGES;
         mbar_wait(bar_full_raw(s), it & 1);
         const uint32_t sa = base + s * STAGE_BYTES + OFF_A + rbase;
         uint32_t hi[32], lo[32];
@@ -246,8 +270,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     } else {
       const int st_ = threadIdx.x - 64;        // 0..127
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES, it = kb / STAGES;
+      int gkb = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x)
+      for (int kb = 0; kb < num_kb; ++kb, ++gkb) {
+        const int s = gkb % STAGES, it = gkb / STAGES;
         mbar_wait(bar_full_raw(s), it & 1);
         const uint32_t sa = base + s * STAGE_BYTES;
 #pragma unroll 4
@@ -274,11 +300,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // =========================================================================== drain + epilogue warps
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access (warps 6..9 -> 2,3,0,1)
     const int r = q * 32 + lane;                   // tile row owned by this thread
+    const int num_chunks = (num_kb + KCHUNK - 1) / KCHUNK;
+    int gchunk0 = 0;
+#pragma unroll 1
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, gchunk0 += num_chunks) {
+    const TileCoord tc_ = tile_coord(t);
+    const int n0 = tc_.n0, m0 = tc_.m0, x0 = tc_.x0, y0 = tc_.y0, b0 = tc_.b0, zb = tc_.zb, zh = tc_.zh;
     float acc[TBN];
 #pragma unroll
     for (int j = 0; j < TBN; ++j) acc[j] = 0.f;
-    const int num_chunks = (num_kb + KCHUNK - 1) / KCHUNK;
-    for (int chunk = 0; chunk < num_chunks; ++chunk) {
+#pragma unroll 1
+    for (int lchunk = 0; lchunk < num_chunks; ++lchunk) {
+      const int chunk = gchunk0 + lchunk;
       const int buf = chunk & 1;
       mbar_wait(bar_acc_full(buf), (chunk >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -327,6 +360,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
     }
+    }   // tile loop
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -398,7 +432,8 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     const CUtensorMap& mA = get_map(q, 4, da, sa, bx);
     const CUtensorMap& mB = get_map(k, 4, db, sb, bx);
     ProfScope ps(e, s, PROF_BATCHED_TC, 2.0 * Nq * Nk * d * B * heads, 4.0 * B * heads * ((double)Nq * d + (double)Nk * d + (double)Nq * Nk), 1);
-    tc_gemm_kernel<false><<<dim3(cdiv(Nq, TBM), cdiv(Nk, TBN), B * heads), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
+    p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(Nk, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
+    tc_gemm_kernel<false><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -422,7 +457,8 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     const CUtensorMap& mA = get_map(S, 4, da, sa, bxa);
     const CUtensorMap& mB = get_map(vt, 4, db, sb, bxb);
     ProfScope ps(e, s, PROF_BATCHED_TC, 2.0 * Nq * Nk * d * B * heads, 4.0 * B * heads * ((double)Nq * Nk + (double)Nk * d + (double)Nq * d), 1);
-    tc_gemm_kernel<false><<<dim3(cdiv(Nq, TBM), cdiv(d, TBN), B * heads), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
+    p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(d, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
+    tc_gemm_kernel<false><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -449,7 +485,6 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   p.alpha = a.alpha;
   p.heads = 1;
   const CUtensorMap *mA, *mA2, *mB, *mBlo;
-  dim3 grid;
   if (a.mode == 0) {
     if (a.K & 3) return false;
     if (a.A2) {
@@ -468,7 +503,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
     } else {
       mA2 = mA;
     }
-    grid = dim3(cdiv(a.M, TBM), cdiv(a.N, TBN), 1);
+    p.tiles_m = cdiv(a.M, TBM);
   } else {
     const int Cin = a.C1;
     if (a.A2 || a.stride != 1 || a.pad != 1 || a.up != 1) return false;
@@ -487,8 +522,11 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
     uint32_t bx[4] = {TBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
     mA = &get_map(a.A, 4, d, st, bx);
     mA2 = mA;
-    grid = dim3(p.tiles_x * p.tiles_y * cdiv(B, bn), cdiv(a.N, TBN), 1);
+    p.tiles_m = p.tiles_x * p.tiles_y * cdiv(B, bn);
   }
+  p.tiles_n = cdiv(a.N, TBN);
+  p.total_tiles = p.tiles_m * p.tiles_n;
+  const int grid = std::min(p.total_tiles, e.num_sms);
   const bool ts = a.Bw_hi != nullptr && a.Bw_lo != nullptr && a16(a.Bw_hi) && a16(a.Bw_lo);
   {
     uint64_t d[2] = {(uint64_t)a.K, (uint64_t)a.N}, st[1] = {(uint64_t)a.ldb * 4};
