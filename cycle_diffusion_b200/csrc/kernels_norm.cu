@@ -38,7 +38,21 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
       double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
       const float* base = (c < C1) ? (x1 + (long long)b * HW * C1 + c) : (x2 + (long long)b * HW * C2 + (c - C1));
       const int ldx = (c < C1) ? C1 : C2;
-      for (int r = r0 + tr; r < r1; r += nrow_par) {
+      int r = r0 + tr;
+      for (; r + 3 * nrow_par < r1; r += 4 * nrow_par) {      // 4 independent 128-bit loads in flight per thread
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(base + (long long)(r + u * nrow_par) * ldx);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double d0 = v[u].x, d1 = v[u].y, d2 = v[u].z, d3 = v[u].w;
+          s[0] += d0; q[0] += d0 * d0;
+          s[1] += d1; q[1] += d1 * d1;
+          s[2] += d2; q[2] += d2 * d2;
+          s[3] += d3; q[3] += d3 * d3;
+        }
+      }
+      for (; r < r1; r += nrow_par) {
         const float4 v = *reinterpret_cast<const float4*>(base + (long long)r * ldx);
         const double d0 = v.x, d1 = v.y, d2 = v.z, d3 = v.w;
         s[0] += d0; q[0] += d0 * d0;
@@ -79,37 +93,61 @@ __global__ void gn_finalize_kernel(const double* __restrict__ part, int nchunk, 
   mean_rstd[(b * GN_GROUPS + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// grid (row chunks, B); thread (tr, tc) owns channel vectors tc, tc+ncol, ... (so group / affine coefficients are hoisted out
+// of the row loop as y = x * sc + sh, the form ATen's CPU kernel uses) and walks the chunk's rows 4 at a time
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ mean_rstd, int silu,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
-                                                       int ld_ss, float* __restrict__ y, int HW, long long total4) {
+                                                       int ld_ss, float* __restrict__ y, int HW, int rows_per_chunk) {
   const int C = C1 + C2;
   const int cpg = C / GN_GROUPS;
   const int C4 = C >> 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / C4;           // b*HW + r
-    const int c = (int)(i % C4) * 4;
-    const int b = (int)(row / HW);
-    const float4 v = (c < C1) ? *reinterpret_cast<const float4*>(x1 + row * C1 + c)
-                              : *reinterpret_cast<const float4*>(x2 + row * C2 + (c - C1));
-    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
-    const float4 be = *reinterpret_cast<const float4*>(beta + c);
-    const float e[4] = {v.x, v.y, v.z, v.w};
-    const float gg[4] = {ga.x, ga.y, ga.z, ga.w};
-    const float bb[4] = {be.x, be.y, be.z, be.w};
-    float o[4];
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_chunk;
+  const int r1 = min(HW, r0 + rows_per_chunk);
+  const int ncol = min(C4, (int)blockDim.x);
+  const int nrow_par = blockDim.x / ncol;
+  const int tr = threadIdx.x / ncol, tc = threadIdx.x - tr * ncol;
+  if (tr >= nrow_par) return;
+  for (int c4 = tc; c4 < C4; c4 += ncol) {
+    const int c = c4 * 4;
+    float sc[4], sh[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int g = (c + j) / cpg;
       const float mean = mean_rstd[(b * GN_GROUPS + g) * 2 + 0];
       const float rstd = mean_rstd[(b * GN_GROUPS + g) * 2 + 1];
-      float t = (e[j] - mean) * rstd * gg[j] + bb[j];
-      if (scale) t = t * (1.f + scale[(long long)b * ld_ss + c + j]) + shift[(long long)b * ld_ss + c + j];
-      if (silu) t = silu_f(t);
-      o[j] = t;
+      float a = rstd * gamma[c + j];
+      float o = beta[c + j] - mean * a;
+      if (scale) {      // gn(x) * (1 + scale) + shift   (improved-DDPM scale-shift norm)
+        const float s1 = 1.f + scale[(long long)b * ld_ss + c + j];
+        a *= s1;
+        o = o * s1 + shift[(long long)b * ld_ss + c + j];
+      }
+      sc[j] = a; sh[j] = o;
     }
-    *reinterpret_cast<float4*>(y + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+    const float* src = (c < C1) ? (x1 + (long long)b * HW * C1 + c) : (x2 + (long long)b * HW * C2 + (c - C1));
+    const int ldx = (c < C1) ? C1 : C2;
+    float* dst = y + (long long)b * HW * C + c;
+    auto act = [&](float4 v) {
+      float t[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
+      if (silu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = __fdividef(t[j], 1.f + __expf(-t[j]));
+      }
+      return make_float4(t[0], t[1], t[2], t[3]);
+    };
+    int r = r0 + tr;
+    for (; r + 3 * nrow_par < r1; r += 4 * nrow_par) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(src + (long long)(r + u * nrow_par) * ldx);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(dst + (long long)(r + u * nrow_par) * C) = act(v[u]);
+    }
+    for (; r < r1; r += nrow_par)
+      *reinterpret_cast<float4*>(dst + (long long)r * C) = act(*reinterpret_cast<const float4*>(src + (long long)r * ldx));
   }
 }
 
@@ -194,9 +232,11 @@ void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, cons
   ProfScope ps(e, s, PROF_GROUPNORM, 0.0, 2.0 * 4.0 * B * (double)HW * C, 3);   // algorithmic: one read + one write
   gn_stats_kernel<<<dim3(nchunk, B), 256, 0, s>>>(x1, C1, x2, C2, HW, rows_per_chunk, part);
   gn_finalize_kernel<<<B, GN_GROUPS, 0, s>>>(part, nchunk, 1.0 / ((double)HW * (C / GN_GROUPS)), eps, mr);
-  const long long total4 = (long long)B * HW * (C / 4);
-  int blocks = (int)std::min<long long>((total4 + 255) / 256, (long long)e.num_sms * 16);
-  gn_apply_kernel<<<blocks, 256, 0, s>>>(x1, C1, x2, C2, gamma, beta, mr, silu ? 1 : 0, scale, shift, ld_ss, y, HW, total4);
+  int achunk = cdiv(8LL * e.num_sms, B);
+  if (achunk > HW) achunk = HW;
+  const int arows = cdiv(HW, achunk);
+  achunk = cdiv(HW, arows);
+  gn_apply_kernel<<<dim3(achunk, B), 256, 0, s>>>(x1, C1, x2, C2, gamma, beta, mr, silu ? 1 : 0, scale, shift, ld_ss, y, HW, arows);
   CDX_CUDA(cudaGetLastError());
   e.launches += 3;
 }

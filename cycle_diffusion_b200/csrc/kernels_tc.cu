@@ -64,11 +64,13 @@ struct TcParams {
   int H, W, B;              // conv: spatial size (in == out) and batch
   int bw, bh, bn;           // conv: pixel box of one M tile (bw*bh*bn == 128)
   int tiles_x, tiles_y;     // conv: tiles per row / column
+  int cstride, cpad;        // conv: stride (1 or 2: TMA element traversal stride) and low-side padding
   float* C; int ldc;
   const float* bias;
   const float* rowvec; int ld_rowvec; int rows_per_batch;
   const float* residual; int ldr;
   float alpha;
+  int out_nchw, rows_per_img;   // store C as [B, N, rows_per_img] (final conv of a network, reference NCHW layout)
   // mode 2 (blockIdx.z = zb*heads + zh): 4D maps, coordinate recipe per operand
   int heads;
   int a_code[4], b_code[4];   // per map dim: 0 -> k0, 1 -> row0, 2 -> zh, 3 -> zb, 4 -> 0
@@ -184,7 +186,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else {
           const int tap = kb / cblocks, cb = kb - tap * cblocks;
           const int dy = tap / 3, dx = tap - dy * 3;
-          tma_load_4d(sa, &mapA, cb * TBK, x0 + dx - 1, y0 + dy - 1, b0, bar_full_raw(s));   // OOB -> zeros = padding
+          tma_load_4d(sa, &mapA, cb * TBK, x0 * p.cstride + dx - p.cpad, y0 * p.cstride + dy - p.cpad, b0, bar_full_raw(s));   // OOB -> zeros = padding
         }
         tma_load_2d(sb, &mapB, k0, n0, bar_full_raw(s));
         if (TS) tma_load_2d(st + OFF_BLO, &mapBlo, k0, n0, bar_full_raw(s));
@@ -340,7 +342,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       row_ok = b < p.B;
       m = ((long long)b * p.H + (y0 + yl)) * p.W + (x0 + xl);
     }
-    if (row_ok) {
+    if (row_ok && p.out_nchw) {
+      const long long bimg = m / p.rows_per_img, rimg = m - bimg * p.rows_per_img;
+#pragma unroll
+      for (int j = 0; j < TBN; ++j) {
+        const int n = n0 + j;
+        if (n < p.N) {
+          float o = p.alpha * acc[j];
+          if (p.bias) o += p.bias[n];
+          p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = o;        // consecutive lanes = consecutive pixels: coalesced
+        }
+      }
+    } else if (row_ok) {
       const float* rv = p.rowvec ? p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec : nullptr;
       const float* rs = p.residual ? p.residual + m * p.ldr : nullptr;
       float* crow = p.C + zb * p.sC_b + zh * p.sC_h + m * p.ldc;
@@ -467,13 +480,16 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
 
 bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   // ---- eligibility (everything else takes the FFMA tiles)
-  if (a.batch * a.heads != 1 || a.b_kn || a.out_nchw) return false;
+  if (a.batch * a.heads != 1 || a.b_kn) return false;
+  if (a.out_nchw && (a.rowvec || a.residual)) return false;
   if ((a.N & 3) || (a.ldc & 3) || !a16(a.Cout) || !a16(a.Bw) || (a.ldb & 3)) return false;
   if (a.bias && !a16(a.bias)) return false;
   if (a.rowvec && (!a16(a.rowvec) || (a.ld_rowvec & 3))) return false;
   if (a.residual && (!a16(a.residual) || (a.ldr & 3))) return false;
   if (!a16(a.A) || (a.lda & 3)) return false;
-  if (a.M < 64 || a.N < 32) return false;           // tiny problems: tile quantisation loses to the FFMA 64x64 tiles
+  if (a.M < 64) return false;
+  if (a.N < 32 && a.M < 2048) return false;         // tiny problems: tile quantisation loses to the FFMA 64x64 tiles; thin-N with a
+                                                    // large M (e.g. the 320 -> 4 output conv) still wins by a wide margin
 
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -483,6 +499,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec; p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
   p.residual = a.residual; p.ldr = a.ldr;
   p.alpha = a.alpha;
+  p.out_nchw = a.out_nchw; p.rows_per_img = a.rows_per_img > 0 ? a.rows_per_img : 1;
   p.heads = 1;
   const CUtensorMap *mA, *mA2, *mB, *mBlo;
   if (a.mode == 0) {
@@ -506,21 +523,24 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
     p.tiles_m = cdiv(a.M, TBM);
   } else {
     const int Cin = a.C1;
-    if (a.A2 || a.stride != 1 || a.pad != 1 || a.up != 1) return false;
+    if (a.A2 || (a.stride != 1 && a.stride != 2) || a.up != 1) return false;
     if (Cin % TBK) return false;
-    if (a.Hin != a.Hout || a.Win != a.Wout || !pow2(a.Hin) || !pow2(a.Win)) return false;
+    if (a.Hin != a.Hout * a.stride || a.Win != a.Wout * a.stride || !pow2(a.Hout) || !pow2(a.Wout)) return false;
     const int B = a.M / (a.Hout * a.Wout);
-    int bw = a.Win < 16 ? a.Win : 16;
-    int bh = a.Hin < TBM / bw ? a.Hin : TBM / bw;
+    int bw = a.Wout < 16 ? a.Wout : 16;
+    int bh = a.Hout < TBM / bw ? a.Hout : TBM / bw;
     int bn = TBM / (bw * bh);
-    if (bn > 256) return false;
-    p.mode = 1; p.Cin = Cin; p.H = a.Hin; p.W = a.Win; p.B = B;
+    if (bn > 256 || bw * a.stride > 256 || bh * a.stride > 256) return false;
+    p.mode = 1; p.Cin = Cin; p.H = a.Hout; p.W = a.Wout; p.B = B;      // H, W: OUTPUT grid (tile -> row mapping)
     p.bw = bw; p.bh = bh; p.bn = bn;
-    p.tiles_x = a.Win / bw; p.tiles_y = a.Hin / bh;
+    p.cstride = a.stride; p.cpad = a.pad;
+    p.tiles_x = a.Wout / bw; p.tiles_y = a.Hout / bh;
     uint64_t d[4] = {(uint64_t)Cin, (uint64_t)a.Win, (uint64_t)a.Hin, (uint64_t)B};
     uint64_t st[3] = {(uint64_t)a.lda * 4, (uint64_t)a.lda * 4 * a.Win, (uint64_t)a.lda * 4 * a.Win * a.Hin};
-    uint32_t bx[4] = {TBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
-    mA = &get_map(a.A, 4, d, st, bx);
+    // stride 2 (Downsample convs): TMA traverses every 2nd pixel; box = 2x the number of pixels wanted
+    uint32_t bx[4] = {TBK, (uint32_t)(bw * a.stride), (uint32_t)(bh * a.stride), (uint32_t)bn};
+    uint32_t es[4] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1};
+    mA = &get_map(a.A, 4, d, st, bx, es);
     mA2 = mA;
     p.tiles_m = p.tiles_x * p.tiles_y * cdiv(B, bn);
   }

@@ -130,19 +130,21 @@ inline EncodeTiledFn get_encode() {
 struct MapKey {
   const void* ptr;
   uint64_t dims[4], strides[3];
-  uint32_t box[4];
+  uint32_t box[4], es[4];
   int rank;
   bool operator<(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
 };
 
 // fp32, 128B swizzle, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
-inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
+// `estr` (optional): element traversal strides; with stride s along a dim, box[i] = n*s loads n elements.
+inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
+                                  const uint32_t* estr = nullptr) {
   static std::map<MapKey, CUtensorMap> cache;
   MapKey k;
   memset(&k, 0, sizeof(k));
   k.ptr = ptr;
   k.rank = rank;
-  for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+  for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.es[i] = estr ? estr[i] : 1; }
   for (int i = 0; i < rank - 1; ++i) k.strides[i] = strides[i];
   auto it = cache.find(k);
   if (it != cache.end()) return it->second;
@@ -151,7 +153,7 @@ inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dim
   cuuint64_t gd[4];
   cuuint64_t gs[3];
   cuuint32_t bx[4], es[4];
-  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estr ? estr[i] : 1; }
   for (int i = 0; i < rank - 1; ++i) gs[i] = strides[i];
   EncodeTiledFn enc = get_encode();
   if (!enc) throw Error(CDX_E_CUDA, "cuTensorMapEncodeTiled entry point not available");

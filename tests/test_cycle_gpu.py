@@ -130,3 +130,70 @@ def test_model_api_and_factory(eng):
     (orig, img), loss, losses = m(torch.tensor([0]), image, ['a'], ['b'])
     assert orig is image and img.shape == (1, 3, 128, 128) and loss.shape == (1,) and losses == {}
     assert torch.isfinite(img).all()
+
+
+def test_ldm_wrapper_vs_oracle(eng):
+    """LatentDiffStochasticTextWrapper (BASELINE config 4 class): posterior MEAN (latentdiff/.../ddpm.py:537-538), 2 ensemble
+    members (two skip_steps) x 1 decoder scale, ranked by an injected scorer."""
+    from cycle_diffusion_b200.wrappers import LatentDiffStochasticTextWrapper, SyntheticTextEncoder
+    from oracle import dpm_encoder, unet_openai, vae_kl
+    usd = specs.synth_state_dict(specs.openai_unet_params(NARROW), 11)
+    vsd = specs.synth_state_dict(specs.kl_vae_params(VAE_SMALL), 21)
+    sd = {'model.diffusion_model.' + k: v for k, v in usd.items()}
+    sd.update({'first_stage_model.' + k: v for k, v in vsd.items()})
+    cond = SyntheticTextEncoder(48)
+    kw = dict(custom_steps=5, eta=0.1, white_box_steps=6, skip_steps=[1, 2], encoder_unconditional_guidance_scales=[1.0],
+              decoder_unconditional_guidance_scales=[2.0], n_trials=1)
+    ranker = lambda img, orig, et, dt: (None, -(img - orig).flatten(1).abs().mean(1))      # stand-in for DirectionalCLIP
+    w = LatentDiffStochasticTextWrapper('synthetic', engine=eng, state_dict=sd, cond_stage=cond, unet_config=NARROW, vae_config=VAE_SMALL,
+                                        latent_size=16, resolution=128, ranker=ranker, **kw)
+    assert w.resolution == 128 and not w.generator.sample_posterior
+    image = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(3))
+    torch.manual_seed(321)
+    z_ens = w.encode(image, ['a', 'b'])
+    img = w(z_ens, image.to(eng.device), ['a', 'b'], ['c', 'd']).cpu()
+    ora = dpm_encoder.LatentCycle(lambda x, t, c: unet_openai.unet_forward(usd, NARROW, x, t, c),
+                                  lambda im: vae_kl.encode_moments(vsd, VAE_SMALL, im), lambda zz: vae_kl.decode(vsd, VAE_SMALL, zz), cond,
+                                  channels=4, latent_size=16, resolution=128, sample_posterior=False, **kw)
+    torch.manual_seed(321)
+    with torch.no_grad():
+        z_ref = ora.encode(image, ['a', 'b'])
+        imgs_ref = ora.forward_all(z_ref, ['c', 'd'])
+    assert len(z_ens) == 2 and z_ens[0].shape[1] == 5 * 4 * 16 * 16 and z_ens[1].shape[1] == 4 * 4 * 16 * 16
+    for a, b in zip(z_ens, z_ref):
+        assert maxdiff(a.cpu(), b) / float(b.abs().max()) < 2e-4
+    scores = torch.stack([ranker(i, image, None, None)[1] for i in imgs_ref], dim=1)
+    best = scores.argmax(1)
+    ref = torch.stack([imgs_ref[best[b].item()][b] for b in range(2)])
+    print(f'ldm wrapper: |d img| {maxdiff(img, ref):.2e}')
+    assert maxdiff(img, ref) < 1e-3
+
+
+def test_pipeline_surface(eng):
+    """CycleDiffusionPipeline.__call__ (Diffusers-style; unpinned surface): same-prompt cycle reproduces the input image's
+    VAE reconstruction, strength maps to skip_steps, tuple / dataclass returns."""
+    from cycle_diffusion_b200.pipeline import CycleDiffusionPipeline
+    from cycle_diffusion_b200.wrappers import SDStochasticTextWrapper, SyntheticTextEncoder
+    usd = specs.synth_state_dict(specs.openai_unet_params(NARROW), 11)
+    vsd = specs.synth_state_dict(specs.kl_vae_params(VAE_SMALL), 21)
+    sd = {'model.diffusion_model.' + k: v for k, v in usd.items()}
+    sd.update({'first_stage_model.' + k: v for k, v in vsd.items()})
+    w = SDStochasticTextWrapper('synthetic', custom_steps=4, eta=0.1, white_box_steps=5, skip_steps=[0], encoder_unconditional_guidance_scales=[1],
+                                decoder_unconditional_guidance_scales=[1], n_trials=1, engine=eng, state_dict=sd, cond_stage=SyntheticTextEncoder(48),
+                                unet_config=NARROW, vae_config=VAE_SMALL, latent_size=16, resolution=128)
+    pipe = CycleDiffusionPipeline.from_wrapper(w)
+    image = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(4))
+    gen = torch.Generator().manual_seed(9)
+    out = pipe('a cat', 'a cat', image, strength=0.75, num_inference_steps=8, guidance_scale=1.0, source_guidance_scale=1.0, eta=0.1, generator=gen)
+    # same prompt + same guidance: the cycle is the identity on the latent, so the output is decode(encode(image))
+    g = w.generator
+    gen = torch.Generator().manual_seed(9)
+    mom = g.encode_first_stage(eng.shift_scale(image, -0.5, 2.0))
+    x0 = eng.vae_posterior(mom, torch.randn(1, 4, 16, 16, generator=gen), 0.18215)
+    rec = eng.shift_scale(g.decode_first_stage(x0), 1.0, 0.5).clamp(0, 1)
+    assert out.images.shape == (1, 3, 128, 128)
+    assert maxdiff(out.images.cpu(), rec.cpu()) < 1e-3
+    tup = pipe(['a dog'], ['a cat'], image, num_inference_steps=4, return_dict=False, output_type='np')
+    assert isinstance(tup, tuple) and tup[0].shape == (1, 128, 128, 3)
+    with pytest.raises(ValueError):
+        pipe('a', 'b', image, strength=1.5)
