@@ -19,7 +19,7 @@
 //             -> split P into hi/lo -> tcgen05.st into TMEM; O_total = O_total * corr + O_j with round-to-nearest fp32
 //             adds in registers (the tensor core's accumulation truncates, see kernels_tc.cu; accumulating per block in
 //             registers also makes the online-softmax rescale free).  Final O / l -> global.
-// TMEM columns: S0 0..63, S1 64..127, P_hi 128..191, P_lo 192..255, O 256..(256+NV), Q_hi 352.., Q_lo 352+d..  (<= 512).
+// TMEM columns (<= 512): [S x SB][P hi|lo x PB][O x PB][Q_hi][Q_lo], see ACfg.
 #include "tc_common.cuh"
 
 namespace cdx {
@@ -51,7 +51,16 @@ struct ACfg {
   static_assert(Q_STAGE == K_STAGE, "Q staging aliases a K stage");
   static constexpr int OFF_XCHG = OFF_BAR + 256;            // float xchg[2 buffers][2 halves][128 rows]
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 2048 + 512;   // 512 B slack: the dynamic window is declared __align__(1024)
-  static constexpr int COL_S = 0, COL_PH = 128, COL_PL = 192, COL_O = 256, COL_QH = 352, COL_QL = 352 + D;
+  // TMEM buffering.  D <= 40 (the N=4096 level, ~90 % of the attention work): ONE score buffer but TWO P and O buffers, so
+  // P_{j+1} is written without waiting for PV_j and the O accumulation of block j leaves the critical path (a profile of the
+  // (2 S, 1 P, 1 O) scheme showed the softmax warps 47 % stalled on s_full / pv_done with the tensor pipe 30 % active).
+  // Larger head dims do not have the TMEM columns for that and keep (2 S, 1 P, 1 O).
+  static constexpr int SB = (D <= 40) ? 1 : 2;
+  static constexpr int PB = (D <= 40) ? 2 : 1;            // P buffers == O buffers
+  static constexpr int COL_S = 0;
+  static constexpr int COL_P = SB * AKV;                    // buffer b: hi at COL_P + b*128, lo at + 64
+  static constexpr int COL_O = COL_P + PB * 2 * AKV;        // buffer b at COL_O + b*NV
+  static constexpr int COL_QH = COL_O + PB * NV, COL_QL = COL_QH + D;
   static_assert(D % 8 == 0 && D >= 16 && D <= 80, "head dim must be a multiple of 8 in [16, 80]");
   static_assert(COL_QL + D <= 512, "TMEM overflow");
   static_assert(SMEM_BYTES <= 232448, "smem overflow");
@@ -112,10 +121,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
   auto bar_v_empty = [&](int s) { return bars + 112u + 8u * s; };    // 3 slots
   auto bar_s_full = [&](int s) { return bars + 136u + 8u * s; };
   auto bar_s_empty = [&](int s) { return bars + 152u + 8u * s; };
-  const uint32_t bar_p_full = bars + 168;
-  const uint32_t bar_pv_done = bars + 176;
-  const uint32_t bar_o_empty = bars + 184;
-  const uint32_t tmem_slot = bars + 192;
+  auto bar_p_full = [&](int s) { return bars + 168u + 8u * s; };
+  auto bar_pv_done = [&](int s) { return bars + 184u + 8u * s; };
+  auto bar_o_empty = [&](int s) { return bars + 200u + 8u * s; };
+  const uint32_t tmem_slot = bars + 216;
+  constexpr int SB = C::SB, PB = C::PB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
@@ -137,9 +147,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       mbar_init(bar_s_full(s), 1);
       mbar_init(bar_s_empty(s), 8);
     }
-    mbar_init(bar_p_full, 8);
-    mbar_init(bar_pv_done, 1);
-    mbar_init(bar_o_empty, 8);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_p_full(s), 8);
+      mbar_init(bar_pv_done(s), 1);
+      mbar_init(bar_o_empty(s), 8);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -190,13 +202,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       const uint32_t idesc_qk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AKV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
       const uint32_t idesc_pv = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
       const uint32_t q_hi = tmem_base + C::COL_QH, q_lo = tmem_base + C::COL_QL;
-      const uint32_t p_hi = tmem_base + C::COL_PH, p_lo = tmem_base + C::COL_PL;
-      const uint32_t o_acc = tmem_base + C::COL_O;
 
       auto issue_qk = [&](int j) {
-        const int s = j & 1, ks = j % KS;
+        const int sb = j % SB, ks = j % KS;
         const uint32_t sk = base + C::OFF_K + ks * C::K_STAGE;
-        const uint32_t s_acc = tmem_base + C::COL_S + s * AKV;
+        const uint32_t s_acc = tmem_base + C::COL_S + sb * AKV;
 #pragma unroll
         for (int c = 0; c < D / 8; ++c) {      // K chunks of 8 floats along the head dim
           const int kb = c >> 2;
@@ -207,7 +217,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           umma_ts(s_acc, q_hi + c * 8, k_lo, idesc_qk, 1u);
           umma_ts(s_acc, q_hi + c * 8, k_hi, idesc_qk, 1u);
         }
-        umma_commit(bar_s_full(s));
+        umma_commit(bar_s_full(sb));
         umma_commit(bar_k_empty(ks));
       };
 
@@ -217,18 +227,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       issue_qk(0);
       for (int j = 0; j < nb; ++j) {
         if (j + 1 < nb) {
-          const int s1 = (j + 1) & 1;
+          const int sb1 = (j + 1) % SB;
           mbar_wait(bar_k_full((j + 1) % KS), ((j + 1) / KS) & 1);
-          if (j + 1 >= 2) mbar_wait(bar_s_empty(s1), (((j + 1) >> 1) - 1) & 1);
+          if (j + 1 >= SB) mbar_wait(bar_s_empty(sb1), (((j + 1) / SB) - 1) & 1);   // softmax has the previous S of this buffer in registers
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           issue_qk(j + 1);
         }
-        const int vs = j % VS;
+        const int vs = j % VS, pb = j % PB;
         mbar_wait(bar_v_full(vs), (j / VS) & 1);
-        mbar_wait(bar_p_full, j & 1);
-        if (j >= 1) mbar_wait(bar_o_empty, (j - 1) & 1);
+        mbar_wait(bar_p_full(pb), (j / PB) & 1);
+        if (j >= PB) mbar_wait(bar_o_empty(pb), ((j / PB) - 1) & 1);                  // O buffer of block j-PB has been accumulated
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sv = base + C::OFF_V + vs * C::V_STAGE;
+        const uint32_t p_hi = tmem_base + C::COL_P + pb * 2 * AKV, p_lo = p_hi + AKV;
+        const uint32_t o_acc = tmem_base + C::COL_O + pb * NV;
 #pragma unroll
         for (int c = 0; c < AKV / 8; ++c) {    // K chunks of 8 keys
           const int kk = c >> 2;
@@ -239,7 +251,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           umma_ts(o_acc, p_hi + c * 8, v_lo, idesc_pv, 1u);
           umma_ts(o_acc, p_hi + c * 8, v_hi, idesc_pv, 1u);
         }
-        umma_commit(bar_pv_done);
+        umma_commit(bar_pv_done(pb));
         umma_commit(bar_v_empty(vs));
       }
     }
@@ -281,26 +293,25 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
 #pragma unroll
     for (int c = 0; c < HO; ++c) o[c] = 0.f;
 
-    auto accumulate_o = [&](int jdone) {          // O_total = O_total * corr + O_blk  (block jdone), this thread's columns
-      mbar_wait(bar_pv_done, jdone & 1);
+    auto accumulate_o = [&](int jdone, float corr_j) {   // O_total = O_total * corr_j + O_blk_j, this thread's columns
+      const int pb = jdone % PB;
+      mbar_wait(bar_pv_done(pb), (jdone / PB) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v[HO];
 #pragma unroll
-      for (int part = 0; part < HO / 8; ++part) {
-        uint32_t v[8];
-        tmem_ld8(tmem_base + lane_base + C::COL_O + hf * HO + part * 8, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int part = 0; part < HO / 8; ++part) tmem_ld8(tmem_base + lane_base + C::COL_O + pb * NV + hf * HO + part * 8, v + part * 8);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int c = 0; c < 8; ++c) o[part * 8 + c] = o[part * 8 + c] * corr_prev + __uint_as_float(v[c]);
-      }
+      for (int c = 0; c < HO; ++c) o[c] = o[c] * corr_j + __uint_as_float(v[c]);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_o_empty);
+      if (lane == 0) mbar_arrive(bar_o_empty(pb));
     };
 
 #pragma unroll 1
     for (int j = 0; j < nb; ++j) {
-      const int s = j & 1;
-      mbar_wait(bar_s_full(s), (j >> 1) & 1);
+      const int s = j % SB;
+      mbar_wait(bar_s_full(s), (j / SB) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float sc[HC];
       {
@@ -335,7 +346,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       l_run = l_run * corr + psum;
       m_run = m_new;
 
-      if (j >= 1) accumulate_o(j - 1);                   // also guarantees PV_{j-1} finished reading the P buffers
+      // corr_prev = corr_{j-1}: the rescale that belongs to adding O_blk_{j-1}
+      if (PB == 1 && j >= 1) accumulate_o(j - 1, corr_prev);     // single P buffer: PV_{j-1} must be done before P_j is written
 
       // P -> hi / lo planes in TMEM (hi rounded to nearest; lo is left to the tensor core's own truncation: |lo| <= 2^-12 p)
 #pragma unroll
@@ -346,16 +358,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           hi[e] = rn_tf32(__float_as_uint(sc[c8 * 8 + e]));
           lo[e] = __float_as_uint(sc[c8 * 8 + e] - __uint_as_float(hi[e]));
         }
-        tmem_st8(tmem_base + lane_base + C::COL_PH + hf * HC + c8 * 8, hi);
-        tmem_st8(tmem_base + lane_base + C::COL_PL + hf * HC + c8 * 8, lo);
+        const uint32_t pcol = tmem_base + lane_base + C::COL_P + (j % PB) * 2 * AKV + hf * HC + c8 * 8;
+        tmem_st8(pcol, hi);
+        tmem_st8(pcol + AKV, lo);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p_full);
+      if (lane == 0) mbar_arrive(bar_p_full(j % PB));
+      // two P/O buffers: P_j went into the other buffer (free since accumulate_o(j-2) below), so the accumulation of
+      // block j-1 happens AFTER handing P_j to the tensor core and is off the critical path
+      if (PB == 2 && j >= 1) accumulate_o(j - 1, corr_prev);
       corr_prev = (j == 0) ? 1.f : corr;                 // corr_j rescales what was accumulated before block j
     }
-    accumulate_o(nb - 1);
+    accumulate_o(nb - 1, corr_prev);
 
     // total row sum = both halves; exchange through smem (buffer 0 of the max exchange is free again: nb >= 2 or resynced below)
     asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
