@@ -165,40 +165,48 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // =========================================================================== TMA producer
-    if (lane == 0) {
+    // =========================================================================== TMA producer (whole warp, elected issue)
+    {
       const uint32_t sq = base + C::OFF_Q;
       // Q: hi plane, then (after the softmax warps moved it to TMEM) lo plane through the same staging buffer
-      mbar_expect_tx(bar_q_full, C::Q_STAGE);
-      for (int kb = 0; kb < KB2; ++kb) tma_load_4d(sq + kb * AQ * 128, &mapQh, kb * 32, h, q0, b, bar_q_full);
+      if (elect_one()) {
+        mbar_expect_tx(bar_q_full, C::Q_STAGE);
+        for (int kb = 0; kb < KB2; ++kb) tma_load_4d(sq + kb * AQ * 128, &mapQh, kb * 32, h, q0, b, bar_q_full);
+      }
       mbar_wait(bar_q_free, 0);
-      mbar_expect_tx(bar_q_full, C::Q_STAGE);
-      for (int kb = 0; kb < KB2; ++kb) tma_load_4d(sq + kb * AQ * 128, &mapQl, kb * 32, h, q0, b, bar_q_full);
+      if (elect_one()) {
+        mbar_expect_tx(bar_q_full, C::Q_STAGE);
+        for (int kb = 0; kb < KB2; ++kb) tma_load_4d(sq + kb * AQ * 128, &mapQl, kb * 32, h, q0, b, bar_q_full);
+      }
       for (int j = 0; j < nb; ++j) {
         const int s = j % KS, it = j / KS;
         // K block j: [64 keys x d] hi + lo
         if (j == KS - 1) mbar_wait(bar_q_ready, 0);            // the last K stage doubles as the Q staging buffer
         mbar_wait(bar_k_empty(s), (it & 1) ^ 1);
         const uint32_t sk = base + C::OFF_K + s * C::K_STAGE;
-        mbar_expect_tx(bar_k_full(s), C::K_STAGE);
-        for (int kb = 0; kb < KB2; ++kb) {
-          tma_load_4d(sk + kb * C::KTILE, &mapKh, kb * 32, h, j * AKV, b, bar_k_full(s));
-          tma_load_4d(sk + (KB2 + kb) * C::KTILE, &mapKl, kb * 32, h, j * AKV, b, bar_k_full(s));
+        if (elect_one()) {
+          mbar_expect_tx(bar_k_full(s), C::K_STAGE);
+          for (int kb = 0; kb < KB2; ++kb) {
+            tma_load_4d(sk + kb * C::KTILE, &mapKh, kb * 32, h, j * AKV, b, bar_k_full(s));
+            tma_load_4d(sk + (KB2 + kb) * C::KTILE, &mapKl, kb * 32, h, j * AKV, b, bar_k_full(s));
+          }
         }
         // V^T block j: [NV channel rows x 64 keys] as two 32-key tiles, hi + lo
         const int sv_ = j % VS, itv = j / VS;
         mbar_wait(bar_v_empty(sv_), (itv & 1) ^ 1);
         const uint32_t sv = base + C::OFF_V + sv_ * C::V_STAGE;
-        mbar_expect_tx(bar_v_full(sv_), C::V_STAGE);
-        for (int kk = 0; kk < 2; ++kk) {
-          tma_load_4d(sv + kk * C::VTILE, &mapVh, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(sv_));
-          tma_load_4d(sv + (2 + kk) * C::VTILE, &mapVl, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(sv_));
+        if (elect_one()) {
+          mbar_expect_tx(bar_v_full(sv_), C::V_STAGE);
+          for (int kk = 0; kk < 2; ++kk) {
+            tma_load_4d(sv + kk * C::VTILE, &mapVh, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(sv_));
+            tma_load_4d(sv + (2 + kk) * C::VTILE, &mapVl, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(sv_));
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================================================================== MMA issuer
-    if (lane == 0) {
+    // =========================================================================== MMA issuer (whole warp, elected issue)
+    {
       const uint32_t idesc_qk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AKV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
       const uint32_t idesc_pv = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
       const uint32_t q_hi = tmem_base + C::COL_QH, q_lo = tmem_base + C::COL_QL;
@@ -207,6 +215,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         const int sb = j % SB, ks = j % KS;
         const uint32_t sk = base + C::OFF_K + ks * C::K_STAGE;
         const uint32_t s_acc = tmem_base + C::COL_S + sb * AKV;
+        if (!elect_one()) return;
 #pragma unroll
         for (int c = 0; c < D / 8; ++c) {      // K chunks of 8 floats along the head dim
           const int kb = c >> 2;
@@ -241,6 +250,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         const uint32_t sv = base + C::OFF_V + vs * C::V_STAGE;
         const uint32_t p_hi = tmem_base + C::COL_P + pb * 2 * AKV, p_lo = p_hi + AKV;
         const uint32_t o_acc = tmem_base + C::COL_O + pb * NV;
+        if (!elect_one()) continue;
 #pragma unroll
         for (int c = 0; c < AKV / 8; ++c) {    // K chunks of 8 keys
           const int kk = c >> 2;

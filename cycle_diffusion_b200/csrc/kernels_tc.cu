@@ -155,8 +155,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   };
 
   if (warp == 0) {
-    // =========================================================================== TMA producer
-    if (lane == 0) {
+    // =========================================================================== TMA producer (whole warp, elected issue)
+    {
       const int cblocks = p.mode == 1 ? p.Cin / TBK : 0;
       int gkb = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -167,8 +167,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(bar_empty(s), (it & 1) ^ 1);
         const uint32_t st = base + s * STAGE_BYTES;
         const uint32_t sa = st + OFF_A, sb = st + OFF_BHI;
-        mbar_expect_tx(bar_full_raw(s), (TS ? 3 : 2) * TILE_BYTES);
         const int k0 = kb * TBK;
+        if (!elect_one()) continue;
+        mbar_expect_tx(bar_full_raw(s), (TS ? 3 : 2) * TILE_BYTES);
         if (p.mode == 0) {
           if (k0 < p.C1) tma_load_2d(sa, &mapA, k0, m0, bar_full_raw(s));
           else tma_load_2d(sa, &mapA2, k0 - p.C1, m0, bar_full_raw(s));
@@ -194,8 +195,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // =========================================================================== MMA issuer
-    if (lane == 0) {
+    // =========================================================================== MMA issuer (whole warp, elected issue)
+    {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
       int gkb = 0, gchunk0 = 0;
       const int chunks_per_tile = (num_kb + KCHUNK - 1) / KCHUNK;
@@ -213,6 +214,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t st = base + s * STAGE_BYTES;
         const uint32_t acc = tmem_base + (uint32_t)(buf * TBN);
         const uint64_t b_hi = make_desc(st + OFF_BHI), b_lo = make_desc(st + OFF_BLO);
+        if (!elect_one()) continue;
         if (TS) {
           const uint32_t a_hi = tmem_base + (uint32_t)(Cfg<TS>::A_COL0 + s * 64), a_lo = a_hi + 32;
 #pragma unroll

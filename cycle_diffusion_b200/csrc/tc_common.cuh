@@ -14,6 +14,20 @@ namespace tc {
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp.  The TMA / MMA warps run their loops with all 32 lanes (so addresses, descriptors
+// and loop counters stay in uniform registers) and predicate only the asynchronous instruction itself with this: issuing
+// from inside `if (lane == 0) { ... }` makes ptxas wrap every UTCHMMA / UTMALDG in an ELECT + BRA.U.ANY loop with R2UR
+// moves (seen in the SASS of the first version: ~100 cycles per MMA issue, 3x the MMA's own execution time at N = 64).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
