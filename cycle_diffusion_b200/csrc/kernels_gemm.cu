@@ -305,8 +305,8 @@ void gemm(Engine& e, const GemmArgs& a, cudaStream_t s) {
   CDX_CHECK(a.batch >= 1 && a.heads >= 1, "gemm: bad batch");
   if (a.mode == 1) CDX_CHECK(a.K == 9 * (a.C1 + a.C2), "conv3x3: K != 9*Cin");
   if (a.mode == 0) CDX_CHECK(a.K == a.C1 + a.C2, "dense: K != C1+C2");
+  if (e.mma_mode == 1 && gemm_tc(e, a, s)) return;      // (handles the arena dry run itself: split-K workspace)
   if (e.dry()) return;
-  if (e.mma_mode == 1 && gemm_tc(e, a, s)) return;
   const double zz = (double)a.batch * a.heads;
   ProfScope ps(e, s, a.batch * a.heads > 1 ? PROF_BATCHED_FFMA : (a.mode == 1 ? PROF_CONV_FFMA : PROF_DENSE_FFMA),
                2.0 * a.M * a.N * a.K * zz, 4.0 * zz * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);

@@ -78,9 +78,14 @@ struct TcParams {
   long long sC_b, sC_h;       // output offsets per zb / zh
   // persistent tile scheduler: tile t -> (tm = t % tiles_m, tn = (t / tiles_m) % tiles_n, z = t / (tiles_m * tiles_n))
   int tiles_m, tiles_n, total_tiles;
+  // split-K (small-M layers that cannot fill 148 SMs): work item = (tile, split); split s covers k-blocks
+  // [s*kb_per_split, min(num_kb, (s+1)*kb_per_split)) and writes its raw partial tile to ws[s][M][N]; splitk_reduce_kernel
+  // then sums the partials in fixed order and applies alpha / bias / row vector / residual
+  int splits, kb_per_split;
+  float* ws;
 };
 
-struct TileCoord { int n0, m0, x0, y0, b0, zb, zh; };
+struct TileCoord { int n0, m0, x0, y0, b0, zb, zh, kb0, kb1, split; };
 
 template <bool TS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -136,6 +141,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // i+1 overlap the global stores of tile i
   auto tile_coord = [&](int t) {
     TileCoord c;
+    const int split = t % p.splits;
+    t /= p.splits;
+    c.split = split;
+    c.kb0 = split * p.kb_per_split;
+    c.kb1 = min(num_kb, c.kb0 + p.kb_per_split);
     const int tm = t % p.tiles_m;
     const int r = t / p.tiles_m;
     const int tn = r % p.tiles_n, z = r / p.tiles_n;
@@ -162,7 +172,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc_ = tile_coord(t);
       const int n0 = tc_.n0, m0 = tc_.m0, x0 = tc_.x0, y0 = tc_.y0, b0 = tc_.b0, zb = tc_.zb, zh = tc_.zh;
-      for (int kb = 0; kb < num_kb; ++kb, ++gkb) {
+      for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
         mbar_wait(bar_empty(s), (it & 1) ^ 1);
         const uint32_t st = base + s * STAGE_BYTES;
@@ -199,9 +209,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
       int gkb = 0, gchunk0 = 0;
-      const int chunks_per_tile = (num_kb + KCHUNK - 1) / KCHUNK;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, gchunk0 += chunks_per_tile)
-      for (int kb = 0; kb < num_kb; ++kb, ++gkb) {
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc_ = tile_coord(t);
+      const int nkb = tc_.kb1 - tc_.kb0;
+      for (int kb = 0; kb < nkb; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
         const int lchunk = kb / KCHUNK, kin = kb - lchunk * KCHUNK;
         const int chunk = gchunk0 + lchunk, buf = chunk & 1;
@@ -235,7 +246,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
         umma_commit(bar_empty(s));          // stage (smem and, for TS, its TMEM A columns) reusable once these MMAs are done
-        if (kin == KCHUNK - 1 || kb == num_kb - 1) umma_commit(bar_acc_full(buf));   // chunk complete
+        if (kin == KCHUNK - 1 || kb == nkb - 1) umma_commit(bar_acc_full(buf));   // chunk complete
+      }
+      gchunk0 += (nkb + KCHUNK - 1) / KCHUNK;
       }
     }
   } else if (warp < 2 + NUM_SPLIT_WARPS) {
@@ -247,8 +260,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t rbase = (uint32_t)row * 128u;
       const uint32_t rx = (uint32_t)(row & 7);
       int gkb = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x)
-      for (int kb = 0; kb < num_kb; ++kb, ++gkb) {
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc_ = tile_coord(t);
+      for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
         mbar_wait(bar_full_raw(s), it & 1);
         const uint32_t sa = base + s * STAGE_BYTES + OFF_A + rbase;
@@ -272,11 +286,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full_split(s));
       }
+      }
     } else {
       const int st_ = threadIdx.x - 64;        // 0..127
       int gkb = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x)
-      for (int kb = 0; kb < num_kb; ++kb, ++gkb) {
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc_ = tile_coord(t);
+      for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
         mbar_wait(bar_full_raw(s), it & 1);
         const uint32_t sa = base + s * STAGE_BYTES;
@@ -299,16 +315,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full_split(s));
       }
+      }
     }
   } else {
     // =========================================================================== drain + epilogue warps
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access (warps 6..9 -> 2,3,0,1)
     const int r = q * 32 + lane;                   // tile row owned by this thread
-    const int num_chunks = (num_kb + KCHUNK - 1) / KCHUNK;
     int gchunk0 = 0;
 #pragma unroll 1
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, gchunk0 += num_chunks) {
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
     const TileCoord tc_ = tile_coord(t);
+    const int num_chunks = (tc_.kb1 - tc_.kb0 + KCHUNK - 1) / KCHUNK;
     const int n0 = tc_.n0, m0 = tc_.m0, x0 = tc_.x0, y0 = tc_.y0, b0 = tc_.b0, zb = tc_.zb, zh = tc_.zh;
     float acc[TBN];
 #pragma unroll
@@ -344,7 +361,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       row_ok = b < p.B;
       m = ((long long)b * p.H + (y0 + yl)) * p.W + (x0 + xl);
     }
-    if (row_ok && p.out_nchw) {
+    gchunk0 += num_chunks;
+    if (row_ok && p.splits > 1) {
+      float* wrow = p.ws + ((long long)tc_.split * p.M + m) * p.N;       // raw partial sums, [split][M][N]
+#pragma unroll
+      for (int j = 0; j < TBN; j += 4) {
+        const int n = n0 + j;
+        if (n < p.N) *reinterpret_cast<float4*>(wrow + n) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      }
+    } else if (row_ok && p.out_nchw) {
       const long long bimg = m / p.rows_per_img, rimg = m - bimg * p.rows_per_img;
 #pragma unroll
       for (int j = 0; j < TBN; ++j) {
@@ -383,6 +408,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// C = alpha * sum_s ws[s] (+bias) (+row vector) (+residual): fixed summation order, so split-K stays deterministic
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, TcParams p) {
+  const long long total4 = (long long)p.M * p.N / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 4;
+    const long long m = e / p.N;
+    const int n = (int)(e - m * p.N);
+    float4 a = *reinterpret_cast<const float4*>(ws + e);
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = *reinterpret_cast<const float4*>(ws + (long long)s * p.M * p.N + e);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    a.x *= p.alpha; a.y *= p.alpha; a.z *= p.alpha; a.w *= p.alpha;
+    if (p.bias) { const float4 t = *reinterpret_cast<const float4*>(p.bias + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+    if (p.rowvec) { const float4 t = *reinterpret_cast<const float4*>(p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+    if (p.residual) { const float4 t = *reinterpret_cast<const float4*>(p.residual + m * p.ldr + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+    *reinterpret_cast<float4*>(p.C + m * p.ldc + n) = a;
   }
 }
 
@@ -447,6 +492,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     const CUtensorMap& mA = get_map(q, 4, da, sa, bx);
     const CUtensorMap& mB = get_map(k, 4, db, sb, bx);
     ProfScope ps(e, s, PROF_BATCHED_TC, 2.0 * Nq * Nk * d * B * heads, 4.0 * B * heads * ((double)Nq * d + (double)Nk * d + (double)Nq * Nk), 1);
+    p.splits = 1; p.kb_per_split = cdiv(d, TBK);
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(Nk, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
     tc_gemm_kernel<false><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
     CDX_CUDA(cudaGetLastError());
@@ -472,6 +518,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     const CUtensorMap& mA = get_map(S, 4, da, sa, bxa);
     const CUtensorMap& mB = get_map(vt, 4, db, sb, bxb);
     ProfScope ps(e, s, PROF_BATCHED_TC, 2.0 * Nq * Nk * d * B * heads, 4.0 * B * heads * ((double)Nq * Nk + (double)Nk * d + (double)Nq * d), 1);
+    p.splits = 1; p.kb_per_split = cdiv(Nk, TBK);
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(d, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
     tc_gemm_kernel<false><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
     CDX_CUDA(cudaGetLastError());
@@ -547,7 +594,26 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
     p.tiles_m = p.tiles_x * p.tiles_y * cdiv(B, bn);
   }
   p.tiles_n = cdiv(a.N, TBN);
-  p.total_tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int num_kb = cdiv(a.K, TBK);
+  // split-K choice: minimise rounds(tiles*S) * (k-blocks per item + fixed per-item overhead)
+  int best_s = 1;
+  if (!a.out_nchw && tiles < e.num_sms) {
+    double best = 1e30;
+    for (int S = 1; S <= 8; ++S) {
+      const int kbs = cdiv(num_kb, S);
+      if (S > 1 && kbs < 8) break;
+      const double cost = (double)cdiv((long long)tiles * S, e.num_sms) * (kbs + 6.0) + (S > 1 ? 2.0 : 0.0);
+      if (cost < best - 1e-9) { best = cost; best_s = S; }
+    }
+  }
+  p.splits = best_s;
+  p.kb_per_split = cdiv(num_kb, best_s);
+  p.splits = cdiv(num_kb, p.kb_per_split);            // no empty splits
+  p.total_tiles = tiles * p.splits;
+  Scope ws_scope(e.arena);
+  if (best_s > 1) p.ws = (float*)e.arena.alloc((size_t)p.splits * a.M * a.N * sizeof(float));
+  if (e.dry()) return true;
   const int grid = std::min(p.total_tiles, e.num_sms);
   const bool ts = a.Bw_hi != nullptr && a.Bw_lo != nullptr && a16(a.Bw_hi) && a16(a.Bw_lo);
   {
@@ -563,6 +629,13 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   else tc_gemm_kernel<false><<<grid, TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
+  if (p.splits > 1) {
+    const long long total4 = (long long)a.M * a.N / 4;
+    const int blocks = (int)std::min<long long>((total4 + 255) / 256, (long long)e.num_sms * 8);
+    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(p.ws, p.splits, p);
+    CDX_CUDA(cudaGetLastError());
+    e.launches++;
+  }
   return true;
 }
 
