@@ -53,7 +53,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = TS ? 3 * TILE_BYTES : 4 * TILE_BYTES;   // TS: A_raw, B_hi, B_lo ; SS: A_hi, A_lo, B_hi, B_lo
   static constexpr int TMEM_COLS = TS ? 512 : 256;
   static constexpr int A_COL0 = 256;               // TS: A stage s lives at columns A_COL0 + 64 s (hi) / + 32 (lo)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048 /*barriers + bias staging*/ + 1024 /*alignment slack*/;
 };
 
 struct TcParams {
@@ -110,6 +110,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   auto bar_acc_full = [&](int b) { return bars + 8u * (3 * STAGES + b); };
   auto bar_acc_empty = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
   const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+  float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 512);   // [2][TBN], epilogue warps only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + TBK - 1) / TBK;
@@ -321,12 +322,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // =========================================================================== drain + epilogue warps
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access (warps 6..9 -> 2,3,0,1)
     const int r = q * 32 + lane;                   // tile row owned by this thread
-    int gchunk0 = 0;
+    const int et = q * 32 + lane;                  // 0..127: column this thread stages for the tile's bias vector
+    int gchunk0 = 0, tile_it = 0;
 #pragma unroll 1
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
     const TileCoord tc_ = tile_coord(t);
     const int num_chunks = (tc_.kb1 - tc_.kb0 + KCHUNK - 1) / KCHUNK;
     const int n0 = tc_.n0, m0 = tc_.m0, x0 = tc_.x0, y0 = tc_.y0, b0 = tc_.b0, zb = tc_.zb, zh = tc_.zh;
+    // the tile's 128 bias values: one coalesced load issued before the drain (latency hidden behind it), handed to
+    // all rows through shared memory; double-buffered by tile parity so a fast warp cannot overwrite a slow warp's tile
+    float bias_v = 0.f;
+    if (p.bias && p.splits == 1 && n0 + et < p.N) bias_v = __ldg(p.bias + n0 + et);
     float acc[TBN];
 #pragma unroll
     for (int j = 0; j < TBN; ++j) acc[j] = 0.f;
@@ -349,6 +355,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty(buf));
     }
+    float* const sb = s_bias + (tile_it & 1) * TBN;
+    sb[et] = bias_v;
+    asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
 
     long long m;
     bool row_ok;
@@ -374,29 +383,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < TBN; ++j) {
         const int n = n0 + j;
-        if (n < p.N) {
-          float o = p.alpha * acc[j];
-          if (p.bias) o += p.bias[n];
-          p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = o;        // consecutive lanes = consecutive pixels: coalesced
-        }
+        if (n < p.N) p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = p.alpha * acc[j] + sb[j];   // lanes = pixels: coalesced
       }
     } else if (row_ok) {
       const float* rv = p.rowvec ? p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec : nullptr;
       const float* rs = p.residual ? p.residual + m * p.ldr : nullptr;
       float* crow = p.C + zb * p.sC_b + zh * p.sC_h + m * p.ldc;
+      // pass 1 (no stores, so every load can be in flight at once): alpha, bias from smem, row vector
 #pragma unroll
       for (int j = 0; j < TBN; j += 4) {
-        const int n = n0 + j;
-        if (n < p.N) {                               // N % 4 == 0 is an eligibility condition
-          float4 o;
-          o.x = p.alpha * acc[j + 0];
-          o.y = p.alpha * acc[j + 1];
-          o.z = p.alpha * acc[j + 2];
-          o.w = p.alpha * acc[j + 3];
-          if (p.bias) { const float4 t = *reinterpret_cast<const float4*>(p.bias + n); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-          if (rv) { const float4 t = *reinterpret_cast<const float4*>(rv + n); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-          if (rs) { const float4 t = *reinterpret_cast<const float4*>(rs + n); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-          *reinterpret_cast<float4*>(crow + n) = o;
+        const float4 t = *reinterpret_cast<const float4*>(sb + j);
+        acc[j + 0] = p.alpha * acc[j + 0] + t.x;
+        acc[j + 1] = p.alpha * acc[j + 1] + t.y;
+        acc[j + 2] = p.alpha * acc[j + 2] + t.z;
+        acc[j + 3] = p.alpha * acc[j + 3] + t.w;
+      }
+      if (rv) {
+#pragma unroll
+        for (int j = 0; j < TBN; j += 4) {
+          if (n0 + j < p.N) {                          // N % 4 == 0 is an eligibility condition
+            const float4 t = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
+            acc[j + 0] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+          }
+        }
+      }
+      // pass 2: residual (may alias C: plain loads, issued eight at a time ahead of the stores of the same columns)
+#pragma unroll
+      for (int j0 = 0; j0 < TBN; j0 += 32) {
+        float4 t[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int n = n0 + j0 + 4 * g;
+          t[g] = (rs && n < p.N) ? *reinterpret_cast<const float4*>(rs + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int j = j0 + 4 * g, n = n0 + j;
+          if (n < p.N)
+            *reinterpret_cast<float4*>(crow + n) =
+                make_float4(acc[j] + t[g].x, acc[j + 1] + t[g].y, acc[j + 2] + t[g].z, acc[j + 3] + t[g].w);
         }
       }
     }
@@ -596,15 +621,19 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   p.tiles_n = cdiv(a.N, TBN);
   const int tiles = p.tiles_m * p.tiles_n;
   const int num_kb = cdiv(a.K, TBK);
-  // split-K choice: minimise rounds(tiles*S) * (k-blocks per item + fixed per-item overhead)
+  // split-K choice: minimise rounds(tiles*S) * (k-blocks per item + fixed per-item overhead) + the partial-sum traffic
+  // (S writes + S reads + 1 write of M*N floats at ~4 TB/s, in units of one k-block of one CTA ~ 0.55 us); a split must
+  // buy at least 10% to be taken
   int best_s = 1;
-  if (!a.out_nchw && tiles < e.num_sms) {
-    double best = 1e30;
+  if (!a.out_nchw && tiles < 4 * e.num_sms) {
+    double best = 1e30, base = 0.0;
     for (int S = 1; S <= 8; ++S) {
       const int kbs = cdiv(num_kb, S);
       if (S > 1 && kbs < 8) break;
-      const double cost = (double)cdiv((long long)tiles * S, e.num_sms) * (kbs + 6.0) + (S > 1 ? 2.0 : 0.0);
-      if (cost < best - 1e-9) { best = cost; best_s = S; }
+      double cost = (double)cdiv((long long)tiles * S, e.num_sms) * (kbs + 6.0);
+      if (S == 1) base = cost;
+      else cost += 2.0 + (2.0 * S + 1.0) * (double)a.M * a.N * 4.0 / 4e12 / 0.55e-6;
+      if (cost < best - 1e-9 && (S == 1 || cost < 0.9 * base)) { best = cost; best_s = S; }
     }
   }
   p.splits = best_s;
