@@ -257,7 +257,7 @@ def run_ours(args):
             'dtype': 'fp32', 'data': 'synthetic (images U[0,1], conditioning N(0,1), random-init SD v1-4-topology weights)',
             'config': {'workload': 'BASELINE configs[1]: Stable Diffusion v1-4 512x512, 50-step DPMEncoder (scale 1) + 50-step CFG decode (scale 7.5), '
                                    'batch 4 per GPU', 'global_batch': world * B, 'steps_encode': S_STEPS, 'steps_decode': S_STEPS, 'eta': ETA,
-                       'parallelism': f'dp{world} (images sharded, one NCCL weight broadcast)', 'mma_mode': 'tcgen05-3xTF32' if args.mma == 1 else 'ffma-fp32',
+                       'parallelism': f'dp{world} (images sharded, one NCCL weight broadcast)', 'mma_mode': 'ffma-fp32' if args.mma == 0 else 'tcgen05-3xTF32 (fp32-faithful)',
                        'l2': 'no flush: 3.8 GB of weights + >1 GB activations per U-Net call are streamed every call (>> 126 MB L2)',
                        'unet_calls_per_step': 2 * S_STEPS, 'unet_ms_cfg_batch8': round(unet_ms, 2) if unet_ms else None},
             'e2e': {'value': round(e2e_value, 4), 'unit': UNIT, 'h2d_bytes_per_step': h2d[0], 'd2h_bytes_per_step': 4 * out_host.numel(),
