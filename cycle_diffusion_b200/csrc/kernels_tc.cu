@@ -53,7 +53,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = TS ? 3 * TILE_BYTES : 4 * TILE_BYTES;   // TS: A_raw, B_hi, B_lo ; SS: A_hi, A_lo, B_hi, B_lo
   static constexpr int TMEM_COLS = TS ? 512 : 256;
   static constexpr int A_COL0 = 256;               // TS: A stage s lives at columns A_COL0 + 64 s (hi) / + 32 (lo)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048 /*barriers + bias staging*/ + 1024 /*alignment slack*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048 /*barriers + bias staging*/ + 16384 /*epilogue transpose*/ + 1024 /*alignment slack*/;
 };
 
 struct TcParams {
@@ -111,6 +111,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   auto bar_acc_empty = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
   const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
   float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 512);   // [2][TBN], epilogue warps only
+  float4* const s_stage = reinterpret_cast<float4*>(smem_raw + (bars - smem_u32(smem_raw)) + 2048);   // 4 warps x 4 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + TBK - 1) / TBK;
@@ -371,58 +372,75 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       m = ((long long)b * p.H + (y0 + yl)) * p.W + (x0 + xl);
     }
     gchunk0 += num_chunks;
-    if (row_ok && p.splits > 1) {
-      float* wrow = p.ws + ((long long)tc_.split * p.M + m) * p.N;       // raw partial sums, [split][M][N]
+    if (p.out_nchw) {
+      if (row_ok) {
+        const long long bimg = m / p.rows_per_img, rimg = m - bimg * p.rows_per_img;
 #pragma unroll
-      for (int j = 0; j < TBN; j += 4) {
-        const int n = n0 + j;
-        if (n < p.N) *reinterpret_cast<float4*>(wrow + n) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        for (int j = 0; j < TBN; ++j) {
+          const int n = n0 + j;
+          if (n < p.N) p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = p.alpha * acc[j] + sb[j];   // lanes = pixels: coalesced
+        }
       }
-    } else if (row_ok && p.out_nchw) {
-      const long long bimg = m / p.rows_per_img, rimg = m - bimg * p.rows_per_img;
-#pragma unroll
-      for (int j = 0; j < TBN; ++j) {
-        const int n = n0 + j;
-        if (n < p.N) p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = p.alpha * acc[j] + sb[j];   // lanes = pixels: coalesced
-      }
-    } else if (row_ok) {
-      const float* rv = p.rowvec ? p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec : nullptr;
-      const float* rs = p.residual ? p.residual + m * p.ldr : nullptr;
-      float* crow = p.C + zb * p.sC_b + zh * p.sC_h + m * p.ldc;
-      // pass 1 (no stores, so every load can be in flight at once): alpha, bias from smem, row vector
-#pragma unroll
-      for (int j = 0; j < TBN; j += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(sb + j);
-        acc[j + 0] = p.alpha * acc[j + 0] + t.x;
-        acc[j + 1] = p.alpha * acc[j + 1] + t.y;
-        acc[j + 2] = p.alpha * acc[j + 2] + t.z;
-        acc[j + 3] = p.alpha * acc[j + 3] + t.w;
-      }
-      if (rv) {
+    } else {
+      const bool fin = p.splits == 1;                // otherwise: raw partial sums to ws[split][M][N]
+      if (fin && row_ok) {
+        // pass 1 (registers only): alpha, bias from smem, per-image row vector
 #pragma unroll
         for (int j = 0; j < TBN; j += 4) {
-          if (n0 + j < p.N) {                          // N % 4 == 0 is an eligibility condition
-            const float4 t = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
-            acc[j + 0] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+          const float4 t = *reinterpret_cast<const float4*>(sb + j);
+          acc[j + 0] = p.alpha * acc[j + 0] + t.x;
+          acc[j + 1] = p.alpha * acc[j + 1] + t.y;
+          acc[j + 2] = p.alpha * acc[j + 2] + t.z;
+          acc[j + 3] = p.alpha * acc[j + 3] + t.w;
+        }
+        if (p.rowvec) {
+          const float* rv = p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec;
+#pragma unroll
+          for (int j = 0; j < TBN; j += 4) {
+            if (n0 + j < p.N) {                          // N % 4 == 0 is an eligibility condition
+              const float4 t = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
+              acc[j + 0] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+            }
           }
         }
       }
-      // pass 2: residual (may alias C: plain loads, issued eight at a time ahead of the stores of the same columns)
+      // pass 2: the thread-per-row accumulator layout would store 16 B to 32 different rows per instruction (32 L1
+      // wavefronts each, which also starves the split warps' LDS behind them); instead each warp transposes 32x32
+      // blocks through a swizzled 4 KB staging buffer so that one instruction covers 4 rows x 128 contiguous bytes,
+      // for the residual loads as well
+      float* const dst = fin ? p.C + zb * p.sC_b + zh * p.sC_h : p.ws + (long long)tc_.split * p.M * p.N;
+      const long long dld = fin ? p.ldc : p.N;
+      const float* const rsd = fin ? p.residual : nullptr;
+      const int m32 = row_ok ? (int)m : -1;
+      float4* const stg = s_stage + q * 256;          // [32 rows][8 float4], chunk index XOR (row & 7)
+      const int g = lane & 7, rsub = lane >> 3;
 #pragma unroll
-      for (int j0 = 0; j0 < TBN; j0 += 32) {
-        float4 t[8];
+      for (int part = 0; part < TBN / 32; ++part) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int n = n0 + j0 + 4 * g;
-          t[g] = (rs && n < p.N) ? *reinterpret_cast<const float4*>(rs + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 8; ++c)
+          stg[lane * 8 + (c ^ (lane & 7))] =
+              make_float4(acc[part * 32 + 4 * c], acc[part * 32 + 4 * c + 1], acc[part * 32 + 4 * c + 2], acc[part * 32 + 4 * c + 3]);
+        __syncwarp();
+        const int n = n0 + part * 32 + 4 * g;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float4 v[4], t[4];
+          int mm[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = 4 * (half * 4 + i) + rsub;
+            mm[i] = __shfl_sync(0xffffffffu, m32, rl);
+            v[i] = stg[rl * 8 + (g ^ (rl & 7))];
+            t[i] = (rsd && mm[i] >= 0 && n < p.N) ? *reinterpret_cast<const float4*>(rsd + (long long)mm[i] * p.ldr + n)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (mm[i] >= 0 && n < p.N)
+              *reinterpret_cast<float4*>(dst + (long long)mm[i] * dld + n) =
+                  make_float4(v[i].x + t[i].x, v[i].y + t[i].y, v[i].z + t[i].z, v[i].w + t[i].w);
         }
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int j = j0 + 4 * g, n = n0 + j;
-          if (n < p.N)
-            *reinterpret_cast<float4*>(crow + n) =
-                make_float4(acc[j] + t[g].x, acc[j + 1] + t[g].y, acc[j + 2] + t[g].z, acc[j + 3] + t[g].w);
-        }
+        __syncwarp();
       }
     }
     }   // tile loop
