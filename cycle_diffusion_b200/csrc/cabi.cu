@@ -554,9 +554,33 @@ int cdx_op_attention(cdx_engine* eh, const float* q, const float* k, const float
           float* vl = (float*)e.arena.alloc((size_t)C * M * sizeof(float));
           split_planes(e, qk, qh, ql, (size_t)M * 2 * C, s);
           split_planes(e, vt, vh, vl, (size_t)C * M, s);
-          done = flash_attention_tc(e, qh, ql, 2 * C, C, vh, vl, out, C, B, Nq, heads, d, scale, s);
+          done = flash_attention_tc(e, qh, ql, 2 * C, qh + C, ql + C, 2 * C, vh, vl, out, C, B, Nq, Nq, Nq, heads, d, scale, s);
         }
         if (!done) done = attention_tc(e, qk, 2 * C, qk + C, 2 * C, d, vt, out, C, B, Nq, Nk, heads, d, scale, s);
+      }
+      if (!done && e.mma_mode == 1 && e.flash_attn && Nq != Nk && (Nq % 128) == 0) {
+        // cross-attention shape: keys padded to a multiple of 4 per image (TMA strides), masked inside the kernel
+        const int Nks = (Nk + 3) & ~3, M = B * Nq, Mk = B * Nks;
+        float* kp = (float*)e.arena.alloc((size_t)Mk * C * sizeof(float));
+        float* vp = (float*)e.arena.alloc((size_t)Mk * C * sizeof(float));
+        float* vt = (float*)e.arena.alloc((size_t)C * Mk * sizeof(float));
+        float* qh = (float*)e.arena.alloc((size_t)M * C * sizeof(float));
+        float* ql = (float*)e.arena.alloc((size_t)M * C * sizeof(float));
+        float* kh = (float*)e.arena.alloc((size_t)Mk * C * sizeof(float));
+        float* kl = (float*)e.arena.alloc((size_t)Mk * C * sizeof(float));
+        float* vh = (float*)e.arena.alloc((size_t)C * Mk * sizeof(float));
+        float* vl = (float*)e.arena.alloc((size_t)C * Mk * sizeof(float));
+        if (!e.dry()) {
+          CDX_CUDA(cudaMemsetAsync(kp, 0, (size_t)Mk * C * 4, s));
+          CDX_CUDA(cudaMemsetAsync(vp, 0, (size_t)Mk * C * 4, s));
+          CDX_CUDA(cudaMemcpy2DAsync(kp, (size_t)Nks * C * 4, k, (size_t)Nk * C * 4, (size_t)Nk * C * 4, B, cudaMemcpyDeviceToDevice, s));
+          CDX_CUDA(cudaMemcpy2DAsync(vp, (size_t)Nks * C * 4, v, (size_t)Nk * C * 4, (size_t)Nk * C * 4, B, cudaMemcpyDeviceToDevice, s));
+        }
+        nhwc_to_nchw(e, vp, vt, 1, C, Mk, s);
+        split_planes(e, q, qh, ql, (size_t)M * C, s);
+        split_planes(e, kp, kh, kl, (size_t)Mk * C, s);
+        split_planes(e, vt, vh, vl, (size_t)C * Mk, s);
+        done = flash_attention_tc(e, qh, ql, C, kh, kl, C, vh, vl, out, C, B, Nq, Nk, Nks, heads, d, scale, s);
       }
       if (!done) attention(e, q, C, k, C, v, C, out, C, B, Nq, Nk, heads, d, d, scale, s);
     });

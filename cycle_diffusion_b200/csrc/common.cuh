@@ -125,6 +125,7 @@ struct GemmArgs {
   const float* Bw = nullptr; int ldb = 0; int b_kn = 0;   // weights [N][K] (b_kn=0) or [K][N] (b_kn=1)
   const float* Bw_hi = nullptr; const float* Bw_lo = nullptr;   // optional pre-split TF32 planes of Bw (same geometry)
   float* Cout = nullptr; int ldc = 0;
+  float* Cout_lo = nullptr;           // if set: Cout receives rn_tf32(C) and Cout_lo rn_tf32(C - hi) (operand planes for tcgen05)
   const float* bias = nullptr;
   const float* rowvec = nullptr; int ld_rowvec = 0; int rows_per_batch = 1;
   const float* residual = nullptr; int ldr = 0;
@@ -138,8 +139,9 @@ struct GemmArgs {
 void gemm(Engine& e, const GemmArgs& a, cudaStream_t s);
 // tcgen05 back end (kernels_tc.cu); returns false when the shape is not eligible
 bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s);
-bool flash_attention_tc(Engine& e, const float* qk_hi, const float* qk_lo, int ld, int k_off, const float* vt_hi, const float* vt_lo, float* out,
-                        int ldo, int B, int N, int heads, int d, float scale, cudaStream_t s);
+bool flash_attention_tc(Engine& e, const float* q_hi, const float* q_lo, int ldq, const float* k_hi, const float* k_lo, int ldk,
+                        const float* vt_hi, const float* vt_lo, float* out, int ldo, int B, int N, int Nk, int Nks, int heads, int d,
+                        float scale, cudaStream_t s);
 void split_planes(Engine& e, const float* w, float* hi, float* lo, size_t n, cudaStream_t s);   // hi = rn_tf32(w), lo = rn_tf32(w - hi)
 bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, int head_stride, const float* vt, float* out, int ldo, int B,
                   int Nq, int Nk, int heads, int d, float scale, cudaStream_t s);

@@ -68,7 +68,7 @@ struct ACfg {
 };
 
 struct AttnParams {
-  int N, heads, d, B;
+  int N, Nk, heads, d, B;   // N queries, Nk keys (cross-attention: Nk != N; keys >= Nk in the last block are masked)
   float scale_log2e;      // scale * log2(e): scores are kept in the log2 domain
   float* out; int ldo;
 };
@@ -129,7 +129,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
-  const int nb = p.N / AKV;
+  const int nb = (p.Nk + AKV - 1) / AKV;
 
   if (warp == 0 && lane == 0) {
     mbar_init(bar_q_full, 1);
@@ -331,6 +331,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
 #pragma unroll
         for (int c = 0; c < HC; ++c) sc[c] = __uint_as_float(v[c]);
       }
+      if (j == nb - 1 && nb * AKV != p.Nk) {           // ragged last key block (TMA zero-filled the missing keys): mask
+        const int k0 = j * AKV + hf * HC;
+#pragma unroll
+        for (int c = 0; c < HC; ++c)
+          if (k0 + c >= p.Nk) sc[c] = -INFINITY;
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_s_empty(s));
@@ -423,32 +429,36 @@ void launch_flash(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMa
 
 }  // namespace
 
-// qk_hi / qk_lo: TF32 planes of the fused q|k projection [B*N, ld] (q at column 0, k at column k_off, head h at h*d);
-// vt_hi / vt_lo: planes of V^T [heads*d, B*N].  out [B, N, ldo], head h at column h*d.
-bool flash_attention_tc(Engine& e, const float* qk_hi, const float* qk_lo, int ld, int k_off, const float* vt_hi, const float* vt_lo, float* out,
-                        int ldo, int B, int N, int heads, int d, float scale, cudaStream_t s) {
-  if ((N % AQ) || (d % 8) || d < 16 || d > 80 || (ld & 3) || (k_off & 3) || (ldo & 3)) return false;
+// q_hi / q_lo: TF32 planes of the query projection [B*N, ldq] (head h at column h*d); k_hi / k_lo: planes of the key
+// projection [B*Nks, ldk] (Nks = stored keys per image >= Nk); vt_hi / vt_lo: planes of V^T [heads*d, B*Nks].
+// out [B, N, ldo], head h at column h*d.  Self-attention: q and k are two column ranges of one fused projection.
+bool flash_attention_tc(Engine& e, const float* q_hi, const float* q_lo, int ldq, const float* k_hi, const float* k_lo, int ldk,
+                        const float* vt_hi, const float* vt_lo, float* out, int ldo, int B, int N, int Nk, int Nks, int heads, int d,
+                        float scale, cudaStream_t s) {
+  if ((N % AQ) || (d % 8) || d < 16 || d > 80 || (ldq & 3) || (ldk & 3) || (ldo & 3) || (Nks & 3) || Nk < 1 || Nk > Nks) return false;
   if (!(d == 16 || d == 32 || d == 40 || d == 64 || d == 80)) return false;
-  if (!a16(qk_hi) || !a16(qk_lo) || !a16(vt_hi) || !a16(vt_lo) || !a16(out)) return false;
+  if (!a16(q_hi) || !a16(q_lo) || !a16(k_hi) || !a16(k_lo) || !a16(vt_hi) || !a16(vt_lo) || !a16(out)) return false;
   if (e.dry()) return true;
   const int NV = (d + 15) / 16 * 16;
   uint64_t dq[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
-  uint64_t sq[3] = {(uint64_t)d * 4, (uint64_t)ld * 4, (uint64_t)N * ld * 4};
+  uint64_t sq[3] = {(uint64_t)d * 4, (uint64_t)ldq * 4, (uint64_t)N * ldq * 4};
+  uint64_t dk[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)Nks, (uint64_t)B};
+  uint64_t sk[3] = {(uint64_t)d * 4, (uint64_t)ldk * 4, (uint64_t)Nks * ldk * 4};
   uint32_t bq[4] = {32, 1, AQ, 1}, bk[4] = {32, 1, AKV, 1};
-  uint64_t dv[4] = {(uint64_t)N, (uint64_t)B, (uint64_t)heads * d, 1};
-  uint64_t sv[3] = {(uint64_t)N * 4, (uint64_t)B * N * 4, (uint64_t)B * N * 4 * heads * d};
+  uint64_t dv[4] = {(uint64_t)Nks, (uint64_t)B, (uint64_t)heads * d, 1};
+  uint64_t sv[3] = {(uint64_t)Nks * 4, (uint64_t)B * Nks * 4, (uint64_t)B * Nks * 4 * heads * d};
   uint32_t bv[4] = {32, 1, (uint32_t)NV, 1};
-  const CUtensorMap& qh = get_map(qk_hi, 4, dq, sq, bq);
-  const CUtensorMap& ql = get_map(qk_lo, 4, dq, sq, bq);
-  const CUtensorMap& kh = get_map(qk_hi + k_off, 4, dq, sq, bk);
-  const CUtensorMap& kl = get_map(qk_lo + k_off, 4, dq, sq, bk);
+  const CUtensorMap& qh = get_map(q_hi, 4, dq, sq, bq);
+  const CUtensorMap& ql = get_map(q_lo, 4, dq, sq, bq);
+  const CUtensorMap& kh = get_map(k_hi, 4, dk, sk, bk);
+  const CUtensorMap& kl = get_map(k_lo, 4, dk, sk, bk);
   const CUtensorMap& vh = get_map(vt_hi, 4, dv, sv, bv);
   const CUtensorMap& vl = get_map(vt_lo, 4, dv, sv, bv);
   AttnParams p;
-  p.N = N; p.heads = heads; p.d = d; p.B = B;
+  p.N = N; p.Nk = Nk; p.heads = heads; p.d = d; p.B = B;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = out; p.ldo = ldo;
-  ProfScope ps(e, s, PROF_BATCHED_TC, 4.0 * N * (double)N * d * B * heads, 4.0 * B * heads * (3.0 * N * d + (double)N * d), 1);
+  ProfScope ps(e, s, PROF_BATCHED_TC, 4.0 * N * (double)Nk * d * B * heads, 4.0 * B * heads * (2.0 * N * d + 2.0 * (double)Nk * d), 1);
   switch (d) {
     case 16: launch_flash<16>(qh, ql, kh, kl, vh, vl, p, s); break;
     case 32: launch_flash<32>(qh, ql, kh, kl, vh, vl, p, s); break;

@@ -307,6 +307,14 @@ void gemm(Engine& e, const GemmArgs& a, cudaStream_t s) {
   if (a.mode == 0) CDX_CHECK(a.K == a.C1 + a.C2, "dense: K != C1+C2");
   if (e.mma_mode == 1 && gemm_tc(e, a, s)) return;      // (handles the arena dry run itself: split-K workspace)
   if (e.dry()) return;
+  if (a.Cout_lo) {     // plane outputs are produced by the tensor-core epilogue; here: exact GEMM, then split in place
+    CDX_CHECK(a.ldc == a.N && a.batch * a.heads == 1 && !a.out_nchw, "gemm: plane output needs a dense [M,N] result");
+    GemmArgs b = a;
+    b.Cout_lo = nullptr;
+    gemm(e, b, s);
+    split_planes(e, a.Cout, a.Cout, a.Cout_lo, (size_t)a.M * a.N, s);
+    return;
+  }
   const double zz = (double)a.batch * a.heads;
   ProfScope ps(e, s, a.batch * a.heads > 1 ? PROF_BATCHED_FFMA : (a.mode == 1 ? PROF_CONV_FFMA : PROF_DENSE_FFMA),
                2.0 * a.M * a.N * a.K * zz, 4.0 * zz * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);

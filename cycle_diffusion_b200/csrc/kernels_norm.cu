@@ -4,7 +4,8 @@
 // on NHWC activations, optionally over the channel concatenation of two tensors (the U-Net skip `th.cat`, OAI:736)
 // so that the concat is never materialised before the norm.  Statistics are accumulated in fp64 (one read),
 // then one read + one write applies  y = (x - mean) * rstd * gamma + beta  [ * (1+scale) + shift ] [ SiLU ].
-// Algorithmic HBM bytes: 2 reads + 1 write of the activation (stats pass + apply pass).
+// Algorithmic HBM bytes: 2 reads + 1 write of the activation (stats pass + apply pass; the apply blocks fold the
+// per-chunk partial sums themselves).
 #include "common.cuh"
 
 namespace cdx {
@@ -76,28 +77,12 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   }
 }
 
-// mean_rstd[(b*32+g)*2 + {0,1}]
-__global__ void gn_finalize_kernel(const double* __restrict__ part, int nchunk, double inv_count, float eps,
-                                   float* __restrict__ mean_rstd) {
-  const int b = blockIdx.x, g = threadIdx.x;
-  double s = 0.0, q = 0.0;
-  for (int c = 0; c < nchunk; ++c) {
-    const double* o = part + (((long long)b * nchunk + c) * GN_GROUPS + g) * 2;
-    s += o[0];
-    q += o[1];
-  }
-  const double mean = s * inv_count;
-  double var = q * inv_count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  mean_rstd[(b * GN_GROUPS + g) * 2 + 0] = (float)mean;
-  mean_rstd[(b * GN_GROUPS + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
-}
-
 // grid (row chunks, B); thread (tr, tc) owns channel vectors tc, tc+ncol, ... (so group / affine coefficients are hoisted out
 // of the row loop as y = x * sc + sh, the form ATen's CPU kernel uses) and walks the chunk's rows 4 at a time
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const float* __restrict__ mean_rstd, int silu,
+                                                       const double* __restrict__ part, int nchunk, double inv_count,
+                                                       float eps, int silu,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        int ld_ss, float* __restrict__ y, int HW, int rows_per_chunk) {
   const int C = C1 + C2;
@@ -109,6 +94,23 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   const int ncol = min(C4, (int)blockDim.x);
   const int nrow_par = blockDim.x / ncol;
   const int tr = threadIdx.x / ncol, tc = threadIdx.x - tr * ncol;
+  // every block folds the stats partials of its image itself (fixed order, fp64): saves a launch per GroupNorm
+  __shared__ float mean_rstd[GN_GROUPS * 2];
+  if (threadIdx.x < GN_GROUPS) {
+    const int g = threadIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+      const double* o = part + (((long long)b * nchunk + c) * GN_GROUPS + g) * 2;
+      s += o[0];
+      q += o[1];
+    }
+    const double mean = s * inv_count;
+    double var = q * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[g * 2 + 0] = (float)mean;
+    mean_rstd[g * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
   if (tr >= nrow_par) return;
   for (int c4 = tc; c4 < C4; c4 += ncol) {
     const int c = c4 * 4;
@@ -116,8 +118,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int g = (c + j) / cpg;
-      const float mean = mean_rstd[(b * GN_GROUPS + g) * 2 + 0];
-      const float rstd = mean_rstd[(b * GN_GROUPS + g) * 2 + 1];
+      const float mean = mean_rstd[g * 2 + 0];
+      const float rstd = mean_rstd[g * 2 + 1];
       float a = rstd * gamma[c + j];
       float o = beta[c + j] - mean * a;
       if (scale) {      // gn(x) * (1 + scale) + shift   (improved-DDPM scale-shift norm)
@@ -227,18 +229,17 @@ void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, cons
   const int rows_per_chunk = cdiv(HW, nchunk);
   nchunk = cdiv(HW, rows_per_chunk);
   double* part = (double*)e.arena.alloc((size_t)B * nchunk * GN_GROUPS * 2 * sizeof(double));
-  float* mr = (float*)e.arena.alloc((size_t)B * GN_GROUPS * 2 * sizeof(float));
   if (e.dry()) return;
-  ProfScope ps(e, s, PROF_GROUPNORM, 0.0, 2.0 * 4.0 * B * (double)HW * C, 3);   // algorithmic: one read + one write
+  ProfScope ps(e, s, PROF_GROUPNORM, 0.0, 2.0 * 4.0 * B * (double)HW * C, 2);   // algorithmic: one read + one write
   gn_stats_kernel<<<dim3(nchunk, B), 256, 0, s>>>(x1, C1, x2, C2, HW, rows_per_chunk, part);
-  gn_finalize_kernel<<<B, GN_GROUPS, 0, s>>>(part, nchunk, 1.0 / ((double)HW * (C / GN_GROUPS)), eps, mr);
   int achunk = cdiv(8LL * e.num_sms, B);
   if (achunk > HW) achunk = HW;
   const int arows = cdiv(HW, achunk);
   achunk = cdiv(HW, arows);
-  gn_apply_kernel<<<dim3(achunk, B), 256, 0, s>>>(x1, C1, x2, C2, gamma, beta, mr, silu ? 1 : 0, scale, shift, ld_ss, y, HW, arows);
+  gn_apply_kernel<<<dim3(achunk, B), 256, 0, s>>>(x1, C1, x2, C2, gamma, beta, part, nchunk, 1.0 / ((double)HW * (C / GN_GROUPS)), eps,
+                                                  silu ? 1 : 0, scale, shift, ld_ss, y, HW, arows);
   CDX_CUDA(cudaGetLastError());
-  e.launches += 3;
+  e.launches += 2;
 }
 
 void layernorm(Engine& e, const float* x, const float* gamma, const float* beta, float* y, int M, int C, cudaStream_t s) {

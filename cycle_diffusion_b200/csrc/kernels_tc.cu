@@ -66,6 +66,7 @@ struct TcParams {
   int tiles_x, tiles_y;     // conv: tiles per row / column
   int cstride, cpad;        // conv: stride (1 or 2: TMA element traversal stride) and low-side padding
   float* C; int ldc;
+  float* C_lo;              // optional: C <- rn_tf32(result), C_lo <- rn_tf32(result - hi)
   const float* bias;
   const float* rowvec; int ld_rowvec; int rows_per_batch;
   const float* residual; int ldr;
@@ -411,6 +412,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       float* const dst = fin ? p.C + zb * p.sC_b + zh * p.sC_h : p.ws + (long long)tc_.split * p.M * p.N;
       const long long dld = fin ? p.ldc : p.N;
       const float* const rsd = fin ? p.residual : nullptr;
+      float* const dst_lo = (fin && p.C_lo) ? p.C_lo + zb * p.sC_b + zh * p.sC_h : nullptr;
       const int m32 = row_ok ? (int)m : -1;
       float4* const stg = s_stage + q * 256;          // [32 rows][8 float4], chunk index XOR (row & 7)
       const int g = lane & 7, rsub = lane >> 3;
@@ -436,9 +438,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (mm[i] >= 0 && n < p.N)
-              *reinterpret_cast<float4*>(dst + (long long)mm[i] * dld + n) =
-                  make_float4(v[i].x + t[i].x, v[i].y + t[i].y, v[i].z + t[i].z, v[i].w + t[i].w);
+            if (mm[i] >= 0 && n < p.N) {
+              float4 o = make_float4(v[i].x + t[i].x, v[i].y + t[i].y, v[i].z + t[i].z, v[i].w + t[i].w);
+              if (dst_lo) {                          // operand planes for a following tcgen05 consumer
+                float4 hi, lo;
+                hi.x = __uint_as_float(rn_tf32(__float_as_uint(o.x))); lo.x = __uint_as_float(rn_tf32(__float_as_uint(o.x - hi.x)));
+                hi.y = __uint_as_float(rn_tf32(__float_as_uint(o.y))); lo.y = __uint_as_float(rn_tf32(__float_as_uint(o.y - hi.y)));
+                hi.z = __uint_as_float(rn_tf32(__float_as_uint(o.z))); lo.z = __uint_as_float(rn_tf32(__float_as_uint(o.z - hi.z)));
+                hi.w = __uint_as_float(rn_tf32(__float_as_uint(o.w))); lo.w = __uint_as_float(rn_tf32(__float_as_uint(o.w - hi.w)));
+                *reinterpret_cast<float4*>(dst_lo + (long long)mm[i] * dld + n) = lo;
+                o = hi;
+              }
+              *reinterpret_cast<float4*>(dst + (long long)mm[i] * dld + n) = o;
+            }
         }
         __syncwarp();
       }
@@ -470,6 +482,15 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, T
     if (p.bias) { const float4 t = *reinterpret_cast<const float4*>(p.bias + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
     if (p.rowvec) { const float4 t = *reinterpret_cast<const float4*>(p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
     if (p.residual) { const float4 t = *reinterpret_cast<const float4*>(p.residual + m * p.ldr + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+    if (p.C_lo) {
+      float4 hi, lo;
+      hi.x = __uint_as_float(rn_tf32(__float_as_uint(a.x))); lo.x = __uint_as_float(rn_tf32(__float_as_uint(a.x - hi.x)));
+      hi.y = __uint_as_float(rn_tf32(__float_as_uint(a.y))); lo.y = __uint_as_float(rn_tf32(__float_as_uint(a.y - hi.y)));
+      hi.z = __uint_as_float(rn_tf32(__float_as_uint(a.z))); lo.z = __uint_as_float(rn_tf32(__float_as_uint(a.z - hi.z)));
+      hi.w = __uint_as_float(rn_tf32(__float_as_uint(a.w))); lo.w = __uint_as_float(rn_tf32(__float_as_uint(a.w - hi.w)));
+      *reinterpret_cast<float4*>(p.C_lo + m * p.ldc + n) = lo;
+      a = hi;
+    }
     *reinterpret_cast<float4*>(p.C + m * p.ldc + n) = a;
   }
 }
@@ -587,6 +608,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   memset(&p, 0, sizeof(p));
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.C = a.Cout; p.ldc = a.ldc;
+  p.C_lo = a.out_nchw ? nullptr : a.Cout_lo;
   p.bias = a.bias;
   p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec; p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
   p.residual = a.residual; p.ldr = a.ldr;

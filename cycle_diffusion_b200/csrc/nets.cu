@@ -392,9 +392,10 @@ struct Exec {
 
   // y[M,N] = x[M,K] (optionally [x | x2]) @ W[N,K]^T (+bias) (+residual)
   void linear_into(const float* x, int lda, int C1, const float* x2, int lda2, int C2, int M, const float* W, int N, const float* bias,
-                   const float* residual, int ldr, float* y, int ldc) {
+                   const float* residual, int ldr, float* y, int ldc, float* y_lo = nullptr) {
     GemmArgs g;
     g.mode = 0;
+    g.Cout_lo = y_lo;            // if set: y / y_lo receive the TF32 hi / lo planes of the result
     g.M = M; g.N = N; g.K = C1 + C2;
     g.A = x; g.lda = lda; g.C1 = C1;
     g.A2 = x2; g.lda2 = lda2; g.C2 = C2;
@@ -434,6 +435,8 @@ struct UNetExec : Exec {
   const float* E = nullptr;   // [B, emb_rows] all ResBlock emb projections
   const float* ctx = nullptr;
   int ctx_len = 0;
+  const float* ctx_pad = nullptr;   // context zero-padded to ctx_lp rows per image (tensor-core cross-attention)
+  int ctx_lp = 0;
   bool oai;
   UNetExec(Net& net, cudaStream_t st) : Exec(net, st), oai(net.kind == NET_UNET_OPENAI) {}
 
@@ -511,29 +514,28 @@ struct UNetExec : Exec {
       Tensor n1 = ln(h, t + ".norm1");
       Tensor a = alloc(B, x.H, x.W, C);
       bool done = false;
-      if (e.mma_mode == 1 && (HW % 32) == 0 && HW >= 128 && (d % 4) == 0) {
-        // tensor-core attention: fused q|k projection, V produced transposed (V^T = Wv . X^T, a swapped-role GEMM)
-        // so that both P.V operands are K-major for tcgen05
+      const bool flash_ok = e.mma_mode == 1 && e.flash_attn && (HW % 128) == 0 && (d == 16 || d == 32 || d == 40 || d == 64 || d == 80);
+      if (flash_ok) {
+        // fused tensor-core attention: q|k projection and V^T (= Wv . X^T, a swapped-role GEMM, so that both P.V operands
+        // are K-major for tcgen05) are written by their GEMM epilogues directly as TF32 hi / lo planes
+        Scope sa(e.arena);
+        const size_t nqk = (size_t)M * 2 * C, nvt = (size_t)C * M;
+        float* qk_hi = (float*)e.arena.alloc(nqk * sizeof(float));
+        float* qk_lo = (float*)e.arena.alloc(nqk * sizeof(float));
+        float* vt_hi = (float*)e.arena.alloc(nvt * sizeof(float));
+        float* vt_lo = (float*)e.arena.alloc(nvt * sizeof(float));
+        linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 2 * C, nullptr, nullptr, 0, qk_hi, 2 * C, qk_lo);
+        linear_into(n.P(t + ".attn1.to_v.weight"), C, C, nullptr, 0, 0, C, n1.p, M, nullptr, nullptr, 0, vt_hi, M, vt_lo);
+        done = flash_attention_tc(e, qk_hi, qk_lo, 2 * C, qk_hi + C, qk_lo + C, 2 * C, vt_hi, vt_lo, a.p, C, B, HW, HW, HW, heads, d, scale, s);
+        CDX_CHECK(done, "flash attention rejected an eligible shape (HW=%d d=%d)", HW, d);
+      } else if (e.mma_mode >= 1 && (HW % 32) == 0 && HW >= 128 && (d % 4) == 0) {
+        // unfused tensor-core attention (mode 2, or shapes the fused kernel does not cover)
         Scope sa(e.arena);
         Tensor qk = alloc(B, x.H, x.W, 2 * C);
         linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 2 * C, nullptr, nullptr, 0, qk.p, 2 * C);
         float* vt = (float*)e.arena.alloc((size_t)C * M * sizeof(float));
         linear_into(n.P(t + ".attn1.to_v.weight"), C, C, nullptr, 0, 0, C, n1.p, M, nullptr, nullptr, 0, vt, M);
-        {
-          // fused flash attention needs the TF32 hi / lo planes of q|k and V^T (one read + two writes each)
-          Scope sf(e.arena);
-          const size_t nqk = (size_t)M * 2 * C, nvt = (size_t)C * M;
-          float* qk_hi = (float*)e.arena.alloc(nqk * sizeof(float));
-          float* qk_lo = (float*)e.arena.alloc(nqk * sizeof(float));
-          float* vt_hi = (float*)e.arena.alloc(nvt * sizeof(float));
-          float* vt_lo = (float*)e.arena.alloc(nvt * sizeof(float));
-          if (e.flash_attn && (HW % 128) == 0 && (d == 16 || d == 32 || d == 40 || d == 64 || d == 80)) {
-            split_planes(e, qk.p, qk_hi, qk_lo, nqk, s);
-            split_planes(e, vt, vt_hi, vt_lo, nvt, s);
-            done = flash_attention_tc(e, qk_hi, qk_lo, 2 * C, C, vt_hi, vt_lo, a.p, C, B, HW, heads, d, scale, s);
-          }
-        }
-        if (!done) done = attention_tc(e, qk.p, 2 * C, qk.p + C, 2 * C, d, vt, a.p, C, B, HW, HW, heads, d, scale, s);
+        done = attention_tc(e, qk.p, 2 * C, qk.p + C, 2 * C, d, vt, a.p, C, B, HW, HW, heads, d, scale, s);
       }
       if (!done) {
         Scope sa(e.arena);
@@ -547,12 +549,35 @@ struct UNetExec : Exec {
     Tensor h3;
     {
       Tensor n2 = ln(h2, t + ".norm2");
-      Tensor q = linear(n2, t + ".attn2.to_q", false);
       const int D = n.ucfg.context_dim;
-      Tensor kv = alloc(B, ctx_len, 1, 2 * C);
-      linear_into(ctx, D, D, nullptr, 0, 0, B * ctx_len, n.P(t + ".attn2.to_k.weight"), 2 * C, nullptr, nullptr, 0, kv.p, 2 * C);
       Tensor a = alloc(B, x.H, x.W, C);
-      attention(e, q.p, C, kv.p, 2 * C, kv.p + C, 2 * C, a.p, C, B, HW, ctx_len, heads, d, d, scale, s);
+      bool done = false;
+      Tensor q;
+      if (ctx_pad && (HW % 128) == 0 && (d == 16 || d == 32 || d == 40 || d == 64 || d == 80)) {
+        // fused tensor-core attention over the zero-padded context (ctx_lp rows per image, keys >= ctx_len masked in the
+        // kernel): q = n2.Wq^T, K = ctx.Wk^T, V^T = Wv.ctx^T (swapped-role GEMM), all written as TF32 planes
+        Scope sa(e.arena);
+        const int Mk = B * ctx_lp;
+        const size_t nq = (size_t)M * C, nk = (size_t)Mk * C;
+        float* q_hi = (float*)e.arena.alloc(nq * sizeof(float));
+        float* q_lo = (float*)e.arena.alloc(nq * sizeof(float));
+        float* k_hi = (float*)e.arena.alloc(nk * sizeof(float));
+        float* k_lo = (float*)e.arena.alloc(nk * sizeof(float));
+        float* vt_hi = (float*)e.arena.alloc(nk * sizeof(float));
+        float* vt_lo = (float*)e.arena.alloc(nk * sizeof(float));
+        linear_into(n2.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn2.to_q.weight"), C, nullptr, nullptr, 0, q_hi, C, q_lo);
+        linear_into(ctx_pad, D, D, nullptr, 0, 0, Mk, n.P(t + ".attn2.to_k.weight"), C, nullptr, nullptr, 0, k_hi, C, k_lo);
+        linear_into(n.P(t + ".attn2.to_v.weight"), D, D, nullptr, 0, 0, C, ctx_pad, Mk, nullptr, nullptr, 0, vt_hi, Mk, vt_lo);
+        done = flash_attention_tc(e, q_hi, q_lo, C, k_hi, k_lo, C, vt_hi, vt_lo, a.p, C, B, HW, ctx_len, ctx_lp, heads, d, scale, s);
+        CDX_CHECK(done, "flash cross-attention rejected an eligible shape (HW=%d d=%d L=%d)", HW, d, ctx_len);
+      }
+      if (!done) q = linear(n2, t + ".attn2.to_q", false);
+      if (!done) {
+        Scope sa(e.arena);
+        Tensor kv = alloc(B, ctx_len, 1, 2 * C);
+        linear_into(ctx, D, D, nullptr, 0, 0, B * ctx_len, n.P(t + ".attn2.to_k.weight"), 2 * C, nullptr, nullptr, 0, kv.p, 2 * C);
+        attention(e, q.p, C, kv.p, 2 * C, kv.p + C, 2 * C, a.p, C, B, HW, ctx_len, heads, d, d, scale, s);
+      }
       h3 = linear(a, t + ".attn2.to_out.0", true, h2.p);
     }
     // --- GEGLU feed-forward (ATT:37-64)
@@ -590,8 +615,20 @@ struct UNetExec : Exec {
     const cdx_unet_config& c = n.ucfg;
     ctx = context;
     ctx_len = L;
+    ctx_pad = nullptr;
+    ctx_lp = (L + 3) & ~3;
     const int mc = c.model_channels, half = mc / 2, ted = n.ted;
     Scope top(e.arena);
+    if (context && L > 0 && e.mma_mode == 1 && e.flash_attn) {
+      // context rows padded to a multiple of 4 per image: TMA needs 16-byte strides for K and V^T of the cross-attention
+      const size_t D = (size_t)c.context_dim;
+      float* cp = (float*)e.arena.alloc((size_t)B * ctx_lp * D * sizeof(float));
+      if (!e.dry()) {
+        if (ctx_lp != L) CDX_CUDA(cudaMemsetAsync(cp, 0, (size_t)B * ctx_lp * D * sizeof(float), s));
+        CDX_CUDA(cudaMemcpy2DAsync(cp, (size_t)ctx_lp * D * 4, context, (size_t)L * D * 4, (size_t)L * D * 4, B, cudaMemcpyDeviceToDevice, s));
+      }
+      ctx_pad = cp;
+    }
     // --- timestep embedding MLP + all ResBlock emb projections in one GEMM
     Tensor temb = alloc(B, 1, 1, mc);
     timestep_embedding(e, t_dev, n.freqs_dev, temb.p, B, half, s);

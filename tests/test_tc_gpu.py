@@ -132,3 +132,28 @@ def test_attention_tc(B, N, heads, d, mode):
     print(f'attention mode {mode} B{B} N{N} h{heads} d{d}: max abs err {err:.2e}  ({ {k_: round(v_["ms"], 3) for k_, v_ in fam.items()} })')
     assert 'batched_tc' in fam
     assert err < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,N,Nk,heads,d', [(2, 256, 77, 2, 40), (1, 128, 77, 2, 80), (2, 128, 130, 1, 64), (3, 128, 64, 2, 32), (2, 256, 5, 1, 16)])
+def test_cross_attention_flash(B, N, Nk, heads, d):
+    """Cross-attention (Nk != N, ragged last key block masked in the kernel; CrossAttention.forward attention.py:170-193)."""
+    from cycle_diffusion_b200.engine import Engine
+    e = Engine(0)
+    e.set_mma_mode(1)
+    g = torch.Generator().manual_seed(N + Nk + d)
+    C = heads * d
+    q = torch.randn(B, N, C, generator=g) * 1.5
+    k, v = (torch.randn(B, Nk, C, generator=g) for _ in range(2))
+    scale = d ** -0.5
+    sp = lambda t: t.reshape(B, -1, heads, d).permute(0, 2, 1, 3)
+    attn = (torch.einsum('bhid,bhjd->bhij', sp(q), sp(k)) * scale).softmax(-1)
+    ref = torch.einsum('bhij,bhjd->bhid', attn, sp(v)).permute(0, 2, 1, 3).reshape(B, N, C)
+    e.profile(True)
+    y = e.op_attention(q.cuda(), k.cuda(), v.cuda(), heads, scale).cpu()
+    fam = e.profile_read()
+    e.profile(False)
+    err = float((y - ref).abs().max())
+    print(f'cross attention B{B} N{N} Nk{Nk} h{heads} d{d}: max abs err {err:.2e}')
+    assert 'batched_tc' in fam, fam.keys()
+    assert err < 2e-5
