@@ -209,7 +209,7 @@ def run_ours(args):
     e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
 
     # ---- roofline pass (untimed): per-kernel-family CUDA-event timing of one CFG U-Net call (batch 2B) on rank 0
-    roof, families, unet_ms = None, {}, None
+    roof, families, unet_ms, stage_ms = None, {}, None, None
     if rank == 0:
         pk = peaks()
         x = torch.randn(2 * B, 4, LAT, LAT, device=d)
@@ -234,8 +234,14 @@ def run_ours(args):
             top = max(tensor_fams, key=lambda k: tensor_fams[k]['ms'])
             f = tensor_fams[top]
             ach = f['flops'] / (f['ms'] * 1e-3) / 1e12
+            traffic = None      # DRAM bytes of one captured launch of this family (ncu --set full; profiles/ncu_traffic.json)
+            try:
+                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_traffic.json')) as fh:
+                    traffic = json.load(fh).get(top)
+            except (OSError, ValueError):
+                pass
             roof = {'kernel': top, 'bound': 'tensor', 'achieved': round(ach, 2), 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
-                    'frac': round(ach / pk['tflops_sustained'], 4), 'traffic': None, 'launches_per_unet_call': f['launches'],
+                    'frac': round(ach / pk['tflops_sustained'], 4), 'traffic': traffic, 'launches_per_unet_call': f['launches'],
                     'avg_launch_ms': round(f['ms'] / f['launches'], 4),
                     'peak_source': pk['source'] + ' -- sustained bf16 dense; this path is fp32-faithful (see DESIGN.md)',
                     'whole_job_tflops': round(value * TFLOP_PER_IMAGE, 2)}
@@ -248,6 +254,22 @@ def run_ours(args):
             if v['flops']:
                 v['tflops'] = round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 2)
 
+        # stage breakdown of one cycle (untimed extra pass, CUDA events on the launching stream)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        x_ = eng.shift_scale(dev['image'], -0.5, 2.0)
+        x0_ = eng.vae_posterior(vae.encode_moments(x_), dev['post'], 0.18215)
+        ev[1].record()
+        z_ = unet.latent_encode(x0_, dev['c_src'], dev['uc'], ENC_SCALE, sched, n_rec, dev['noise'])
+        ev[2].record()
+        s_ = unet.latent_decode(z_, dev['c_tgt'], dev['uc'], DEC_SCALE, sched)
+        ev[3].record()
+        eng.shift_scale(vae.decode(eng.affine(s_, 1. / 0.18215, 0.0)), 1.0, 0.5)
+        ev[4].record()
+        torch.cuda.synchronize()
+        stage_ms = {k: round(ev[i].elapsed_time(ev[i + 1]), 1) for i, k in
+                    enumerate(['vae_encode', f'dpm_encode_{S_STEPS}x_unet_b{B}', f'decode_{S_STEPS}x_unet_b{2 * B}', 'vae_decode'])}
+
     cpu = cpu_baseline_sample(quick=True) if (rank == 0 and not args.no_cpu) else None
 
     if rank == 0:
@@ -259,7 +281,7 @@ def run_ours(args):
                                    'batch 4 per GPU', 'global_batch': world * B, 'steps_encode': S_STEPS, 'steps_decode': S_STEPS, 'eta': ETA,
                        'parallelism': f'dp{world} (images sharded, one NCCL weight broadcast)', 'mma_mode': 'ffma-fp32' if args.mma == 0 else 'tcgen05-3xTF32 (fp32-faithful)',
                        'l2': 'no flush: 3.8 GB of weights + >1 GB activations per U-Net call are streamed every call (>> 126 MB L2)',
-                       'unet_calls_per_step': 2 * S_STEPS, 'unet_ms_cfg_batch8': round(unet_ms, 2) if unet_ms else None},
+                       'unet_calls_per_step': 2 * S_STEPS, 'unet_ms_cfg_batch8': round(unet_ms, 2) if unet_ms else None, 'stage_ms': stage_ms},
             'e2e': {'value': round(e2e_value, 4), 'unit': UNIT, 'h2d_bytes_per_step': h2d[0], 'd2h_bytes_per_step': 4 * out_host.numel(),
                     'steps': e2e_steps, 'api': 'SDStochasticTextWrapper.encode + forward (host tensors in, pinned host tensor out)'},
             'gpu_launches': launches, 'clocks': clk, 'roofline': roof, 'kernel_families': families, 'cpu_baseline': cpu,

@@ -1,6 +1,8 @@
 // cabi.cu -- the extern "C" surface declared in include/cdx.h, plus the in-library loop drivers
 // (DPM-Encoder inversion and decode-with-recovered-noise) so that a whole chain is enqueued without
 // returning to the host language between steps.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -179,10 +181,12 @@ int cdx_engine_profile_read(cdx_engine* e, int tag, double* ms, double* flops, d
     CDX_CUDA(cudaSetDevice(e->e.device));
     CDX_CUDA(cudaDeviceSynchronize());
     *ms = 0; *flops = 0; *bytes = 0; *launches = 0;
+    const bool dump = getenv("CDX_PROF_DUMP") != nullptr;
     for (const ProfRec& r : e->e.prof.recs) {
       if (r.tag != tag) continue;
       float t = 0.f;
       CDX_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+      if (dump) fprintf(stderr, "[cdx prof] tag %d  %8.3f ms  %8.1f GFLOP  %7.1f TF/s  %s\n", tag, t, r.flops * 1e-9, t > 0 ? r.flops / (t * 1e9) : 0.0, r.note);
       *ms += t; *flops += r.flops; *bytes += r.bytes; *launches += (uint64_t)r.launches;
     }
   });

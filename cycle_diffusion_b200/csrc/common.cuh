@@ -61,7 +61,7 @@ enum ProfTag {
   PROF_CONV_FFMA = 0, PROF_DENSE_FFMA = 1, PROF_BATCHED_FFMA = 2, PROF_CONV_TC = 3, PROF_DENSE_TC = 4, PROF_BATCHED_TC = 5,
   PROF_GROUPNORM = 6, PROF_LAYERNORM = 7, PROF_SOFTMAX = 8, PROF_ELEMENTWISE = 9, PROF_NTAGS = 10
 };
-struct ProfRec { cudaEvent_t a, b; int tag; double flops, bytes; int launches; };
+struct ProfRec { cudaEvent_t a, b; int tag; double flops, bytes; int launches; char note[56]; };
 struct Profiler {
   bool on = false;
   std::vector<ProfRec> recs;
@@ -86,6 +86,7 @@ struct ProfScope {
   int idx = -1;
   ProfScope(Engine& eng, cudaStream_t st, int tag, double flops, double bytes, int launches);
   ~ProfScope();
+  void note(const char* fmt, ...);     // free-form shape note, printed per launch when CDX_PROF_DUMP is set
 };
 
 struct Scope {   // RAII arena scope
@@ -130,6 +131,7 @@ struct GemmArgs {
   const float* rowvec = nullptr; int ld_rowvec = 0; int rows_per_batch = 1;
   const float* residual = nullptr; int ldr = 0;
   float alpha = 1.f;
+  int geglu = 0;                     // columns are [32 value | 32 gate] blocks: store value * gelu(gate) as [M, N/2] (attention.py:42-44)
   int out_nchw = 0;                  // store C as [B, N, rows_per_img] instead of [M, N]
   int rows_per_img = 0;
   // batching over blockIdx.z = zb*heads + zh
@@ -156,7 +158,9 @@ void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, cons
 void layernorm(Engine& e, const float* x, const float* gamma, const float* beta, float* y, int M, int C, cudaStream_t s);
 void softmax_rows(Engine& e, float* x, long long rows, int L, int ld, cudaStream_t s);   // in place
 void silu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s);
-void geglu(Engine& e, const float* x, float* y, int M, int C, cudaStream_t s);   // x [M,2C] -> y [M,C] = x[:, :C]*gelu(x[:, C:])
+// x [M,2C] -> y [M,C] = value * gelu(gate); plain: value = x[:, :C], gate = x[:, C:]; interleaved: blocks of [32 value | 32 gate]
+void geglu(Engine& e, const float* x, float* y, int M, int C, cudaStream_t s, bool interleaved = false);
+void interleave_geglu_rows(Engine& e, const float* src, float* dst, int rows, int rowlen, cudaStream_t s);
 void add(Engine& e, const float* a, const float* b, float* y, size_t n, cudaStream_t s);
 void avgpool2(Engine& e, const float* x, float* y, int B, int H, int W, int C, cudaStream_t s);      // -> [B,H/2,W/2,C]
 void upsample2(Engine& e, const float* x, float* y, int B, int H, int W, int C, cudaStream_t s);     // -> [B,2H,2W,C]

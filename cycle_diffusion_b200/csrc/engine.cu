@@ -1,4 +1,7 @@
 // engine.cu -- per-device context: workspace arena, error state.
+#include <cstdarg>
+#include <cstdio>
+
 #include "common.cuh"
 
 namespace cdx {
@@ -47,9 +50,17 @@ ProfScope::ProfScope(Engine& eng, cudaStream_t st, int tag, double flops, double
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   r.tag = tag; r.flops = flops; r.bytes = bytes; r.launches = launches;
+  r.note[0] = 0;
   cudaEventRecord(r.a, s);
   idx = (int)e.prof.recs.size();
   e.prof.recs.push_back(r);
+}
+void ProfScope::note(const char* fmt, ...) {
+  if (idx < 0) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(e.prof.recs[idx].note, sizeof(e.prof.recs[idx].note), fmt, ap);
+  va_end(ap);
 }
 ProfScope::~ProfScope() {
   if (idx >= 0) cudaEventRecord(e.prof.recs[idx].b, s);

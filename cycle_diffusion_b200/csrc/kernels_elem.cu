@@ -44,14 +44,28 @@ __global__ void copy_kernel(const float* __restrict__ a, float* __restrict__ y, 
   GRID_STRIDE(i, n) y[i] = a[i];
 }
 // x [M,2C] -> y [M,C] = x[:, :C] * gelu_erf(x[:, C:])   (attention.py:42-44)
-__global__ void geglu_kernel(const float* __restrict__ x, float* __restrict__ y, size_t M, int C) {
+__global__ void geglu_kernel(const float* __restrict__ x, float* __restrict__ y, size_t M, int C, int interleaved) {
   const size_t n = M * (size_t)C;
   GRID_STRIDE(i, n) {
     const size_t m = i / C;
     const int c = (int)(i - m * C);
-    const float v = x[m * 2 * C + c];
-    const float g = x[m * 2 * C + C + c];
+    const int cv = interleaved ? ((c >> 5) << 6) + (c & 31) : c;      // [32 value | 32 gate] blocks (see Param::geglu)
+    const int cg = interleaved ? cv + 32 : C + c;
+    const float v = x[m * 2 * C + cv];
+    const float g = x[m * 2 * C + cg];
     y[i] = v * (0.5f * g * (1.f + erff(g * 0.70710678118654752440f)));
+  }
+}
+// rows [0, rows/2) are value rows, [rows/2, rows) gate rows -> blocks of 32 value rows followed by their 32 gate rows
+__global__ void interleave_geglu_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int rowlen) {
+  const size_t n = (size_t)rows * rowlen;
+  const int half = rows / 2;
+  GRID_STRIDE(i, n) {
+    const int r = (int)(i / rowlen);
+    const int c = (int)(i - (size_t)r * rowlen);
+    const int j = r < half ? r : r - half;
+    const int dr = ((j >> 5) << 6) + (j & 31) + (r < half ? 0 : 32);
+    dst[(size_t)dr * rowlen + c] = src[i];
   }
 }
 __global__ void avgpool2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
@@ -233,7 +247,13 @@ void q_sample(Engine& e, const float* x0, const float* nz, float sa, float s1, f
 void silu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s) { LAUNCH1(silu_kernel, n, x, y, n); }
 void add(Engine& e, const float* a, const float* b, float* y, size_t n, cudaStream_t s) { LAUNCH1(add_kernel, n, a, b, y, n); }
 void copy_rows(Engine& e, const float* a, float* y, size_t n, cudaStream_t s) { LAUNCH1(copy_kernel, n, a, y, n); }
-void geglu(Engine& e, const float* x, float* y, int M, int C, cudaStream_t s) { LAUNCH1(geglu_kernel, (size_t)M * C, x, y, (size_t)M, C); }
+void geglu(Engine& e, const float* x, float* y, int M, int C, cudaStream_t s, bool interleaved) {
+  LAUNCH1(geglu_kernel, (size_t)M * C, x, y, (size_t)M, C, interleaved ? 1 : 0);
+}
+void interleave_geglu_rows(Engine& e, const float* src, float* dst, int rows, int rowlen, cudaStream_t s) {
+  CDX_CHECK(rows % 128 == 0, "interleave_geglu_rows: %d rows", rows);
+  LAUNCH1(interleave_geglu_rows_kernel, (size_t)rows * rowlen, src, dst, rows, rowlen);
+}
 void avgpool2(Engine& e, const float* x, float* y, int B, int H, int W, int C, cudaStream_t s) {
   CDX_CHECK(H % 2 == 0 && W % 2 == 0, "avgpool2: odd size %dx%d", H, W);
   LAUNCH1(avgpool2_kernel, (size_t)B * (H / 2) * (W / 2) * C, x, y, B, H, W, C);

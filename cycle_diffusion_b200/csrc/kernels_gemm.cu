@@ -306,6 +306,19 @@ void gemm(Engine& e, const GemmArgs& a, cudaStream_t s) {
   if (a.mode == 1) CDX_CHECK(a.K == 9 * (a.C1 + a.C2), "conv3x3: K != 9*Cin");
   if (a.mode == 0) CDX_CHECK(a.K == a.C1 + a.C2, "dense: K != C1+C2");
   if (e.mma_mode == 1 && gemm_tc(e, a, s)) return;      // (handles the arena dry run itself: split-K workspace)
+  if (a.geglu) {       // fused only in the tensor-core epilogue; here: plain GEMM into a temporary, then the GEGLU kernel
+    CDX_CHECK(a.N % 128 == 0 && a.batch * a.heads == 1 && !a.out_nchw && !a.Cout_lo, "gemm: bad GEGLU problem");
+    Scope sc(e.arena);
+    float* tmp = (float*)e.arena.alloc((size_t)a.M * a.N * sizeof(float));
+    if (e.dry()) return;
+    GemmArgs b = a;
+    b.geglu = 0;
+    b.Cout = tmp; b.ldc = a.N;
+    gemm(e, b, s);
+    CDX_CHECK(a.ldc == a.N / 2, "gemm: GEGLU output must be dense [M, N/2]");
+    geglu(e, tmp, a.Cout, a.M, a.N / 2, s, true);
+    return;
+  }
   if (e.dry()) return;
   if (a.Cout_lo) {     // plane outputs are produced by the tensor-core epilogue; here: exact GEMM, then split in place
     CDX_CHECK(a.ldc == a.N && a.batch * a.heads == 1 && !a.out_nchw, "gemm: plane output needs a dense [M,N] result");

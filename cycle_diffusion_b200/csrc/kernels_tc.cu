@@ -19,7 +19,8 @@
 //               over (k, head, row, batch) for the attention contractions.
 //   warp 1      MMA issuer: one lane issues 12 tcgen05.mma per K block, tcgen05.commit hands the stage back.
 //   warps 2-5   split warps.
-//   warps 6-9   drain + epilogue: tcgen05.ld 32x32b.x32 per chunk -> RN add into 128 fp32 registers per thread; at the
+//   warps 6-13  drain + epilogue (two warps per TMEM lane quadrant, 32 rows x 64 columns each): tcgen05.ld 32x32b.x32 per
+//               chunk -> RN add into 64 fp32 registers per thread; at the
 //               end alpha, +bias, +per-sample row vector (timestep embedding), +residual -> 128-bit global stores.
 //
 // Two variants of the operand path (template parameter TS):
@@ -43,7 +44,7 @@ using namespace tc;
 constexpr int TBM = 128, TBN = 128, TBK = 32;
 constexpr int TILE_BYTES = TBM * TBK * 4;          // 16 KB
 constexpr int NUM_SPLIT_WARPS = 4;
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 8;
 constexpr int KCHUNK = 8;                          // k-blocks per TMEM accumulation chunk (256 K elements)
 constexpr int TC_THREADS = 64 + (NUM_SPLIT_WARPS + NUM_EPI_WARPS) * 32;
 
@@ -53,7 +54,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = TS ? 3 * TILE_BYTES : 4 * TILE_BYTES;   // TS: A_raw, B_hi, B_lo ; SS: A_hi, A_lo, B_hi, B_lo
   static constexpr int TMEM_COLS = TS ? 512 : 256;
   static constexpr int A_COL0 = 256;               // TS: A stage s lives at columns A_COL0 + 64 s (hi) / + 32 (lo)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048 /*barriers + bias staging*/ + 16384 /*epilogue transpose*/ + 1024 /*alignment slack*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048 /*barriers + bias staging*/ + 32768 /*epilogue transpose: 8 warps x 4 KB*/ + 1024 /*alignment slack*/;
 };
 
 struct TcParams {
@@ -71,6 +72,7 @@ struct TcParams {
   const float* rowvec; int ld_rowvec; int rows_per_batch;
   const float* residual; int ldr;
   float alpha;
+  int geglu;                    // N tiles hold [32 value | 32 gate] column blocks: store value * gelu(gate) to [M, N/2]
   int out_nchw, rows_per_img;   // store C as [B, N, rows_per_img] (final conv of a network, reference NCHW layout)
   // mode 2 (blockIdx.z = zb*heads + zh): 4D maps, coordinate recipe per operand
   int heads;
@@ -112,7 +114,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   auto bar_acc_empty = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
   const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
   float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 512);   // [2][TBN], epilogue warps only
-  float4* const s_stage = reinterpret_cast<float4*>(smem_raw + (bars - smem_u32(smem_raw)) + 2048);   // 4 warps x 4 KB
+  float4* const s_stage = reinterpret_cast<float4*>(smem_raw + (bars - smem_u32(smem_raw)) + 2048);   // 8 warps x 4 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + TBK - 1) / TBK;
@@ -322,9 +324,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else {
     // =========================================================================== drain + epilogue warps
-    const int q = warp & 3;                        // TMEM lane quadrant this warp may access (warps 6..9 -> 2,3,0,1)
+    // eight warps: two per TMEM lane quadrant, each owning 32 rows x 64 columns (hf = column half) of the tile
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may access (warps 6..13 -> 2,3,0,1,2,3,0,1)
+    const int ew = warp - (2 + NUM_SPLIT_WARPS);   // 0..7
+    const int hf = ew >> 2;                        // column half
     const int r = q * 32 + lane;                   // tile row owned by this thread
-    const int et = q * 32 + lane;                  // 0..127: column this thread stages for the tile's bias vector
+    const int et = hf * 128 + q * 32 + lane;       // 0..255: threads 0..127 stage the tile's bias vector
+    constexpr int HN = TBN / 2;                    // 64 columns per thread
     int gchunk0 = 0, tile_it = 0;
 #pragma unroll 1
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
@@ -334,19 +340,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // the tile's 128 bias values: one coalesced load issued before the drain (latency hidden behind it), handed to
     // all rows through shared memory; double-buffered by tile parity so a fast warp cannot overwrite a slow warp's tile
     float bias_v = 0.f;
-    if (p.bias && p.splits == 1 && n0 + et < p.N) bias_v = __ldg(p.bias + n0 + et);
-    float acc[TBN];
+    if (et < TBN && p.bias && p.splits == 1 && n0 + et < p.N) bias_v = __ldg(p.bias + n0 + et);
+    float acc[HN];
 #pragma unroll
-    for (int j = 0; j < TBN; ++j) acc[j] = 0.f;
+    for (int j = 0; j < HN; ++j) acc[j] = 0.f;
 #pragma unroll 1
     for (int lchunk = 0; lchunk < num_chunks; ++lchunk) {
       const int chunk = gchunk0 + lchunk;
       const int buf = chunk & 1;
       mbar_wait(bar_acc_full(buf), (chunk >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TBN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TBN + hf * HN);
 #pragma unroll
-      for (int part = 0; part < TBN / 32; ++part) {
+      for (int part = 0; part < HN / 32; ++part) {
         uint32_t v[32];
         tmem_ld32(taddr + part * 32, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -358,7 +364,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (lane == 0) mbar_arrive(bar_acc_empty(buf));
     }
     float* const sb = s_bias + (tile_it & 1) * TBN;
-    sb[et] = bias_v;
+    if (et < TBN) sb[et] = bias_v;
     asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
 
     long long m;
@@ -377,82 +383,107 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (row_ok) {
         const long long bimg = m / p.rows_per_img, rimg = m - bimg * p.rows_per_img;
 #pragma unroll
-        for (int j = 0; j < TBN; ++j) {
-          const int n = n0 + j;
-          if (n < p.N) p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = p.alpha * acc[j] + sb[j];   // lanes = pixels: coalesced
+        for (int j = 0; j < HN; ++j) {
+          const int n = n0 + hf * HN + j;
+          if (n < p.N) p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = p.alpha * acc[j] + sb[hf * HN + j];   // lanes = pixels: coalesced
         }
       }
     } else {
       const bool fin = p.splits == 1;                // otherwise: raw partial sums to ws[split][M][N]
-      if (fin && row_ok) {
-        // pass 1 (registers only): alpha, bias from smem, per-image row vector
-#pragma unroll
-        for (int j = 0; j < TBN; j += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(sb + j);
-          acc[j + 0] = p.alpha * acc[j + 0] + t.x;
-          acc[j + 1] = p.alpha * acc[j + 1] + t.y;
-          acc[j + 2] = p.alpha * acc[j + 2] + t.z;
-          acc[j + 3] = p.alpha * acc[j + 3] + t.w;
-        }
-        if (p.rowvec) {
-          const float* rv = p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec;
-#pragma unroll
-          for (int j = 0; j < TBN; j += 4) {
-            if (n0 + j < p.N) {                          // N % 4 == 0 is an eligibility condition
-              const float4 t = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
-              acc[j + 0] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
-            }
-          }
-        }
-      }
-      // pass 2: the thread-per-row accumulator layout would store 16 B to 32 different rows per instruction (32 L1
-      // wavefronts each, which also starves the split warps' LDS behind them); instead each warp transposes 32x32
-      // blocks through a swizzled 4 KB staging buffer so that one instruction covers 4 rows x 128 contiguous bytes,
-      // for the residual loads as well
+      // the thread-per-row accumulator layout would store 16 B to 32 different rows per instruction (32 L1 wavefronts
+      // each, which also starves the split warps' LDS behind them); instead each warp transposes 32x32 blocks through a
+      // swizzled 4 KB staging buffer so that one instruction covers 4 rows x 128 contiguous bytes -- for the residual
+      // loads as well, which are issued a whole 32-column block ahead of their use (L2 latency off the critical path)
       float* const dst = fin ? p.C + zb * p.sC_b + zh * p.sC_h : p.ws + (long long)tc_.split * p.M * p.N;
       const long long dld = fin ? p.ldc : p.N;
       const float* const rsd = fin ? p.residual : nullptr;
       float* const dst_lo = (fin && p.C_lo) ? p.C_lo + zb * p.sC_b + zh * p.sC_h : nullptr;
       const int m32 = row_ok ? (int)m : -1;
-      float4* const stg = s_stage + q * 256;          // [32 rows][8 float4], chunk index XOR (row & 7)
+      float4* const stg = s_stage + ew * 256;         // [32 rows][8 float4], chunk index XOR (row & 7)
       const int g = lane & 7, rsub = lane >> 3;
+      // GEGLU tiles are [32 value | 32 gate | 32 value | 32 gate]: this thread's 64 columns are 32 values + their gates
+      const int nparts = p.geglu ? 1 : HN / 32;
+      const int ncol0 = p.geglu ? (n0 >> 1) + hf * 32 : n0 + hf * HN, nlim = p.geglu ? (p.N >> 1) : p.N;
+      int mm[8];
 #pragma unroll
-      for (int part = 0; part < TBN / 32; ++part) {
+      for (int i = 0; i < 8; ++i) mm[i] = __shfl_sync(0xffffffffu, m32, 4 * i + rsub);
+      float4 t[8];
+      auto load_residual = [&](int part) {
+        const int n = ncol0 + part * 32 + 4 * g;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          t[i] = (rsd && mm[i] >= 0 && n < nlim) ? *reinterpret_cast<const float4*>(rsd + (long long)mm[i] * p.ldr + n)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      load_residual(0);
+      if (fin && row_ok) {
+        // pass 1 (registers only): alpha, bias from smem, per-image row vector
+#pragma unroll
+        for (int j = 0; j < HN; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(sb + hf * HN + j);
+          acc[j + 0] = p.alpha * acc[j + 0] + bv.x;
+          acc[j + 1] = p.alpha * acc[j + 1] + bv.y;
+          acc[j + 2] = p.alpha * acc[j + 2] + bv.z;
+          acc[j + 3] = p.alpha * acc[j + 3] + bv.w;
+        }
+        if (p.rowvec) {
+          const float* rv = p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec + n0 + hf * HN;
+#pragma unroll
+          for (int j = 0; j < HN; j += 4) {
+            if (n0 + hf * HN + j < p.N) {                // N % 4 == 0 is an eligibility condition
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(rv + j));
+              acc[j + 0] += bv.x; acc[j + 1] += bv.y; acc[j + 2] += bv.z; acc[j + 3] += bv.w;
+            }
+          }
+        }
+        if (p.geglu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float gt = acc[32 + j];
+            acc[j] *= 0.5f * gt * (1.f + erff(gt * 0.70710678118654752440f));     // exact-erf GELU as F.gelu
+          }
+        }
+      }
+#pragma unroll
+      for (int part = 0; part < HN / 32; ++part) {
+        if (part >= nparts) break;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           stg[lane * 8 + (c ^ (lane & 7))] =
               make_float4(acc[part * 32 + 4 * c], acc[part * 32 + 4 * c + 1], acc[part * 32 + 4 * c + 2], acc[part * 32 + 4 * c + 3]);
         __syncwarp();
-        const int n = n0 + part * 32 + 4 * g;
+        const int n = ncol0 + part * 32 + 4 * g;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          float4 v[4], t[4];
-          int mm[4];
+          float4 o[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rl = 4 * (half * 4 + i) + rsub;
-            mm[i] = __shfl_sync(0xffffffffu, m32, rl);
-            v[i] = stg[rl * 8 + (g ^ (rl & 7))];
-            t[i] = (rsd && mm[i] >= 0 && n < p.N) ? *reinterpret_cast<const float4*>(rsd + (long long)mm[i] * p.ldr + n)
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v = stg[rl * 8 + (g ^ (rl & 7))];
+            const float4 tt = t[half * 4 + i];
+            o[i] = make_float4(v.x + tt.x, v.y + tt.y, v.z + tt.z, v.w + tt.w);
+          }
+          if (half == 1) {
+            __syncwarp();                                         // staging buffer free for the next block
+            if (part + 1 < nparts) load_residual(part + 1);      // in flight while this block is stored
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (mm[i] >= 0 && n < p.N) {
-              float4 o = make_float4(v[i].x + t[i].x, v[i].y + t[i].y, v[i].z + t[i].z, v[i].w + t[i].w);
+          for (int i = 0; i < 4; ++i) {
+            const int mi = mm[half * 4 + i];
+            if (mi >= 0 && n < nlim) {
               if (dst_lo) {                          // operand planes for a following tcgen05 consumer
                 float4 hi, lo;
-                hi.x = __uint_as_float(rn_tf32(__float_as_uint(o.x))); lo.x = __uint_as_float(rn_tf32(__float_as_uint(o.x - hi.x)));
-                hi.y = __uint_as_float(rn_tf32(__float_as_uint(o.y))); lo.y = __uint_as_float(rn_tf32(__float_as_uint(o.y - hi.y)));
-                hi.z = __uint_as_float(rn_tf32(__float_as_uint(o.z))); lo.z = __uint_as_float(rn_tf32(__float_as_uint(o.z - hi.z)));
-                hi.w = __uint_as_float(rn_tf32(__float_as_uint(o.w))); lo.w = __uint_as_float(rn_tf32(__float_as_uint(o.w - hi.w)));
-                *reinterpret_cast<float4*>(dst_lo + (long long)mm[i] * dld + n) = lo;
-                o = hi;
+                hi.x = __uint_as_float(rn_tf32(__float_as_uint(o[i].x))); lo.x = __uint_as_float(rn_tf32(__float_as_uint(o[i].x - hi.x)));
+                hi.y = __uint_as_float(rn_tf32(__float_as_uint(o[i].y))); lo.y = __uint_as_float(rn_tf32(__float_as_uint(o[i].y - hi.y)));
+                hi.z = __uint_as_float(rn_tf32(__float_as_uint(o[i].z))); lo.z = __uint_as_float(rn_tf32(__float_as_uint(o[i].z - hi.z)));
+                hi.w = __uint_as_float(rn_tf32(__float_as_uint(o[i].w))); lo.w = __uint_as_float(rn_tf32(__float_as_uint(o[i].w - hi.w)));
+                *reinterpret_cast<float4*>(dst_lo + (long long)mi * dld + n) = lo;
+                o[i] = hi;
               }
-              *reinterpret_cast<float4*>(dst + (long long)mm[i] * dld + n) = o;
+              *reinterpret_cast<float4*>(dst + (long long)mi * dld + n) = o[i];
             }
+          }
         }
-        __syncwarp();
       }
     }
     }   // tile loop
@@ -594,6 +625,8 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
 bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   // ---- eligibility (everything else takes the FFMA tiles)
   if (a.batch * a.heads != 1 || a.b_kn) return false;
+  if (a.geglu && ((a.N % TBN) || a.out_nchw || a.Cout_lo || a.residual || a.rowvec || a.mode != 0)) return false;
+  if (a.Cout_lo && a.out_nchw) return false;
   if (a.out_nchw && (a.rowvec || a.residual)) return false;
   if ((a.N & 3) || (a.ldc & 3) || !a16(a.Cout) || !a16(a.Bw) || (a.ldb & 3)) return false;
   if (a.bias && !a16(a.bias)) return false;
@@ -613,6 +646,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec; p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
   p.residual = a.residual; p.ldr = a.ldr;
   p.alpha = a.alpha;
+  p.geglu = a.geglu;
   p.out_nchw = a.out_nchw; p.rows_per_img = a.rows_per_img > 0 ? a.rows_per_img : 1;
   p.heads = 1;
   const CUtensorMap *mA, *mA2, *mB, *mBlo;
@@ -665,7 +699,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   // (S writes + S reads + 1 write of M*N floats at ~4 TB/s, in units of one k-block of one CTA ~ 0.55 us); a split must
   // buy at least 10% to be taken
   int best_s = 1;
-  if (!a.out_nchw && tiles < 4 * e.num_sms) {
+  if (!a.out_nchw && !a.geglu && tiles < 4 * e.num_sms) {
     double best = 1e30, base = 0.0;
     for (int S = 1; S <= 8; ++S) {
       const int kbs = cdiv(num_kb, S);
@@ -694,6 +728,8 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   ensure_attr();
   ProfScope ps(e, s, a.mode == 1 ? PROF_CONV_TC : PROF_DENSE_TC, 2.0 * a.M * a.N * a.K,
                4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
+  ps.note("M%d N%d K%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, tiles, p.splits, ts ? "TS" : "SS", a.Cout_lo ? " planes" : "", a.geglu ? " geglu" : "",
+          a.residual ? " res" : "");
   if (ts) tc_gemm_kernel<true><<<grid, TC_THREADS, Cfg<true>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
   else tc_gemm_kernel<false><<<grid, TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
   CDX_CUDA(cudaGetLastError());

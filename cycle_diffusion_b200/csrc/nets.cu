@@ -95,6 +95,10 @@ void build_unet_inventory(Net& n) {
       v.lin(ap + ".to_out.0", ch, ch);
     }
     v.lin(t + ".ff.net.0.proj", ch, 8 * ch);
+    if ((4 * ch) % 64 == 0) {   // value / gate rows interleaved in blocks of 32: each epilogue thread's 64 columns then hold 32 values and their gates
+      n.params[n.index.at(t + ".ff.net.0.proj.weight")].geglu = true;
+      n.params[n.index.at(t + ".ff.net.0.proj.bias")].geglu = true;
+    }
     v.lin(t + ".ff.net.2", 4 * ch, ch);
     v.norm(t + ".norm1", ch);
     v.norm(t + ".norm2", ch);
@@ -307,6 +311,13 @@ void net_load_param(Net& n, const char* name, const float* data, bool on_device,
     CDX_CUDA(cudaMalloc(&tmp, p.numel * sizeof(float)));
     CDX_CUDA(cudaMemcpy(tmp, data, p.numel * sizeof(float), kind));
     repack_conv3x3(e, tmp, dst, (int)p.dims[0], (int)p.dims[1], 0);
+    CDX_CUDA(cudaDeviceSynchronize());
+    CDX_CUDA(cudaFree(tmp));
+  } else if (p.geglu) {
+    float* tmp = nullptr;
+    CDX_CUDA(cudaMalloc(&tmp, p.numel * sizeof(float)));
+    CDX_CUDA(cudaMemcpy(tmp, data, p.numel * sizeof(float), kind));
+    interleave_geglu_rows(e, tmp, dst, (int)p.dims[0], p.rank == 2 ? (int)p.dims[1] : 1, 0);
     CDX_CUDA(cudaDeviceSynchronize());
     CDX_CUDA(cudaFree(tmp));
   } else {
@@ -584,9 +595,22 @@ struct UNetExec : Exec {
     Tensor h4;
     {
       Tensor n3 = ln(h3, t + ".norm3");
-      Tensor f = linear(n3, t + ".ff.net.0.proj", true);
       Tensor g = alloc(B, x.H, x.W, 4 * C);
-      geglu(e, f.p, g.p, M, 4 * C, s);
+      if (n.param(t + ".ff.net.0.proj.weight").geglu) {
+        // value * gelu(gate) applied in the projection's epilogue (weights stored [32 value | 32 gate] row blocks)
+        GemmArgs ga;
+        ga.mode = 0;
+        ga.M = M; ga.N = 8 * C; ga.K = C;
+        ga.A = n3.p; ga.lda = C; ga.C1 = C;
+        ga.Bw = n.P(t + ".ff.net.0.proj.weight"); ga.ldb = C;
+        ga.bias = n.P(t + ".ff.net.0.proj.bias");
+        ga.geglu = 1;
+        ga.Cout = g.p; ga.ldc = 4 * C;
+        run(ga);
+      } else {
+        Tensor f = linear(n3, t + ".ff.net.0.proj", true);
+        geglu(e, f.p, g.p, M, 4 * C, s);
+      }
       h4 = linear(g, t + ".ff.net.2", true, h3.p);
     }
     linear_into(h4.p, C, C, nullptr, 0, 0, M, n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C);

@@ -16,6 +16,7 @@ struct Param {
   size_t off = 0;        // float offset into the blob
   int segment = 0;       // 0 general, 1 emb-proj weights (concatenated), 2 emb-proj biases (concatenated)
   bool conv3 = false;    // stored repacked O,kh,kw,I
+  bool geglu = false;    // GEGLU projection: rows stored as alternating blocks of 32 value rows | their 32 gate rows
   bool loaded = false;
 };
 
