@@ -34,6 +34,10 @@
 //               4 stages x 48 KB; TMEM: 2 x 128 accumulator columns + 4 x 64 A columns = 512.
 #include <algorithm>
 
+#include <unordered_map>
+#include <vector>
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace cdx {
@@ -81,6 +85,8 @@ struct TcParams {
   long long sC_b, sC_h;       // output offsets per zb / zh
   // persistent tile scheduler: tile t -> (tm = t % tiles_m, tn = (t / tiles_m) % tiles_n, z = t / (tiles_m * tiles_n))
   int tiles_m, tiles_n, total_tiles;
+  int tn_w;                 // tile width along N (multiple of 16, <= TBN): chosen per problem against wave quantisation;
+                            // the MMA of a tile is issued with N = its valid columns rounded up to 16
   // split-K (small-M layers that cannot fill 148 SMs): work item = (tile, split); split s covers k-blocks
   // [s*kb_per_split, min(num_kb, (s+1)*kb_per_split)) and writes its raw partial tile to ws[s][M][N]; splitk_reduce_kernel
   // then sums the partials in fixed order and applies alpha / bias / row vector / residual
@@ -88,7 +94,7 @@ struct TcParams {
   float* ws;
 };
 
-struct TileCoord { int n0, m0, x0, y0, b0, zb, zh, kb0, kb1, split; };
+struct TileCoord { int n0, nend, nw, m0, x0, y0, b0, zb, zh, kb0, kb1, split; };
 
 template <bool TS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -154,7 +160,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int tm = t % p.tiles_m;
     const int r = t / p.tiles_m;
     const int tn = r % p.tiles_n, z = r / p.tiles_n;
-    c.n0 = tn * TBN;
+    c.n0 = tn * p.tn_w;
+    c.nend = min(p.N, c.n0 + p.tn_w);
+    c.nw = ((c.nend - c.n0 + 15) >> 4) << 4;
     c.m0 = 0; c.x0 = 0; c.y0 = 0; c.b0 = 0; c.zb = 0; c.zh = 0;
     if (p.mode == 1) {
       int u = tm;
@@ -184,7 +192,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t sa = st + OFF_A, sb = st + OFF_BHI;
         const int k0 = kb * TBK;
         if (!elect_one()) continue;
-        mbar_expect_tx(bar_full_raw(s), (TS ? 3 : 2) * TILE_BYTES);
+        mbar_expect_tx(bar_full_raw(s), TILE_BYTES + (TS ? 2 : 1) * p.tn_w * TBK * 4);
         if (p.mode == 0) {
           if (k0 < p.C1) tma_load_2d(sa, &mapA, k0, m0, bar_full_raw(s));
           else tma_load_2d(sa, &mapA2, k0 - p.C1, m0, bar_full_raw(s));
@@ -212,11 +220,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp == 1) {
     // =========================================================================== MMA issuer (whole warp, elected issue)
     {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
       int gkb = 0, gchunk0 = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc_ = tile_coord(t);
       const int nkb = tc_.kb1 - tc_.kb0;
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tc_.nw >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
       for (int kb = 0; kb < nkb; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
         const int lchunk = kb / KCHUNK, kin = kb - lchunk * KCHUNK;
@@ -385,7 +393,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < HN; ++j) {
           const int n = n0 + hf * HN + j;
-          if (n < p.N) p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = p.alpha * acc[j] + sb[hf * HN + j];   // lanes = pixels: coalesced
+          if (n < tc_.nend) p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = p.alpha * acc[j] + sb[hf * HN + j];   // lanes = pixels: coalesced
         }
       }
     } else {
@@ -403,7 +411,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int g = lane & 7, rsub = lane >> 3;
       // GEGLU tiles are [32 value | 32 gate | 32 value | 32 gate]: this thread's 64 columns are 32 values + their gates
       const int nparts = p.geglu ? 1 : HN / 32;
-      const int ncol0 = p.geglu ? (n0 >> 1) + hf * 32 : n0 + hf * HN, nlim = p.geglu ? (p.N >> 1) : p.N;
+      const int ncol0 = p.geglu ? (n0 >> 1) + hf * 32 : n0 + hf * HN, nlim = p.geglu ? (p.N >> 1) : tc_.nend;
       int mm[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) mm[i] = __shfl_sync(0xffffffffu, m32, 4 * i + rsub);
@@ -588,6 +596,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     const CUtensorMap& mB = get_map(k, 4, db, sb, bx);
     ProfScope ps(e, s, PROF_BATCHED_TC, 2.0 * Nq * Nk * d * B * heads, 4.0 * B * heads * ((double)Nq * d + (double)Nk * d + (double)Nq * Nk), 1);
     p.splits = 1; p.kb_per_split = cdiv(d, TBK);
+    p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(Nk, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
     tc_gemm_kernel<false><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
     CDX_CUDA(cudaGetLastError());
@@ -614,6 +623,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     const CUtensorMap& mB = get_map(vt, 4, db, sb, bxb);
     ProfScope ps(e, s, PROF_BATCHED_TC, 2.0 * Nq * Nk * d * B * heads, 4.0 * B * heads * ((double)Nq * Nk + (double)Nk * d + (double)Nq * d), 1);
     p.splits = 1; p.kb_per_split = cdiv(Nk, TBK);
+    p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(d, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
     tc_gemm_kernel<false><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
     CDX_CUDA(cudaGetLastError());
@@ -692,24 +702,62 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
     mA2 = mA;
     p.tiles_m = p.tiles_x * p.tiles_y * cdiv(B, bn);
   }
-  p.tiles_n = cdiv(a.N, TBN);
-  const int tiles = p.tiles_m * p.tiles_n;
   const int num_kb = cdiv(a.K, TBK);
-  // split-K choice: minimise rounds(tiles*S) * (k-blocks per item + fixed per-item overhead) + the partial-sum traffic
-  // (S writes + S reads + 1 write of M*N floats at ~4 TB/s, in units of one k-block of one CTA ~ 0.55 us); a split must
-  // buy at least 10% to be taken
-  int best_s = 1;
-  if (!a.out_nchw && !a.geglu && tiles < 4 * e.num_sms) {
-    double best = 1e30, base = 0.0;
-    for (int S = 1; S <= 8; ++S) {
-      const int kbs = cdiv(num_kb, S);
-      if (S > 1 && kbs < 8) break;
-      double cost = (double)cdiv((long long)tiles * S, e.num_sms) * (kbs + 6.0);
-      if (S == 1) base = cost;
-      else cost += 2.0 + (2.0 * S + 1.0) * (double)a.M * a.N * 4.0 / 4e12 / 0.55e-6;
-      if (cost < best - 1e-9 && (S == 1 || cost < 0.9 * base)) { best = cost; best_s = S; }
+  // Work partition: tile width w along N (MMA N = valid columns rounded up to 16, so a ragged last tile costs only its
+  // share) and split-K factor S, chosen together against wave quantisation on num_sms persistent CTAs by replaying the
+  // kernel's static schedule (CTA c runs items c, c + grid, ...) with a cost model in cycles: one k-block of a w-wide
+  // tile ~ 540 + 4.2 w (fitted on B200: ~1080 at w = 128, 0.80x at w = 80 -- the A-side work of a k-block does not shrink
+  // with w), ~5000 per work item for drain + epilogue, plus the split-K
+  // partial-sum traffic (S writes + S reads + 1 write of M*N floats at ~4 TB/s); a split must buy >= 10 %.
+  int best_w = TBN, best_s = 1;
+  {
+    static const bool fixed_w = getenv("CDX_TC_FIXED_W") != nullptr;      // tuning aid: always 128-wide tiles
+    static std::unordered_map<uint64_t, int> plan_cache;
+    const uint64_t key = ((uint64_t)p.tiles_m << 40) ^ ((uint64_t)a.N << 20) ^ ((uint64_t)num_kb << 2) ^ (a.geglu ? 1u : 0u) ^
+                         (a.out_nchw ? 2u : 0u) ^ ((uint64_t)e.num_sms << 56);
+    auto it = plan_cache.find(key);
+    if (it != plan_cache.end()) {
+      best_w = it->second >> 8;
+      best_s = it->second & 255;
+    } else {
+      const int wmin = (a.geglu || a.N <= 64 || fixed_w) ? TBN : 64;
+      const int G = e.num_sms;
+      double best = 1e30;
+      std::vector<double> load((size_t)G);
+      for (int w = TBN; w >= wmin; w -= 16) {
+        const int tn = cdiv(a.N, w);
+        const int wl = ((a.N - (tn - 1) * w + 15) >> 4) << 4;               // MMA width of the last column tile
+        double base = 0.0;
+        for (int S = 1; S <= 8; ++S) {
+          const int kbs = cdiv(num_kb, S);
+          const int Sx = cdiv(num_kb, kbs);                                  // no empty splits
+          if (S > 1 && (Sx != S || kbs < 8 || a.out_nchw || a.geglu || (long long)p.tiles_m * tn >= 4LL * G)) continue;
+          const long long items = (long long)p.tiles_m * tn * S;
+          const int kb_last = num_kb - (S - 1) * kbs;
+          double cost;
+          if (items <= 200000) {
+            const int g = (int)std::min<long long>(items, G);
+            std::fill(load.begin(), load.end(), 0.0);
+            for (long long t = 0; t < items; ++t) {                          // t -> (split fastest, then tm, then tn)
+              const int sp = (int)(t % S);
+              const int col = (int)((t / S / p.tiles_m) % tn);
+              load[(size_t)(t % g)] += (sp == S - 1 ? kb_last : kbs) * (540.0 + 4.2 * (col == tn - 1 ? wl : w)) + 5000.0;
+            }
+            cost = *std::max_element(load.begin(), load.begin() + g);
+          } else {
+            cost = (double)cdiv(items, (long long)G) * (kbs * (540.0 + 4.2 * w) + 5000.0);
+          }
+          if (S == 1) base = cost;
+          else cost += 4000.0 + (2.0 * S + 1.0) * (double)a.M * a.N * 4.0 / 4e12 * 1.9e9;
+          if (cost < best - 1e-9 && (S == 1 || cost < 0.9 * base)) { best = cost; best_w = w; best_s = S; }
+        }
+      }
+      plan_cache[key] = (best_w << 8) | best_s;
     }
   }
+  p.tn_w = best_w;
+  p.tiles_n = cdiv(a.N, best_w);
+  const int tiles = p.tiles_m * p.tiles_n;
   p.splits = best_s;
   p.kb_per_split = cdiv(num_kb, best_s);
   p.splits = cdiv(num_kb, p.kb_per_split);            // no empty splits
@@ -721,14 +769,14 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   const bool ts = a.Bw_hi != nullptr && a.Bw_lo != nullptr && a16(a.Bw_hi) && a16(a.Bw_lo);
   {
     uint64_t d[2] = {(uint64_t)a.K, (uint64_t)a.N}, st[1] = {(uint64_t)a.ldb * 4};
-    uint32_t bx[2] = {TBK, TBN};
+    uint32_t bx[2] = {TBK, (uint32_t)p.tn_w};
     mB = &get_map(ts ? a.Bw_hi : a.Bw, 2, d, st, bx);
     mBlo = ts ? &get_map(a.Bw_lo, 2, d, st, bx) : mB;
   }
   ensure_attr();
   ProfScope ps(e, s, a.mode == 1 ? PROF_CONV_TC : PROF_DENSE_TC, 2.0 * a.M * a.N * a.K,
                4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
-  ps.note("M%d N%d K%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, tiles, p.splits, ts ? "TS" : "SS", a.Cout_lo ? " planes" : "", a.geglu ? " geglu" : "",
+  ps.note("M%d N%d K%d w%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, p.tn_w, tiles, p.splits, ts ? "TS" : "SS", a.Cout_lo ? " planes" : "", a.geglu ? " geglu" : "",
           a.residual ? " res" : "");
   if (ts) tc_gemm_kernel<true><<<grid, TC_THREADS, Cfg<true>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
   else tc_gemm_kernel<false><<<grid, TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
