@@ -91,6 +91,7 @@ struct Guided {
   Guided(Net& u, int B_, int C_, int h_, int w_, int L_, float scale_, const float* c_, const float* uc_, cudaStream_t s)
       : unet(u), e(*u.eng), B(B_), C(C_), h(h_), w(w_), L(L_), scale(scale_), c(c_), uc(uc_) {
     cfg = (uc != nullptr) && scale != 1.0f && scale != 0.0f;
+    unet.ctxkv.valid = false;                  // the conditioning is fixed for this loop: its K / V are computed by the first step only
     const size_t n = (size_t)B * C * h * w;
     const int D = unet.ucfg.context_dim;
     eout = (float*)e.arena.alloc((cfg ? 2 : 1) * n * sizeof(float));
@@ -101,18 +102,19 @@ struct Guided {
       copy_dd(e, c, ctx_in + (size_t)B * L * D, (size_t)B * L * D, s);
     }
   }
+  ~Guided() { unet.ctxkv.valid = false; }
   // t_dev2: device vector holding the timestep 2B times
   void run(const float* x, const float* t_dev2, const float** e_c, const float** e_uc, cudaStream_t s) {
     const size_t n = (size_t)B * C * h * w;
     if (cfg) {
       copy_dd(e, x, x_in, n, s);
       copy_dd(e, x, x_in + n, n, s);
-      unet_forward(unet, x_in, t_dev2, ctx_in, L, eout, 2 * B, h, w, s);
+      unet_forward(unet, x_in, t_dev2, ctx_in, L, eout, 2 * B, h, w, s, true);
       *e_uc = eout;
       *e_c = eout + n;
     } else {
       const float* cond = (uc != nullptr && scale == 0.0f) ? uc : c;
-      unet_forward(unet, x, t_dev2, cond, L, eout, B, h, w, s);
+      unet_forward(unet, x, t_dev2, cond, L, eout, B, h, w, s, true);
       *e_c = eout;
       *e_uc = nullptr;
     }

@@ -286,6 +286,7 @@ void destroy_net(Net* n) {
   if (n->blob_hi) cudaFree(n->blob_hi);
   if (n->blob_lo) cudaFree(n->blob_lo);
   if (n->freqs_dev) cudaFree(n->freqs_dev);
+  if (n->ctxkv.buf) cudaFree(n->ctxkv.buf);
   delete n;
 }
 
@@ -326,6 +327,7 @@ void net_load_param(Net& n, const char* name, const float* data, bool on_device,
   p.loaded = true;
   n.finalized = false;
   n.planes_valid = false;
+  n.ctxkv.valid = false;
 }
 
 void net_finalize(Net& n) {
@@ -448,6 +450,15 @@ struct UNetExec : Exec {
   int ctx_len = 0;
   const float* ctx_pad = nullptr;   // context zero-padded to ctx_lp rows per image (tensor-core cross-attention)
   int ctx_lp = 0;
+  bool kv_reuse = false, kv_hit = false;   // loop mode: context K / V live in n.ctxkv (kv_hit: already computed)
+  size_t kv_off = 0;
+  float* kv_take(size_t floats) {
+    if (!kv_reuse) return (float*)e.arena.alloc(floats * sizeof(float));
+    float* p = n.ctxkv.buf + kv_off;
+    kv_off += (floats + 63) & ~(size_t)63;
+    CDX_CHECK(kv_off <= n.ctxkv.cap, "context K/V cache overflow (%zu > %zu floats)", kv_off, n.ctxkv.cap);
+    return p;
+  }
   bool oai;
   UNetExec(Net& net, cudaStream_t st) : Exec(net, st), oai(net.kind == NET_UNET_OPENAI) {}
 
@@ -570,24 +581,26 @@ struct UNetExec : Exec {
         Scope sa(e.arena);
         const int Mk = B * ctx_lp;
         const size_t nq = (size_t)M * C, nk = (size_t)Mk * C;
+        float* k_hi = kv_take(nk);
+        float* k_lo = kv_take(nk);
+        float* vt_hi = kv_take(nk);
+        float* vt_lo = kv_take(nk);
         float* q_hi = (float*)e.arena.alloc(nq * sizeof(float));
         float* q_lo = (float*)e.arena.alloc(nq * sizeof(float));
-        float* k_hi = (float*)e.arena.alloc(nk * sizeof(float));
-        float* k_lo = (float*)e.arena.alloc(nk * sizeof(float));
-        float* vt_hi = (float*)e.arena.alloc(nk * sizeof(float));
-        float* vt_lo = (float*)e.arena.alloc(nk * sizeof(float));
         linear_into(n2.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn2.to_q.weight"), C, nullptr, nullptr, 0, q_hi, C, q_lo);
-        linear_into(ctx_pad, D, D, nullptr, 0, 0, Mk, n.P(t + ".attn2.to_k.weight"), C, nullptr, nullptr, 0, k_hi, C, k_lo);
-        linear_into(n.P(t + ".attn2.to_v.weight"), D, D, nullptr, 0, 0, C, ctx_pad, Mk, nullptr, nullptr, 0, vt_hi, Mk, vt_lo);
+        if (!kv_hit) {
+          linear_into(ctx_pad, D, D, nullptr, 0, 0, Mk, n.P(t + ".attn2.to_k.weight"), C, nullptr, nullptr, 0, k_hi, C, k_lo);
+          linear_into(n.P(t + ".attn2.to_v.weight"), D, D, nullptr, 0, 0, C, ctx_pad, Mk, nullptr, nullptr, 0, vt_hi, Mk, vt_lo);
+        }
         done = flash_attention_tc(e, q_hi, q_lo, C, k_hi, k_lo, C, vt_hi, vt_lo, a.p, C, B, HW, ctx_len, ctx_lp, heads, d, scale, s);
         CDX_CHECK(done, "flash cross-attention rejected an eligible shape (HW=%d d=%d L=%d)", HW, d, ctx_len);
       }
       if (!done) q = linear(n2, t + ".attn2.to_q", false);
       if (!done) {
         Scope sa(e.arena);
-        Tensor kv = alloc(B, ctx_len, 1, 2 * C);
-        linear_into(ctx, D, D, nullptr, 0, 0, B * ctx_len, n.P(t + ".attn2.to_k.weight"), 2 * C, nullptr, nullptr, 0, kv.p, 2 * C);
-        attention(e, q.p, C, kv.p, 2 * C, kv.p + C, 2 * C, a.p, C, B, HW, ctx_len, heads, d, d, scale, s);
+        float* kv = kv_take((size_t)B * ctx_len * 2 * C);
+        if (!kv_hit) linear_into(ctx, D, D, nullptr, 0, 0, B * ctx_len, n.P(t + ".attn2.to_k.weight"), 2 * C, nullptr, nullptr, 0, kv, 2 * C);
+        attention(e, q.p, C, kv, 2 * C, kv + C, 2 * C, a.p, C, B, HW, ctx_len, heads, d, d, scale, s);
       }
       h3 = linear(a, t + ".attn2.to_out.0", true, h2.p);
     }
@@ -643,11 +656,28 @@ struct UNetExec : Exec {
     ctx_lp = (L + 3) & ~3;
     const int mc = c.model_channels, half = mc / 2, ted = n.ted;
     Scope top(e.arena);
+    kv_off = 0;
+    kv_hit = false;
+    if (kv_reuse && context && L > 0) {
+      Net::CtxKV& kc = n.ctxkv;
+      size_t sumC = 0;
+      for (const Param& pp : n.params)
+        if (pp.name.size() > 17 && pp.name.compare(pp.name.size() - 17, 17, "attn2.to_k.weight") == 0) sumC += (size_t)pp.dims[0] + 64;
+      const size_t need = 4 * (size_t)B * ctx_lp * sumC;
+      if (kc.cap < need) {
+        CDX_CUDA(cudaDeviceSynchronize());
+        if (kc.buf) CDX_CUDA(cudaFree(kc.buf));
+        kc.buf = nullptr; kc.cap = 0; kc.valid = false;
+        CDX_CUDA(cudaMalloc(&kc.buf, need * sizeof(float)));
+        kc.cap = need;
+      }
+      kv_hit = kc.valid && kc.ctx == context && kc.L == L && kc.B == B && !e.dry();
+    }
     if (context && L > 0 && e.mma_mode == 1 && e.flash_attn) {
       // context rows padded to a multiple of 4 per image: TMA needs 16-byte strides for K and V^T of the cross-attention
       const size_t D = (size_t)c.context_dim;
       float* cp = (float*)e.arena.alloc((size_t)B * ctx_lp * D * sizeof(float));
-      if (!e.dry()) {
+      if (!e.dry() && !kv_hit) {
         if (ctx_lp != L) CDX_CUDA(cudaMemsetAsync(cp, 0, (size_t)B * ctx_lp * D * sizeof(float), s));
         CDX_CUDA(cudaMemcpy2DAsync(cp, (size_t)ctx_lp * D * 4, context, (size_t)L * D * 4, (size_t)L * D * 4, B, cudaMemcpyDeviceToDevice, s));
       }
@@ -801,14 +831,19 @@ struct VaeExec : Exec {
 }  // namespace
 
 void unet_forward(Net& n, const float* x_nchw, const float* t_dev, const float* ctx, int ctx_len, float* out_nchw, int B, int H, int W,
-                  cudaStream_t s) {
+                  cudaStream_t s, bool reuse_ctx) {
   CDX_CHECK(n.kind == NET_UNET_OPENAI || n.kind == NET_UNET_IDDPM, "unet_forward on a non-U-Net");
   CDX_CHECK(n.finalized, "unet_forward before finalize");
   if (n.kind == NET_UNET_OPENAI) CDX_CHECK(ctx != nullptr && ctx_len > 0, "unet_forward: the SD/LDM U-Net needs a context");
   const int down = 1 << (n.ucfg.n_mult - 1);
   CDX_CHECK(H % down == 0 && W % down == 0, "unet_forward: %dx%d not divisible by %d", H, W, down);
   UNetExec ex(n, s);
+  ex.kv_reuse = reuse_ctx && n.kind == NET_UNET_OPENAI;
   ex.forward(x_nchw, t_dev, ctx, ctx_len, out_nchw, B, H, W);
+  if (ex.kv_reuse && !n.eng->dry()) {
+    n.ctxkv.valid = true;
+    n.ctxkv.ctx = ctx; n.ctxkv.L = ctx_len; n.ctxkv.B = B;
+  }
 }
 
 void vae_encode(Net& n, const float* img, float* moments, int B, int R, cudaStream_t s) {

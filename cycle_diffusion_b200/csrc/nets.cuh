@@ -38,6 +38,9 @@ struct Net {
   // timestep embedding
   std::vector<float> freqs_host;
   float* freqs_dev = nullptr;
+  // cross-attention K / V of a context that stays fixed over a sampling loop (set up by the loop drivers in cabi.cu):
+  // computed by the first U-Net call of the loop, reused by the others (the reference recomputes them every step)
+  struct CtxKV { bool valid = false; const float* ctx = nullptr; int L = 0, B = 0; float* buf = nullptr; size_t cap = 0; } ctxkv;
   // concatenated ResBlock emb projections: weights [emb_rows][ted] at emb_w_off, biases at emb_b_off
   size_t emb_w_off = 0, emb_b_off = 0;
   int emb_rows = 0, ted = 0;
@@ -57,8 +60,10 @@ void net_finalize(Net& n);
 void net_ensure_blob(Net& n);
 
 // forward executors (enqueue only; caller handles arena dry-run)
+// reuse_ctx: the caller guarantees `ctx` is unchanged since the previous call with reuse_ctx (and n.ctxkv was invalidated
+// at the start of the loop) -> context K / V projections are taken from n.ctxkv instead of being recomputed
 void unet_forward(Net& n, const float* x_nchw, const float* t_dev, const float* ctx, int ctx_len, float* out_nchw, int B, int H,
-                  int W, cudaStream_t s);
+                  int W, cudaStream_t s, bool reuse_ctx = false);
 void vae_encode(Net& n, const float* img_nchw, float* moments_nchw, int B, int R, cudaStream_t s);
 void vae_decode(Net& n, const float* z_nchw, float* img_nchw, int B, int h, cudaStream_t s);
 
