@@ -280,10 +280,13 @@ def golden_pixel_cycle():
         image = torch.rand(1, 3, 64, 64, generator=g)
         out['image'] = image
         for tag, kw in (('ddim', dict(sample_type='ddim', eta=0.1, custom_steps=10, es_steps=10)),
-                        ('ddpm', dict(sample_type='ddpm', eta=None, custom_steps=20, es_steps=6))):
+                        ('ddpm', dict(sample_type='ddpm', eta=None, custom_steps=20, es_steps=6)),
+                        # eta=1 refinement after the decode (DW:431-453): 3 steps, 2 iterations, fresh noise each
+                        ('ddim_refine', dict(sample_type='ddim', eta=0.1, custom_steps=10, es_steps=10, refine_steps=3, refine_iterations=2))):
+            kw = dict(kw)
+            kw.setdefault('refine_steps', 0)
             with _quiet():
-                w = W.DDPMDDIMWrapper(source_model_type='afhqcat256', source_model_path='ckpts/ddpm/afhq64.pt',
-                                      refine_steps=0, **kw)
+                w = W.DDPMDDIMWrapper(source_model_type='afhqcat256', source_model_path='ckpts/ddpm/afhq64.pt', **kw)
             torch.manual_seed(2000)
             with torch.no_grad(), _quiet():
                 z = w.encode(image)

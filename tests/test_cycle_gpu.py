@@ -55,7 +55,9 @@ def test_latent_cycle_vs_reference_fixture(eng, tag):
 
 
 @pytest.mark.parametrize('tag,kw', [('ddim', dict(sample_type='ddim', eta=0.1, custom_steps=10, es_steps=10)),
-                                    ('ddpm', dict(sample_type='ddpm', eta=None, custom_steps=20, es_steps=6))])
+                                    ('ddpm', dict(sample_type='ddpm', eta=None, custom_steps=20, es_steps=6)),
+                                    ('ddim_refine', dict(sample_type='ddim', eta=0.1, custom_steps=10, es_steps=10, refine_steps=3,
+                                                         refine_iterations=2))])
 def test_pixel_wrapper_vs_reference_fixture(eng, tag, kw):
     """BASELINE config 1: DDPMDDIMWrapper on the 64x64 i-DDPM U-Net, fixture from the unmodified reference wrapper."""
     from cycle_diffusion_b200.wrappers import DDPMDDIMWrapper
@@ -68,6 +70,7 @@ def test_pixel_wrapper_vs_reference_fixture(eng, tag, kw):
     z = w.encode(g['image'])
     zref = g[f'z_{tag}']
     rz = maxdiff(z.cpu(), zref) / float(zref.abs().max())
+    # (the fixture's decode continues the encode's CPU RNG stream; our encode consumed the same number of draws)
     img = w(zref).cpu()
     print(f'pixel[{tag}]: rel|dz| {rz:.2e}  |d img| {maxdiff(img, g[f"img_{tag}"]):.2e}')
     assert z.shape == zref.shape
