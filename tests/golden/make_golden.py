@@ -290,9 +290,16 @@ def golden_pixel_cycle():
             torch.manual_seed(2000)
             with torch.no_grad(), _quiet():
                 z = w.encode(image)
+                st = torch.get_rng_state()
                 img = w(z)
+                # conditioning of the decode map: the reference's own output change for a 1-ulp relative change of z
+                # under identical noise draws (the GPU tests scale their tolerance with it)
+                torch.set_rng_state(st)
+                img_p = w(z * (1 + 2.0 ** -23))
             out[f'z_{tag}'] = z
             out[f'img_{tag}'] = img
+            out[f'sens_{tag}'] = (img_p - img).abs().max().reshape(1)
+            print(f'pixel_cycle[{tag}]: 1-ulp sensitivity of the reference decode {float(out[f"sens_{tag}"]):.3e}')
             print(f'pixel_cycle[{tag}]: z {tuple(z.shape)} |z|max {z.abs().max():.2f}  recon max|img-image| '
                   f'{(img - image).abs().max():.3e}')
         save('pixel_cycle_iddpm64', **out)

@@ -75,7 +75,11 @@ def test_pixel_wrapper_vs_reference_fixture(eng, tag, kw):
     print(f'pixel[{tag}]: rel|dz| {rz:.2e}  |d img| {maxdiff(img, g[f"img_{tag}"]):.2e}')
     assert z.shape == zref.shape
     assert rz < 5e-4
-    assert maxdiff(img, g[f'img_{tag}']) < 1e-3
+    # tolerance: 1e-3, widened only where the reference's OWN decode is ill-conditioned: sens_* is the change of the reference
+    # output for a 1-ulp relative perturbation of z under identical noise (5.5e-4 for the eta=1 refinement, whose output
+    # leaves [0,1] and reaches 2.7 with synthetic weights)
+    tol = max(1e-3, 8 * float(g[f'sens_{tag}']))
+    assert maxdiff(img, g[f'img_{tag}']) < tol
     with pytest.raises(AssertionError):
         w.encode(torch.rand(1, 3, 32, 32))                 # DW:472 resolution check
 
