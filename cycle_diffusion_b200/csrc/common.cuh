@@ -167,7 +167,8 @@ void upsample2(Engine& e, const float* x, float* y, int B, int H, int W, int C, 
 void nchw_to_nhwc(Engine& e, const float* x, float* y, int B, int C, int HW, cudaStream_t s);
 void nhwc_to_nchw(Engine& e, const float* x, float* y, int B, int C, int HW, cudaStream_t s);
 void timestep_embedding(Engine& e, const float* t, const float* freqs, float* emb, int B, int half, cudaStream_t s);
-void repack_conv3x3(Engine& e, const float* w_oihw, float* w_ohwi, int O, int I, cudaStream_t s);
+void repack_conv3x3(Engine& e, const float* w, float* o, int O, int I, cudaStream_t s, int Ipad = 0);   // OIHW -> O,kh,kw,I (I zero-padded to Ipad)
+void pad_channels(Engine& e, const float* x, float* y, size_t rows, int C, int Cp, cudaStream_t s);     // [rows,C] -> [rows,Cp], zero fill
 void copy_rows(Engine& e, const float* src, float* dst, size_t n, cudaStream_t s);
 void attention(Engine& e, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
                int B, int Nq, int Nk, int heads, int d, int head_stride, float scale, cudaStream_t s);

@@ -122,14 +122,24 @@ __global__ void temb_kernel(const float* __restrict__ t, const float* __restrict
   }
 }
 // OIHW (3x3) -> O,kh,kw,I
-__global__ void repack_conv_kernel(const float* __restrict__ w, float* __restrict__ o, int O, int I) {
-  const size_t n = (size_t)O * I * 9;
+// OIHW -> O,kh,kw,Ip with the input channels zero-padded from I to Ip (Ip == I: plain repack)
+__global__ void repack_conv_kernel(const float* __restrict__ w, float* __restrict__ o, int O, int I, int Ip) {
+  const size_t n = (size_t)O * Ip * 9;
   GRID_STRIDE(idx, n) {
-    const int i = (int)(idx % I);
-    size_t r = idx / I;
+    const int i = (int)(idx % Ip);
+    size_t r = idx / Ip;
     const int tap = (int)(r % 9);
     const int oc = (int)(r / 9);
-    o[idx] = w[((size_t)oc * I + i) * 9 + tap];
+    o[idx] = i < I ? w[((size_t)oc * I + i) * 9 + tap] : 0.f;
+  }
+}
+// x [rows][C] -> y [rows][Cp], zero fill
+__global__ void pad_channels_kernel(const float* __restrict__ x, float* __restrict__ y, size_t rows, int C, int Cp) {
+  const size_t n = rows * (size_t)Cp;
+  GRID_STRIDE(idx, n) {
+    const int c = (int)(idx % Cp);
+    const size_t r = idx / Cp;
+    y[idx] = c < C ? x[r * C + c] : 0.f;
   }
 }
 
@@ -280,7 +290,13 @@ void timestep_embedding(Engine& e, const float* t, const float* freqs, float* em
   CDX_CUDA(cudaGetLastError());
   e.launches++;
 }
-void repack_conv3x3(Engine& e, const float* w, float* o, int O, int I, cudaStream_t s) { LAUNCH1(repack_conv_kernel, (size_t)O * I * 9, w, o, O, I); }
+void repack_conv3x3(Engine& e, const float* w, float* o, int O, int I, cudaStream_t s, int Ipad) {
+  const int Ip = Ipad > 0 ? Ipad : I;
+  LAUNCH1(repack_conv_kernel, (size_t)O * Ip * 9, w, o, O, I, Ip);
+}
+void pad_channels(Engine& e, const float* x, float* y, size_t rows, int C, int Cp, cudaStream_t s) {
+  LAUNCH1(pad_channels_kernel, rows * (size_t)Cp, x, y, rows, C, Cp);
+}
 void vae_posterior(Engine& e, const float* mom, const float* nz, float sf, float* out, int B, int C, int hw, cudaStream_t s) {
   LAUNCH1(vae_posterior_kernel, (size_t)B * C * hw, mom, nz, sf, out, B, C, hw);
 }

@@ -638,8 +638,8 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   if (a.geglu && ((a.N % TBN) || a.out_nchw || a.Cout_lo || a.residual || a.rowvec || a.mode != 0)) return false;
   if (a.Cout_lo && a.out_nchw) return false;
   if (a.out_nchw && (a.rowvec || a.residual)) return false;
-  if ((a.N & 3) || (a.ldc & 3) || !a16(a.Cout) || !a16(a.Bw) || (a.ldb & 3)) return false;
-  if (a.bias && !a16(a.bias)) return false;
+  if (!a.out_nchw && ((a.N & 3) || (a.ldc & 3) || !a16(a.Cout))) return false;   // (the NCHW epilogue stores scalars: any N)
+  if (!a16(a.Bw) || (a.ldb & 3)) return false;
   if (a.rowvec && (!a16(a.rowvec) || (a.ld_rowvec & 3))) return false;
   if (a.residual && (!a16(a.residual) || (a.ldr & 3))) return false;
   if (!a16(a.A) || (a.lda & 3)) return false;

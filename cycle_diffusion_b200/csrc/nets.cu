@@ -44,6 +44,7 @@ struct Inv {
   }
   void conv(const std::string& name, int cin, int cout, int k) {
     add(name + ".weight", {cout, cin, k, k}, 0, k == 3);
+    if (k == 3 && cin < 32) n.params.back().cin_pad = 32;      // conv_in layers (3 / 4 channels): run on the tensor-core path too
     add(name + ".bias", {cout});
   }
   void lin(const std::string& name, int cin, int cout, bool bias = true, int seg = 0) {
@@ -227,7 +228,7 @@ void assign_offsets(Net& n) {
   auto align = [&](size_t a) { off = (off + a - 1) / a * a; };
   // general segment: inventory order, 16-byte aligned starts (adjacent q/k/v weights stay contiguous)
   for (Param& p : n.params)
-    if (p.segment == 0) { align(4); p.off = off; off += p.numel; }
+    if (p.segment == 0) { align(4); p.off = off; off += p.store(); }
   align(64);
   n.emb_w_off = off;
   for (Param& p : n.params)
@@ -311,7 +312,7 @@ void net_load_param(Net& n, const char* name, const float* data, bool on_device,
     float* tmp = nullptr;
     CDX_CUDA(cudaMalloc(&tmp, p.numel * sizeof(float)));
     CDX_CUDA(cudaMemcpy(tmp, data, p.numel * sizeof(float), kind));
-    repack_conv3x3(e, tmp, dst, (int)p.dims[0], (int)p.dims[1], 0);
+    repack_conv3x3(e, tmp, dst, (int)p.dims[0], (int)p.dims[1], 0, p.cin_pad);
     CDX_CUDA(cudaDeviceSynchronize());
     CDX_CUDA(cudaFree(tmp));
   } else if (p.geglu) {
@@ -369,11 +370,17 @@ struct Exec {
   }
 
   // y = conv3x3(x [, x2 concat]) + bias (+ rowvec per sample) (+ residual); up: nearest-2x folded into the gather
-  Tensor conv3(const Tensor& x, const std::string& name, int stride = 1, int pad = 1, int up = 1, const float* rowvec = nullptr,
+  Tensor conv3(const Tensor& x0, const std::string& name, int stride = 1, int pad = 1, int up = 1, const float* rowvec = nullptr,
                int ld_rowvec = 0, const float* residual = nullptr, float* out_nchw = nullptr) {
     const Param& w = n.param(name + ".weight");
-    const int Cout = (int)w.dims[0], Cin = (int)w.dims[1];
-    CDX_CHECK(Cin == x.C, "conv %s: input has %d channels, weight expects %d", name.c_str(), x.C, Cin);
+    const int Cout = (int)w.dims[0];
+    CDX_CHECK((int)w.dims[1] == x0.C, "conv %s: input has %d channels, weight expects %d", name.c_str(), x0.C, (int)w.dims[1]);
+    Tensor x = x0;
+    if (w.cin_pad && x0.C != w.cin_pad) {          // few-channel network inputs: zero-pad to the stored Cin (one small pass)
+      x = alloc(x0.B, x0.H, x0.W, w.cin_pad);
+      pad_channels(e, x0.p, x.p, (size_t)x0.rows(), x0.C, w.cin_pad, s);
+    }
+    const int Cin = x.C;
     if (up == 2 && e.mma_mode == 1 && (Cin % 32) == 0 && !out_nchw) {
       // tcgen05 path: the TMA box gather cannot express the >>1 source index, so materialise the nearest-2x upsample
       // (one extra write+read of the activation, <2% of the conv's time) and run the plain tensor-core conv on it

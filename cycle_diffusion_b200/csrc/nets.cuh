@@ -16,6 +16,8 @@ struct Param {
   size_t off = 0;        // float offset into the blob
   int segment = 0;       // 0 general, 1 emb-proj weights (concatenated), 2 emb-proj biases (concatenated)
   bool conv3 = false;    // stored repacked O,kh,kw,I
+  int cin_pad = 0;       // 3x3 conv with < 32 input channels: stored with Cin zero-padded to this (tensor-core K blocks are 32 wide)
+  size_t store() const { return cin_pad ? (size_t)dims[0] * 9 * cin_pad : numel; }   // floats occupied in the blob
   bool geglu = false;    // GEGLU projection: rows stored as alternating blocks of 32 value rows | their 32 gate rows
   bool loaded = false;
 };
