@@ -790,7 +790,16 @@ struct VaeExec : Exec {
     Tensor k = linear(xn, p + ".k", true);
     Tensor v = linear(xn, p + ".v", true);
     Tensor a = alloc(x.B, x.H, x.W, C);
-    attention(e, q.p, C, k.p, C, v.p, C, a.p, C, x.B, HW, HW, 1, C, C, (float)pow((double)C, -0.5), s);
+    const float scale = (float)pow((double)C, -0.5);
+    bool done = false;
+    if (e.mma_mode == 1 && (HW % 32) == 0 && HW >= 128) {
+      // tensor-core path: S = q k^T, row softmax, O = P V with V transposed to [C, B*HW] (both P.V operands K-major)
+      Scope sa(e.arena);
+      float* vt = (float*)e.arena.alloc((size_t)C * x.rows() * sizeof(float));
+      nhwc_to_nchw(e, v.p, vt, 1, C, x.rows(), s);
+      done = attention_tc(e, q.p, C, k.p, C, C, vt, a.p, C, x.B, HW, HW, 1, C, scale, s);
+    }
+    if (!done) attention(e, q.p, C, k.p, C, v.p, C, a.p, C, x.B, HW, HW, 1, C, C, scale, s);
     linear_into(a.p, C, C, nullptr, 0, 0, x.rows(), n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C);
     return out;
   }
