@@ -29,10 +29,15 @@ using namespace tc;
 
 constexpr int AQ = 128;        // queries per CTA
 constexpr int AKV = 64;        // keys per block
-constexpr int ATTN_THREADS = 320;      // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quadrant)
 
 template <int D>
 struct ACfg {
+  // softmax warps per TMEM lane quadrant (each takes AKV / NSUB score columns and NV / NSUB output columns of its 32 rows):
+  // 4 (16 softmax warps) hides the tcgen05.ld / MUFU / barrier latencies of the softmax chain better than 2 (a profile of the
+  // 2-per-quadrant version had the tensor pipe 50 % active with 36 % issue utilisation); D >= 64 has no smem left for the wider
+  // max exchange and keeps 2
+  static constexpr int NSUB = (D <= 40) ? 4 : 2;
+  static constexpr int THREADS = 128 + 4 * NSUB * 32;       // TMA warp, three MMA issuer warps (QK, PV even / odd blocks), softmax warps
   static constexpr int KB2 = (D + 31) / 32;                 // 32-float k-blocks covering the head dim
   static constexpr int NV = (D + 15) / 16 * 16;             // PV MMA N (rows of the V^T tile)
   static constexpr int KTILE = AKV * 128;                   // one k-block tile of K: 64 rows x 128 B
@@ -49,8 +54,8 @@ struct ACfg {
   static constexpr int OFF_Q = (KS - 1) * K_STAGE;
   static constexpr int OFF_BAR = OFF_V + VS * V_STAGE;
   static_assert(Q_STAGE == K_STAGE, "Q staging aliases a K stage");
-  static constexpr int OFF_XCHG = OFF_BAR + 256;            // float xchg[2 buffers][2 halves][128 rows]
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 2048 + 512;   // 512 B slack: the dynamic window is declared __align__(1024)
+  static constexpr int OFF_XCHG = OFF_BAR + 256;            // float xchg[2 buffers][NSUB parts][128 rows]
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 2 * NSUB * 512 + 512;   // 512 B slack: the dynamic window is declared __align__(1024)
   // TMEM buffering.  D <= 40 (the N=4096 level, ~90 % of the attention work): ONE score buffer but TWO P and O buffers, so
   // P_{j+1} is written without waiting for PV_j and the O accumulation of block j leaves the critical path (a profile of the
   // (2 S, 1 P, 1 O) scheme showed the softmax warps 47 % stalled on s_full / pv_done with the tensor pipe 30 % active).
@@ -94,6 +99,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -101,12 +109,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(ATTN_THREADS, 1)
+__global__ void __launch_bounds__(ACfg<D>::THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_constant__ CUtensorMap mapQl,
                   const __grid_constant__ CUtensorMap mapKh, const __grid_constant__ CUtensorMap mapKl,
                   const __grid_constant__ CUtensorMap mapVh, const __grid_constant__ CUtensorMap mapVl, const AttnParams p) {
   using C = ACfg<D>;
-  constexpr int KB2 = C::KB2, NV = C::NV;
+  constexpr int KB2 = C::KB2, NV = C::NV, NSUB = C::NSUB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + C::OFF_BAR;
@@ -145,12 +153,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_s_full(s), 1);
-      mbar_init(bar_s_empty(s), 8);
+      mbar_init(bar_s_empty(s), 4 * NSUB);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_p_full(s), 8);
+      mbar_init(bar_p_full(s), 4 * NSUB);
       mbar_init(bar_pv_done(s), 1);
-      mbar_init(bar_o_empty(s), 8);
+      mbar_init(bar_o_empty(s), 4 * NSUB);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -205,10 +213,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // =========================================================================== MMA issuer (whole warp, elected issue)
+    // =========================================================================== MMA issuer of the Q.K^T stream (whole warp, elected issue)
     {
       const uint32_t idesc_qk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AKV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
-      const uint32_t idesc_pv = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
       const uint32_t q_hi = tmem_base + C::COL_QH, q_lo = tmem_base + C::COL_QL;
 
       auto issue_qk = [&](int j) {
@@ -230,18 +237,25 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         umma_commit(bar_k_empty(ks));
       };
 
+      // QK stream: S_j = Q K_j^T as soon as K_j has landed and the softmax warps have taken S_{j-SB} out of the buffer
       mbar_wait(bar_q_ready, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      mbar_wait(bar_k_full(0), 0);
-      issue_qk(0);
       for (int j = 0; j < nb; ++j) {
-        if (j + 1 < nb) {
-          const int sb1 = (j + 1) % SB;
-          mbar_wait(bar_k_full((j + 1) % KS), ((j + 1) / KS) & 1);
-          if (j + 1 >= SB) mbar_wait(bar_s_empty(sb1), (((j + 1) / SB) - 1) & 1);   // softmax has the previous S of this buffer in registers
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          issue_qk(j + 1);
-        }
+        mbar_wait(bar_k_full(j % KS), (j / KS) & 1);
+        if (j >= SB) mbar_wait(bar_s_empty(j % SB), ((j / SB) - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_qk(j);
+      }
+    }
+  } else if (warp == 2 || warp == 3) {
+    // =========================================================================== MMA issuers of the P.V stream
+    // (a profile of the single-issuer version showed the issuing thread itself -- ~40 cycles per tcgen05.mma through the
+    // uniform datapath, 39 MMAs per key block -- as the bottleneck: tensor pipe 49 % active, softmax warps waiting on S).
+    // With two P/O buffers the even and the odd key blocks are independent streams: one issuer warp each.
+    constexpr int NPV = (PB == 2) ? 2 : 1;
+    if (warp - 2 < NPV) {
+      const uint32_t idesc_pv = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
+      for (int j = warp - 2; j < nb; j += NPV) {
         const int vs = j % VS, pb = j % PB;
         mbar_wait(bar_v_full(vs), (j / VS) & 1);
         mbar_wait(bar_p_full(pb), (j / PB) & 1);
@@ -267,13 +281,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
     }
   } else {
     // =========================================================================== softmax + accumulation warps
-    const int qd = warp & 3;                       // TMEM lane quadrant (warps 2..9 -> 2,3,0,1,2,3,0,1)
-    const int hf = (warp - 2) >> 2;                // 0: key columns 0..31 / O columns [0, NV/2), 1: the other halves
+    const int qd = warp & 3;                       // TMEM lane quadrant (warps 4.. -> 0,1,2,3,...)
+    const int hf = (warp - 4) >> 2;                // 0..NSUB-1: which AKV/NSUB key columns and NV/NSUB O columns of the row
     const int row = qd * 32 + lane;                // query row of this thread
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     const uint32_t rbase = (uint32_t)row * 128u, rx = (uint32_t)(row & 7);
-    constexpr int HC = AKV / 2;                    // 32 score columns per thread
-    constexpr int HO = NV / 2;                     // O columns per thread (8, 16, 24, 32, 40)
+    constexpr int HC = AKV / NSUB;                 // 16 score columns per thread
+    constexpr int HO = NV / NSUB;                  // O columns per thread (4, 8, 12, 16, 20)
     const uint32_t xchg = base + C::OFF_XCHG;      // [buffer][half][row] floats
 
     // ---- Q planes: staging smem -> TMEM (this thread's row); done by the first four warps
@@ -309,7 +323,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t v[HO];
 #pragma unroll
-      for (int part = 0; part < HO / 8; ++part) tmem_ld8(tmem_base + lane_base + C::COL_O + pb * NV + hf * HO + part * 8, v + part * 8);
+      for (int part = 0; part < HO / 4; ++part) tmem_ld4(tmem_base + lane_base + C::COL_O + pb * NV + hf * HO + part * 4, v + part * 4);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
       for (int c = 0; c < HO; ++c) o[c] = o[c] * corr_j + __uint_as_float(v[c]);
@@ -325,8 +339,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float sc[HC];
       {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_base + C::COL_S + s * AKV + hf * HC, v);
+        uint32_t v[HC];
+        if constexpr (HC == 32) tmem_ld32(tmem_base + lane_base + C::COL_S + s * AKV + hf * HC, v);
+        else tmem_ld16(tmem_base + lane_base + C::COL_S + s * AKV + hf * HC, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int c = 0; c < HC; ++c) sc[c] = __uint_as_float(v[c]);
@@ -345,12 +360,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       float mx = sc[0];
 #pragma unroll
       for (int c = 1; c < HC; ++c) mx = fmaxf(mx, sc[c]);
-      const uint32_t xa = xchg + (uint32_t)(((j & 1) * 2) * 128 + row) * 4u;
+      const uint32_t xa = xchg + (uint32_t)(((j & 1) * NSUB) * 128 + row) * 4u;
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(xa + (uint32_t)hf * 512u), "f"(mx) : "memory");
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-      float other;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xa + (uint32_t)(hf ^ 1) * 512u) : "memory");
-      mx = fmaxf(mx, other) * p.scale_log2e;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + qd), "n"(NSUB * 32) : "memory");
+#pragma unroll
+      for (int o2 = 1; o2 < NSUB; ++o2) {
+        float other;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xa + (uint32_t)((hf + o2) % NSUB) * 512u) : "memory");
+        mx = fmaxf(mx, other);
+      }
+      mx *= p.scale_log2e;
       const float m_new = fmaxf(m_run, mx);
       const float corr = ex2_approx(m_run - m_new);      // 0 on the first block (m_run = -inf)
       float psum = 0.f;
@@ -390,13 +409,18 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
     accumulate_o(nb - 1, corr_prev);
 
     // total row sum = both halves; exchange through smem (buffer 0 of the max exchange is free again: nb >= 2 or resynced below)
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + qd), "n"(NSUB * 32) : "memory");
     const uint32_t xl = xchg + (uint32_t)row * 4u;
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(xl + (uint32_t)hf * 512u), "f"(l_run) : "memory");
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-    float l_other;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(xl + (uint32_t)(hf ^ 1) * 512u) : "memory");
-    const float inv_l = 1.f / (l_run + l_other);
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + qd), "n"(NSUB * 32) : "memory");
+    float l_tot = 0.f;
+#pragma unroll
+    for (int o2 = 0; o2 < NSUB; ++o2) {               // fixed order 0..NSUB-1: every thread of the row gets the same sum
+      float lv;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lv) : "r"(xl + (uint32_t)o2 * 512u) : "memory");
+      l_tot += lv;
+    }
+    const float inv_l = 1.f / l_tot;
     float* dst = p.out + ((long long)b * p.N + q0 + row) * p.ldo + h * p.d + hf * HO;
 #pragma unroll
     for (int c = 0; c < HO; c += 4) {
@@ -424,7 +448,7 @@ void launch_flash(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMa
     CDX_CUDA(cudaFuncSetAttribute(flash_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<D>::SMEM_BYTES));
     attr = true;
   }
-  flash_attn_kernel<D><<<dim3(p.N / AQ, p.heads, p.B), ATTN_THREADS, ACfg<D>::SMEM_BYTES, s>>>(qh, ql, kh, kl, vh, vl, p);
+  flash_attn_kernel<D><<<dim3(p.N / AQ, p.heads, p.B), ACfg<D>::THREADS, ACfg<D>::SMEM_BYTES, s>>>(qh, ql, kh, kl, vh, vl, p);
 }
 
 }  // namespace
