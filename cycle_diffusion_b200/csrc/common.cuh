@@ -127,6 +127,9 @@ struct GemmArgs {
   const float* Bw_hi = nullptr; const float* Bw_lo = nullptr;   // optional pre-split TF32 planes of Bw (same geometry)
   float* Cout = nullptr; int ldc = 0;
   float* Cout_lo = nullptr;           // if set: Cout receives rn_tf32(C) and Cout_lo rn_tf32(C - hi) (operand planes for tcgen05)
+  // optional: columns n >= t_col0 are stored TRANSPOSED as TF32 planes, Ct_hi / Ct_lo [(n - t_col0) * ldt + m] (dense mode,
+  // no split-K): the value projection of a fused q|k|v GEMM lands directly as the K-major V^T operand of the attention kernel
+  float* Ct_hi = nullptr; float* Ct_lo = nullptr; int t_col0 = 0; long long ldt = 0;
   const float* bias = nullptr;
   const float* rowvec = nullptr; int ld_rowvec = 0; int rows_per_batch = 1;
   const float* residual = nullptr; int ldr = 0;

@@ -306,6 +306,7 @@ void gemm(Engine& e, const GemmArgs& a, cudaStream_t s) {
   if (a.mode == 1) CDX_CHECK(a.K == 9 * (a.C1 + a.C2), "conv3x3: K != 9*Cin");
   if (a.mode == 0) CDX_CHECK(a.K == a.C1 + a.C2, "dense: K != C1+C2");
   if (e.mma_mode == 1 && gemm_tc(e, a, s)) return;      // (handles the arena dry run itself: split-K workspace)
+  CDX_CHECK(!a.Ct_hi, "gemm: transposed plane output is only available on the tensor-core path (caller must check eligibility)");
   if (a.geglu) {       // fused only in the tensor-core epilogue; here: plain GEMM into a temporary, then the GEGLU kernel
     CDX_CHECK(a.N % 128 == 0 && a.batch * a.heads == 1 && !a.out_nchw && !a.Cout_lo, "gemm: bad GEGLU problem");
     Scope sc(e.arena);

@@ -72,6 +72,7 @@ struct TcParams {
   int cstride, cpad;        // conv: stride (1 or 2: TMA element traversal stride) and low-side padding
   float* C; int ldc;
   float* C_lo;              // optional: C <- rn_tf32(result), C_lo <- rn_tf32(result - hi)
+  float* Ct_hi; float* Ct_lo; int t_col0; long long ldt;   // optional transposed plane output for columns >= t_col0
   const float* bias;
   const float* rowvec; int ld_rowvec; int rows_per_batch;
   const float* residual; int ldr;
@@ -396,6 +397,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (n < tc_.nend) p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = p.alpha * acc[j] + sb[hf * HN + j];   // lanes = pixels: coalesced
         }
       }
+    } else if (p.Ct_hi && n0 >= p.t_col0) {
+      // transposed TF32-plane output (V^T): thread = row m, so for a fixed column the 32 lanes write 32 consecutive floats
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < HN; ++j) {
+          const int n = n0 + hf * HN + j;
+          if (n < tc_.nend) {
+            const float o = p.alpha * acc[j] + sb[hf * HN + j];
+            const float hi = __uint_as_float(rn_tf32(__float_as_uint(o)));
+            const long long at = (long long)(n - p.t_col0) * p.ldt + m;
+            p.Ct_hi[at] = hi;
+            p.Ct_lo[at] = __uint_as_float(rn_tf32(__float_as_uint(o - hi)));
+          }
+        }
+      }
     } else {
       const bool fin = p.splits == 1;                // otherwise: raw partial sums to ws[split][M][N]
       // the thread-per-row accumulator layout would store 16 B to 32 different rows per instruction (32 L1 wavefronts
@@ -637,6 +653,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   if (a.batch * a.heads != 1 || a.b_kn) return false;
   if (a.geglu && ((a.N % TBN) || a.out_nchw || a.Cout_lo || a.residual || a.rowvec || a.mode != 0)) return false;
   if (a.Cout_lo && a.out_nchw) return false;
+  if (a.Ct_hi && (a.mode != 0 || !a.Ct_lo || a.out_nchw || a.geglu || a.residual || a.rowvec || (a.t_col0 % TBN) || a.t_col0 >= a.N)) return false;
   if (a.out_nchw && (a.rowvec || a.residual)) return false;
   if (!a.out_nchw && ((a.N & 3) || (a.ldc & 3) || !a16(a.Cout))) return false;   // (the NCHW epilogue stores scalars: any N)
   if (!a16(a.Bw) || (a.ldb & 3)) return false;
@@ -652,6 +669,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.C = a.Cout; p.ldc = a.ldc;
   p.C_lo = a.out_nchw ? nullptr : a.Cout_lo;
+  p.Ct_hi = a.Ct_hi; p.Ct_lo = a.Ct_lo; p.t_col0 = a.t_col0; p.ldt = a.ldt;
   p.bias = a.bias;
   p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec; p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
   p.residual = a.residual; p.ldr = a.ldr;
@@ -713,14 +731,14 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   {
     static const bool fixed_w = getenv("CDX_TC_FIXED_W") != nullptr;      // tuning aid: always 128-wide tiles
     static std::unordered_map<uint64_t, int> plan_cache;
-    const uint64_t key = ((uint64_t)p.tiles_m << 40) ^ ((uint64_t)a.N << 20) ^ ((uint64_t)num_kb << 2) ^ (a.geglu ? 1u : 0u) ^
+    const uint64_t key = ((uint64_t)p.tiles_m << 40) ^ ((uint64_t)a.N << 20) ^ ((uint64_t)num_kb << 2) ^ ((a.geglu || a.Ct_hi) ? 1u : 0u) ^
                          (a.out_nchw ? 2u : 0u) ^ ((uint64_t)e.num_sms << 56);
     auto it = plan_cache.find(key);
     if (it != plan_cache.end()) {
       best_w = it->second >> 8;
       best_s = it->second & 255;
     } else {
-      const int wmin = (a.geglu || a.N <= 64 || fixed_w) ? TBN : 64;
+      const int wmin = (a.geglu || a.Ct_hi || a.N <= 64 || fixed_w) ? TBN : 64;
       const int G = e.num_sms;
       double best = 1e30;
       std::vector<double> load((size_t)G);
@@ -731,7 +749,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
         for (int S = 1; S <= 8; ++S) {
           const int kbs = cdiv(num_kb, S);
           const int Sx = cdiv(num_kb, kbs);                                  // no empty splits
-          if (S > 1 && (Sx != S || kbs < 8 || a.out_nchw || a.geglu || (long long)p.tiles_m * tn >= 4LL * G)) continue;
+          if (S > 1 && (Sx != S || kbs < 8 || a.out_nchw || a.geglu || a.Ct_hi || (long long)p.tiles_m * tn >= 4LL * G)) continue;
           const long long items = (long long)p.tiles_m * tn * S;
           const int kb_last = num_kb - (S - 1) * kbs;
           double cost;

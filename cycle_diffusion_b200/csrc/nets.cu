@@ -19,6 +19,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <cstdlib>
+
 #include "nets.cuh"
 
 namespace cdx {
@@ -553,8 +555,22 @@ struct UNetExec : Exec {
         float* qk_lo = (float*)e.arena.alloc(nqk * sizeof(float));
         float* vt_hi = (float*)e.arena.alloc(nvt * sizeof(float));
         float* vt_lo = (float*)e.arena.alloc(nvt * sizeof(float));
-        linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 2 * C, nullptr, nullptr, 0, qk_hi, 2 * C, qk_lo);
-        linear_into(n.P(t + ".attn1.to_v.weight"), C, C, nullptr, 0, 0, C, n1.p, M, nullptr, nullptr, 0, vt_hi, M, vt_lo);
+        static const bool no_fused_qkv = getenv("CDX_NO_FUSED_QKV") != nullptr;     // tuning aid
+        if (!no_fused_qkv && (2 * C) % 128 == 0 && M >= 64 && (C % 4) == 0) {
+          // one fused q|k|v projection (weights adjacent in the blob): q|k stored row-major as planes, the v columns stored
+          // transposed by the epilogue (thread = row, so a column is 32 consecutive floats per warp) -> V^T planes
+          GemmArgs g;
+          g.mode = 0;
+          g.M = M; g.N = 3 * C; g.K = C;
+          g.A = n1.p; g.lda = C; g.C1 = C;
+          g.Bw = n.P(t + ".attn1.to_q.weight"); g.ldb = C;
+          g.Cout = qk_hi; g.ldc = 2 * C; g.Cout_lo = qk_lo;
+          g.Ct_hi = vt_hi; g.Ct_lo = vt_lo; g.t_col0 = 2 * C; g.ldt = M;
+          run(g);
+        } else {
+          linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 2 * C, nullptr, nullptr, 0, qk_hi, 2 * C, qk_lo);
+          linear_into(n.P(t + ".attn1.to_v.weight"), C, C, nullptr, 0, 0, C, n1.p, M, nullptr, nullptr, 0, vt_hi, M, vt_lo);   // V^T = Wv . X^T
+        }
         done = flash_attention_tc(e, qk_hi, qk_lo, 2 * C, qk_hi + C, qk_lo + C, 2 * C, vt_hi, vt_lo, a.p, C, B, HW, HW, HW, heads, d, scale, s);
         CDX_CHECK(done, "flash attention rejected an eligible shape (HW=%d d=%d)", HW, d);
       } else if (e.mma_mode >= 1 && (HW % 32) == 0 && HW >= 128 && (d % 4) == 0) {
