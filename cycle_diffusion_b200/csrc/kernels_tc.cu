@@ -34,6 +34,7 @@
 //               4 stages x 48 KB; TMEM: 2 x 128 accumulator columns + 4 x 64 A columns = 512.
 #include <algorithm>
 
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 #include <cstdlib>
@@ -731,6 +732,8 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   {
     static const bool fixed_w = getenv("CDX_TC_FIXED_W") != nullptr;      // tuning aid: always 128-wide tiles
     static std::unordered_map<uint64_t, int> plan_cache;
+    static std::mutex plan_mutex;                                          // engines on different devices may plan concurrently
+    std::lock_guard<std::mutex> plan_lock(plan_mutex);
     const uint64_t key = ((uint64_t)p.tiles_m << 40) ^ ((uint64_t)a.N << 20) ^ ((uint64_t)num_kb << 2) ^ ((a.geglu || a.Ct_hi) ? 1u : 0u) ^
                          (a.out_nchw ? 2u : 0u) ^ ((uint64_t)e.num_sms << 56);
     auto it = plan_cache.find(key);

@@ -4,6 +4,7 @@
 #include <cuda.h>
 
 #include <map>
+#include <mutex>
 #include <string.h>
 
 #include "common.cuh"
@@ -153,7 +154,11 @@ struct MapKey {
 // `estr` (optional): element traversal strides; with stride s along a dim, box[i] = n*s loads n elements.
 inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
                                   const uint32_t* estr = nullptr) {
-  static std::map<MapKey, CUtensorMap> cache;
+  // node-based map: returned references stay valid; on overflow the live generation is parked in `old` (and the generation
+  // before it dropped), so a reference handed out earlier in the same call can never dangle
+  static std::map<MapKey, CUtensorMap> cache, old;
+  static std::mutex mtx;                       // engines on different devices may encode concurrently
+  std::lock_guard<std::mutex> lock(mtx);
   MapKey k;
   memset(&k, 0, sizeof(k));
   k.ptr = ptr;
@@ -162,7 +167,10 @@ inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dim
   for (int i = 0; i < rank - 1; ++i) k.strides[i] = strides[i];
   auto it = cache.find(k);
   if (it != cache.end()) return it->second;
-  if (cache.size() > 65536) cache.clear();
+  if (cache.size() > 65536) {
+    old.clear();
+    old.swap(cache);
+  }
   CUtensorMap m;
   cuuint64_t gd[4];
   cuuint64_t gs[3];
