@@ -243,7 +243,9 @@ def run_ours(args):
             except (OSError, ValueError):
                 pass
             roof = {'kernel': top, 'bound': 'tensor', 'achieved': round(ach, 2), 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
-                    'frac': round(ach / pk['tflops_sustained'], 4), 'traffic': traffic, 'launches_per_unet_call': f['launches'],
+                    'frac': round(ach / pk['tflops_sustained'], 4),
+                    # the fp32-faithful path issues 3 TF32 MMAs per product at half the bf16 rate: its own ceiling is peak / 6
+                    'frac_of_3xtf32_ceiling': round(ach / (pk['tflops_sustained'] / 6.0), 4), 'traffic': traffic, 'launches_per_unet_call': f['launches'],
                     'avg_launch_ms': round(f['ms'] / f['launches'], 4),
                     'peak_source': pk['source'] + ' -- sustained bf16 dense; this path is fp32-faithful (see DESIGN.md)',
                     'whole_job_tflops': round(value * TFLOP_PER_IMAGE, 2)}
