@@ -25,6 +25,11 @@ class VaeConfig(C.Structure):
                 ('in_channels', C.c_int), ('out_ch', C.c_int), ('z_channels', C.c_int), ('embed_dim', C.c_int)]
 
 
+class TextConfig(C.Structure):
+    _fields_ = [('vocab_size', C.c_int), ('width', C.c_int), ('layers', C.c_int), ('heads', C.c_int), ('max_len', C.c_int),
+                ('mlp_width', C.c_int)]
+
+
 class DdimCoef(C.Structure):
     _fields_ = [('sqrt_at', C.c_float), ('sqrt_1m_at', C.c_float), ('sqrt_1m_at_tab', C.c_float),
                 ('sqrt_aprev', C.c_float), ('dir_coef', C.c_float), ('sigma', C.c_float)]
@@ -54,6 +59,7 @@ SIGNATURES = {
     'cdx_engine_profile_read': (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     'cdx_unet_create': (_I, [_P, C.POINTER(UnetConfig), C.POINTER(_P)]),
     'cdx_vae_create': (_I, [_P, C.POINTER(VaeConfig), C.POINTER(_P)]),
+    'cdx_text_create': (_I, [_P, C.POINTER(TextConfig), C.POINTER(_P)]),
     'cdx_net_destroy': (None, [_P]),
     'cdx_net_num_params': (_I, [_P]),
     'cdx_net_param_name': (C.c_char_p, [_P, _I]),
@@ -65,6 +71,7 @@ SIGNATURES = {
     'cdx_unet_set_time_freqs': (_I, [_P, C.POINTER(_F), _I]),
     'cdx_unet_forward': (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _P]),
     'cdx_vae_encode': (_I, [_P, _P, _P, _I, _I, _P]),
+    'cdx_text_encode': (_I, [_P, _P, _I, _I, _P, _P]),
     'cdx_vae_decode': (_I, [_P, _P, _P, _I, _I, _P]),
     'cdx_affine': (_I, [_P, _P, _F, _F, _P, _S, _P]),
     'cdx_shift_scale': (_I, [_P, _P, _F, _F, _P, _S, _P]),

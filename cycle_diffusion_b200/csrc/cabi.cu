@@ -215,6 +215,16 @@ int cdx_vae_create(cdx_engine* e, const cdx_vae_config* cfg, cdx_net** out) {
     *out = h;
   });
 }
+int cdx_text_create(cdx_engine* e, const cdx_text_config* cfg, cdx_net** out) {
+  return guard([&] {
+    CDX_CHECK(cfg && out, "text_create: null argument");
+    cdx_net* h = new cdx_net();
+    h->owner = e;
+    static Engine host_only;
+    h->n = make_text(e ? &e->e : &host_only, *cfg);
+    *out = h;
+  });
+}
 void cdx_net_destroy(cdx_net* n) {
   if (!n) return;
   destroy_net(n->n);
@@ -280,6 +290,12 @@ int cdx_vae_encode(cdx_net* n, const float* img, float* moments, int B, int R, v
   return guard([&] {
     CDX_CHECK(n && n->owner && img && moments && B > 0, "vae_encode: bad arguments");
     with_arena(n->owner->e, [&] { vae_encode(*n->n, img, moments, B, R, S(stream)); });
+  });
+}
+int cdx_text_encode(cdx_net* n, const int* ids, int B, int L, float* out, void* stream) {
+  return guard([&] {
+    CDX_CHECK(n && n->owner && ids && out && B > 0, "text_encode: bad arguments");
+    with_arena(n->owner->e, [&] { text_encode(*n->n, ids, out, B, L, S(stream)); });
   });
 }
 int cdx_vae_decode(cdx_net* n, const float* z, float* img, int B, int h, void* stream) {

@@ -159,7 +159,8 @@ void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, cons
                float eps, bool silu, const float* scale, const float* shift, int ld_ss, float* y, int B, int HW,
                cudaStream_t s);
 void layernorm(Engine& e, const float* x, const float* gamma, const float* beta, float* y, int M, int C, cudaStream_t s);
-void softmax_rows(Engine& e, float* x, long long rows, int L, int ld, cudaStream_t s);   // in place
+// in place; causal_nq > 0: row r may only see columns j <= r % causal_nq (the rest become 0)
+void softmax_rows(Engine& e, float* x, long long rows, int L, int ld, cudaStream_t s, int causal_nq = 0);
 void silu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s);
 // x [M,2C] -> y [M,C] = value * gelu(gate); plain: value = x[:, :C], gate = x[:, C:]; interleaved: blocks of [32 value | 32 gate]
 void geglu(Engine& e, const float* x, float* y, int M, int C, cudaStream_t s, bool interleaved = false);
@@ -171,10 +172,12 @@ void nchw_to_nhwc(Engine& e, const float* x, float* y, int B, int C, int HW, cud
 void nhwc_to_nchw(Engine& e, const float* x, float* y, int B, int C, int HW, cudaStream_t s);
 void timestep_embedding(Engine& e, const float* t, const float* freqs, float* emb, int B, int half, cudaStream_t s);
 void repack_conv3x3(Engine& e, const float* w, float* o, int O, int I, cudaStream_t s, int Ipad = 0);   // OIHW -> O,kh,kw,I (I zero-padded to Ipad)
-void pad_channels(Engine& e, const float* x, float* y, size_t rows, int C, int Cp, cudaStream_t s);     // [rows,C] -> [rows,Cp], zero fill
+void pad_channels(Engine& e, const float* x, float* y, size_t rows, int C, int Cp, cudaStream_t s);
+void embed_tokens(Engine& e, const int* ids, const float* tok, const float* pos, float* out, int B, int L, int W, int vocab, cudaStream_t s);
+void quick_gelu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s);     // x * sigmoid(1.702 x)     // [rows,C] -> [rows,Cp], zero fill
 void copy_rows(Engine& e, const float* src, float* dst, size_t n, cudaStream_t s);
 void attention(Engine& e, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
-               int B, int Nq, int Nk, int heads, int d, int head_stride, float scale, cudaStream_t s);
+               int B, int Nq, int Nk, int heads, int d, int head_stride, float scale, cudaStream_t s, bool causal = false);
 
 // scheduler kernels (kernels_elem.cu)
 void affine(Engine& e, const float* x, float a, float b, float* out, size_t n, cudaStream_t s);

@@ -133,6 +133,26 @@ __global__ void repack_conv_kernel(const float* __restrict__ w, float* __restric
     o[idx] = i < I ? w[((size_t)oc * I + i) * 9 + tap] : 0.f;
   }
 }
+// CLIPTextEmbeddings: out[b, l, :] = token_embedding[ids[b, l]] + position_embedding[l]
+__global__ void embed_tokens_kernel(const int* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                                    float* __restrict__ out, int B, int L, int W, int vocab) {
+  const size_t n = (size_t)B * L * W;
+  GRID_STRIDE(idx, n) {
+    const int c = (int)(idx % W);
+    const size_t bl = idx / W;
+    const int l = (int)(bl % L);
+    int id = ids[bl];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    out[idx] = tok[(size_t)id * W + c] + pos[(size_t)l * W + c];
+  }
+}
+// quick-GELU (HF activations.QuickGELUActivation): x * sigmoid(1.702 x)
+__global__ void quick_gelu_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  GRID_STRIDE(i, n) {
+    const float v = x[i];
+    y[i] = v * (1.f / (1.f + expf(-1.702f * v)));
+  }
+}
 // x [rows][C] -> y [rows][Cp], zero fill
 __global__ void pad_channels_kernel(const float* __restrict__ x, float* __restrict__ y, size_t rows, int C, int Cp) {
   const size_t n = rows * (size_t)Cp;
@@ -294,6 +314,10 @@ void repack_conv3x3(Engine& e, const float* w, float* o, int O, int I, cudaStrea
   const int Ip = Ipad > 0 ? Ipad : I;
   LAUNCH1(repack_conv_kernel, (size_t)O * Ip * 9, w, o, O, I, Ip);
 }
+void embed_tokens(Engine& e, const int* ids, const float* tok, const float* pos, float* out, int B, int L, int W, int vocab, cudaStream_t s) {
+  LAUNCH1(embed_tokens_kernel, (size_t)B * L * W, ids, tok, pos, out, B, L, W, vocab);
+}
+void quick_gelu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s) { LAUNCH1(quick_gelu_kernel, n, x, y, n); }
 void pad_channels(Engine& e, const float* x, float* y, size_t rows, int C, int Cp, cudaStream_t s) {
   LAUNCH1(pad_channels_kernel, rows * (size_t)Cp, x, y, rows, C, Cp);
 }
@@ -326,7 +350,7 @@ void pixel_step_with_eps(Engine& e, const float* xt, const float* et, const floa
 // softmax(q k^T * scale) v through two batched contractions and a row softmax.  Scores live in the arena
 // ([B*heads, Nq, ldS]); the fused tcgen05 flash kernel supersedes this when eligible.
 void attention(Engine& e, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo, int B, int Nq,
-               int Nk, int heads, int d, int head_stride, float scale, cudaStream_t s) {
+               int Nk, int heads, int d, int head_stride, float scale, cudaStream_t s, bool causal) {
   Scope sc(e.arena);
   const int ldS = (Nk + 3) & ~3;
   float* S = (float*)e.arena.alloc((size_t)B * heads * Nq * ldS * sizeof(float));
@@ -340,7 +364,7 @@ void attention(Engine& e, const float* q, int ldq, const float* k, int ldk, cons
   g.sB_b = (long long)Nk * ldk; g.sB_h = head_stride;
   g.sC_b = (long long)heads * Nq * ldS; g.sC_h = (long long)Nq * ldS;
   gemm(e, g, s);
-  softmax_rows(e, S, (long long)B * heads * Nq, Nk, ldS, s);
+  softmax_rows(e, S, (long long)B * heads * Nq, Nk, ldS, s, causal ? Nq : 0);
   GemmArgs h;
   h.M = Nq; h.N = d; h.K = Nk; h.mode = 0;
   h.A = S; h.lda = ldS; h.C1 = Nk;

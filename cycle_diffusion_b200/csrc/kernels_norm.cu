@@ -194,11 +194,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // in-place softmax over rows of length L (row stride ld); one warp per row, three passes (row stays in L1/L2)
-__global__ void __launch_bounds__(256) softmax_kernel(float* __restrict__ x, long long rows, int L, int ld) {
+__global__ void __launch_bounds__(256) softmax_kernel(float* __restrict__ x, long long rows, int L0, int ld, int causal_nq) {
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   float* r = x + warp * ld;
+  int L = L0;
+  if (causal_nq > 0) {                       // causal mask (CLIP text tower): query i attends to keys 0..i, masked probabilities are 0
+    L = min(L0, (int)(warp % causal_nq) + 1);
+    for (int i = L + lane; i < L0; i += 32) r[i] = 0.f;
+  }
   float mx = -INFINITY;
   for (int i = lane; i < L; i += 32) mx = fmaxf(mx, r[i]);
 #pragma unroll
@@ -251,10 +256,10 @@ void layernorm(Engine& e, const float* x, const float* gamma, const float* beta,
   e.launches++;
 }
 
-void softmax_rows(Engine& e, float* x, long long rows, int L, int ld, cudaStream_t s) {
+void softmax_rows(Engine& e, float* x, long long rows, int L, int ld, cudaStream_t s, int causal_nq) {
   if (e.dry()) return;
   ProfScope ps(e, s, PROF_SOFTMAX, 0.0, 2.0 * 4.0 * (double)rows * L, 1);
-  softmax_kernel<<<cdiv(rows * 32, 256), 256, 0, s>>>(x, rows, L, ld);
+  softmax_kernel<<<cdiv(rows * 32, 256), 256, 0, s>>>(x, rows, L, ld, causal_nq);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
 }

@@ -283,6 +283,32 @@ Net* make_vae(Engine* e, const cdx_vae_config& cfg) {
   return n;
 }
 
+// HF CLIPTextModel state_dict order (transformers modeling_clip.py: CLIPTextEmbeddings, CLIPEncoderLayer {self_attn k,v,q,out;
+// layer_norm1; mlp fc1, fc2; layer_norm2}, final_layer_norm)
+Net* make_text(Engine* e, const cdx_text_config& cfg) {
+  CDX_CHECK(cfg.vocab_size > 0 && cfg.width > 0 && cfg.layers > 0 && cfg.heads > 0 && cfg.max_len > 0 && cfg.mlp_width > 0, "text: bad config");
+  CDX_CHECK(cfg.width % cfg.heads == 0 && cfg.width % 4 == 0 && cfg.mlp_width % 4 == 0, "text: width %d / heads %d", cfg.width, cfg.heads);
+  Net* n = new Net();
+  n->eng = e;
+  n->kind = NET_CLIP_TEXT;
+  n->tcfg = cfg;
+  Inv v(*n);
+  const std::string T = "text_model.";
+  v.add(T + "embeddings.token_embedding.weight", {cfg.vocab_size, cfg.width});
+  v.add(T + "embeddings.position_embedding.weight", {cfg.max_len, cfg.width});
+  for (int l = 0; l < cfg.layers; ++l) {
+    const std::string p = T + "encoder.layers." + std::to_string(l);
+    for (const char* nm : {"k_proj", "v_proj", "q_proj", "out_proj"}) v.lin(p + ".self_attn." + nm, cfg.width, cfg.width);
+    v.norm(p + ".layer_norm1", cfg.width);
+    v.lin(p + ".mlp.fc1", cfg.width, cfg.mlp_width);
+    v.lin(p + ".mlp.fc2", cfg.mlp_width, cfg.width);
+    v.norm(p + ".layer_norm2", cfg.width);
+  }
+  v.norm(T + "final_layer_norm", cfg.width);
+  assign_offsets(*n);
+  return n;
+}
+
 void destroy_net(Net* n) {
   if (!n) return;
   if (n->blob) cudaFree(n->blob);
@@ -876,6 +902,44 @@ void unet_forward(Net& n, const float* x_nchw, const float* t_dev, const float* 
     n.ctxkv.valid = true;
     n.ctxkv.ctx = ctx; n.ctxkv.L = ctx_len; n.ctxkv.B = B;
   }
+}
+
+// CLIPTextTransformer.forward (HF modeling_clip.py; call site ldm/modules/encoders/modules.py:152-157): embeddings, pre-LN
+// encoder layers with causal self-attention (q scaled by d^-1/2) and quick-GELU MLP, final LayerNorm -> last_hidden_state
+void text_encode(Net& n, const int* ids, float* out, int B, int L, cudaStream_t s) {
+  CDX_CHECK(n.kind == NET_CLIP_TEXT && n.finalized, "text_encode: not a finalized text encoder");
+  const cdx_text_config& c = n.tcfg;
+  CDX_CHECK(L >= 1 && L <= c.max_len, "text_encode: %d tokens, the position table has %d", L, c.max_len);
+  Exec ex(n, s);
+  Engine& e = *n.eng;
+  const int W = c.width, d = W / c.heads;
+  const std::string T = "text_model.";
+  Scope top(e.arena);
+  Tensor x = ex.alloc(B, L, 1, W);
+  embed_tokens(e, ids, n.P(T + "embeddings.token_embedding.weight"), n.P(T + "embeddings.position_embedding.weight"), x.p, B, L, W, c.vocab_size, s);
+  const float scale = (float)pow((double)d, -0.5);
+  for (int l = 0; l < c.layers; ++l) {
+    const std::string p = T + "encoder.layers." + std::to_string(l);
+    Tensor y = ex.alloc(B, L, 1, W);          // layer output (outlives the layer's temporaries)
+    {
+      Scope sc(e.arena);
+      Tensor n1 = ex.ln(x, p + ".layer_norm1");
+      Tensor q = ex.linear(n1, p + ".self_attn.q_proj", true);
+      Tensor k = ex.linear(n1, p + ".self_attn.k_proj", true);
+      Tensor v = ex.linear(n1, p + ".self_attn.v_proj", true);
+      Tensor a = ex.alloc(B, L, 1, W);
+      attention(e, q.p, W, k.p, W, v.p, W, a.p, W, B, L, L, c.heads, d, d, scale, s, true);
+      Tensor h = ex.linear(a, p + ".self_attn.out_proj", true, x.p);                 // + residual
+      Tensor n2 = ex.ln(h, p + ".layer_norm2");
+      Tensor f = ex.linear(n2, p + ".mlp.fc1", true);
+      quick_gelu(e, f.p, f.p, f.numel(), s);
+      const Param& w2 = n.param(p + ".mlp.fc2.weight");
+      ex.linear_into(f.p, c.mlp_width, c.mlp_width, nullptr, 0, 0, B * L, n.blob + w2.off, W, n.P(p + ".mlp.fc2.bias"), h.p, W, y.p, W);
+    }
+    x = y;
+  }
+  // final LayerNorm straight into the caller's buffer
+  layernorm(e, x.p, n.P(T + "final_layer_norm.weight"), n.P(T + "final_layer_norm.bias"), out, B * L, W, s);
 }
 
 void vae_encode(Net& n, const float* img, float* moments, int B, int R, cudaStream_t s) {

@@ -22,13 +22,14 @@ struct Param {
   bool loaded = false;
 };
 
-enum NetKind { NET_UNET_OPENAI = 1, NET_UNET_IDDPM = 2, NET_VAE = 3 };
+enum NetKind { NET_UNET_OPENAI = 1, NET_UNET_IDDPM = 2, NET_VAE = 3, NET_CLIP_TEXT = 4 };
 
 struct Net {
   Engine* eng = nullptr;
   int kind = 0;
   cdx_unet_config ucfg{};
   cdx_vae_config vcfg{};
+  cdx_text_config tcfg{};
   std::vector<Param> params;
   std::unordered_map<std::string, int> index;
   float* blob = nullptr;
@@ -56,6 +57,7 @@ struct Net {
 
 Net* make_unet(Engine* e, const cdx_unet_config& cfg);
 Net* make_vae(Engine* e, const cdx_vae_config& cfg);
+Net* make_text(Engine* e, const cdx_text_config& cfg);
 void destroy_net(Net* n);
 void net_load_param(Net& n, const char* name, const float* data, bool on_device, const int64_t* dims, int rank);
 void net_finalize(Net& n);
@@ -68,5 +70,6 @@ void unet_forward(Net& n, const float* x_nchw, const float* t_dev, const float* 
                   int W, cudaStream_t s, bool reuse_ctx = false);
 void vae_encode(Net& n, const float* img_nchw, float* moments_nchw, int B, int R, cudaStream_t s);
 void vae_decode(Net& n, const float* z_nchw, float* img_nchw, int B, int h, cudaStream_t s);
+void text_encode(Net& n, const int* ids, float* out, int B, int L, cudaStream_t s);
 
 }  // namespace cdx

@@ -10,7 +10,7 @@ import math
 import torch
 
 from . import _cabi
-from ._cabi import lib, check, UnetConfig, VaeConfig, DdimCoef, PixelCoef
+from ._cabi import lib, check, UnetConfig, VaeConfig, TextConfig, DdimCoef, PixelCoef
 
 
 def _ptr(t):
@@ -420,3 +420,35 @@ class VAE(Net):
         out = e.empty(B, self.cfg['out_ch'], h * self.down, h * self.down)
         check(lib.cdx_vae_decode(self.h, _ptr(z), _ptr(out), B, h, e.stream))
         return out
+
+
+class TextEncoder(Net):
+    """CLIP text tower (HF CLIPTextModel layout) -> last_hidden_state; the conditioning model FrozenCLIPEmbedder wraps
+    (ldm/modules/encoders/modules.py:140-158).  Tokenisation stays on the host (BPE vocabulary files are not part of the engine)."""
+
+    def __init__(self, engine, cfg):
+        self.cfg = dict(cfg)
+        c = TextConfig()
+        c.vocab_size, c.width, c.layers = cfg['vocab_size'], cfg['width'], cfg['layers']
+        c.heads, c.max_len, c.mlp_width = cfg['heads'], cfg['max_len'], cfg['mlp_width']
+        h = C.c_void_p()
+        check(lib.cdx_text_create(engine.h if engine is not None else None, C.byref(c), C.byref(h)))
+        super().__init__(engine, h)
+
+    def load_state_dict(self, sd, prefix='', strict=True):
+        # older transformers versions register `embeddings.position_ids` as a persistent buffer: not a parameter
+        sd = {k: v for k, v in sd.items() if not k.endswith('embeddings.position_ids')}
+        return super().load_state_dict(sd, prefix, strict)
+
+    def forward(self, input_ids):
+        """input_ids [B, L] integer tensor -> [B, L, width] fp32 on the engine's device."""
+        e = self.engine
+        ids = input_ids.to(device=e.device, dtype=torch.int32).contiguous()
+        B, L = ids.shape
+        assert L <= self.cfg['max_len'], f'{L} tokens > {self.cfg["max_len"]} positions'
+        out = torch.empty(B, L, self.cfg['width'], device=e.device, dtype=torch.float32)
+        check(lib.cdx_text_encode(self.h, _ptr(ids), B, L, _ptr(out), e.stream))
+        return out
+
+    __call__ = forward
+

@@ -248,6 +248,29 @@ def kl_vae_params(cfg, prefix=''):
 
 # ------------------------------------------------------------------ synthetic weights
 
+def clip_text_config(vocab_size=49408, width=768, layers=12, heads=12, max_len=77, mlp_width=3072):
+    """CLIP ViT-L/14 text tower ("openai/clip-vit-large-patch14", the SD v1 conditioning model; encoders/modules.py:140-146)."""
+    return dict(vocab_size=vocab_size, width=width, layers=layers, heads=heads, max_len=max_len, mlp_width=mlp_width)
+
+
+def clip_text_params(cfg, prefix=''):
+    """Ordered (name, shape, kind) list in HF CLIPTextModel.state_dict() order (without the position_ids buffer)."""
+    W, M = cfg['width'], cfg['mlp_width']
+    T = prefix + 'text_model.'
+    out = [(T + 'embeddings.token_embedding.weight', (cfg['vocab_size'], W), 'w'),
+           (T + 'embeddings.position_embedding.weight', (cfg['max_len'], W), 'w')]
+    for l in range(cfg['layers']):
+        p = f'{T}encoder.layers.{l}'
+        for nm in ('k_proj', 'v_proj', 'q_proj', 'out_proj'):
+            out += [(f'{p}.self_attn.{nm}.weight', (W, W), 'w'), (f'{p}.self_attn.{nm}.bias', (W,), 'b')]
+        out += [(f'{p}.layer_norm1.weight', (W,), 'nw'), (f'{p}.layer_norm1.bias', (W,), 'nb')]
+        out += [(f'{p}.mlp.fc1.weight', (M, W), 'w'), (f'{p}.mlp.fc1.bias', (M,), 'b')]
+        out += [(f'{p}.mlp.fc2.weight', (W, M), 'w'), (f'{p}.mlp.fc2.bias', (W,), 'b')]
+        out += [(f'{p}.layer_norm2.weight', (W,), 'nw'), (f'{p}.layer_norm2.bias', (W,), 'nb')]
+    out += [(T + 'final_layer_norm.weight', (W,), 'nw'), (T + 'final_layer_norm.bias', (W,), 'nb')]
+    return out
+
+
 def synth_state_dict(params, seed, gain=1.0):
     """Deterministic CPU fp32 weights for an inventory; identical on every machine with the same torch build.
 

@@ -27,6 +27,28 @@ from .engine import Engine, UNet, VAE
 from .schedule import DDIMSchedule, PixelSchedule
 
 
+class ClipTextCondStage:
+    """In-engine conditioning model: drop-in for ``model.get_learned_conditioning`` with FrozenCLIPEmbedder behind it
+    (ddpm.py:545-556 -> encoders/modules.py:148-158): ``list[str] -> [B, 77, 768]`` on the engine's device.
+
+    ``tokenizer``: callable ``list[str] -> LongTensor [B, L]`` -- e.g. ``lambda t: hf_tok(t, truncation=True, max_length=77,
+    padding='max_length', return_tensors='pt')['input_ids']`` with HF ``CLIPTokenizer`` (the BPE vocabulary is host data and
+    not part of the engine).  ``state_dict``: HF CLIPTextModel keys, optionally under ``prefix`` (the SD checkpoint keeps them
+    under ``cond_stage_model.transformer.``)."""
+
+    def __init__(self, engine, state_dict, tokenizer, cfg=None, prefix=''):
+        from .engine import TextEncoder
+        self.cfg = cfg or specs.clip_text_config()
+        self.tokenizer = tokenizer
+        self.encoder = TextEncoder(engine, self.cfg)
+        self.encoder.load_state_dict({k: v for k, v in state_dict.items() if k.startswith(prefix)}, prefix=prefix)
+
+    def __call__(self, texts):
+        ids = self.tokenizer(list(texts))
+        assert ids.dim() == 2 and ids.shape[0] == len(texts), 'tokenizer must return [B, L] ids'
+        return self.encoder(ids)
+
+
 class SyntheticTextEncoder:
     """Deterministic stand-in for FrozenCLIPEmbedder / BERTEmbedder: prompt string -> N(0,1) tokens [77, dim].
 

@@ -89,9 +89,17 @@ typedef struct cdx_vae_config { /* AutoencoderKL ddconfig, v1-inference.yaml:51-
   int in_channels, out_ch, z_channels, embed_dim;
 } cdx_vae_config;
 
+typedef struct cdx_text_config { /* CLIP ViT-L/14 text tower as FrozenCLIPEmbedder uses it: HF CLIPTextModel
+                                    "openai/clip-vit-large-patch14": 12 layers, width 768, 12 heads, 77 positions, quick-GELU */
+  int vocab_size, width, layers, heads, max_len, mlp_width;
+} cdx_text_config;
+
 /* Build the host-side execution plan and parameter inventory (no GPU work). */
 int cdx_unet_create(cdx_engine* e, const cdx_unet_config* cfg, cdx_net** out);
 int cdx_vae_create(cdx_engine* e, const cdx_vae_config* cfg, cdx_net** out);
+/* Text tower; parameter names are HF CLIPTextModel's (text_model.embeddings.token_embedding.weight, ...), i.e. the SD
+ * checkpoint's cond_stage_model.transformer.* keys with that prefix stripped. */
+int cdx_text_create(cdx_engine* e, const cdx_text_config* cfg, cdx_net** out);
 void cdx_net_destroy(cdx_net* n);
 
 /* Parameter inventory in the reference checkpoint's own key names, so a
@@ -125,6 +133,11 @@ int cdx_unet_forward(cdx_net* n, const float* x_dev, const float* t_dev, const f
 /* AutoencoderKL.encode (autoencoder.py:324-328 + AEM:434-459): img [B,3,R,R] in [-1,1] ->
  * moments [B, 2*embed_dim, R/8, R/8] (mean | logvar), both NCHW dev. */
 int cdx_vae_encode(cdx_net* n, const float* img_dev, float* moments_dev, int B, int R, void* stream);
+/* FrozenCLIPEmbedder.forward after tokenisation (ldm/modules/encoders/modules.py:140-158 -> transformer(input_ids=tokens)
+ * .last_hidden_state; HF modeling_clip.py CLIPTextTransformer.forward, transformers==4.19.2 pinned by environment.yml:466):
+ * token + position embedding, `layers` pre-LN blocks with causal self-attention and quick-GELU MLP, final LayerNorm.
+ * ids_dev [B, L] int32 token ids (L <= max_len); out_dev [B, L, width] fp32. */
+int cdx_text_encode(cdx_net* n, const int* ids_dev, int B, int L, float* out_dev, void* stream);
 /* AutoencoderKL.decode (autoencoder.py:330-333 + AEM:535-568): z [B,embed_dim,h,h] (already
  * divided by scale_factor) -> img [B, out_ch, 8h, 8h]. */
 int cdx_vae_decode(cdx_net* n, const float* z_dev, float* img_dev, int B, int h, void* stream);

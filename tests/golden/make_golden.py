@@ -307,6 +307,33 @@ def golden_pixel_cycle():
         os.chdir(cwd)
 
 
+def golden_clip_text():
+    """CLIP text tower: the installed transformers CLIPTextModel (the third-party model FrozenCLIPEmbedder wraps,
+    encoders/modules.py:140-158) on two reduced configs with our synthetic weights loaded strict=True."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    out = {}
+    for tag, c in (('small', specs.clip_text_config(vocab_size=1000, width=64, layers=2, heads=4, max_len=77, mlp_width=256)),
+                   ('wide', specs.clip_text_config(vocab_size=2000, width=128, layers=3, heads=2, max_len=77, mlp_width=512))):
+        hf = CLIPTextConfig(vocab_size=c['vocab_size'], hidden_size=c['width'], intermediate_size=c['mlp_width'],
+                            num_hidden_layers=c['layers'], num_attention_heads=c['heads'], max_position_embeddings=c['max_len'],
+                            hidden_act='quick_gelu', layer_norm_eps=1e-5)
+        m = CLIPTextModel(hf).eval()
+        sd = specs.synth_state_dict(specs.clip_text_params(c), 77 + c['width'], gain=2.0)
+        want = {k for k in m.state_dict() if not k.endswith('position_ids')}
+        assert want == set(sd), (sorted(want ^ set(sd))[:6])
+        m.load_state_dict(sd, strict=False)
+        g = torch.Generator().manual_seed(5 + c['width'])
+        ids = torch.randint(0, c['vocab_size'], (3, 77), generator=g)
+        ids_short = ids[:2, :19].contiguous()
+        with torch.no_grad():
+            y = m(input_ids=ids).last_hidden_state
+            ys = m(input_ids=ids_short).last_hidden_state
+        out.update({f'ids_{tag}': ids, f'out_{tag}': y, f'ids_short_{tag}': ids_short, f'out_short_{tag}': ys,
+                    f'cfg_{tag}': np.asarray([c[k] for k in ('vocab_size', 'width', 'layers', 'heads', 'max_len', 'mlp_width')], dtype=np.int64)})
+        print(f'clip_text[{tag}]: out {tuple(y.shape)} |y|max {y.abs().max():.3f}')
+    save('clip_text', **out)
+
+
 if __name__ == '__main__':
     _shim_omegaconf()
     sys.path.insert(0, os.path.join(REF, 'model/lib/stable_diffusion'))
@@ -317,3 +344,4 @@ if __name__ == '__main__':
     golden_ddim_cycle()
     golden_iddpm()
     golden_pixel_cycle()
+    golden_clip_text()

@@ -100,3 +100,23 @@ def test_pixel_cycle(tag, kw):
         assert maxdiff(z, zref) <= 2e-4 * float(zref.abs().max())
         img = cyc.forward(zref)
     assert maxdiff(img, g[f'img_{tag}']) <= 1e-3
+
+
+@pytest.mark.parametrize('tag', ['small', 'wide'])
+def test_clip_text_oracle_vs_transformers_fixture(tag):
+    """oracle/clip_text.py against the installed transformers CLIPTextModel (the third-party model behind FrozenCLIPEmbedder)."""
+    from oracle import clip_text
+    g = golden('clip_text')
+    cfg = dict(zip(('vocab_size', 'width', 'layers', 'heads', 'max_len', 'mlp_width'), (int(v) for v in g[f'cfg_{tag}'])))
+    sd = specs.synth_state_dict(specs.clip_text_params(cfg), 77 + cfg['width'], gain=2.0)
+    with torch.no_grad():
+        y = clip_text.text_forward(sd, cfg, g[f'ids_{tag}'])
+        ys = clip_text.text_forward(sd, cfg, g[f'ids_short_{tag}'])
+    assert maxdiff(y, g[f'out_{tag}']) <= 2e-5
+    assert maxdiff(ys, g[f'out_short_{tag}']) <= 2e-5
+    # causality: a token's output must not depend on later tokens
+    ids2 = g[f'ids_{tag}'].clone()
+    ids2[:, 40:] = (ids2[:, 40:] + 1) % cfg['vocab_size']
+    with torch.no_grad():
+        y2 = clip_text.text_forward(sd, cfg, ids2)
+    assert torch.equal(y2[:, :40], y[:, :40]) and not torch.equal(y2[:, 40:], y[:, 40:])
