@@ -27,7 +27,7 @@ class VaeConfig(C.Structure):
 
 class TextConfig(C.Structure):
     _fields_ = [('vocab_size', C.c_int), ('width', C.c_int), ('layers', C.c_int), ('heads', C.c_int), ('max_len', C.c_int),
-                ('mlp_width', C.c_int)]
+                ('mlp_width', C.c_int), ('kind', C.c_int), ('dim_head', C.c_int)]
 
 
 class DdimCoef(C.Structure):

@@ -153,6 +153,13 @@ __global__ void quick_gelu_kernel(const float* __restrict__ x, float* __restrict
     y[i] = v * (1.f / (1.f + expf(-1.702f * v)));
   }
 }
+// exact (erf) GELU, nn.GELU() default
+__global__ void gelu_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  GRID_STRIDE(i, n) {
+    const float v = x[i];
+    y[i] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  }
+}
 // x [rows][C] -> y [rows][Cp], zero fill
 __global__ void pad_channels_kernel(const float* __restrict__ x, float* __restrict__ y, size_t rows, int C, int Cp) {
   const size_t n = rows * (size_t)Cp;
@@ -318,6 +325,7 @@ void embed_tokens(Engine& e, const int* ids, const float* tok, const float* pos,
   LAUNCH1(embed_tokens_kernel, (size_t)B * L * W, ids, tok, pos, out, B, L, W, vocab);
 }
 void quick_gelu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s) { LAUNCH1(quick_gelu_kernel, n, x, y, n); }
+void gelu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s) { LAUNCH1(gelu_kernel, n, x, y, n); }
 void pad_channels(Engine& e, const float* x, float* y, size_t rows, int C, int Cp, cudaStream_t s) {
   LAUNCH1(pad_channels_kernel, rows * (size_t)Cp, x, y, rows, C, Cp);
 }

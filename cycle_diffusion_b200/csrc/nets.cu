@@ -293,6 +293,28 @@ Net* make_text(Engine* e, const cdx_text_config& cfg) {
   n->kind = NET_CLIP_TEXT;
   n->tcfg = cfg;
   Inv v(*n);
+  if (cfg.kind == CDX_TEXT_XTRANSFORMER) {
+    // x_transformer TransformerWrapper(Encoder(dim, depth)) state_dict order (x_transformer.py:548-596, 370-480, 215-266, 194-208)
+    CDX_CHECK(cfg.dim_head > 0 && (cfg.heads * cfg.dim_head) % 4 == 0, "text: dim_head %d", cfg.dim_head);
+    const int inner = cfg.heads * cfg.dim_head;
+    const std::string T = "transformer.";
+    v.add(T + "token_emb.weight", {cfg.vocab_size, cfg.width});
+    v.add(T + "pos_emb.emb.weight", {cfg.max_len, cfg.width});
+    for (int l = 0; l < cfg.layers; ++l) {
+      const std::string pa = T + "attn_layers.layers." + std::to_string(2 * l), pf = T + "attn_layers.layers." + std::to_string(2 * l + 1);
+      v.norm(pa + ".0", cfg.width);
+      v.lin(pa + ".1.to_q", cfg.width, inner, false);
+      v.lin(pa + ".1.to_k", cfg.width, inner, false);
+      v.lin(pa + ".1.to_v", cfg.width, inner, false);
+      v.lin(pa + ".1.to_out", inner, cfg.width);
+      v.norm(pf + ".0", cfg.width);
+      v.lin(pf + ".1.net.0.0", cfg.width, cfg.mlp_width);
+      v.lin(pf + ".1.net.2", cfg.mlp_width, cfg.width);
+    }
+    v.norm(T + "norm", cfg.width);
+    assign_offsets(*n);
+    return n;
+  }
   const std::string T = "text_model.";
   v.add(T + "embeddings.token_embedding.weight", {cfg.vocab_size, cfg.width});
   v.add(T + "embeddings.position_embedding.weight", {cfg.max_len, cfg.width});
@@ -912,6 +934,38 @@ void text_encode(Net& n, const int* ids, float* out, int B, int L, cudaStream_t 
   CDX_CHECK(L >= 1 && L <= c.max_len, "text_encode: %d tokens, the position table has %d", L, c.max_len);
   Exec ex(n, s);
   Engine& e = *n.eng;
+  if (c.kind == CDX_TEXT_XTRANSFORMER) {
+    // TransformerWrapper.forward(return_embeddings=True) (x_transformer.py:598-626) over AttentionLayers.forward (481-523):
+    // x = tok + pos; per layer x += to_out(softmax(q k^T d^-1/2) v) of LN(x), x += W2 gelu(W1 LN(x)); final LN
+    const int W = c.width, inner = c.heads * c.dim_head;
+    const std::string T = "transformer.";
+    Scope top(e.arena);
+    Tensor x = ex.alloc(B, L, 1, W);
+    embed_tokens(e, ids, n.P(T + "token_emb.weight"), n.P(T + "pos_emb.emb.weight"), x.p, B, L, W, c.vocab_size, s);
+    const float scale = (float)pow((double)c.dim_head, -0.5);
+    for (int l = 0; l < c.layers; ++l) {
+      const std::string pa = T + "attn_layers.layers." + std::to_string(2 * l), pf = T + "attn_layers.layers." + std::to_string(2 * l + 1);
+      Tensor y = ex.alloc(B, L, 1, W);
+      {
+        Scope sc(e.arena);
+        Tensor n1 = ex.ln(x, pa + ".0");
+        Tensor q = ex.linear(n1, pa + ".1.to_q", false);
+        Tensor k = ex.linear(n1, pa + ".1.to_k", false);
+        Tensor v = ex.linear(n1, pa + ".1.to_v", false);
+        Tensor a = ex.alloc(B, L, 1, inner);
+        attention(e, q.p, inner, k.p, inner, v.p, inner, a.p, inner, B, L, L, c.heads, c.dim_head, c.dim_head, scale, s, false);
+        Tensor h = ex.linear(a, pa + ".1.to_out", true, x.p);                         // + residual
+        Tensor n2 = ex.ln(h, pf + ".0");
+        Tensor f = ex.linear(n2, pf + ".1.net.0.0", true);
+        gelu(e, f.p, f.p, f.numel(), s);
+        const Param& w2 = n.param(pf + ".1.net.2.weight");
+        ex.linear_into(f.p, c.mlp_width, c.mlp_width, nullptr, 0, 0, B * L, n.blob + w2.off, W, n.P(pf + ".1.net.2.bias"), h.p, W, y.p, W);
+      }
+      x = y;
+    }
+    layernorm(e, x.p, n.P(T + "norm.weight"), n.P(T + "norm.bias"), out, B * L, W, s);
+    return;
+  }
   const int W = c.width, d = W / c.heads;
   const std::string T = "text_model.";
   Scope top(e.arena);

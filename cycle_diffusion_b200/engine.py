@@ -423,21 +423,25 @@ class VAE(Net):
 
 
 class TextEncoder(Net):
-    """CLIP text tower (HF CLIPTextModel layout) -> last_hidden_state; the conditioning model FrozenCLIPEmbedder wraps
-    (ldm/modules/encoders/modules.py:140-158).  Tokenisation stays on the host (BPE vocabulary files are not part of the engine)."""
+    """Text conditioning towers: CLIP (HF CLIPTextModel layout -> last_hidden_state; FrozenCLIPEmbedder,
+    ldm/modules/encoders/modules.py:140-158) or, with ``cfg['kind'] == 'xtransformer'``, the LDM BERTEmbedder's in-tree
+    encoder (modules.py:79-98, x_transformer.py).  Tokenisation stays on the host (vocabulary files are not part of the engine)."""
 
     def __init__(self, engine, cfg):
         self.cfg = dict(cfg)
         c = TextConfig()
         c.vocab_size, c.width, c.layers = cfg['vocab_size'], cfg['width'], cfg['layers']
         c.heads, c.max_len, c.mlp_width = cfg['heads'], cfg['max_len'], cfg['mlp_width']
+        c.kind = 2 if cfg.get('kind', 'clip') == 'xtransformer' else 1
+        c.dim_head = cfg.get('dim_head', cfg['width'] // cfg['heads'])
         h = C.c_void_p()
         check(lib.cdx_text_create(engine.h if engine is not None else None, C.byref(c), C.byref(h)))
         super().__init__(engine, h)
 
     def load_state_dict(self, sd, prefix='', strict=True):
         # older transformers versions register `embeddings.position_ids` as a persistent buffer: not a parameter
-        sd = {k: v for k, v in sd.items() if not k.endswith('embeddings.position_ids')}
+        # (and x_transformer's TransformerWrapper carries an unused `to_logits` head)
+        sd = {k: v for k, v in sd.items() if not k.endswith('embeddings.position_ids') and '.to_logits.' not in k}
         return super().load_state_dict(sd, prefix, strict)
 
     def forward(self, input_ids):

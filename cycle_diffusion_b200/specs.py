@@ -271,6 +271,30 @@ def clip_text_params(cfg, prefix=''):
     return out
 
 
+def bert_text_config(vocab_size=30522, width=1280, layers=32, heads=8, dim_head=64, max_len=77, mlp_width=None):
+    """LDM text2img-large conditioning model: BERTEmbedder(n_embed=1280, n_layer=32) (txt2img-1p4B-eval.yaml:66-71;
+    encoders/modules.py:79-98): x_transformer Encoder defaults heads=8, dim_head=64, ff mult 4."""
+    return dict(kind='xtransformer', vocab_size=vocab_size, width=width, layers=layers, heads=heads, dim_head=dim_head, max_len=max_len,
+                mlp_width=mlp_width or 4 * width)
+
+
+def bert_text_params(cfg, prefix=''):
+    """Ordered (name, shape, kind) list of TransformerWrapper(Encoder(dim, depth)).state_dict() without the unused to_logits."""
+    W, M, inner = cfg['width'], cfg['mlp_width'], cfg['heads'] * cfg['dim_head']
+    T = prefix + 'transformer.'
+    out = [(T + 'token_emb.weight', (cfg['vocab_size'], W), 'w'), (T + 'pos_emb.emb.weight', (cfg['max_len'], W), 'w')]
+    for l in range(cfg['layers']):
+        pa, pf = f'{T}attn_layers.layers.{2 * l}', f'{T}attn_layers.layers.{2 * l + 1}'
+        out += [(pa + '.0.weight', (W,), 'nw'), (pa + '.0.bias', (W,), 'nb')]
+        out += [(pa + '.1.to_q.weight', (inner, W), 'w'), (pa + '.1.to_k.weight', (inner, W), 'w'), (pa + '.1.to_v.weight', (inner, W), 'w')]
+        out += [(pa + '.1.to_out.weight', (W, inner), 'w'), (pa + '.1.to_out.bias', (W,), 'b')]
+        out += [(pf + '.0.weight', (W,), 'nw'), (pf + '.0.bias', (W,), 'nb')]
+        out += [(pf + '.1.net.0.0.weight', (M, W), 'w'), (pf + '.1.net.0.0.bias', (M,), 'b')]
+        out += [(pf + '.1.net.2.weight', (W, M), 'w'), (pf + '.1.net.2.bias', (W,), 'b')]
+    out += [(T + 'norm.weight', (W,), 'nw'), (T + 'norm.bias', (W,), 'nb')]
+    return out
+
+
 def synth_state_dict(params, seed, gain=1.0):
     """Deterministic CPU fp32 weights for an inventory; identical on every machine with the same torch build.
 

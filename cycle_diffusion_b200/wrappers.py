@@ -49,6 +49,15 @@ class ClipTextCondStage:
         return self.encoder(ids)
 
 
+class BertTextCondStage(ClipTextCondStage):
+    """Same for the LDM text2img-large conditioning model: BERTEmbedder (encoders/modules.py:79-102; 32 x 1280 x_transformer
+    encoder over BERT word pieces).  ``tokenizer``: e.g. HF ``BertTokenizerFast`` with ``padding='max_length', max_length=77``
+    (modules.py:66-72); the LDM checkpoint keeps the weights under ``cond_stage_model.``."""
+
+    def __init__(self, engine, state_dict, tokenizer, cfg=None, prefix=''):
+        super().__init__(engine, state_dict, tokenizer, cfg or specs.bert_text_config(), prefix)
+
+
 class SyntheticTextEncoder:
     """Deterministic stand-in for FrozenCLIPEmbedder / BERTEmbedder: prompt string -> N(0,1) tokens [77, dim].
 

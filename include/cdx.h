@@ -92,7 +92,13 @@ typedef struct cdx_vae_config { /* AutoencoderKL ddconfig, v1-inference.yaml:51-
 typedef struct cdx_text_config { /* CLIP ViT-L/14 text tower as FrozenCLIPEmbedder uses it: HF CLIPTextModel
                                     "openai/clip-vit-large-patch14": 12 layers, width 768, 12 heads, 77 positions, quick-GELU */
   int vocab_size, width, layers, heads, max_len, mlp_width;
+  int kind;     /* CDX_TEXT_CLIP (0 also accepted) or CDX_TEXT_XTRANSFORMER: the LDM BERTEmbedder's in-tree encoder
+                   (encoders/modules.py:79-98 -> x_transformer.py TransformerWrapper(Encoder(dim, depth))): pre-LN blocks of
+                   bias-free q/k/v (heads x dim_head), full attention, exact-GELU feed-forward; 30522 BERT word pieces */
+  int dim_head; /* XTRANSFORMER: per-head width (x_transformer DEFAULT_DIM_HEAD = 64; heads * dim_head may differ from width) */
 } cdx_text_config;
+#define CDX_TEXT_CLIP 1
+#define CDX_TEXT_XTRANSFORMER 2
 
 /* Build the host-side execution plan and parameter inventory (no GPU work). */
 int cdx_unet_create(cdx_engine* e, const cdx_unet_config* cfg, cdx_net** out);
@@ -136,7 +142,9 @@ int cdx_vae_encode(cdx_net* n, const float* img_dev, float* moments_dev, int B, 
 /* FrozenCLIPEmbedder.forward after tokenisation (ldm/modules/encoders/modules.py:140-158 -> transformer(input_ids=tokens)
  * .last_hidden_state; HF modeling_clip.py CLIPTextTransformer.forward, transformers==4.19.2 pinned by environment.yml:466):
  * token + position embedding, `layers` pre-LN blocks with causal self-attention and quick-GELU MLP, final LayerNorm.
- * ids_dev [B, L] int32 token ids (L <= max_len); out_dev [B, L, width] fp32. */
+ * ids_dev [B, L] int32 token ids (L <= max_len); out_dev [B, L, width] fp32.
+ * kind XTRANSFORMER: BERTEmbedder.forward after tokenisation = transformer(tokens, return_embeddings=True)
+ * (x_transformer.py:598-626, 481-523): parameter names transformer.token_emb.weight, transformer.attn_layers.layers.N.* ... */
 int cdx_text_encode(cdx_net* n, const int* ids_dev, int B, int L, float* out_dev, void* stream);
 /* AutoencoderKL.decode (autoencoder.py:330-333 + AEM:535-568): z [B,embed_dim,h,h] (already
  * divided by scale_factor) -> img [B, out_ch, 8h, 8h]. */

@@ -334,6 +334,30 @@ def golden_clip_text():
     save('clip_text', **out)
 
 
+def golden_bert_text():
+    """LDM BERTEmbedder: the reference's own x_transformer TransformerWrapper(Encoder(dim, depth)) exactly as
+    encoders/modules.py:88-90 builds it (the module file itself imports clip/kornia, so its three lines are restated here)."""
+    from ldm.modules.x_transformer import Encoder, TransformerWrapper
+    out = {}
+    for tag, c in (('small', specs.bert_text_config(vocab_size=500, width=96, layers=2)),
+                   ('wide', specs.bert_text_config(vocab_size=800, width=256, layers=3))):
+        m = TransformerWrapper(num_tokens=c['vocab_size'], max_seq_len=c['max_len'], attn_layers=Encoder(dim=c['width'], depth=c['layers']),
+                               emb_dropout=0.0).eval()
+        sd = specs.synth_state_dict(specs.bert_text_params(c), 11 + c['width'], gain=2.0)
+        want = {k[len('transformer.'):] for k in sd}
+        have = {k for k in m.state_dict() if not k.startswith('to_logits.')}
+        assert want == have, sorted(want ^ have)[:6]
+        m.load_state_dict({k[len('transformer.'):]: v for k, v in sd.items()}, strict=False)
+        g = torch.Generator().manual_seed(9 + c['width'])
+        tok = torch.randint(0, c['vocab_size'], (3, 77), generator=g)
+        with torch.no_grad():
+            y = m(tok, return_embeddings=True)
+        out.update({f'tok_{tag}': tok, f'out_{tag}': y,
+                    f'cfg_{tag}': np.asarray([c[k] for k in ('vocab_size', 'width', 'layers', 'heads', 'dim_head', 'max_len', 'mlp_width')], dtype=np.int64)})
+        print(f'bert_text[{tag}]: out {tuple(y.shape)} |y|max {y.abs().max():.3f}')
+    save('bert_text', **out)
+
+
 if __name__ == '__main__':
     _shim_omegaconf()
     sys.path.insert(0, os.path.join(REF, 'model/lib/stable_diffusion'))
@@ -345,3 +369,4 @@ if __name__ == '__main__':
     golden_iddpm()
     golden_pixel_cycle()
     golden_clip_text()
+    golden_bert_text()

@@ -120,3 +120,16 @@ def test_clip_text_oracle_vs_transformers_fixture(tag):
     with torch.no_grad():
         y2 = clip_text.text_forward(sd, cfg, ids2)
     assert torch.equal(y2[:, :40], y[:, :40]) and not torch.equal(y2[:, 40:], y[:, 40:])
+
+
+@pytest.mark.parametrize('tag', ['small', 'wide'])
+def test_bert_text_oracle_vs_reference_fixture(tag):
+    """oracle/bert_text.py against the reference's own x_transformer TransformerWrapper (the LDM BERTEmbedder)."""
+    from oracle import bert_text
+    g = golden('bert_text')
+    keys = ('vocab_size', 'width', 'layers', 'heads', 'dim_head', 'max_len', 'mlp_width')
+    cfg = dict(zip(keys, (int(v) for v in g[f'cfg_{tag}'])), kind='xtransformer')
+    sd = specs.synth_state_dict(specs.bert_text_params(cfg), 11 + cfg['width'], gain=2.0)
+    with torch.no_grad():
+        y = bert_text.text_forward(sd, cfg, g[f'tok_{tag}'])
+    assert maxdiff(y, g[f'out_{tag}']) <= 2e-5

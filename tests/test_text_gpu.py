@@ -56,3 +56,19 @@ def test_text_encoder_full_size_vs_oracle(eng):
         ref = clip_text.text_forward(sd, cfg, ids)
     print(f'text[ViT-L/14 shape]: |dy| {maxdiff(y, ref):.2e}  |y|max {float(ref.abs().max()):.2f}')
     assert maxdiff(y, ref) < 1e-4
+
+
+@pytest.mark.parametrize('tag', ['small', 'wide'])
+def test_bert_text_encoder_vs_reference_fixture(eng, tag):
+    """LDM BERTEmbedder transformer (x_transformer) through the C ABI against the fixture from the reference's own module."""
+    from cycle_diffusion_b200.engine import TextEncoder
+    g = golden('bert_text')
+    keys = ('vocab_size', 'width', 'layers', 'heads', 'dim_head', 'max_len', 'mlp_width')
+    cfg = dict(zip(keys, (int(v) for v in g[f'cfg_{tag}'])), kind='xtransformer')
+    sd = specs.synth_state_dict(specs.bert_text_params(cfg), 11 + cfg['width'], gain=2.0)
+    enc = TextEncoder(eng, cfg)
+    assert [n for n, _ in enc.inventory()] == [n for n, _, _ in specs.bert_text_params(cfg)]
+    enc.load_state_dict(sd)
+    y = enc(g[f'tok_{tag}']).cpu()
+    print(f'bert_text[{tag}]: |dy| {maxdiff(y, g[f"out_{tag}"]):.2e}')
+    assert maxdiff(y, g[f'out_{tag}']) < 5e-5
