@@ -274,7 +274,8 @@ def run_ours(args):
         stage_ms = {k: round(ev[i].elapsed_time(ev[i + 1]), 1) for i, k in
                     enumerate(['vae_encode', f'dpm_encode_{S_STEPS}x_unet_b{B}', f'decode_{S_STEPS}x_unet_b{2 * B}', 'vae_decode'])}
 
-    cpu = cpu_baseline_sample(quick=True) if (rank == 0 and not args.no_cpu) else None
+    # the CPU leg is timed on rank 0 of the single-GPU run only (the other ranks would just wait at the closing barrier)
+    cpu = cpu_baseline_sample(quick=True) if (rank == 0 and world == 1 and not args.no_cpu) else None
 
     if rank == 0:
         line = {
