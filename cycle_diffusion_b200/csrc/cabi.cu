@@ -32,8 +32,11 @@ int guard(F&& f) {
 }
 
 // run `f` once in sizing mode, grow the arena, then for real
+// The arena, the context K/V cache and the weight planes are reused from call to call with no synchronisation of their own,
+// which is only safe in stream order.  A caller that switches streams between calls is handed over explicitly: every call
+// records an event at its end, and a call arriving on a different stream first waits for it.
 template <class F>
-void with_arena(Engine& e, F&& f) {
+void with_arena(Engine& e, cudaStream_t s, F&& f) {
   CDX_CUDA(cudaSetDevice(e.device));
   e.arena.begin_dry();
   try {
@@ -44,8 +47,13 @@ void with_arena(Engine& e, F&& f) {
     throw;
   }
   e.arena.end_dry();
+  if (!e.done_ev) CDX_CUDA(cudaEventCreateWithFlags(&e.done_ev, cudaEventDisableTiming));
+  if (e.ev_recorded && e.last_stream != s) CDX_CUDA(cudaStreamWaitEvent(s, e.done_ev, 0));
   f();
   e.arena.off = 0;
+  CDX_CUDA(cudaEventRecord(e.done_ev, s));
+  e.ev_recorded = true;
+  e.last_stream = s;
 }
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -155,6 +163,7 @@ void cdx_engine_destroy(cdx_engine* e) {
   cudaSetDevice(e->e.device);
   cudaDeviceSynchronize();
   e->e.arena.destroy();
+  if (e->e.done_ev) cudaEventDestroy(e->e.done_ev);
   delete e;
 }
 size_t cdx_engine_workspace_bytes(const cdx_engine* e) { return e ? e->e.arena.cap : 0; }
@@ -266,6 +275,10 @@ int cdx_net_adopt_blob(cdx_net* n) {
     CDX_CHECK(n && n->owner, "adopt_blob: null / inventory-only net");
     net_ensure_blob(*n->n);
     for (Param& p : n->n->params) p.loaded = true;
+    // the blob contents changed under us: everything derived from it (operand planes, cached context K/V) is stale
+    n->n->planes_valid = false;
+    n->n->ctxkv.valid = false;
+    n->n->finalized = false;
     net_finalize(*n->n);
   });
 }
@@ -283,25 +296,25 @@ int cdx_unet_forward(cdx_net* n, const float* x, const float* t_dev, const float
                      void* stream) {
   return guard([&] {
     CDX_CHECK(n && n->owner && x && t_dev && out && B > 0, "unet_forward: bad arguments");
-    with_arena(n->owner->e, [&] { unet_forward(*n->n, x, t_dev, ctx, ctx_len, out, B, H, W, S(stream)); });
+    with_arena(n->owner->e, S(stream), [&] { unet_forward(*n->n, x, t_dev, ctx, ctx_len, out, B, H, W, S(stream)); });
   });
 }
 int cdx_vae_encode(cdx_net* n, const float* img, float* moments, int B, int R, void* stream) {
   return guard([&] {
     CDX_CHECK(n && n->owner && img && moments && B > 0, "vae_encode: bad arguments");
-    with_arena(n->owner->e, [&] { vae_encode(*n->n, img, moments, B, R, S(stream)); });
+    with_arena(n->owner->e, S(stream), [&] { vae_encode(*n->n, img, moments, B, R, S(stream)); });
   });
 }
 int cdx_text_encode(cdx_net* n, const int* ids, int B, int L, float* out, void* stream) {
   return guard([&] {
     CDX_CHECK(n && n->owner && ids && out && B > 0, "text_encode: bad arguments");
-    with_arena(n->owner->e, [&] { text_encode(*n->n, ids, out, B, L, S(stream)); });
+    with_arena(n->owner->e, S(stream), [&] { text_encode(*n->n, ids, out, B, L, S(stream)); });
   });
 }
 int cdx_vae_decode(cdx_net* n, const float* z, float* img, int B, int h, void* stream) {
   return guard([&] {
     CDX_CHECK(n && n->owner && z && img && B > 0, "vae_decode: bad arguments");
-    with_arena(n->owner->e, [&] { vae_decode(*n->n, z, img, B, h, S(stream)); });
+    with_arena(n->owner->e, S(stream), [&] { vae_decode(*n->n, z, img, B, h, S(stream)); });
   });
 }
 
@@ -357,7 +370,7 @@ int cdx_latent_encode(cdx_net* un, const float* x0, const float* c, const float*
     cudaStream_t s = S(stream);
     const int chw = C * h * w;
     const size_t n = (size_t)B * chw;
-    with_arena(e, [&] {
+    with_arena(e, s, [&] {
       Scope sc(e.arena);
       float* xt = (float*)e.arena.alloc(n * sizeof(float));
       float* xn = (float*)e.arena.alloc(n * sizeof(float));
@@ -394,7 +407,7 @@ int cdx_latent_decode(cdx_net* un, const float* z, int n_eps, const float* c, co
     cudaStream_t s = S(stream);
     const int chw = C * h * w;
     const size_t n = (size_t)B * chw;
-    with_arena(e, [&] {
+    with_arena(e, s, [&] {
       Scope sc(e.arena);
       float* xa = (float*)e.arena.alloc(n * sizeof(float));
       float* xb = (float*)e.arena.alloc(n * sizeof(float));
@@ -429,7 +442,7 @@ int cdx_pixel_encode(cdx_net* un, const float* x0, const cdx_pixel_coef* coef, c
     const int chw = C * R * R;
     const int net_chw = unet.ucfg.out_channels * R * R;
     const size_t n = (size_t)B * chw;
-    with_arena(e, [&] {
+    with_arena(e, s, [&] {
       Scope sc(e.arena);
       float* xt = (float*)e.arena.alloc(n * sizeof(float));
       float* xn = (float*)e.arena.alloc(n * sizeof(float));
@@ -462,7 +475,7 @@ int cdx_pixel_decode(cdx_net* un, const float* z, int n_eps, const cdx_pixel_coe
     const int chw = C * R * R;
     const int net_chw = unet.ucfg.out_channels * R * R;
     const size_t n = (size_t)B * chw;
-    with_arena(e, [&] {
+    with_arena(e, s, [&] {
       Scope sc(e.arena);
       float* xa = (float*)e.arena.alloc(n * sizeof(float));
       float* xb = (float*)e.arena.alloc(n * sizeof(float));
@@ -492,7 +505,7 @@ int cdx_op_conv3x3(cdx_engine* eh, const float* x, const float* w_oihw, const fl
     CDX_CHECK(eh && x && w_oihw && y, "op_conv3x3: null argument");
     Engine& e = eh->e;
     cudaStream_t s = S(stream);
-    with_arena(e, [&] {
+    with_arena(e, s, [&] {
       Scope sc(e.arena);
       float* wr = (float*)e.arena.alloc((size_t)Cout * Cin * 9 * sizeof(float));
       repack_conv3x3(e, w_oihw, wr, Cout, Cin, s);
@@ -521,7 +534,7 @@ int cdx_op_linear(cdx_engine* eh, const float* x, const float* w, const float* b
   return guard([&] {
     CDX_CHECK(eh && x && w && y, "op_linear: null argument");
     Engine& e = eh->e;
-    with_arena(e, [&] {
+    with_arena(e, S(stream), [&] {
       Scope sc(e.arena);
       GemmArgs g;
       g.M = M; g.N = N; g.K = K;
@@ -543,7 +556,7 @@ int cdx_op_groupnorm(cdx_engine* eh, const float* x, const float* gamma, const f
                      void* stream) {
   return guard([&] {
     CDX_CHECK(eh && x && gamma && beta && y, "op_groupnorm: null argument");
-    with_arena(eh->e, [&] { groupnorm(eh->e, x, C, nullptr, 0, gamma, beta, eps, silu_ != 0, nullptr, nullptr, 0, y, B, HW, S(stream)); });
+    with_arena(eh->e, S(stream), [&] { groupnorm(eh->e, x, C, nullptr, 0, gamma, beta, eps, silu_ != 0, nullptr, nullptr, 0, y, B, HW, S(stream)); });
   });
 }
 int cdx_op_layernorm(cdx_engine* eh, const float* x, const float* gamma, const float* beta, float* y, int M, int C, void* stream) {
@@ -556,7 +569,7 @@ int cdx_op_attention(cdx_engine* eh, const float* q, const float* k, const float
     const int C = heads * d;
     Engine& e = eh->e;
     cudaStream_t s = S(stream);
-    with_arena(e, [&] {
+    with_arena(e, s, [&] {
       Scope sc(e.arena);
       bool done = false;
       if (e.mma_mode == 1 && Nq == Nk && (Nq % 32) == 0 && Nq >= 128 && (d % 4) == 0) {

@@ -75,6 +75,9 @@ struct Engine {
   bool flash_attn = true;        // fused tcgen05 attention kernel (kernels_attn.cu); false -> unfused QK^T / softmax / PV
   int mma_mode = 1;              // 0 SIMT FFMA (exact fp32), 1 tcgen05 3xTF32 (default)
   Arena arena;
+  cudaStream_t last_stream = nullptr;   // stream of the previous arena-using call and the event recorded at its end
+  cudaEvent_t done_ev = nullptr;
+  bool ev_recorded = false;
   uint64_t launches = 0;
   bool dry() const { return arena.dry; }
 };

@@ -443,10 +443,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
 template <int D>
 void launch_flash(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& kh, const CUtensorMap& kl, const CUtensorMap& vh,
                   const CUtensorMap& vl, const AttnParams& p, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};          // per device (cudaFuncSetAttribute is device state); engines are single-threaded per device
+  int dev = 0;
+  CDX_CUDA(cudaGetDevice(&dev));
+  if (!attr[dev & 63]) {
     CDX_CUDA(cudaFuncSetAttribute(flash_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<D>::SMEM_BYTES));
-    attr = true;
+    attr[dev & 63] = true;
   }
   flash_attn_kernel<D><<<dim3(p.N / AQ, p.heads, p.B), ACfg<D>::THREADS, ACfg<D>::SMEM_BYTES, s>>>(qh, ql, kh, kl, vh, vl, p);
 }

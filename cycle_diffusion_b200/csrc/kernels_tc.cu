@@ -35,6 +35,8 @@
 #include <algorithm>
 
 #include <mutex>
+#include <array>
+#include <map>
 #include <unordered_map>
 #include <vector>
 #include <cstdlib>
@@ -50,15 +52,29 @@ constexpr int TBM = 128, TBN = 128, TBK = 32;
 constexpr int TILE_BYTES = TBM * TBK * 4;          // 16 KB
 constexpr int NUM_SPLIT_WARPS = 4;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int KCHUNK = 8;                          // k-blocks per TMEM accumulation chunk (256 K elements)
 constexpr int TC_THREADS = 64 + (NUM_SPLIT_WARPS + NUM_EPI_WARPS) * 32;
 
-template <bool TS>
+// Operand path of the kernel (template parameter MODE):
+//   MODE_SS   both operands raw fp32 in smem, split in smem into TF32 hi / lo (generic: B may be an activation)
+//   MODE_TS   B = pre-split TF32 planes by TMA, A split by the split warps into TMEM (3 x kind::tf32 per 8-wide K chunk)
+//   MODE_H16  fp16 split at the kind::f16 rate (3 x kind::f16 per 16-wide K chunk = half the tensor time and half the
+//             B bytes of MODE_TS): x' = x * 2^e (e from the tensor's tracked max: |x'| < 2^15), hi = fp16(x'), lo = fp16(x' - hi).
+//             hi + lo carries >= 22 significant bits of x' down to |x'| = 2^-3 and an absolute error <= 2^-25 below that
+//             (2^-40 of the tensor's max), products of 11-bit significands are exact in the fp32 accumulator, and the result is
+//             rescaled by the exact power of two 2^-(ea + eb) in the epilogue.  B planes are pre-scaled fp16 in HBM.
+enum { MODE_SS = 0, MODE_TS = 1, MODE_H16 = 2 };
+
+template <int MODE>
 struct Cfg {
-  static constexpr int STAGES = TS ? 4 : 3;
-  static constexpr int STAGE_BYTES = TS ? 3 * TILE_BYTES : 4 * TILE_BYTES;   // TS: A_raw, B_hi, B_lo ; SS: A_hi, A_lo, B_hi, B_lo
+  static constexpr bool TS = MODE != MODE_SS;
+  static constexpr bool H16 = MODE == MODE_H16;
+  static constexpr int BK = H16 ? 64 : 32;         // K elements per pipeline stage
+  static constexpr int KCHUNK = 256 / BK;          // stages per TMEM accumulation chunk (256 K elements)
+  static constexpr int STAGES = MODE == MODE_TS ? 4 : 3;
+  // SS: A_hi, A_lo, B_hi, B_lo ; TS: A_raw, B_hi, B_lo ; H16: A_raw(k 0..31), A_raw(k 32..63), B_hi, B_lo (fp16, 128 B rows)
+  static constexpr int STAGE_BYTES = MODE == MODE_TS ? 3 * TILE_BYTES : 4 * TILE_BYTES;
   static constexpr int TMEM_COLS = TS ? 512 : 256;
-  static constexpr int A_COL0 = 256;               // TS: A stage s lives at columns A_COL0 + 64 s (hi) / + 32 (lo)
+  static constexpr int A_COL0 = 256;               // TS / H16: A stage s lives at columns A_COL0 + 64 s (hi) / + 32 (lo)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048 /*barriers + bias staging*/ + 32768 /*epilogue transpose: 8 warps x 4 KB*/ + 1024 /*alignment slack*/;
 };
 
@@ -94,22 +110,45 @@ struct TcParams {
   // then sums the partials in fixed order and applies alpha / bias / row vector / residual
   int splits, kb_per_split;
   float* ws;
+  // MODE_H16: tracked max |A| (device scalars written by the producers of A / A2), exponent of the pre-scaled fp16 weight
+  // planes, `fast` = hi*hi term only (the separately reported reduced-precision path)
+  const float* a_amax; const float* a2_amax;
+  int b_exp;
+  int fast;
+  float* c_amax;            // optional: atomic max of |C| over everything this launch stores (operand range for the consumer GEMM)
 };
+
+// exponent e such that amax * 2^e lies in [2^14, 2^15): |x * 2^e| < 2^15 for every |x| <= amax (0 for an all-zero tensor)
+__device__ __forceinline__ int h16_exp_of(float amax) {
+  const int be = (int)((__float_as_uint(amax) >> 23) & 0xffu);
+  if (be == 0 || be == 0xff) return 0;
+  return min(max(14 - (be - 127), -100), 100);
+}
+__device__ __forceinline__ int h16_a_exp(const TcParams& p) {
+  float m = p.a_amax ? *p.a_amax : 0.f;
+  if (p.a2_amax) m = fmaxf(m, *p.a2_amax);
+  return h16_exp_of(m);
+}
+__device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(min(max(e, -126), 127) + 127) << 23); }
 
 struct TileCoord { int n0, nend, nw, m0, x0, y0, b0, zb, zh, kb0, kb1, split; };
 
-template <bool TS>
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
-  constexpr int STAGES = Cfg<TS>::STAGES;
-  constexpr int STAGE_BYTES = Cfg<TS>::STAGE_BYTES;
-  constexpr int TMEM_COLS = Cfg<TS>::TMEM_COLS;
+  constexpr bool TS = Cfg<MODE>::TS;
+  constexpr bool H16 = Cfg<MODE>::H16;
+  constexpr int BK = Cfg<MODE>::BK;
+  constexpr int KCHUNK = Cfg<MODE>::KCHUNK;
+  constexpr int STAGES = Cfg<MODE>::STAGES;
+  constexpr int STAGE_BYTES = Cfg<MODE>::STAGE_BYTES;
+  constexpr int TMEM_COLS = Cfg<MODE>::TMEM_COLS;
   // smem offsets inside a stage
-  constexpr int OFF_A = 0;                                   // SS: A_hi (raw in place) ; TS: A_raw
+  constexpr int OFF_A = 0;                                   // SS: A_hi (raw in place) ; TS: A_raw ; H16: A_raw k 0..31, then k 32..63
   constexpr int OFF_ALO = TILE_BYTES;                        // SS only
-  constexpr int OFF_BHI = TS ? TILE_BYTES : 2 * TILE_BYTES;
-  constexpr int OFF_BLO = TS ? 2 * TILE_BYTES : 3 * TILE_BYTES;
+  constexpr int OFF_BHI = MODE == MODE_TS ? TILE_BYTES : 2 * TILE_BYTES;
+  constexpr int OFF_BLO = MODE == MODE_TS ? 2 * TILE_BYTES : 3 * TILE_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 1024-byte aligned (swizzle atoms)
@@ -125,7 +164,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   float4* const s_stage = reinterpret_cast<float4*>(smem_raw + (bars - smem_u32(smem_raw)) + 2048);   // 8 warps x 4 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = (p.K + TBK - 1) / TBK;
+  const int num_kb = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -192,8 +231,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(bar_empty(s), (it & 1) ^ 1);
         const uint32_t st = base + s * STAGE_BYTES;
         const uint32_t sa = st + OFF_A, sb = st + OFF_BHI;
-        const int k0 = kb * TBK;
+        const int k0 = kb * BK;
         if (!elect_one()) continue;
+        if (H16) {
+          // two 32-float A sub-blocks (each its own tap / source: a stage may straddle) + fp16 B planes of 64 k (128 B rows)
+          const int nsub = (k0 + TBK < p.K) ? 2 : 1;               // K % 32 == 0; an odd tail stage carries one sub-block
+          mbar_expect_tx(bar_full_raw(s), nsub * TILE_BYTES + 2 * p.tn_w * BK * 2);
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int ks = k0 + sub * TBK;
+            const uint32_t dst = sa + sub * TILE_BYTES;
+            if (p.mode == 0) {
+              if (ks < p.C1) tma_load_2d(dst, &mapA, ks, m0, bar_full_raw(s));
+              else tma_load_2d(dst, &mapA2, ks - p.C1, m0, bar_full_raw(s));
+            } else {
+              const int kq = ks / TBK;
+              const int tap = kq / cblocks, cb = kq - tap * cblocks;
+              const int dy = tap / 3, dx = tap - dy * 3;
+              tma_load_4d(dst, &mapA, cb * TBK, x0 * p.cstride + dx - p.cpad, y0 * p.cstride + dy - p.cpad, b0, bar_full_raw(s));
+            }
+          }
+          tma_load_2d(sb, &mapB, k0, n0, bar_full_raw(s));
+          tma_load_2d(st + OFF_BLO, &mapBlo, k0, n0, bar_full_raw(s));
+          continue;
+        }
         mbar_expect_tx(bar_full_raw(s), TILE_BYTES + (TS ? 2 : 1) * p.tn_w * TBK * 4);
         if (p.mode == 0) {
           if (k0 < p.C1) tma_load_2d(sa, &mapA, k0, m0, bar_full_raw(s));
@@ -226,7 +286,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc_ = tile_coord(t);
       const int nkb = tc_.kb1 - tc_.kb0;
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tc_.nw >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+      // instruction descriptor: D fp32; A / B format tf32 (2) or f16 (0), both K-major; N >> 3; M >> 4
+      const uint32_t idesc = (1u << 4) | (H16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(tc_.nw >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
       for (int kb = 0; kb < nkb; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
         const int lchunk = kb / KCHUNK, kin = kb - lchunk * KCHUNK;
@@ -241,8 +302,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t acc = tmem_base + (uint32_t)(buf * TBN);
         const uint64_t b_hi = make_desc(st + OFF_BHI), b_lo = make_desc(st + OFF_BLO);
         if (!elect_one()) continue;
-        if (TS) {
-          const uint32_t a_hi = tmem_base + (uint32_t)(Cfg<TS>::A_COL0 + s * 64), a_lo = a_hi + 32;
+        if (H16) {
+          // A: packed fp16 pairs in TMEM (hi: 32 columns = 64 k, lo: the next 32); a K = 16 MMA consumes 8 columns of A and
+          // 32 bytes of each B row
+          const uint32_t a_hi = tmem_base + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64), a_lo = a_hi + 32;
+          const int nj = ((tc_.kb0 + kb) * BK + TBK < p.K) ? 4 : 2;     // odd tail stage: only the first sub-block is valid
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j >= nj) break;
+            const uint64_t adv = (uint64_t)((j * 16 * 2) >> 4);
+            if (!p.fast) {
+              umma_ts_f16(acc, a_lo + j * 8, b_hi + adv, idesc, (kin > 0 || j > 0) ? 1u : 0u);      // small terms first
+              umma_ts_f16(acc, a_hi + j * 8, b_lo + adv, idesc, 1u);
+              umma_ts_f16(acc, a_hi + j * 8, b_hi + adv, idesc, 1u);
+            } else {
+              umma_ts_f16(acc, a_hi + j * 8, b_hi + adv, idesc, (kin > 0 || j > 0) ? 1u : 0u);
+            }
+          }
+        } else if (TS) {
+          const uint32_t a_hi = tmem_base + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64), a_lo = a_hi + 32;
 #pragma unroll
           for (int j = 0; j < TBK / 8; ++j) {
             const uint64_t adv = (uint64_t)((j * 8 * 4) >> 4);    // 32 bytes per K chunk of 8 tf32 in smem; 8 columns in TMEM
@@ -268,7 +346,51 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp < 2 + NUM_SPLIT_WARPS) {
     // =========================================================================== split warps
-    if (TS) {
+    if (H16) {
+      // thread = one tile row: per stage two sub-blocks of 32 raw floats -> x' = x * 2^ea, hi = fp16(x'), lo = fp16(x' - hi),
+      // packed two per 32-bit TMEM column (even k in the low half)
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const uint32_t rbase = (uint32_t)row * 128u;
+      const uint32_t rx = (uint32_t)(row & 7);
+      const float asc = exp2i(h16_a_exp(p));
+      int gkb = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc_ = tile_coord(t);
+      for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
+        const int s = gkb % STAGES, it = gkb / STAGES;
+        mbar_wait(bar_full_raw(s), it & 1);
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64);
+        const int nsub = (kb * BK + TBK < p.K) ? 2 : 1;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          if (sub >= nsub) break;
+          const uint32_t sa = base + s * STAGE_BYTES + OFF_A + sub * TILE_BYTES + rbase;
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t v[4];
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(sa + (((uint32_t)c ^ rx) << 4)));
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const float x0 = __uint_as_float(v[2 * e2]) * asc, x1 = __uint_as_float(v[2 * e2 + 1]) * asc;
+              const __half2 h = __floats2half2_rn(x0, x1);          // .x (low half) = even k
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+              hi[c * 2 + e2] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[c * 2 + e2] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+          }
+          tmem_st16(ta + sub * 16, hi);
+          tmem_st16(ta + 32 + sub * 16, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full_split(s));
+      }
+      }
+    } else if (TS) {
       // thread = one tile row: read its 128 raw bytes (8 swizzled 16-byte chunks), store hi / lo into TMEM lane `row`
       const int q = warp & 3;                    // TMEM lane quadrant (warps 2..5 -> 2,3,0,1)
       const int row = q * 32 + lane;
@@ -293,7 +415,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             lo[c * 4 + e] = rn_tf32(__float_as_uint(__uint_as_float(v[e]) - __uint_as_float(h)));
           }
         }
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<TS>::A_COL0 + s * 64);
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64);
         tmem_st32(ta, hi);
         tmem_st32(ta + 32, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -341,6 +463,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int r = q * 32 + lane;                   // tile row owned by this thread
     const int et = hf * 128 + q * 32 + lane;       // 0..255: threads 0..127 stage the tile's bias vector
     constexpr int HN = TBN / 2;                    // 64 columns per thread
+    // MODE_H16: the accumulator holds 2^(ea + eb) times the product -> exact power-of-two rescale folded into alpha
+    const float alpha = H16 ? p.alpha * exp2i(-h16_a_exp(p)) * exp2i(-p.b_exp) : p.alpha;
+    float omax = 0.f;                              // max |C| stored by this thread (p.c_amax)
     int gchunk0 = 0, tile_it = 0;
 #pragma unroll 1
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
@@ -395,7 +520,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < HN; ++j) {
           const int n = n0 + hf * HN + j;
-          if (n < tc_.nend) p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = p.alpha * acc[j] + sb[hf * HN + j];   // lanes = pixels: coalesced
+          if (n < tc_.nend) p.C[(bimg * p.N + n) * p.rows_per_img + rimg] = alpha * acc[j] + sb[hf * HN + j];   // lanes = pixels: coalesced
         }
       }
     } else if (p.Ct_hi && n0 >= p.t_col0) {
@@ -405,7 +530,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int j = 0; j < HN; ++j) {
           const int n = n0 + hf * HN + j;
           if (n < tc_.nend) {
-            const float o = p.alpha * acc[j] + sb[hf * HN + j];
+            const float o = alpha * acc[j] + sb[hf * HN + j];
             const float hi = __uint_as_float(rn_tf32(__float_as_uint(o)));
             const long long at = (long long)(n - p.t_col0) * p.ldt + m;
             p.Ct_hi[at] = hi;
@@ -446,10 +571,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < HN; j += 4) {
           const float4 bv = *reinterpret_cast<const float4*>(sb + hf * HN + j);
-          acc[j + 0] = p.alpha * acc[j + 0] + bv.x;
-          acc[j + 1] = p.alpha * acc[j + 1] + bv.y;
-          acc[j + 2] = p.alpha * acc[j + 2] + bv.z;
-          acc[j + 3] = p.alpha * acc[j + 3] + bv.w;
+          acc[j + 0] = alpha * acc[j + 0] + bv.x;
+          acc[j + 1] = alpha * acc[j + 1] + bv.y;
+          acc[j + 2] = alpha * acc[j + 2] + bv.z;
+          acc[j + 3] = alpha * acc[j + 3] + bv.w;
         }
         if (p.rowvec) {
           const float* rv = p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec + n0 + hf * HN;
@@ -506,12 +631,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 o[i] = hi;
               }
               *reinterpret_cast<float4*>(dst + (long long)mi * dld + n) = o[i];
+              omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o[i].x), fabsf(o[i].y)), fmaxf(fabsf(o[i].z), fabsf(o[i].w))));
             }
           }
         }
       }
     }
     }   // tile loop
+    if (p.c_amax && p.splits == 1) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
+      if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(p.c_amax), __float_as_uint(omax));     // non-negative floats order like their bit patterns
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -523,8 +654,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // C = alpha * sum_s ws[s] (+bias) (+row vector) (+residual): fixed summation order, so split-K stays deterministic
-__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, TcParams p) {
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, TcParams p, int h16) {
   const long long total4 = (long long)p.M * p.N / 4;
+  const float alpha = h16 ? p.alpha * exp2i(-h16_a_exp(p)) * exp2i(-p.b_exp) : p.alpha;
+  float omax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 4;
     const long long m = e / p.N;
@@ -534,7 +667,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, T
       const float4 b = *reinterpret_cast<const float4*>(ws + (long long)s * p.M * p.N + e);
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
-    a.x *= p.alpha; a.y *= p.alpha; a.z *= p.alpha; a.w *= p.alpha;
+    a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
     if (p.bias) { const float4 t = *reinterpret_cast<const float4*>(p.bias + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
     if (p.rowvec) { const float4 t = *reinterpret_cast<const float4*>(p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
     if (p.residual) { const float4 t = *reinterpret_cast<const float4*>(p.residual + m * p.ldr + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
@@ -548,6 +681,12 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, T
       a = hi;
     }
     *reinterpret_cast<float4*>(p.C + m * p.ldc + n) = a;
+    omax = fmaxf(omax, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+  }
+  if (p.c_amax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(p.c_amax), __float_as_uint(omax));
   }
 }
 
@@ -561,12 +700,16 @@ __global__ void split_planes_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
-void ensure_attr() {
-  static bool attr_set = false;
-  if (!attr_set) {
+// cudaFuncSetAttribute is per DEVICE: remember which devices of this process have it (engines on several devices share the library)
+void ensure_attr(int device) {
+  static bool attr_set[64] = {};
+  static std::mutex mtx;
+  std::lock_guard<std::mutex> lock(mtx);
+  const int d = device & 63;
+  if (!attr_set[d]) {
     CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
     CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
-    attr_set = true;
+    attr_set[d] = true;
   }
 }
 
@@ -594,7 +737,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
   const int ldS = Nk;
   float* S = (float*)e.arena.alloc((size_t)B * heads * Nq * ldS * sizeof(float));
   if (e.dry()) return true;
-  ensure_attr();
+  ensure_attr(e.device);
   TcParams p;
   // ---- S = scale * Q K^T
   {
@@ -731,11 +874,10 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   int best_w = TBN, best_s = 1;
   {
     static const bool fixed_w = getenv("CDX_TC_FIXED_W") != nullptr;      // tuning aid: always 128-wide tiles
-    static std::unordered_map<uint64_t, int> plan_cache;
+    static std::map<std::array<int64_t, 5>, int> plan_cache;      // exact key (no hashing of packed fields: nothing can collide)
     static std::mutex plan_mutex;                                          // engines on different devices may plan concurrently
     std::lock_guard<std::mutex> plan_lock(plan_mutex);
-    const uint64_t key = ((uint64_t)p.tiles_m << 40) ^ ((uint64_t)a.N << 20) ^ ((uint64_t)num_kb << 2) ^ ((a.geglu || a.Ct_hi) ? 1u : 0u) ^
-                         (a.out_nchw ? 2u : 0u) ^ ((uint64_t)e.num_sms << 56);
+    const std::array<int64_t, 5> key = {p.tiles_m, a.N, num_kb, ((a.geglu || a.Ct_hi) ? 1 : 0) | (a.out_nchw ? 2 : 0), e.num_sms};
     auto it = plan_cache.find(key);
     if (it != plan_cache.end()) {
       best_w = it->second >> 8;
@@ -794,7 +936,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
     mB = &get_map(ts ? a.Bw_hi : a.Bw, 2, d, st, bx);
     mBlo = ts ? &get_map(a.Bw_lo, 2, d, st, bx) : mB;
   }
-  ensure_attr();
+  ensure_attr(e.device);
   ProfScope ps(e, s, a.mode == 1 ? PROF_CONV_TC : PROF_DENSE_TC, 2.0 * a.M * a.N * a.K,
                4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
   ps.note("M%d N%d K%d w%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, p.tn_w, tiles, p.splits, ts ? "TS" : "SS", a.Cout_lo ? " planes" : "", a.geglu ? " geglu" : "",

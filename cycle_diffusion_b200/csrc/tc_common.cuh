@@ -84,6 +84,15 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] . B[smem], fp16 operands (A: two fp16 per 32-bit TMEM column, K = 16 per instruction), fp32 accumulate
+__device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -107,6 +116,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
       "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
       "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 
@@ -147,13 +165,14 @@ struct MapKey {
   uint64_t dims[4], strides[3];
   uint32_t box[4], es[4];
   int rank;
+  int esize;
   bool operator<(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
 };
 
-// fp32, 128B swizzle, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
+// fp32 (esize 4) or fp16 (esize 2), 128B swizzle, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
 // `estr` (optional): element traversal strides; with stride s along a dim, box[i] = n*s loads n elements.
 inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
-                                  const uint32_t* estr = nullptr) {
+                                  const uint32_t* estr = nullptr, int esize = 4) {
   // node-based map: returned references stay valid; on overflow the live generation is parked in `old` (and the generation
   // before it dropped), so a reference handed out earlier in the same call can never dangle
   static std::map<MapKey, CUtensorMap> cache, old;
@@ -163,6 +182,7 @@ inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dim
   memset(&k, 0, sizeof(k));
   k.ptr = ptr;
   k.rank = rank;
+  k.esize = esize;
   for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.es[i] = estr ? estr[i] : 1; }
   for (int i = 0; i < rank - 1; ++i) k.strides[i] = strides[i];
   auto it = cache.find(k);
@@ -179,7 +199,7 @@ inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dim
   for (int i = 0; i < rank - 1; ++i) gs[i] = strides[i];
   EncodeTiledFn enc = get_encode();
   if (!enc) throw Error(CDX_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(&m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char b[256];

@@ -4,9 +4,9 @@ The key names are the reference checkpoint's own:
   * SD / LDM U-Net      ``model.diffusion_model.*``   built by UNetModel.__init__, ref ldm/modules/diffusionmodules/openaimodel.py:506-686
   * KL-f8 VAE           ``first_stage_model.*``       ref ldm/modules/diffusionmodules/model.py:368-533, ldm/models/autoencoder.py:302-303
   * i-DDPM U-Net        bare keys                     ref model/lib/ddpm_ddim/models/improved_ddpm/unet.py:476-626
-The C++ graph executors (csrc/nets.cpp) enumerate the same names through ``cdx_net_param_*``;
-``tests/test_specs.py`` cross-checks the two lists, and ``tests/golden/make_golden.py`` checks them
-against the reference modules with ``load_state_dict(strict=True)``.
+The C++ graph executors (csrc/nets.cu) enumerate the same names through ``cdx_net_param_*``;
+``tests/test_cabi.py`` cross-checks the two lists on the CPU (inventory-only nets need no GPU), and
+``tests/golden/make_golden.py`` checks them against the reference modules with ``load_state_dict(strict=True)``.
 
 There are no checkpoints in this environment, so benchmarks and tests use ``synth_state_dict``:
 fan-in-scaled uniform weights for *every* tensor, including the ones the reference zero-initialises

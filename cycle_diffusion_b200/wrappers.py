@@ -9,8 +9,10 @@ Mirrors (same constructor kwargs, method names, argument meaning, return layouts
 Differences that are deliberate and documented in INTEGRATION.md:
   * weights come from a reference-format ``state_dict`` / checkpoint path given by keyword (or ``'synthetic'``);
     the packed blob can be shared between wrappers and broadcast across ranks;
-  * the text encoder is an injected callable ``cond_stage(list[str]) -> [B,77,D]`` (CLIP / BERT text towers are
-    out of scope for this engine, SURVEY.md 8f-1); a deterministic stand-in is provided for tests and benchmarks;
+  * the text encoder is ``cond_stage(list[str]) -> [B,77,D]``: either an injected callable or the in-engine towers
+    (``ClipTextCondStage`` / ``BertTextCondStage``), which are built automatically from the checkpoint's
+    ``cond_stage_model.*`` keys when a host ``tokenizer`` is given.  The deterministic ``SyntheticTextEncoder`` stand-in is
+    used ONLY together with ``state_dict='synthetic'``; a real checkpoint without a conditioning model raises;
   * random draws are taken from the torch CPU generator in the reference's order and uploaded, so a run is
     reproducible against the reference CPU path under the same ``torch.manual_seed``;
   * Directional-CLIP ranking of the ensemble is an injected callable; with a single ensemble
@@ -122,11 +124,18 @@ class _StochasticTextWrapperBase(torch.nn.Module):
     CONTEXT_DIM = 768
     SAMPLE_POSTERIOR = True
     CKPT_DIR = 'ckpts/stable_diffusion'
+    COND_PREFIX = 'cond_stage_model.transformer.'     # FrozenCLIPEmbedder.transformer (encoders/modules.py:140-146)
+    COND_CLASS = ClipTextCondStage
+
+    @classmethod
+    def default_checkpoint(cls, source_model_type):
+        """SDW:21-23: ``ckpts/stable_diffusion/<source_model_type>``."""
+        return os.path.join(cls.CKPT_DIR, str(source_model_type))
 
     def __init__(self, source_model_type, custom_steps, eta, white_box_steps, skip_steps,
                  encoder_unconditional_guidance_scales=None, decoder_unconditional_guidance_scales=None, n_trials=None, *,
                  engine=None, device=0, state_dict=None, cond_stage=None, ranker=None, unet_config=None, vae_config=None,
-                 latent_size=None, resolution=None, generator=None, seed=1234):
+                 latent_size=None, resolution=None, generator=None, seed=1234, tokenizer=None):
         super().__init__()
         self.encoder_unconditional_guidance_scales = encoder_unconditional_guidance_scales
         self.decoder_unconditional_guidance_scales = decoder_unconditional_guidance_scales
@@ -143,15 +152,29 @@ class _StochasticTextWrapperBase(torch.nn.Module):
             ucfg = unet_config or specs.sd_unet_config(self.CONTEXT_DIM)
             vcfg = vae_config or specs.kl_f8_config()
             unet, vae = UNet(self.engine, ucfg, 'openai'), VAE(self.engine, vcfg)
-            ckpt = os.path.join(self.CKPT_DIR, str(source_model_type))
+            ckpt = self.default_checkpoint(source_model_type)
+            cond = cond_stage
             if state_dict == 'synthetic':
                 unet.load_state_dict(specs.synth_state_dict(specs.openai_unet_params(ucfg), seed))
                 vae.load_state_dict(specs.synth_state_dict(specs.kl_vae_params(vcfg), seed + 1))
+                if cond is None:
+                    cond = SyntheticTextEncoder(ucfg['context_dim'])        # random-init weights: random (but reproducible) conditioning
             else:
                 sd = _load_sd(state_dict, ckpt, None, seed)
                 unet.load_state_dict(sd, prefix='model.diffusion_model.', strict=False)
                 vae.load_state_dict(sd, prefix='first_stage_model.', strict=False)
-            cond = cond_stage or SyntheticTextEncoder(ucfg['context_dim'])
+                if cond is None:
+                    # the reference builds the conditioning model from the same checkpoint (txt2img.py:27-45); do the same, and never
+                    # fall back silently to noise tokens when real weights were loaded
+                    has_tower = any(k.startswith(self.COND_PREFIX) for k in sd)
+                    if tokenizer is not None and has_tower:
+                        cond = self.COND_CLASS(self.engine, sd, tokenizer, prefix=self.COND_PREFIX)
+                    else:
+                        raise ValueError(
+                            f'{type(self).__name__}: a checkpoint was loaded but no conditioning model is available '
+                            f'({"no " + self.COND_PREFIX + "* keys in the checkpoint" if not has_tower else "no tokenizer= given"}). '
+                            'Pass cond_stage=<callable list[str] -> [B,77,D]> or tokenizer=<callable list[str] -> ids [B,L]> '
+                            '(the in-engine text tower is then built from the checkpoint).')
             self.generator = _LatentGenerator(self.engine, unet, vae, cond, ucfg['in_channels'], latent_size or self.LATENT, 0.18215,
                                               self.SAMPLE_POSTERIOR)
         self._dummy = torch.nn.Parameter(torch.zeros(1, device=self.engine.device), requires_grad=False)
@@ -246,7 +269,14 @@ class LatentDiffStochasticTextWrapper(_StochasticTextWrapperBase):
     LATENT = 32
     CONTEXT_DIM = 1280
     SAMPLE_POSTERIOR = False
-    CKPT_DIR = 'ckpts/text2img-large'
+    CKPT_DIR = 'ckpts/ldm_models'
+    COND_PREFIX = 'cond_stage_model.'                 # BERTEmbedder (encoders/modules.py:79-98)
+    COND_CLASS = BertTextCondStage
+
+    @classmethod
+    def default_checkpoint(cls, source_model_type):
+        """LDW:21-23: ``ckpts/ldm_models/<source_model_type>/model.ckpt``."""
+        return os.path.join(cls.CKPT_DIR, str(source_model_type), 'model.ckpt')
 
 
 class DDPMDDIMWrapper(torch.nn.Module):

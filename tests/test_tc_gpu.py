@@ -134,6 +134,27 @@ def test_attention_tc(B, N, heads, d, mode):
     assert err < 2e-5
 
 
+def test_attention_tc_vae_shape():
+    """The KL-f8 mid-block attention at 512x512 (AEM:178-202): one head, d = 512, 4096 tokens.  It is outside the fused kernel's
+    head dims, so it must take the unfused tcgen05 route (two batched contractions around the row softmax), not the FFMA tiles."""
+    from cycle_diffusion_b200.engine import Engine
+    e = Engine(0)
+    e.set_mma_mode(1)
+    B, N, heads, d = 1, 4096, 1, 512
+    g = torch.Generator().manual_seed(512)
+    q, k, v = (torch.randn(B, N, d, generator=g) for _ in range(3))
+    scale = d ** -0.5
+    ref = torch.einsum('bij,bjd->bid', (torch.einsum('bid,bjd->bij', q, k) * scale).softmax(-1), v)
+    e.profile(True)
+    y = e.op_attention(q.cuda(), k.cuda(), v.cuda(), heads, scale).cpu()
+    fam = e.profile_read()
+    e.profile(False)
+    err = float((y - ref).abs().max())
+    print(f'attention d=512 N=4096: max abs err {err:.2e}  families {sorted(fam)}')
+    assert 'batched_tc' in fam and 'batched_ffma' not in fam, sorted(fam)
+    assert err < 2e-5
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('B,N,Nk,heads,d', [(2, 256, 77, 2, 40), (1, 128, 77, 2, 80), (2, 128, 130, 1, 64), (3, 128, 64, 2, 32), (2, 256, 5, 1, 16)])
 def test_cross_attention_flash(B, N, Nk, heads, d):
