@@ -84,50 +84,131 @@ void copy_dd(Engine& e, const float* src, float* dst, size_t n, cudaStream_t s) 
   CDX_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
 }
 
-// One guided eps-prediction: fills e_c / e_uc pointers (e_uc = nullptr when no CFG batch ran).  ddim.py:550-559
-struct Guided {
-  Net& unet;
-  Engine& e;
-  int B, C, h, w, L;
-  float scale;
-  const float* c;
-  const float* uc;
-  float* x_in = nullptr;     // [2B, C,h,w]
-  float* ctx_in = nullptr;   // [2B, L, D]
-  float* eout = nullptr;     // [2B, C,h,w]
-  bool cfg;
-  Guided(Net& u, int B_, int C_, int h_, int w_, int L_, float scale_, const float* c_, const float* uc_, cudaStream_t s)
-      : unet(u), e(*u.eng), B(B_), C(C_), h(h_), w(w_), L(L_), scale(scale_), c(c_), uc(uc_) {
-    cfg = (uc != nullptr) && scale != 1.0f && scale != 0.0f;
-    unet.ctxkv.valid = false;                  // the conditioning is fixed for this loop: its K / V are computed by the first step only
-    const size_t n = (size_t)B * C * h * w;
-    const int D = unet.ucfg.context_dim;
-    eout = (float*)e.arena.alloc((cfg ? 2 : 1) * n * sizeof(float));
-    if (cfg) {
-      x_in = (float*)e.arena.alloc(2 * n * sizeof(float));
-      ctx_in = (float*)e.arena.alloc((size_t)2 * B * L * D * sizeof(float));
-      copy_dd(e, uc, ctx_in, (size_t)B * L * D, s);                          // cat([uc, c]): uncond first
-      copy_dd(e, c, ctx_in + (size_t)B * L * D, (size_t)B * L * D, s);
-    }
-  }
-  ~Guided() { unet.ctxkv.valid = false; }
-  // t_dev2: device vector holding the timestep 2B times
-  void run(const float* x, const float* t_dev2, const float** e_c, const float** e_uc, cudaStream_t s) {
-    const size_t n = (size_t)B * C * h * w;
-    if (cfg) {
-      copy_dd(e, x, x_in, n, s);
-      copy_dd(e, x, x_in + n, n, s);
-      unet_forward(unet, x_in, t_dev2, ctx_in, L, eout, 2 * B, h, w, s, true);
-      *e_uc = eout;
-      *e_c = eout + n;
-    } else {
-      const float* cond = (uc != nullptr && scale == 0.0f) ? uc : c;
-      unet_forward(unet, x, t_dev2, cond, L, eout, B, h, w, s, true);
-      *e_c = eout;
-      *e_uc = nullptr;
-    }
-  }
+// test hooks: build the fp16-split planes of an ad-hoc weight matrix on the fly (networks do this once at finalize)
+void hook_h16_planes(Engine& e, const float* w, size_t n, GemmArgs& g, cudaStream_t s) {
+  if (e.tc_kind < 1 || (n & 7)) return;
+  void* hi = e.arena.alloc(n * 2);
+  void* lo = e.arena.alloc(n * 2);
+  if (e.dry()) { g.Bw_h_hi = hi; g.Bw_h_lo = lo; return; }
+  float* slot = e.amax_slot();
+  amax_rows(e, w, 1, (int)n, (long long)n, slot, s);
+  float wmax = 0.f;
+  CDX_CUDA(cudaMemcpyAsync(&wmax, slot, sizeof(float), cudaMemcpyDeviceToHost, s));
+  CDX_CUDA(cudaStreamSynchronize(s));
+  g.b_exp = h16_exp_host(wmax);
+  split_planes_h16(e, w, hi, lo, n, g.b_exp, s);
+  g.Bw_h_hi = hi; g.Bw_h_lo = lo;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The latent sampling loops (DDIMSampler._ddpm_ddim_encoding ddim.py:450-501, ddim_sampling_with_eps ddim.py:395-448) as ONE
+// driver with three modes: DPM-Encoder only, decode only, or both chains in lock-step (the source chain under the source
+// condition and the target chain under the target condition share one U-Net call per step; the noise recovered at step i is
+// consumed by the target chain in registers, so no z buffer is needed -- the Diffusers CycleDiffusionPipeline loop shape).
+// Per step: one U-Net call on the batch [src segments | tgt segments] (a chain contributes [uncond, cond] when it runs with
+// classifier-free guidance, ddim.py:550-559, else one segment) and ONE fused elementwise launch (latent_step).
+// ---------------------------------------------------------------------------------------------------------------------
+enum { LOOP_ENC = 1, LOOP_DEC = 2, LOOP_LOCK = 3 };
+struct LatentLoopArgs {
+  int mode = 0;
+  const float* x0 = nullptr;                       // ENC / LOCK
+  const float* c_src = nullptr; const float* c_tgt = nullptr; const float* uc = nullptr; int L = 0;
+  float s_scale = 1.f, t_scale = 1.f;
+  const cdx_ddim_coef* coef = nullptr; const float* t_host = nullptr; int n_steps = 0;
+  int n_rec = 0; const float* noise = nullptr; float sa = 0.f, s1 = 0.f;      // ENC / LOCK: noise [n_rec+1, B, chw]
+  float* z_out = nullptr;                           // ENC: [B, n_rec+1, chw]; LOCK: optional
+  const float* z_in = nullptr; int n_eps = 0; const float* extra = nullptr;   // DEC
+  float* x_out = nullptr;                           // DEC / LOCK
+  int B = 0, C = 0, h = 0, w = 0;
 };
+
+void run_latent_loop(Net& unet, const LatentLoopArgs& a, cudaStream_t s) {
+  Engine& e = *unet.eng;
+  const int B = a.B, chw = a.C * a.h * a.w;
+  const size_t n = (size_t)B * chw;
+  const bool enc = a.mode & LOOP_ENC, dec = a.mode & LOOP_DEC;
+  const bool cfg_s = enc && a.uc && a.s_scale != 1.0f && a.s_scale != 0.0f;
+  const bool cfg_t = dec && a.uc && a.t_scale != 1.0f && a.t_scale != 0.0f;
+  const int nseg_src = enc ? (cfg_s ? 2 : 1) : 0, nseg_tgt = dec ? (cfg_t ? 2 : 1) : 0, nseg = nseg_src + nseg_tgt;
+  const int nb = nseg * B;
+  const int D = unet.ucfg.context_dim;
+  const size_t ctx_n = (size_t)B * a.L * D;
+  Scope sc(e.arena);
+  unet.ctxkv.valid = false;                    // the conditioning is fixed for this loop: its K / V are computed by the first step only
+  struct Invalidate { Net& u; ~Invalidate() { u.ctxkv.valid = false; } } inval{unet};
+  float* xin = (float*)e.arena.alloc((size_t)nseg * n * sizeof(float));
+  float* eout = (float*)e.arena.alloc((size_t)nseg * n * sizeof(float));
+  float* ctx_in = (float*)e.arena.alloc((size_t)nseg * ctx_n * sizeof(float));
+  float* xb[3] = {nullptr, nullptr, nullptr};
+  float* yb[2] = {nullptr, nullptr};
+  if (enc) for (int k = 0; k < 3; ++k) xb[k] = (float*)e.arena.alloc(n * sizeof(float));
+  if (dec) for (int k = 0; k < 2; ++k) yb[k] = (float*)e.arena.alloc(n * sizeof(float));
+  const int loop_steps = enc && !dec ? a.n_rec : a.n_steps;
+  float* tdev = (float*)e.arena.alloc((size_t)std::max(loop_steps, 1) * nb * sizeof(float));
+  upload_timesteps(e, a.t_host, loop_steps, nb, tdev, s);
+  {   // cat([uc, c]) per chain: uncond first (ddim.py:555-557)
+    int sg = 0;
+    if (enc) {
+      if (cfg_s) copy_dd(e, a.uc, ctx_in + (size_t)(sg++) * ctx_n, ctx_n, s);
+      copy_dd(e, (a.uc && a.s_scale == 0.0f) ? a.uc : a.c_src, ctx_in + (size_t)(sg++) * ctx_n, ctx_n, s);
+    }
+    if (dec) {
+      if (cfg_t) copy_dd(e, a.uc, ctx_in + (size_t)(sg++) * ctx_n, ctx_n, s);
+      copy_dd(e, (a.uc && a.t_scale == 0.0f) ? a.uc : a.c_tgt, ctx_in + (size_t)(sg++) * ctx_n, ctx_n, s);
+    }
+  }
+  const float* es_uc = cfg_s ? eout : nullptr;
+  const float* es_c = eout + (cfg_s ? n : 0);
+  const float* et_uc = cfg_t ? eout + (size_t)nseg_src * n : nullptr;
+  const float* et_c = eout + (size_t)nseg_src * n + (cfg_t ? n : 0);
+  auto next_kind = [&](int i_next) {             // how x_{t-1} of iteration i_next is obtained (0: that iteration does not exist)
+    if (i_next >= a.n_rec) return 0;
+    return (a.n_steps - 1 - i_next) == 0 ? 2 : 1;                               // ddim.py:583-584
+  };
+  if (enc) {
+    LatentInit in;
+    in.n = n; in.chw = chw;
+    in.x0 = a.x0; in.noise0 = a.noise; in.sa = a.sa; in.s1 = a.s1;
+    in.z_out = a.z_out; in.z_stride = (long long)(a.n_rec + 1) * chw;
+    in.xt = xb[0]; in.yt = dec ? yb[0] : nullptr;
+    in.next = next_kind(0);
+    if (in.next) { in.noise_next = a.noise + n; in.cnext = a.coef[0]; }
+    in.xn = xb[1];
+    in.xin = xin; in.nseg_src = nseg_src; in.nseg_tgt = nseg_tgt;
+    latent_init(e, in, s);
+  } else {
+    gather_slot(e, a.z_in, yb[0], B, chw, a.n_eps + 1, 0, s);                   // x_T = eps_list[:, 0], SDW:153
+    for (int sg = 0; sg < nseg_tgt; ++sg) copy_dd(e, yb[0], xin + (size_t)sg * n, n, s);
+  }
+  const int iters = e.dry() ? std::min(loop_steps, 1) : loop_steps;
+  for (int i = 0; i < iters; ++i) {
+    unet_forward(unet, xin, tdev + (size_t)i * nb, ctx_in, a.L, eout, nb, a.h, a.w, s, true);
+    LatentStep st;
+    st.n = n; st.chw = chw;
+    if (enc) {
+      st.enc = 1;
+      st.x0 = a.x0; st.xt = xb[0]; st.xn = xb[1];
+      st.es_c = es_c; st.es_uc = es_uc; st.s_scale = a.s_scale; st.cs = a.coef[i];
+      if (a.z_out) { st.z_out = a.z_out + (size_t)(1 + i) * chw; st.z_stride = (long long)(a.n_rec + 1) * chw; }
+      st.next = next_kind(i + 1);
+      if (st.next) { st.noise_next = a.noise + (size_t)(2 + i) * n; st.cnext = a.coef[i + 1]; }
+      st.xn2 = xb[2];
+    }
+    if (dec) {
+      st.dec = 1;
+      st.yt = yb[0]; st.et_c = et_c; st.et_uc = et_uc; st.t_scale = a.t_scale; st.ct = a.coef[i];
+      if (!enc) {
+        if (i < a.n_eps) { st.eps_in = a.z_in + (size_t)(1 + i) * chw; st.eps_stride = (long long)(a.n_eps + 1) * chw; }
+        else { st.eps_in = a.extra + (size_t)(i - a.n_eps) * n; st.eps_stride = chw; }
+      }
+      st.y_out = (i == loop_steps - 1) ? a.x_out : yb[1];
+    }
+    st.xin = xin; st.nseg_src = nseg_src; st.nseg_tgt = nseg_tgt;
+    latent_step(e, st, s);
+    if (enc) { float* t0 = xb[0]; xb[0] = xb[1]; xb[1] = xb[2]; xb[2] = t0; }
+    if (dec) std::swap(yb[0], yb[1]);
+  }
+}
 
 }  // namespace
 }  // namespace cdx
@@ -164,15 +245,17 @@ void cdx_engine_destroy(cdx_engine* e) {
   cudaDeviceSynchronize();
   e->e.arena.destroy();
   if (e->e.done_ev) cudaEventDestroy(e->e.done_ev);
+  if (e->e.amax_pool) cudaFree(e->e.amax_pool);
   delete e;
 }
 size_t cdx_engine_workspace_bytes(const cdx_engine* e) { return e ? e->e.arena.cap : 0; }
 uint64_t cdx_engine_launch_count(const cdx_engine* e) { return e ? e->e.launches : 0; }
 int cdx_engine_set_mma_mode(cdx_engine* e, int mode) {
   return guard([&] {
-    CDX_CHECK(e != nullptr && (mode == 0 || mode == 1 || mode == 2), "set_mma_mode: bad arguments");
+    CDX_CHECK(e != nullptr && mode >= 0 && mode <= 5, "set_mma_mode: bad arguments");
     e->e.mma_mode = mode == 0 ? 0 : 1;       // 2 = tcgen05 contractions but unfused attention (A/B comparisons)
-    e->e.flash_attn = mode == 1;
+    e->e.flash_attn = mode != 2 && mode != 0;
+    e->e.tc_kind = mode == 3 ? 0 : mode == 4 ? 2 : 1;    // 3 = 3xTF32 contractions, 4 = single-term fp16 (fast path), else fp16 split
   });
 }
 
@@ -365,34 +448,12 @@ int cdx_latent_encode(cdx_net* un, const float* x0, const float* c, const float*
     CDX_CHECK(un && un->owner && x0 && c && coef && t_host && noise && z_out, "latent_encode: null argument");
     CDX_CHECK(n_steps >= 1 && n_rec >= 0 && n_rec <= n_steps, "latent_encode: n_steps=%d n_rec=%d", n_steps, n_rec);
     for (int i = 0; i < n_rec; ++i) CDX_CHECK(coef[i].sigma > 0.f, "latent_encode: eta must be > 0 (sigma[%d] == 0), ddim.py:268", i);
-    Engine& e = un->owner->e;
-    Net& unet = *un->n;
-    cudaStream_t s = S(stream);
-    const int chw = C * h * w;
-    const size_t n = (size_t)B * chw;
-    with_arena(e, s, [&] {
-      Scope sc(e.arena);
-      float* xt = (float*)e.arena.alloc(n * sizeof(float));
-      float* xn = (float*)e.arena.alloc(n * sizeof(float));
-      float* eps = (float*)e.arena.alloc(n * sizeof(float));
-      float* tdev = (float*)e.arena.alloc((size_t)n_steps * 2 * B * sizeof(float));
-      upload_timesteps(e, t_host, n_steps, 2 * B, tdev, s);
-      Guided g(unet, B, C, h, w, L, scale, c, uc, s);
-      q_sample(e, x0, noise, sqrt_a_T, sqrt_1ma_T, xt, n, s);                         // ddim.py:477-479
-      scatter_slot(e, xt, z_out, B, chw, n_rec + 1, 0, s);
-      const int iters = e.dry() ? std::min(n_rec, 1) : n_rec;
-      for (int i = 0; i < iters; ++i) {
-        const int index = n_steps - 1 - i;
-        const float* xt_next = xn;
-        if (index == 0) xt_next = x0;                                                 // ddim.py:583-584
-        else ddim_posterior_sample(e, x0, xt, noise + (size_t)(1 + i) * n, coef[i], xn, n, s);
-        const float *e_c, *e_uc;
-        g.run(xt, tdev + (size_t)i * 2 * B, &e_c, &e_uc, s);
-        ddim_compute_eps(e, xt, xt_next, e_c, e_uc, scale, coef[i], eps, n, s);
-        scatter_slot(e, eps, z_out, B, chw, n_rec + 1, 1 + i, s);
-        if (index != 0) std::swap(xt, xn);
-      }
-    });
+    LatentLoopArgs a;
+    a.mode = LOOP_ENC;
+    a.x0 = x0; a.c_src = c; a.uc = uc; a.L = L; a.s_scale = scale;
+    a.coef = coef; a.t_host = t_host; a.n_steps = n_steps; a.n_rec = n_rec; a.noise = noise; a.sa = sqrt_a_T; a.s1 = sqrt_1ma_T;
+    a.z_out = z_out; a.B = B; a.C = C; a.h = h; a.w = w;
+    with_arena(un->owner->e, S(stream), [&] { run_latent_loop(*un->n, a, S(stream)); });
   });
 }
 
@@ -402,32 +463,29 @@ int cdx_latent_decode(cdx_net* un, const float* z, int n_eps, const float* c, co
     CDX_CHECK(un && un->owner && z && c && coef && t_host && x_out, "latent_decode: null argument");
     CDX_CHECK(n_steps >= 1 && n_eps >= 0, "latent_decode: n_steps=%d n_eps=%d", n_steps, n_eps);
     CDX_CHECK(n_eps >= n_steps || extra_noise != nullptr, "latent_decode: %d steps but only %d recovered noises and no extra noise", n_steps, n_eps);
-    Engine& e = un->owner->e;
-    Net& unet = *un->n;
-    cudaStream_t s = S(stream);
-    const int chw = C * h * w;
-    const size_t n = (size_t)B * chw;
-    with_arena(e, s, [&] {
-      Scope sc(e.arena);
-      float* xa = (float*)e.arena.alloc(n * sizeof(float));
-      float* xb = (float*)e.arena.alloc(n * sizeof(float));
-      float* eps = (float*)e.arena.alloc(n * sizeof(float));
-      float* tdev = (float*)e.arena.alloc((size_t)n_steps * 2 * B * sizeof(float));
-      upload_timesteps(e, t_host, n_steps, 2 * B, tdev, s);
-      Guided g(unet, B, C, h, w, L, scale, c, uc, s);
-      gather_slot(e, z, xa, B, chw, n_eps + 1, 0, s);                                  // x_T = eps_list[:, 0], SDW:153
-      const int iters = e.dry() ? 1 : n_steps;
-      for (int i = 0; i < iters; ++i) {
-        const float *e_c, *e_uc;
-        g.run(xa, tdev + (size_t)i * 2 * B, &e_c, &e_uc, s);
-        const float* nz;
-        if (i < n_eps) { gather_slot(e, z, eps, B, chw, n_eps + 1, 1 + i, s); nz = eps; }
-        else nz = extra_noise + (size_t)(i - n_eps) * n;
-        float* dst = (i == n_steps - 1) ? x_out : xb;
-        ddim_step_with_eps(e, xa, e_c, e_uc, scale, nz, coef[i], dst, n, s);
-        std::swap(xa, xb);
-      }
-    });
+    LatentLoopArgs a;
+    a.mode = LOOP_DEC;
+    a.c_tgt = c; a.uc = uc; a.L = L; a.t_scale = scale;
+    a.coef = coef; a.t_host = t_host; a.n_steps = n_steps;
+    a.z_in = z; a.n_eps = n_eps; a.extra = extra_noise; a.x_out = x_out;
+    a.B = B; a.C = C; a.h = h; a.w = w;
+    with_arena(un->owner->e, S(stream), [&] { run_latent_loop(*un->n, a, S(stream)); });
+  });
+}
+
+int cdx_cycle_lockstep(cdx_net* un, const float* x0, const float* c_src, const float* c_tgt, const float* uc, int L, float src_scale,
+                       float tgt_scale, const cdx_ddim_coef* coef, const float* t_host, int n_steps, const float* noise, float sqrt_a_T,
+                       float sqrt_1ma_T, float* x_out, float* z_out, int B, int C, int h, int w, void* stream) {
+  return guard([&] {
+    CDX_CHECK(un && un->owner && x0 && c_src && c_tgt && coef && t_host && noise && x_out, "cycle_lockstep: null argument");
+    CDX_CHECK(n_steps >= 1, "cycle_lockstep: n_steps=%d", n_steps);
+    for (int i = 0; i < n_steps; ++i) CDX_CHECK(coef[i].sigma > 0.f, "cycle_lockstep: eta must be > 0 (sigma[%d] == 0), ddim.py:268", i);
+    LatentLoopArgs a;
+    a.mode = LOOP_LOCK;
+    a.x0 = x0; a.c_src = c_src; a.c_tgt = c_tgt; a.uc = uc; a.L = L; a.s_scale = src_scale; a.t_scale = tgt_scale;
+    a.coef = coef; a.t_host = t_host; a.n_steps = n_steps; a.n_rec = n_steps; a.noise = noise; a.sa = sqrt_a_T; a.s1 = sqrt_1ma_T;
+    a.z_out = z_out; a.x_out = x_out; a.B = B; a.C = C; a.h = h; a.w = w;
+    with_arena(un->owner->e, S(stream), [&] { run_latent_loop(*un->n, a, S(stream)); });
   });
 }
 
@@ -507,6 +565,7 @@ int cdx_op_conv3x3(cdx_engine* eh, const float* x, const float* w_oihw, const fl
     cudaStream_t s = S(stream);
     with_arena(e, s, [&] {
       Scope sc(e.arena);
+      e.pools_reset(s);
       float* wr = (float*)e.arena.alloc((size_t)Cout * Cin * 9 * sizeof(float));
       repack_conv3x3(e, w_oihw, wr, Cout, Cin, s);
       const int Hl = H * upsample, Wl = W * upsample;
@@ -525,6 +584,7 @@ int cdx_op_conv3x3(cdx_engine* eh, const float* x, const float* w_oihw, const fl
         float* lo = (float*)e.arena.alloc((size_t)Cout * Cin * 9 * sizeof(float));
         split_planes(e, wr, hi, lo, (size_t)Cout * Cin * 9, s);
         g.Bw_hi = hi; g.Bw_lo = lo;
+        hook_h16_planes(e, wr, (size_t)Cout * Cin * 9, g, s);
       }
       gemm(e, g, s);
     });
@@ -536,6 +596,7 @@ int cdx_op_linear(cdx_engine* eh, const float* x, const float* w, const float* b
     Engine& e = eh->e;
     with_arena(e, S(stream), [&] {
       Scope sc(e.arena);
+      e.pools_reset(S(stream));
       GemmArgs g;
       g.M = M; g.N = N; g.K = K;
       g.A = x; g.lda = K; g.C1 = K;
@@ -547,6 +608,7 @@ int cdx_op_linear(cdx_engine* eh, const float* x, const float* w, const float* b
         float* lo = (float*)e.arena.alloc((size_t)N * K * sizeof(float));
         split_planes(e, w, hi, lo, (size_t)N * K, S(stream));
         g.Bw_hi = hi; g.Bw_lo = lo;
+        hook_h16_planes(e, w, (size_t)N * K, g, S(stream));
       }
       gemm(e, g, S(stream));
     });
@@ -556,7 +618,7 @@ int cdx_op_groupnorm(cdx_engine* eh, const float* x, const float* gamma, const f
                      void* stream) {
   return guard([&] {
     CDX_CHECK(eh && x && gamma && beta && y, "op_groupnorm: null argument");
-    with_arena(eh->e, S(stream), [&] { groupnorm(eh->e, x, C, nullptr, 0, gamma, beta, eps, silu_ != 0, nullptr, nullptr, 0, y, B, HW, S(stream)); });
+    with_arena(eh->e, S(stream), [&] { eh->e.pools_reset(S(stream)); groupnorm(eh->e, x, C, nullptr, 0, gamma, beta, eps, silu_ != 0, nullptr, nullptr, 0, y, B, HW, S(stream)); });
   });
 }
 int cdx_op_layernorm(cdx_engine* eh, const float* x, const float* gamma, const float* beta, float* y, int M, int C, void* stream) {

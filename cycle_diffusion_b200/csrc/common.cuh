@@ -73,7 +73,18 @@ struct Engine {
   int device = 0;
   int num_sms = 148;
   bool flash_attn = true;        // fused tcgen05 attention kernel (kernels_attn.cu); false -> unfused QK^T / softmax / PV
-  int mma_mode = 1;              // 0 SIMT FFMA (exact fp32), 1 tcgen05 3xTF32 (default)
+  int mma_mode = 1;              // 0 SIMT FFMA (exact fp32), 1 tcgen05
+  int tc_kind = 1;               // tcgen05 product scheme: 0 3xTF32, 1 3x fp16-split at the kind::f16 rate (default), 2 1x fp16 (fast, not fp32-faithful)
+  // tracked |max| scalars of activation tensors (operand range of the fp16-split GEMMs): a pool of device floats, handed out
+  // per tensor by the graph executors and zeroed at the start of every network call
+  float* amax_pool = nullptr;
+  int amax_cap = 1 << 15, amax_used = 0, amax_high = 0;
+  float* amax_slot();
+  // per-(image, channel) fp64 statistics buffers of activation tensors (GroupNorm inputs), same life cycle as the amax slots
+  double* stat_pool = nullptr;
+  size_t stat_cap = (size_t)8 << 20, stat_used = 0, stat_high = 0;      // doubles (64 MB)
+  double* stat_alloc(size_t n);
+  void pools_reset(cudaStream_t s);   // start of a network call: zero what the previous call dirtied, rewind
   Arena arena;
   cudaStream_t last_stream = nullptr;   // stream of the previous arena-using call and the event recorded at its end
   cudaEvent_t done_ev = nullptr;
@@ -103,6 +114,8 @@ struct Scope {   // RAII arena scope
 struct Tensor {
   float* p = nullptr;
   int B = 0, H = 0, W = 0, C = 0;
+  float* amax = nullptr;      // device scalar >= max |element| (maintained by the producing kernel), or null when not tracked
+  double* stats = nullptr;    // per-(image, channel) fp64 {sum, sum of squares} accumulated by the producing kernel, or null
   size_t numel() const { return (size_t)B * H * W * C; }
   int rows() const { return B * H * W; }
 };
@@ -128,6 +141,12 @@ struct GemmArgs {
   int Hin = 0, Win = 0, Hout = 0, Wout = 0, stride = 1, pad = 1, up = 1;
   const float* Bw = nullptr; int ldb = 0; int b_kn = 0;   // weights [N][K] (b_kn=0) or [K][N] (b_kn=1)
   const float* Bw_hi = nullptr; const float* Bw_lo = nullptr;   // optional pre-split TF32 planes of Bw (same geometry)
+  // optional fp16-split planes of Bw, pre-scaled by 2^b_exp (same geometry, element index = float index), and the tracked max |A|
+  // scalars (device) of the A operand(s); c_amax: device scalar that receives max |C| (atomic max) for a consumer GEMM
+  const void* Bw_h_hi = nullptr; const void* Bw_h_lo = nullptr; int b_exp = 0;
+  const float* a_amax = nullptr; const float* a2_amax = nullptr;
+  float* c_amax = nullptr;
+  double* c_stats = nullptr;         // optional: += per-(image, channel) {sum, sum sq} of C (rows_per_batch rows per image), zeroed by the caller
   float* Cout = nullptr; int ldc = 0;
   float* Cout_lo = nullptr;           // if set: Cout receives rn_tf32(C) and Cout_lo rn_tf32(C - hi) (operand planes for tcgen05)
   // optional: columns n >= t_col0 are stored TRANSPOSED as TF32 planes, Ct_hi / Ct_lo [(n - t_col0) * ldt + m] (dense mode,
@@ -146,11 +165,16 @@ struct GemmArgs {
 };
 void gemm(Engine& e, const GemmArgs& a, cudaStream_t s);
 // tcgen05 back end (kernels_tc.cu); returns false when the shape is not eligible
-bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s);
+bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done = nullptr);   // side_done bit 0: c_amax fused, bit 1: c_stats fused
 bool flash_attention_tc(Engine& e, const float* q_hi, const float* q_lo, int ldq, const float* k_hi, const float* k_lo, int ldk,
                         const float* vt_hi, const float* vt_lo, float* out, int ldo, int B, int N, int Nk, int Nks, int heads, int d,
                         float scale, cudaStream_t s);
 void split_planes(Engine& e, const float* w, float* hi, float* lo, size_t n, cudaStream_t s);   // hi = rn_tf32(w), lo = rn_tf32(w - hi)
+// fp16 split of w * 2^exp: hi = fp16(w'), lo = fp16(w' - hi)  (hi / lo: __half arrays)
+void split_planes_h16(Engine& e, const float* w, void* hi, void* lo, size_t n, int exp, cudaStream_t s);
+// slot <- max(slot, max |x[r, 0..C)|) over `rows` rows of stride ld (atomic max on the bit pattern)
+void amax_rows(Engine& e, const float* x, long long rows, int C, long long ld, float* slot, cudaStream_t s);
+int h16_exp_host(float amax);   // exponent e with amax * 2^e in [2^14, 2^15)
 bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, int head_stride, const float* vt, float* out, int ldo, int B,
                   int Nq, int Nk, int heads, int d, float scale, cudaStream_t s);
 
@@ -158,10 +182,14 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
 // normalisation / softmax / elementwise ops (kernels_norm.cu, kernels_elem.cu)
 // ------------------------------------------------------------------------------------------------
 // GroupNorm(32) over NHWC, optionally over the channel-concat of two sources; y = [silu]( gn(x)*(1+scale)+shift )
+// st1 / st2: per-(image, channel) fp64 {sum, sum of squares} of the sources when their producer already accumulated them
+// (stats[(b*C + c)*2 + k]); null -> computed here by one extra read.  amax: optional device scalar <- atomic max |y|.
 void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, const float* gamma, const float* beta,
                float eps, bool silu, const float* scale, const float* shift, int ld_ss, float* y, int B, int HW,
-               cudaStream_t s);
-void layernorm(Engine& e, const float* x, const float* gamma, const float* beta, float* y, int M, int C, cudaStream_t s);
+               cudaStream_t s, const double* st1 = nullptr, const double* st2 = nullptr, float* amax = nullptr);
+double* gn_channel_stats(Engine& e, const float* x, int C, int B, int HW, cudaStream_t s);
+void gn_channel_stats_into(Engine& e, const float* x, int C, int B, int HW, double* stats, cudaStream_t s);   // stats += (zeroed by the caller)
+void layernorm(Engine& e, const float* x, const float* gamma, const float* beta, float* y, int M, int C, cudaStream_t s, float* amax = nullptr);
 // in place; causal_nq > 0: row r may only see columns j <= r % causal_nq (the rest become 0)
 void softmax_rows(Engine& e, float* x, long long rows, int L, int ld, cudaStream_t s, int causal_nq = 0);
 void silu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s);
@@ -193,6 +221,43 @@ void ddim_compute_eps(Engine& e, const float* xt, const float* xt_next, const fl
                       const cdx_ddim_coef& c, float* out, size_t n, cudaStream_t s);
 void ddim_step_with_eps(Engine& e, const float* x, const float* e_c, const float* e_uc, float scale, const float* eps,
                         const cdx_ddim_coef& c, float* out, size_t n, cudaStream_t s);
+// One fused elementwise launch per sampling step of the latent loops (DPM-Encoder, decode, or both in lock-step): recovers the
+// noise of step i from the U-Net output (compute_eps), draws the next posterior sample of the source chain (sample_xt_next),
+// advances the target chain with the recovered noise (p_sample_ddim_with_eps) and writes the next U-Net input batch.  Op order
+// inside is that of the three single-purpose kernels above (bit-exact against the reference formulas).
+struct LatentStep {
+  size_t n = 0; int chw = 0;                 // B*chw elements
+  // --- source chain (enc != 0)
+  int enc = 0;
+  const float* x0 = nullptr; const float* xt = nullptr; const float* xn = nullptr;    // x_t and x_{t-1} (already drawn)
+  const float* es_c = nullptr; const float* es_uc = nullptr; float s_scale = 1.f;     // eps-hat under the source condition
+  cdx_ddim_coef cs{};
+  float* z_out = nullptr; long long z_stride = 0;   // optional: eps -> z_out[b*z_stride + r]
+  int next = 0;                              // 0 none, 1 posterior sample x_{t-2} from (x0, xn, noise_next), 2 x_{t-2} = x0 (index 0)
+  const float* noise_next = nullptr; cdx_ddim_coef cnext{};
+  float* xn2 = nullptr;
+  // --- target chain (dec != 0)
+  int dec = 0;
+  const float* yt = nullptr; const float* et_c = nullptr; const float* et_uc = nullptr; float t_scale = 1.f;
+  cdx_ddim_coef ct{};
+  const float* eps_in = nullptr; long long eps_stride = 0;    // dec without enc: recovered noise read from z (or extra noise, stride chw)
+  float* y_out = nullptr;
+  // --- next U-Net input batch [nseg, B, chw]: segments [0, nseg_src) <- x_{t-1}, [nseg_src, nseg_src + nseg_tgt) <- y_{t-1}
+  float* xin = nullptr; int nseg_src = 0, nseg_tgt = 0;
+};
+void latent_step(Engine& e, const LatentStep& a, cudaStream_t s);
+// x_T = sqrt(a_T) x0 + sqrt(1 - a_T) noise0 (ddim.py:477-479) -> z slot 0 (optional), x_T buffer, y_T buffer (optional), first
+// posterior sample x_{T-1} (next as in LatentStep) and the first U-Net input batch
+struct LatentInit {
+  size_t n = 0; int chw = 0;
+  const float* x0 = nullptr; const float* noise0 = nullptr; float sa = 0.f, s1 = 0.f;
+  float* z_out = nullptr; long long z_stride = 0;
+  float* xt = nullptr; float* yt = nullptr;
+  int next = 0; const float* noise_next = nullptr; cdx_ddim_coef cnext{}; float* xn = nullptr;
+  float* xin = nullptr; int nseg_src = 0, nseg_tgt = 0;
+};
+void latent_init(Engine& e, const LatentInit& a, cudaStream_t s);
+
 void pixel_posterior_sample(Engine& e, const float* x0, const float* xt, const float* noise, const cdx_pixel_coef& c, float* out, size_t n, cudaStream_t s);
 void pixel_compute_eps(Engine& e, const float* xt, const float* xt_next, const float* et, const cdx_pixel_coef& c, float* out,
                        int B, int chw, int net_chw, cudaStream_t s);

@@ -66,6 +66,38 @@ ProfScope::~ProfScope() {
   if (idx >= 0) cudaEventRecord(e.prof.recs[idx].b, s);
 }
 
+float* Engine::amax_slot() {
+  if (dry()) return reinterpret_cast<float*>((uintptr_t)0x100);   // never dereferenced
+  if (!amax_pool) {
+    if (cudaMalloc(&amax_pool, (size_t)amax_cap * sizeof(float)) != cudaSuccess) throw Error(CDX_E_NOMEM, "amax pool allocation failed");
+    if (cudaMemset(amax_pool, 0, (size_t)amax_cap * sizeof(float)) != cudaSuccess) throw Error(CDX_E_CUDA, "amax pool memset failed");
+  }
+  if (amax_used >= amax_cap) throw Error(CDX_E_NOMEM, "amax pool exhausted (engine bug: amax_reset not called per network call)");
+  return amax_pool + amax_used++;
+}
+double* Engine::stat_alloc(size_t n) {
+  n = (n + 31) & ~(size_t)31;
+  if (dry()) return reinterpret_cast<double*>((uintptr_t)0x1000);   // never dereferenced
+  if (!stat_pool) {
+    if (cudaMalloc(&stat_pool, stat_cap * sizeof(double)) != cudaSuccess) throw Error(CDX_E_NOMEM, "statistics pool allocation failed");
+    if (cudaMemset(stat_pool, 0, stat_cap * sizeof(double)) != cudaSuccess) throw Error(CDX_E_CUDA, "statistics pool memset failed");
+  }
+  if (stat_used + n > stat_cap) throw Error(CDX_E_NOMEM, "statistics pool exhausted");
+  double* p = stat_pool + stat_used;
+  stat_used += n;
+  return p;
+}
+// Both pools are fully zero when created; a call dirties [0, used), so zeroing [0, high-water) keeps everything beyond clean.
+void Engine::pools_reset(cudaStream_t s) {
+  if (dry()) return;
+  if (amax_used > amax_high) amax_high = amax_used;
+  if (stat_used > stat_high) stat_high = stat_used;
+  if (amax_pool && amax_high) cudaMemsetAsync(amax_pool, 0, (size_t)amax_high * sizeof(float), s);
+  if (stat_pool && stat_high) cudaMemsetAsync(stat_pool, 0, stat_high * sizeof(double), s);
+  amax_high = 0; stat_high = 0;
+  amax_used = 0; stat_used = 0;
+}
+
 void Arena::destroy() {
   if (base) cudaFree(base);
   base = nullptr;

@@ -224,6 +224,59 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
+__device__ __forceinline__ float ddim_posterior_f(float x0, float xt, float nz, const cdx_ddim_coef& c) {
+  const float e_t = DIV(SUB(xt, MUL(c.sqrt_at, x0)), c.sqrt_1m_at);       // ddim.py:597
+  const float dir = MUL(c.dir_coef, e_t);                                 // :598
+  const float noise = MUL(c.sigma, nz);                                   // :599
+  return ADD(ADD(MUL(c.sqrt_aprev, x0), dir), noise);                     // :600
+}
+
+__global__ void latent_step_kernel(const LatentStep a) {
+  const size_t seg = a.n;
+  GRID_STRIDE(i, a.n) {
+    const size_t b = i / a.chw, r = i - b * a.chw;
+    float eps = 0.f;
+    if (a.enc) {
+      const float e_t = cfg_combine(a.es_c, a.es_uc, a.s_scale, i);
+      const float xt = a.xt[i], xn = a.xn[i];
+      const float pred_x0 = DIV(SUB(xt, MUL(a.cs.sqrt_1m_at_tab, e_t)), a.cs.sqrt_at);          // ddim.py:576
+      const float dir = MUL(a.cs.dir_coef, e_t);                                                // :578
+      eps = DIV(DIV(SUB(SUB(xn, MUL(a.cs.sqrt_aprev, pred_x0)), dir), a.cs.sigma), 1.0f);       // :579 (temperature 1)
+      if (a.z_out) a.z_out[b * a.z_stride + r] = eps;
+      if (a.next == 1) a.xn2[i] = ddim_posterior_f(a.x0[i], xn, a.noise_next[i], a.cnext);
+      else if (a.next == 2) a.xn2[i] = a.x0[i];                                                 // ddim.py:583-584
+      for (int sg = 0; sg < a.nseg_src; ++sg) a.xin[sg * seg + i] = xn;
+    } else if (a.dec) {
+      eps = a.eps_in[b * a.eps_stride + r];
+    }
+    if (a.dec) {
+      const float e_t = cfg_combine(a.et_c, a.et_uc, a.t_scale, i);
+      const float y = a.yt[i];
+      const float pred_x0 = DIV(SUB(y, MUL(a.ct.sqrt_1m_at_tab, e_t)), a.ct.sqrt_at);           // ddim.py:634
+      const float dir = MUL(a.ct.dir_coef, e_t);                                                // :638
+      const float noise = MUL(MUL(a.ct.sigma, eps), 1.0f);                                      // :642
+      const float yn = ADD(ADD(MUL(a.ct.sqrt_aprev, pred_x0), dir), noise);                     // :645
+      a.y_out[i] = yn;
+      for (int sg = 0; sg < a.nseg_tgt; ++sg) a.xin[(a.nseg_src + sg) * seg + i] = yn;
+    }
+  }
+}
+
+__global__ void latent_init_kernel(const LatentInit a) {
+  const size_t seg = a.n;
+  GRID_STRIDE(i, a.n) {
+    const size_t b = i / a.chw, r = i - b * a.chw;
+    const float x0 = a.x0[i];
+    const float xT = ADD(MUL(a.sa, x0), MUL(a.s1, a.noise0[i]));                                // ddim.py:477-479
+    if (a.z_out) a.z_out[b * a.z_stride + r] = xT;
+    a.xt[i] = xT;
+    if (a.yt) a.yt[i] = xT;
+    if (a.next == 1) a.xn[i] = ddim_posterior_f(x0, xT, a.noise_next[i], a.cnext);
+    else if (a.next == 2) a.xn[i] = x0;
+    for (int sg = 0; sg < a.nseg_src + a.nseg_tgt; ++sg) a.xin[sg * seg + i] = xT;
+  }
+}
+
 __global__ void pixel_posterior_kernel(const float* __restrict__ x0, const float* __restrict__ xt, const float* __restrict__ nz,
                                        cdx_pixel_coef c, float* __restrict__ out, size_t n) {
   GRID_STRIDE(i, n) {
@@ -278,6 +331,8 @@ __global__ void pixel_step_kernel(const float* __restrict__ xt, const float* __r
     e.launches++;                                                 \
   } while (0)
 
+void latent_step(Engine& e, const LatentStep& a, cudaStream_t s) { LAUNCH1(latent_step_kernel, a.n, a); }
+void latent_init(Engine& e, const LatentInit& a, cudaStream_t s) { LAUNCH1(latent_init_kernel, a.n, a); }
 void affine(Engine& e, const float* x, float a, float b, float* out, size_t n, cudaStream_t s) { LAUNCH1(affine_kernel, n, x, a, b, out, n); }
 void shift_scale(Engine& e, const float* x, float b, float a, float* out, size_t n, cudaStream_t s) { LAUNCH1(shift_scale_kernel, n, x, b, a, out, n); }
 void q_sample(Engine& e, const float* x0, const float* nz, float sa, float s1, float* out, size_t n, cudaStream_t s) { LAUNCH1(q_sample_kernel, n, x0, nz, sa, s1, out, n); }

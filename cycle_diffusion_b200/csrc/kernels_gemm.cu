@@ -300,12 +300,36 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+// side outputs a caller may ask for (range / GroupNorm statistics of C): fused into the tensor-core epilogue when it can,
+// otherwise produced here by one extra pass over C (small / ragged shapes, the FFMA back end, split-K)
+static void gemm_side_outputs(Engine& e, const GemmArgs& a, bool amax_done, bool stats_done, cudaStream_t s) {
+  if (a.out_nchw) return;
+  if (a.c_amax && !amax_done) amax_rows(e, a.Cout, a.M, a.geglu ? a.N / 2 : a.N, a.ldc, a.c_amax, s);
+  if (a.c_stats && !stats_done) {
+    CDX_CHECK(a.ldc == a.N && a.rows_per_batch > 0 && a.M % a.rows_per_batch == 0, "gemm: statistics need a dense [B*HW, N] result");
+    gn_channel_stats_into(e, a.Cout, a.N, a.M / a.rows_per_batch, a.rows_per_batch, a.c_stats, s);
+  }
+}
+
 void gemm(Engine& e, const GemmArgs& a, cudaStream_t s) {
   CDX_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
   CDX_CHECK(a.batch >= 1 && a.heads >= 1, "gemm: bad batch");
   if (a.mode == 1) CDX_CHECK(a.K == 9 * (a.C1 + a.C2), "conv3x3: K != 9*Cin");
   if (a.mode == 0) CDX_CHECK(a.K == a.C1 + a.C2, "dense: K != C1+C2");
-  if (e.mma_mode == 1 && gemm_tc(e, a, s)) return;      // (handles the arena dry run itself: split-K workspace)
+  if (e.mma_mode == 1) {
+    int done = 0;                                          // bit 0: c_amax written, bit 1: c_stats written
+    if (gemm_tc(e, a, s, &done)) {                         // (handles the arena dry run itself: split-K workspace)
+      gemm_side_outputs(e, a, done & 1, done & 2, s);
+      return;
+    }
+  }
+  if (a.c_amax || a.c_stats) {
+    GemmArgs b = a;
+    b.c_amax = nullptr; b.c_stats = nullptr;
+    gemm(e, b, s);
+    gemm_side_outputs(e, a, false, false, s);
+    return;
+  }
   CDX_CHECK(!a.Ct_hi, "gemm: transposed plane output is only available on the tensor-core path (caller must check eligibility)");
   if (a.geglu) {       // fused only in the tensor-core epilogue; here: plain GEMM into a temporary, then the GEGLU kernel
     CDX_CHECK(a.N % 128 == 0 && a.batch * a.heads == 1 && !a.out_nchw && !a.Cout_lo, "gemm: bad GEGLU problem");

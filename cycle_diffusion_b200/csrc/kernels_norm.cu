@@ -2,10 +2,15 @@
 //
 // GroupNorm follows GroupNorm32 / Normalize (util.py:215-217 eps 1e-5; attention.py:76-77 and model.py:38-39 eps 1e-6)
 // on NHWC activations, optionally over the channel concatenation of two tensors (the U-Net skip `th.cat`, OAI:736)
-// so that the concat is never materialised before the norm.  Statistics are accumulated in fp64 (one read),
-// then one read + one write applies  y = (x - mean) * rstd * gamma + beta  [ * (1+scale) + shift ] [ SiLU ].
-// Algorithmic HBM bytes: 2 reads + 1 write of the activation (stats pass + apply pass; the apply blocks fold the
-// per-chunk partial sums themselves).
+// so that the concat is never materialised before the norm.
+//
+// Statistics are per-(image, channel) fp64 sums  stats[(b*C + c)*2 + {sum, sum of squares}]  attached to the TENSOR, not to the
+// norm: the tcgen05 GEMM that produces an activation adds them from its epilogue registers (kernels_tc.cu), so a GroupNorm
+// over it -- or over the concat of two such tensors, channel sums being additive -- costs no statistics pass at all; tensors
+// from other producers get them from gn_stats_kernel (one read).  The apply kernel then is the algorithmic one read + one write:
+// every block folds the channel sums of its image into the 32 group means / rstds (fp64), y = x * sc + sh per channel (the form
+// ATen's CPU kernel uses), optional (1 + scale) / shift of the improved-DDPM scale-shift norm, optional SiLU, and it tracks
+// max |y| for the fp16-split GEMM that consumes y.
 #include "common.cuh"
 
 namespace cdx {
@@ -13,78 +18,59 @@ namespace {
 
 constexpr int GN_GROUPS = 32;
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.f + expf(-v)); }
-
-// partial sums: part[((b*nchunk + chunk)*32 + g)*2 + {0,1}]
-__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
-                                                       int C2, int HW, int rows_per_chunk, double* __restrict__ part) {
-  const int C = C1 + C2;
-  const int cpg = C / GN_GROUPS;
+// per-(image, channel) sums of one source: grid (row chunks, B); thread (tr, tc) owns float4 channel slots tc, tc+ncol, ...
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int C, int HW, int rows_per_chunk, double* __restrict__ stats) {
   const int b = blockIdx.y, chunk = blockIdx.x;
-  __shared__ double ssum[GN_GROUPS], ssq[GN_GROUPS];
-  if (threadIdx.x < GN_GROUPS) { ssum[threadIdx.x] = 0.0; ssq[threadIdx.x] = 0.0; }
-  __syncthreads();
   const int r0 = chunk * rows_per_chunk;
   const int r1 = min(HW, r0 + rows_per_chunk);
-  // thread (tr, tc): tc owns float4 channel slots tc, tc+ncol, ...; tr strides over the rows of the chunk.  A float4 may
-  // straddle two groups when cpg % 4 != 0 (C=320 -> cpg=10), so each of its 4 lanes accumulates separately and is
-  // flushed to its own group's shared accumulator once per slot.
   const int C4 = C >> 2;
   const int ncol = min(C4, (int)blockDim.x);
   const int nrow_par = blockDim.x / ncol;
   const int tr = threadIdx.x / ncol, tc = threadIdx.x - tr * ncol;
-  if (tr < nrow_par) {
-    for (int c4 = tc; c4 < C4; c4 += ncol) {
-      const int c = c4 * 4;
-      double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
-      const float* base = (c < C1) ? (x1 + (long long)b * HW * C1 + c) : (x2 + (long long)b * HW * C2 + (c - C1));
-      const int ldx = (c < C1) ? C1 : C2;
-      int r = r0 + tr;
-      for (; r + 3 * nrow_par < r1; r += 4 * nrow_par) {      // 4 independent 128-bit loads in flight per thread
-        float4 v[4];
+  if (tr >= nrow_par) return;
+  for (int c4 = tc; c4 < C4; c4 += ncol) {
+    const int c = c4 * 4;
+    double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+    const float* base = x + (long long)b * HW * C + c;
+    int r = r0 + tr;
+    for (; r + 3 * nrow_par < r1; r += 4 * nrow_par) {      // 4 independent 128-bit loads in flight per thread
+      float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(base + (long long)(r + u * nrow_par) * ldx);
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(base + (long long)(r + u * nrow_par) * C);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const double d0 = v[u].x, d1 = v[u].y, d2 = v[u].z, d3 = v[u].w;
-          s[0] += d0; q[0] += d0 * d0;
-          s[1] += d1; q[1] += d1 * d1;
-          s[2] += d2; q[2] += d2 * d2;
-          s[3] += d3; q[3] += d3 * d3;
-        }
-      }
-      for (; r < r1; r += nrow_par) {
-        const float4 v = *reinterpret_cast<const float4*>(base + (long long)r * ldx);
-        const double d0 = v.x, d1 = v.y, d2 = v.z, d3 = v.w;
+      for (int u = 0; u < 4; ++u) {
+        const double d0 = v[u].x, d1 = v[u].y, d2 = v[u].z, d3 = v[u].w;
         s[0] += d0; q[0] += d0 * d0;
         s[1] += d1; q[1] += d1 * d1;
         s[2] += d2; q[2] += d2 * d2;
         s[3] += d3; q[3] += d3 * d3;
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int g = (c + j) / cpg;
-        atomicAdd(&ssum[g], s[j]);
-        atomicAdd(&ssq[g], q[j]);
-      }
     }
-  }
-  __syncthreads();
-  if (threadIdx.x < GN_GROUPS) {
-    double* o = part + (((long long)b * gridDim.x + chunk) * GN_GROUPS + threadIdx.x) * 2;
-    o[0] = ssum[threadIdx.x];
-    o[1] = ssq[threadIdx.x];
+    for (; r < r1; r += nrow_par) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (long long)r * C);
+      const double d0 = v.x, d1 = v.y, d2 = v.z, d3 = v.w;
+      s[0] += d0; q[0] += d0 * d0;
+      s[1] += d1; q[1] += d1 * d1;
+      s[2] += d2; q[2] += d2 * d2;
+      s[3] += d3; q[3] += d3 * d3;
+    }
+    double* o = stats + ((long long)b * C + c) * 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(o + 2 * j, s[j]);
+      atomicAdd(o + 2 * j + 1, q[j]);
+    }
   }
 }
 
 // grid (row chunks, B); thread (tr, tc) owns channel vectors tc, tc+ncol, ... (so group / affine coefficients are hoisted out
-// of the row loop as y = x * sc + sh, the form ATen's CPU kernel uses) and walks the chunk's rows 4 at a time
+// of the row loop) and walks the chunk's rows 4 at a time.  Dynamic smem: float2 (sc, sh) per channel.
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const double* __restrict__ part, int nchunk, double inv_count,
+                                                       const double* __restrict__ st1, const double* __restrict__ st2, double inv_count,
                                                        float eps, int silu,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
-                                                       int ld_ss, float* __restrict__ y, int HW, int rows_per_chunk) {
+                                                       int ld_ss, float* __restrict__ y, int HW, int rows_per_chunk, float* __restrict__ amax) {
   const int C = C1 + C2;
   const int cpg = C / GN_GROUPS;
   const int C4 = C >> 2;
@@ -94,102 +80,132 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   const int ncol = min(C4, (int)blockDim.x);
   const int nrow_par = blockDim.x / ncol;
   const int tr = threadIdx.x / ncol, tc = threadIdx.x - tr * ncol;
-  // every block folds the stats partials of its image itself (fixed order, fp64): saves a launch per GroupNorm
+  // every block folds the channel sums of its image into the group statistics itself (fixed order, fp64)
   __shared__ float mean_rstd[GN_GROUPS * 2];
-  if (threadIdx.x < GN_GROUPS) {
-    const int g = threadIdx.x;
+  extern __shared__ float2 s_aff[];     // [C]: y = x * .x + .y
+  {
+    const int g = threadIdx.x >> 3, l8 = threadIdx.x & 7;     // 8 threads per group
     double s = 0.0, q = 0.0;
-    for (int c = 0; c < nchunk; ++c) {
-      const double* o = part + (((long long)b * nchunk + c) * GN_GROUPS + g) * 2;
+    for (int j = l8; j < cpg; j += 8) {
+      const int c = g * cpg + j;
+      const double* o = (c < C1) ? st1 + ((long long)b * C1 + c) * 2 : st2 + ((long long)b * C2 + (c - C1)) * 2;
       s += o[0];
       q += o[1];
     }
-    const double mean = s * inv_count;
-    double var = q * inv_count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    mean_rstd[g * 2 + 0] = (float)mean;
-    mean_rstd[g * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (l8 == 0) {
+      const double mean = s * inv_count;
+      double var = q * inv_count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mean_rstd[g * 2 + 0] = (float)mean;
+      mean_rstd[g * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
   }
   __syncthreads();
-  if (tr >= nrow_par) return;
-  for (int c4 = tc; c4 < C4; c4 += ncol) {
-    const int c = c4 * 4;
-    float sc[4], sh[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int g = (c + j) / cpg;
-      const float mean = mean_rstd[g * 2 + 0];
-      const float rstd = mean_rstd[g * 2 + 1];
-      float a = rstd * gamma[c + j];
-      float o = beta[c + j] - mean * a;
-      if (scale) {      // gn(x) * (1 + scale) + shift   (improved-DDPM scale-shift norm)
-        const float s1 = 1.f + scale[(long long)b * ld_ss + c + j];
-        a *= s1;
-        o = o * s1 + shift[(long long)b * ld_ss + c + j];
-      }
-      sc[j] = a; sh[j] = o;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = mean_rstd[g * 2 + 0], rstd = mean_rstd[g * 2 + 1];
+    float a = rstd * gamma[c];
+    float o = beta[c] - mean * a;
+    if (scale) {      // gn(x) * (1 + scale) + shift   (improved-DDPM scale-shift norm)
+      const float s1 = 1.f + scale[(long long)b * ld_ss + c];
+      a *= s1;
+      o = o * s1 + shift[(long long)b * ld_ss + c];
     }
-    const float* src = (c < C1) ? (x1 + (long long)b * HW * C1 + c) : (x2 + (long long)b * HW * C2 + (c - C1));
-    const int ldx = (c < C1) ? C1 : C2;
-    float* dst = y + (long long)b * HW * C + c;
-    auto act = [&](float4 v) {
-      float t[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
-      if (silu) {
+    s_aff[c] = make_float2(a, o);
+  }
+  __syncthreads();
+  float vmax = 0.f;
+  if (tr < nrow_par) {
+    for (int c4 = tc; c4 < C4; c4 += ncol) {
+      const int c = c4 * 4;
+      const float2 a0 = s_aff[c], a1 = s_aff[c + 1], a2 = s_aff[c + 2], a3 = s_aff[c + 3];
+      const float* src = (c < C1) ? (x1 + (long long)b * HW * C1 + c) : (x2 + (long long)b * HW * C2 + (c - C1));
+      const int ldx = (c < C1) ? C1 : C2;
+      float* dst = y + (long long)b * HW * C + c;
+      auto act = [&](float4 v) {
+        float t[4] = {fmaf(v.x, a0.x, a0.y), fmaf(v.y, a1.x, a1.y), fmaf(v.z, a2.x, a2.y), fmaf(v.w, a3.x, a3.y)};
+        if (silu) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) t[j] = __fdividef(t[j], 1.f + __expf(-t[j]));
+          for (int j = 0; j < 4; ++j) t[j] = __fdividef(t[j], 1.f + __expf(-t[j]));
+        }
+        vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(t[0]), fabsf(t[1])), fmaxf(fabsf(t[2]), fabsf(t[3]))));
+        return make_float4(t[0], t[1], t[2], t[3]);
+      };
+      int r = r0 + tr;
+      for (; r + 3 * nrow_par < r1; r += 4 * nrow_par) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(src + (long long)(r + u * nrow_par) * ldx);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(dst + (long long)(r + u * nrow_par) * C) = act(v[u]);
       }
-      return make_float4(t[0], t[1], t[2], t[3]);
-    };
-    int r = r0 + tr;
-    for (; r + 3 * nrow_par < r1; r += 4 * nrow_par) {
-      float4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(src + (long long)(r + u * nrow_par) * ldx);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(dst + (long long)(r + u * nrow_par) * C) = act(v[u]);
+      for (; r < r1; r += nrow_par)
+        *reinterpret_cast<float4*>(dst + (long long)r * C) = act(*reinterpret_cast<const float4*>(src + (long long)r * ldx));
     }
-    for (; r < r1; r += nrow_par)
-      *reinterpret_cast<float4*>(dst + (long long)r * C) = act(*reinterpret_cast<const float4*>(src + (long long)r * ldx));
+  }
+  if (amax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if ((threadIdx.x & 31) == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(vmax));
   }
 }
 
-// one warp per row
+// one warp per row, the row held in registers (NV float4 per lane: C <= 128 NV): one read, one write
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ y, int M, int C,
-                                                        float eps) {
+                                                        float eps, float* __restrict__ amax) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
-  const float* xr = x + (long long)warp * C;
-  float* yr = y + (long long)warp * C;
-  const int C4 = C >> 2;
-  float s = 0.f;
-  for (int i = lane; i < C4; i += 32) {
-    const float4 v = *reinterpret_cast<const float4*>(xr + i * 4);
-    s += (v.x + v.y) + (v.z + v.w);
-  }
+  float vmax = 0.f;
+  if (warp < M) {
+    const float* xr = x + (long long)warp * C;
+    float* yr = y + (long long)warp * C;
+    const int C4 = C >> 2;
+    float4 v[NV];
+    float s = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)C;
-  float q = 0.f;
-  for (int i = lane; i < C4; i += 32) {
-    const float4 v = *reinterpret_cast<const float4*>(xr + i * 4);
-    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      v[i] = c4 < C4 ? *reinterpret_cast<const float4*>(xr + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = 1.f / sqrtf(q / (float)C + eps);
-  for (int i = lane; i < C4; i += 32) {
-    const float4 v = *reinterpret_cast<const float4*>(xr + i * 4);
-    const float4 g = *reinterpret_cast<const float4*>(gamma + i * 4);
-    const float4 b = *reinterpret_cast<const float4*>(beta + i * 4);
-    float4 o;
-    o.x = (v.x - mean) * rstd * g.x + b.x;
-    o.y = (v.y - mean) * rstd * g.y + b.y;
-    o.z = (v.z - mean) * rstd * g.z + b.z;
-    o.w = (v.w - mean) * rstd * g.w + b.w;
-    *reinterpret_cast<float4*>(yr + i * 4) = o;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < C4) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.f / sqrtf(q / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < C4) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c4 * 4);
+        const float4 b = *reinterpret_cast<const float4*>(beta + c4 * 4);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+        *reinterpret_cast<float4*>(yr + c4 * 4) = o;
+      }
+    }
+  }
+  if (amax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(vmax));
   }
 }
 
@@ -222,36 +238,56 @@ __global__ void __launch_bounds__(256) softmax_kernel(float* __restrict__ x, lon
 
 }  // namespace
 
-void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, const float* gamma, const float* beta, float eps,
-               bool silu, const float* scale, const float* shift, int ld_ss, float* y, int B, int HW, cudaStream_t s) {
-  const int C = C1 + C2;
-  CDX_CHECK(C % GN_GROUPS == 0, "groupnorm: C=%d not divisible by 32", C);
-  CDX_CHECK(C1 % 4 == 0 && C2 % 4 == 0, "groupnorm: channel counts must be multiples of 4 (C1=%d C2=%d)", C1, C2);
-  Scope sc(e.arena);
+double* gn_channel_stats(Engine& e, const float* x, int C, int B, int HW, cudaStream_t s) {
+  double* st = e.stat_alloc((size_t)B * C * 2);
+  gn_channel_stats_into(e, x, C, B, HW, st, s);
+  return st;
+}
+
+void gn_channel_stats_into(Engine& e, const float* x, int C, int B, int HW, double* st, cudaStream_t s) {
+  CDX_CHECK(C % 4 == 0, "groupnorm stats: C=%d must be a multiple of 4", C);
+  if (e.dry()) return;
   int nchunk = cdiv(4LL * e.num_sms, B);
   if (nchunk > HW) nchunk = HW;
   if (nchunk < 1) nchunk = 1;
   const int rows_per_chunk = cdiv(HW, nchunk);
   nchunk = cdiv(HW, rows_per_chunk);
-  double* part = (double*)e.arena.alloc((size_t)B * nchunk * GN_GROUPS * 2 * sizeof(double));
+  ProfScope ps(e, s, PROF_GROUPNORM, 0.0, 0.0, 1);      // (the algorithmic bytes are booked by the apply pass)
+  gn_stats_kernel<<<dim3(nchunk, B), 256, 0, s>>>(x, C, HW, rows_per_chunk, st);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+
+void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, const float* gamma, const float* beta, float eps,
+               bool silu, const float* scale, const float* shift, int ld_ss, float* y, int B, int HW, cudaStream_t s,
+               const double* st1, const double* st2, float* amax) {
+  const int C = C1 + C2;
+  CDX_CHECK(C % GN_GROUPS == 0, "groupnorm: C=%d not divisible by 32", C);
+  CDX_CHECK(C1 % 4 == 0 && C2 % 4 == 0, "groupnorm: channel counts must be multiples of 4 (C1=%d C2=%d)", C1, C2);
+  if (!st1) st1 = gn_channel_stats(e, x1, C1, B, HW, s);
+  if (x2 && !st2) st2 = gn_channel_stats(e, x2, C2, B, HW, s);
   if (e.dry()) return;
-  ProfScope ps(e, s, PROF_GROUPNORM, 0.0, 2.0 * 4.0 * B * (double)HW * C, 2);   // algorithmic: one read + one write
-  gn_stats_kernel<<<dim3(nchunk, B), 256, 0, s>>>(x1, C1, x2, C2, HW, rows_per_chunk, part);
+  ProfScope ps(e, s, PROF_GROUPNORM, 0.0, 2.0 * 4.0 * B * (double)HW * C, 1);   // algorithmic: one read + one write
   int achunk = cdiv(8LL * e.num_sms, B);
   if (achunk > HW) achunk = HW;
   const int arows = cdiv(HW, achunk);
   achunk = cdiv(HW, arows);
-  gn_apply_kernel<<<dim3(achunk, B), 256, 0, s>>>(x1, C1, x2, C2, gamma, beta, part, nchunk, 1.0 / ((double)HW * (C / GN_GROUPS)), eps,
-                                                  silu ? 1 : 0, scale, shift, ld_ss, y, HW, arows);
+  gn_apply_kernel<<<dim3(achunk, B), 256, (size_t)C * sizeof(float2), s>>>(x1, C1, x2, C2, gamma, beta, st1, st2, 1.0 / ((double)HW * (C / GN_GROUPS)), eps,
+                                                                          silu ? 1 : 0, scale, shift, ld_ss, y, HW, arows, amax);
   CDX_CUDA(cudaGetLastError());
-  e.launches += 2;
+  e.launches++;
 }
 
-void layernorm(Engine& e, const float* x, const float* gamma, const float* beta, float* y, int M, int C, cudaStream_t s) {
-  CDX_CHECK(C % 4 == 0, "layernorm: C=%d must be a multiple of 4", C);
+void layernorm(Engine& e, const float* x, const float* gamma, const float* beta, float* y, int M, int C, cudaStream_t s, float* amax) {
+  CDX_CHECK(C % 4 == 0 && C <= 128 * 16, "layernorm: C=%d must be a multiple of 4 and <= 2048", C);
   if (e.dry()) return;
   ProfScope ps(e, s, PROF_LAYERNORM, 0.0, 2.0 * 4.0 * (double)M * C, 1);
-  layernorm_kernel<<<cdiv((long long)M * 32, 256), 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f);
+  const int nv = cdiv(C, 128);
+  const int blocks = cdiv((long long)M * 32, 256);
+  if (nv <= 3) layernorm_kernel<3><<<blocks, 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f, amax);
+  else if (nv <= 6) layernorm_kernel<6><<<blocks, 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f, amax);
+  else if (nv <= 10) layernorm_kernel<10><<<blocks, 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f, amax);
+  else layernorm_kernel<16><<<blocks, 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f, amax);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
 }

@@ -40,6 +40,9 @@
 #include <unordered_map>
 #include <vector>
 #include <cstdlib>
+#include <cmath>
+
+#include <cuda_fp16.h>
 
 #include "tc_common.cuh"
 
@@ -49,6 +52,7 @@ namespace {
 using namespace tc;
 
 constexpr int TBM = 128, TBN = 128, TBK = 32;
+constexpr double CDX_H16_KC0 = 640.0, CDX_H16_KC1 = 4.2;   // planner cost of one 64-k stage of the fp16-split kernel (cycles)
 constexpr int TILE_BYTES = TBM * TBK * 4;          // 16 KB
 constexpr int NUM_SPLIT_WARPS = 4;
 constexpr int NUM_EPI_WARPS = 8;
@@ -116,6 +120,8 @@ struct TcParams {
   int b_exp;
   int fast;
   float* c_amax;            // optional: atomic max of |C| over everything this launch stores (operand range for the consumer GEMM)
+  double* c_stats;          // optional: per-(image, channel) fp64 {sum, sum sq} of C, for the GroupNorm that consumes it; requires
+                            // every 32-row quadrant of a tile to lie inside one image (checked on the host)
 };
 
 // exponent e such that amax * 2^e lies in [2^14, 2^15): |x * 2^e| < 2^15 for every |x| <= amax (0 for an all-zero tensor)
@@ -535,6 +541,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const long long at = (long long)(n - p.t_col0) * p.ldt + m;
             p.Ct_hi[at] = hi;
             p.Ct_lo[at] = __uint_as_float(rn_tf32(__float_as_uint(o - hi)));
+            omax = fmaxf(omax, fabsf(o));
           }
         }
       }
@@ -603,6 +610,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               make_float4(acc[part * 32 + 4 * c], acc[part * 32 + 4 * c + 1], acc[part * 32 + 4 * c + 2], acc[part * 32 + 4 * c + 3]);
         __syncwarp();
         const int n = ncol0 + part * 32 + 4 * g;
+        float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float4 o[4];
@@ -616,6 +624,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (half == 1) {
             __syncwarp();                                         // staging buffer free for the next block
             if (part + 1 < nparts) load_residual(part + 1);      // in flight while this block is stored
+          }
+          if (p.c_stats) {
+            // GroupNorm statistics of the tensor being written: this thread holds 4 columns x 4 rows here (8 rows over both
+            // halves); rows of one quadrant belong to one image
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (mm[half * 4 + i] >= 0) {
+                gs[0] += o[i].x; gq[0] += o[i].x * o[i].x;
+                gs[1] += o[i].y; gq[1] += o[i].y * o[i].y;
+                gs[2] += o[i].z; gq[2] += o[i].z * o[i].z;
+                gs[3] += o[i].w; gq[3] += o[i].w * o[i].w;
+              }
+            }
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -632,6 +653,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               }
               *reinterpret_cast<float4*>(dst + (long long)mi * dld + n) = o[i];
               omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o[i].x), fabsf(o[i].y)), fmaxf(fabsf(o[i].z), fabsf(o[i].w))));
+            }
+          }
+        }
+        if (p.c_stats) {
+          // fold the 4 row-subgroups (lanes g, g+8, g+16, g+24), then one fp64 atomic per (column, statistic)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            gs[j] += __shfl_xor_sync(0xffffffffu, gs[j], 8);  gq[j] += __shfl_xor_sync(0xffffffffu, gq[j], 8);
+            gs[j] += __shfl_xor_sync(0xffffffffu, gs[j], 16); gq[j] += __shfl_xor_sync(0xffffffffu, gq[j], 16);
+          }
+          const int mq = __shfl_sync(0xffffffffu, m32, 0) >= 0 ? __shfl_sync(0xffffffffu, m32, 0) : -1;   // first row of the quadrant
+          if (rsub == 0 && mq >= 0 && n < nlim && fin) {
+            double* st = p.c_stats + ((long long)(mq / p.rows_per_batch) * p.N + n) * 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              atomicAdd(st + 2 * j, (double)gs[j]);
+              atomicAdd(st + 2 * j + 1, (double)gq[j]);
             }
           }
         }
@@ -700,6 +738,31 @@ __global__ void split_planes_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+// w' = w * 2^exp ; hi = fp16(w'), lo = fp16(w' - hi): one-time preparation of the weight planes for MODE_H16
+__global__ void split_planes_h16_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, size_t n, float scale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float x = w[i] * scale;
+    const __half h = __float2half_rn(x);
+    hi[i] = h;
+    lo[i] = __float2half_rn(x - __half2float(h));
+  }
+}
+
+__global__ void amax_rows_kernel(const float* __restrict__ x, long long rows, int C, long long ld, float* __restrict__ slot) {
+  float m = 0.f;
+  const long long total = rows * (long long)(C >> 2);
+  const int c4n = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4n;
+    const int c4 = (int)(i - r * c4n);
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ld + 4 * c4);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(m));
+}
+
 // cudaFuncSetAttribute is per DEVICE: remember which devices of this process have it (engines on several devices share the library)
 void ensure_attr(int device) {
   static bool attr_set[64] = {};
@@ -707,8 +770,9 @@ void ensure_attr(int device) {
   std::lock_guard<std::mutex> lock(mtx);
   const int d = device & 63;
   if (!attr_set[d]) {
-    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
-    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_SS>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_TS>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_H16>::SMEM_BYTES));
     attr_set[d] = true;
   }
 }
@@ -722,6 +786,32 @@ void split_planes(Engine& e, const float* w, float* hi, float* lo, size_t n, cud
   split_planes_kernel<<<(unsigned)(blocks ? blocks : 1), 256, 0, s>>>(w, hi, lo, n);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
+}
+
+void split_planes_h16(Engine& e, const float* w, void* hi, void* lo, size_t n, int exp, cudaStream_t s) {
+  if (e.dry()) return;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)e.num_sms * 16) blocks = (size_t)e.num_sms * 16;
+  split_planes_h16_kernel<<<(unsigned)(blocks ? blocks : 1), 256, 0, s>>>(w, (__half*)hi, (__half*)lo, n, ldexpf(1.f, exp));
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+
+void amax_rows(Engine& e, const float* x, long long rows, int C, long long ld, float* slot, cudaStream_t s) {
+  if (e.dry()) return;
+  CDX_CHECK((C & 3) == 0 && (ld & 3) == 0 && a16(x), "amax_rows: C=%d ld=%lld must be multiples of 4 (16-byte rows)", C, ld);
+  const long long total = rows * (long long)(C >> 2);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e.num_sms * 8);
+  amax_rows_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, rows, C, ld, slot);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+
+int h16_exp_host(float amax) {
+  if (!(amax > 0.f) || !std::isfinite(amax)) return 0;
+  int ex;
+  frexpf(amax, &ex);                    // amax = f * 2^ex, f in [0.5, 1)  ->  floor(log2 amax) = ex - 1
+  return std::min(std::max(14 - (ex - 1), -100), 100);
 }
 
 // softmax(q k^T * scale) v on the tensor cores: two batched 3xTF32 contractions around the row-softmax kernel.
@@ -758,7 +848,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     p.splits = 1; p.kb_per_split = cdiv(d, TBK);
     p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(Nk, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
-    tc_gemm_kernel<false><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
+    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -785,14 +875,14 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     p.splits = 1; p.kb_per_split = cdiv(Nk, TBK);
     p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(d, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
-    tc_gemm_kernel<false><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
+    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
   return true;
 }
 
-bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
+bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   // ---- eligibility (everything else takes the FFMA tiles)
   if (a.batch * a.heads != 1 || a.b_kn) return false;
   if (a.geglu && ((a.N % TBN) || a.out_nchw || a.Cout_lo || a.residual || a.rowvec || a.mode != 0)) return false;
@@ -864,7 +954,13 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
     mA2 = mA;
     p.tiles_m = p.tiles_x * p.tiles_y * cdiv(B, bn);
   }
-  const int num_kb = cdiv(a.K, TBK);
+  // ---- operand path: fp16-split (MODE_H16) when the engine selects it, the weights have fp16 planes and the geometry allows it
+  // (K a multiple of 32: the stage's two 32-float A sub-blocks; fp16 B rows 16-byte aligned); else TF32 planes (MODE_TS); else SS
+  const bool ts = a.Bw_hi != nullptr && a.Bw_lo != nullptr && a16(a.Bw_hi) && a16(a.Bw_lo);
+  const bool h16 = e.tc_kind >= 1 && a.Bw_h_hi && a.Bw_h_lo && a16(a.Bw_h_hi) && a16(a.Bw_h_lo) && (a.K % TBK) == 0 && (a.ldb % 8) == 0 &&
+                   (a.mode == 1 || !a.A2 || (a.C2 % TBK) == 0);
+  const int bk = h16 ? Cfg<MODE_H16>::BK : TBK;
+  const int num_kb = cdiv(a.K, bk);
   // Work partition: tile width w along N (MMA N = valid columns rounded up to 16, so a ragged last tile costs only its
   // share) and split-K factor S, chosen together against wave quantisation on num_sms persistent CTAs by replaying the
   // kernel's static schedule (CTA c runs items c, c + grid, ...) with a cost model in cycles: one k-block of a w-wide
@@ -877,7 +973,10 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
     static std::map<std::array<int64_t, 5>, int> plan_cache;      // exact key (no hashing of packed fields: nothing can collide)
     static std::mutex plan_mutex;                                          // engines on different devices may plan concurrently
     std::lock_guard<std::mutex> plan_lock(plan_mutex);
-    const std::array<int64_t, 5> key = {p.tiles_m, a.N, num_kb, ((a.geglu || a.Ct_hi) ? 1 : 0) | (a.out_nchw ? 2 : 0), e.num_sms};
+    const std::array<int64_t, 5> key = {p.tiles_m, a.N, num_kb, ((a.geglu || a.Ct_hi) ? 1 : 0) | (a.out_nchw ? 2 : 0) | (h16 ? 4 : 0), e.num_sms};
+    // cycles per pipeline stage of a w-wide tile (fitted on B200): TF32 planes 540 + 4.2 w per 32 k; fp16 split per 64 k
+    const double kc0 = h16 ? CDX_H16_KC0 : 540.0, kc1 = h16 ? CDX_H16_KC1 : 4.2;
+    const int min_kbs = h16 ? 4 : 8;
     auto it = plan_cache.find(key);
     if (it != plan_cache.end()) {
       best_w = it->second >> 8;
@@ -894,7 +993,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
         for (int S = 1; S <= 8; ++S) {
           const int kbs = cdiv(num_kb, S);
           const int Sx = cdiv(num_kb, kbs);                                  // no empty splits
-          if (S > 1 && (Sx != S || kbs < 8 || a.out_nchw || a.geglu || a.Ct_hi || (long long)p.tiles_m * tn >= 4LL * G)) continue;
+          if (S > 1 && (Sx != S || kbs < min_kbs || a.out_nchw || a.geglu || a.Ct_hi || (long long)p.tiles_m * tn >= 4LL * G)) continue;
           const long long items = (long long)p.tiles_m * tn * S;
           const int kb_last = num_kb - (S - 1) * kbs;
           double cost;
@@ -904,11 +1003,11 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
             for (long long t = 0; t < items; ++t) {                          // t -> (split fastest, then tm, then tn)
               const int sp = (int)(t % S);
               const int col = (int)((t / S / p.tiles_m) % tn);
-              load[(size_t)(t % g)] += (sp == S - 1 ? kb_last : kbs) * (540.0 + 4.2 * (col == tn - 1 ? wl : w)) + 5000.0;
+              load[(size_t)(t % g)] += (sp == S - 1 ? kb_last : kbs) * (kc0 + kc1 * (col == tn - 1 ? wl : w)) + 5000.0;
             }
             cost = *std::max_element(load.begin(), load.begin() + g);
           } else {
-            cost = (double)cdiv(items, (long long)G) * (kbs * (540.0 + 4.2 * w) + 5000.0);
+            cost = (double)cdiv(items, (long long)G) * (kbs * (kc0 + kc1 * w) + 5000.0);
           }
           if (S == 1) base = cost;
           else cost += 4000.0 + (2.0 * S + 1.0) * (double)a.M * a.N * 4.0 / 4e12 * 1.9e9;
@@ -927,10 +1026,39 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   p.total_tiles = tiles * p.splits;
   Scope ws_scope(e.arena);
   if (best_s > 1) p.ws = (float*)e.arena.alloc((size_t)p.splits * a.M * a.N * sizeof(float));
+  // fp16-split path: the A operand's range.  Tracked by its producer (a.a_amax), else measured here (one small extra launch).
+  if (h16) {
+    p.a_amax = a.a_amax;
+    p.a2_amax = a.A2 ? a.a2_amax : nullptr;
+    if (!p.a_amax) {
+      float* slot = e.amax_slot();
+      if (a.mode == 1) amax_rows(e, a.A, (long long)(a.M / (a.Hout * a.Wout)) * a.Hin * a.Win, a.C1, a.lda, slot, s);
+      else amax_rows(e, a.A, a.M, a.C1, a.lda, slot, s);
+      p.a_amax = slot;
+    }
+    if (a.A2 && !p.a2_amax) {
+      float* slot = e.amax_slot();
+      amax_rows(e, a.A2, a.M, a.C2, a.lda2, slot, s);
+      p.a2_amax = slot;
+    }
+    p.b_exp = a.b_exp;
+    p.fast = e.tc_kind == 2;
+  }
+  // side outputs fused into the epilogue: range of C always (the split-K reduce kernel covers the split case); GroupNorm
+  // statistics when every 32-row quadrant of a tile lies inside one image and the epilogue is the final one
+  p.c_amax = a.out_nchw ? nullptr : a.c_amax;
+  const bool quad_ok = a.mode == 1 ? ((p.bw * p.bh) % 32 == 0) : (a.rows_per_batch % 32 == 0);
+  p.c_stats = (a.c_stats && quad_ok && p.splits == 1 && !a.out_nchw && !a.geglu && !a.Ct_hi && !a.Cout_lo && a.ldc == a.N) ? a.c_stats : nullptr;
+  if (side_done) *side_done = (p.c_amax ? 1 : 0) | (p.c_stats ? 2 : 0);
   if (e.dry()) return true;
-  const int grid = std::min(p.total_tiles, e.num_sms);
-  const bool ts = a.Bw_hi != nullptr && a.Bw_lo != nullptr && a16(a.Bw_hi) && a16(a.Bw_lo);
-  {
+  static const int grid_cap = getenv("CDX_TC_GRID") ? atoi(getenv("CDX_TC_GRID")) : 0;      // experiment aid: run on fewer SMs
+  const int grid = std::min(p.total_tiles, grid_cap > 0 ? std::min(grid_cap, e.num_sms) : e.num_sms);
+  if (h16) {
+    uint64_t d[2] = {(uint64_t)a.K, (uint64_t)a.N}, st[1] = {(uint64_t)a.ldb * 2};
+    uint32_t bx[2] = {(uint32_t)Cfg<MODE_H16>::BK, (uint32_t)p.tn_w};
+    mB = &get_map(a.Bw_h_hi, 2, d, st, bx, nullptr, 2);
+    mBlo = &get_map(a.Bw_h_lo, 2, d, st, bx, nullptr, 2);
+  } else {
     uint64_t d[2] = {(uint64_t)a.K, (uint64_t)a.N}, st[1] = {(uint64_t)a.ldb * 4};
     uint32_t bx[2] = {TBK, (uint32_t)p.tn_w};
     mB = &get_map(ts ? a.Bw_hi : a.Bw, 2, d, st, bx);
@@ -939,16 +1067,17 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s) {
   ensure_attr(e.device);
   ProfScope ps(e, s, a.mode == 1 ? PROF_CONV_TC : PROF_DENSE_TC, 2.0 * a.M * a.N * a.K,
                4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
-  ps.note("M%d N%d K%d w%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, p.tn_w, tiles, p.splits, ts ? "TS" : "SS", a.Cout_lo ? " planes" : "", a.geglu ? " geglu" : "",
-          a.residual ? " res" : "");
-  if (ts) tc_gemm_kernel<true><<<grid, TC_THREADS, Cfg<true>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
-  else tc_gemm_kernel<false><<<grid, TC_THREADS, Cfg<false>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
+  ps.note("M%d N%d K%d w%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, p.tn_w, tiles, p.splits, h16 ? (p.fast ? "H16x1" : "H16") : ts ? "TS" : "SS",
+          a.Cout_lo ? " planes" : "", a.geglu ? " geglu" : "", a.residual ? " res" : "");
+  if (h16) tc_gemm_kernel<MODE_H16><<<grid, TC_THREADS, Cfg<MODE_H16>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
+  else if (ts) tc_gemm_kernel<MODE_TS><<<grid, TC_THREADS, Cfg<MODE_TS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
+  else tc_gemm_kernel<MODE_SS><<<grid, TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
   if (p.splits > 1) {
     const long long total4 = (long long)a.M * a.N / 4;
     const int blocks = (int)std::min<long long>((total4 + 255) / 256, (long long)e.num_sms * 8);
-    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(p.ws, p.splits, p);
+    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(p.ws, p.splits, p, h16 ? 1 : 0);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }

@@ -230,7 +230,7 @@ void assign_offsets(Net& n) {
   auto align = [&](size_t a) { off = (off + a - 1) / a * a; };
   // general segment: inventory order, 16-byte aligned starts (adjacent q/k/v weights stay contiguous)
   for (Param& p : n.params)
-    if (p.segment == 0) { align(4); p.off = off; off += p.store(); }
+    if (p.segment == 0) { align(8); p.off = off; off += p.store(); }     // 8: the fp16 planes (2 B / element) must be 16-byte aligned for TMA
   align(64);
   n.emb_w_off = off;
   for (Param& p : n.params)
@@ -336,8 +336,11 @@ void destroy_net(Net* n) {
   if (n->blob) cudaFree(n->blob);
   if (n->blob_hi) cudaFree(n->blob_hi);
   if (n->blob_lo) cudaFree(n->blob_lo);
+  if (n->blob_h_hi) cudaFree(n->blob_h_hi);
+  if (n->blob_h_lo) cudaFree(n->blob_h_lo);
   if (n->freqs_dev) cudaFree(n->freqs_dev);
   if (n->ctxkv.buf) cudaFree(n->ctxkv.buf);
+  if (n->ctxkv.amax) cudaFree(n->ctxkv.amax);
   delete n;
 }
 
@@ -392,6 +395,21 @@ void net_finalize(Net& n) {
     if (!n.blob_hi) CDX_CUDA(cudaMalloc(&n.blob_hi, n.blob_floats * sizeof(float)));
     if (!n.blob_lo) CDX_CUDA(cudaMalloc(&n.blob_lo, n.blob_floats * sizeof(float)));
     split_planes(*n.eng, n.blob, n.blob_hi, n.blob_lo, n.blob_floats, 0);
+    // fp16-split planes: one power-of-two scale per network, from the largest GEMM weight (+2 bytes x 2 per parameter)
+    {
+      float* slot = nullptr;
+      CDX_CUDA(cudaMalloc(&slot, sizeof(float)));
+      CDX_CUDA(cudaMemset(slot, 0, sizeof(float)));
+      for (const Param& p : n.params)
+        if (p.rank >= 2 && (p.store() % 4) == 0 && (p.off % 4) == 0) amax_rows(*n.eng, n.blob + p.off, 1, (int)std::min<size_t>(p.store(), (size_t)1 << 30), (long long)p.store(), slot, 0);
+      float wmax = 0.f;
+      CDX_CUDA(cudaMemcpy(&wmax, slot, sizeof(float), cudaMemcpyDeviceToHost));
+      CDX_CUDA(cudaFree(slot));
+      n.w_exp = h16_exp_host(wmax);
+      if (!n.blob_h_hi) CDX_CUDA(cudaMalloc(&n.blob_h_hi, n.blob_floats * 2));
+      if (!n.blob_h_lo) CDX_CUDA(cudaMalloc(&n.blob_h_lo, n.blob_floats * 2));
+      split_planes_h16(*n.eng, n.blob, n.blob_h_hi, n.blob_h_lo, n.blob_floats, n.w_exp, 0);
+    }
     CDX_CUDA(cudaDeviceSynchronize());
     n.planes_valid = true;
   }
@@ -415,8 +433,23 @@ struct Exec {
       const size_t off = (size_t)(g.Bw - n.blob);
       g.Bw_hi = n.blob_hi + off;
       g.Bw_lo = n.blob_lo + off;
+      g.Bw_h_hi = (const char*)n.blob_h_hi + 2 * off;
+      g.Bw_h_lo = (const char*)n.blob_h_lo + 2 * off;
+      g.b_exp = n.w_exp;
     }
     gemm(e, g, s);
+  }
+
+  // side outputs of a GEMM that writes tensor t: its range (for a consumer fp16-split GEMM) and, optionally, its per-(image,
+  // channel) sums (for a consumer GroupNorm) -- both produced by the epilogue that holds the tile in registers
+  void track(Tensor& t, GemmArgs& g, bool stats) {
+    t.amax = e.amax_slot();
+    g.c_amax = t.amax;
+    if (stats) {
+      t.stats = e.stat_alloc((size_t)t.B * t.C * 2);
+      g.c_stats = t.stats;
+      g.rows_per_batch = t.H * t.W;
+    }
   }
 
   // y = conv3x3(x [, x2 concat]) + bias (+ rowvec per sample) (+ residual); up: nearest-2x folded into the gather
@@ -429,6 +462,7 @@ struct Exec {
     if (w.cin_pad && x0.C != w.cin_pad) {          // few-channel network inputs: zero-pad to the stored Cin (one small pass)
       x = alloc(x0.B, x0.H, x0.W, w.cin_pad);
       pad_channels(e, x0.p, x.p, (size_t)x0.rows(), x0.C, w.cin_pad, s);
+      x.amax = x0.amax;                            // zero padding does not change the range
     }
     const int Cin = x.C;
     if (up == 2 && e.mma_mode == 1 && (Cin % 32) == 0 && !out_nchw) {
@@ -436,6 +470,7 @@ struct Exec {
       // (one extra write+read of the activation, <2% of the conv's time) and run the plain tensor-core conv on it
       Tensor xu = alloc(x.B, x.H * 2, x.W * 2, x.C);
       upsample2(e, x.p, xu.p, x.B, x.H, x.W, x.C, s);
+      xu.amax = x.amax;
       return conv3(xu, name, stride, pad, 1, rowvec, ld_rowvec, residual, out_nchw);
     }
     const int Hl = x.H * up, Wl = x.W * up;
@@ -456,15 +491,20 @@ struct Exec {
     g.rowvec = rowvec; g.ld_rowvec = ld_rowvec; g.rows_per_batch = Ho * Wo;
     g.residual = residual; g.ldr = Cout;
     if (out_nchw) { g.out_nchw = 1; g.rows_per_img = Ho * Wo; }
+    else track(y, g, true);
+    g.a_amax = x.amax;
     run(g);
     return y;
   }
 
   // y[M,N] = x[M,K] (optionally [x | x2]) @ W[N,K]^T (+bias) (+residual)
   void linear_into(const float* x, int lda, int C1, const float* x2, int lda2, int C2, int M, const float* W, int N, const float* bias,
-                   const float* residual, int ldr, float* y, int ldc, float* y_lo = nullptr) {
+                   const float* residual, int ldr, float* y, int ldc, float* y_lo = nullptr, const float* a_amax = nullptr,
+                   const float* a2_amax = nullptr, float* c_amax = nullptr, double* c_stats = nullptr, int rows_per_img = 0) {
     GemmArgs g;
     g.mode = 0;
+    g.a_amax = a_amax; g.a2_amax = a2_amax; g.c_amax = c_amax; g.c_stats = c_stats;
+    if (rows_per_img > 0) g.rows_per_batch = rows_per_img;
     g.Cout_lo = y_lo;            // if set: y / y_lo receive the TF32 hi / lo planes of the result
     g.M = M; g.N = N; g.K = C1 + C2;
     g.A = x; g.lda = lda; g.C1 = C1;
@@ -476,12 +516,16 @@ struct Exec {
     run(g);
   }
   // single-source convenience: named weight [N,K(,1,1)], optional named bias
-  Tensor linear(const Tensor& x, const std::string& name, bool bias, const float* residual = nullptr) {
+  // track: the result's range is recorded (it is the A operand of a later GEMM); stats: also its GroupNorm sums
+  Tensor linear(const Tensor& x, const std::string& name, bool bias, const float* residual = nullptr, bool track_amax = false, bool stats = false) {
     const Param& w = n.param(name + ".weight");
     const int N = (int)w.dims[0], K = (int)w.dims[1];
     CDX_CHECK(K == x.C, "linear %s: input width %d, weight expects %d", name.c_str(), x.C, K);
     Tensor y = alloc(x.B, x.H, x.W, N);
-    linear_into(x.p, x.C, x.C, nullptr, 0, 0, x.rows(), n.blob + w.off, N, bias ? n.P(name + ".bias") : nullptr, residual, N, y.p, N);
+    if (track_amax || stats) y.amax = e.amax_slot();
+    if (stats) y.stats = e.stat_alloc((size_t)y.B * N * 2);
+    linear_into(x.p, x.C, x.C, nullptr, 0, 0, x.rows(), n.blob + w.off, N, bias ? n.P(name + ".bias") : nullptr, residual, N, y.p, N, nullptr, x.amax,
+                nullptr, y.amax, y.stats, x.H * x.W);
     return y;
   }
 
@@ -489,13 +533,15 @@ struct Exec {
             const float* shift = nullptr, int ld_ss = 0) {
     const int C = x.C + (x2 ? x2->C : 0);
     Tensor y = alloc(x.B, x.H, x.W, C);
+    y.amax = e.amax_slot();
     groupnorm(e, x.p, x.C, x2 ? x2->p : nullptr, x2 ? x2->C : 0, n.P(name + ".weight"), n.P(name + ".bias"), eps, act, scale, shift, ld_ss,
-              y.p, x.B, x.H * x.W, s);
+              y.p, x.B, x.H * x.W, s, x.stats, x2 ? x2->stats : nullptr, y.amax);
     return y;
   }
   Tensor ln(const Tensor& x, const std::string& name) {
     Tensor y = alloc(x.B, x.H, x.W, x.C);
-    layernorm(e, x.p, n.P(name + ".weight"), n.P(name + ".bias"), y.p, x.rows(), x.C, s);
+    y.amax = e.amax_slot();
+    layernorm(e, x.p, n.P(name + ".weight"), n.P(name + ".bias"), y.p, x.rows(), x.C, s, y.amax);
     return y;
   }
 };
@@ -516,6 +562,15 @@ struct UNetExec : Exec {
     CDX_CHECK(kv_off <= n.ctxkv.cap, "context K/V cache overflow (%zu > %zu floats)", kv_off, n.ctxkv.cap);
     return p;
   }
+  // range slots: of the context itself (A operand of the K / V projections) and of each layer's V (bounds the attention output).
+  // In loop mode the projections run only in the first call, so their slots live with the cached K / V, outside the per-call pool.
+  float* ctx_amax = nullptr;
+  int kv_layer = 0;
+  float* kv_amax() {
+    if (!kv_reuse) return e.amax_slot();
+    CDX_CHECK(kv_layer < Net::CtxKV::MAX_LAYERS, "too many cross-attention layers for the context cache");
+    return e.dry() ? reinterpret_cast<float*>((uintptr_t)0x100) : n.ctxkv.amax + 1 + kv_layer++;
+  }
   bool oai;
   UNetExec(Net& net, cudaStream_t st) : Exec(net, st), oai(net.kind == NET_UNET_OPENAI) {}
 
@@ -534,13 +589,16 @@ struct UNetExec : Exec {
       CDX_CHECK(!x2, "res down with concat input");
       Tensor hp = alloc(x.B, oH, oW, x.C);
       avgpool2(e, h1.p, hp.p, x.B, x.H, x.W, x.C, s);
+      hp.amax = h1.amax;                                         // |average| <= max
       xs = alloc(x.B, oH, oW, x.C);
       avgpool2(e, x.p, xs.p, x.B, x.H, x.W, x.C, s);
+      xs.amax = x.amax;
       h2 = conv3(hp, p + ".in_layers.2");
     } else if (updown == 2) {
       CDX_CHECK(!x2, "res up with concat input");
       xs = alloc(x.B, oH, oW, x.C);
       upsample2(e, x.p, xs.p, x.B, x.H, x.W, x.C, s);
+      xs.amax = x.amax;
       h2 = conv3(h1, p + ".in_layers.2", 1, 1, 2);
     } else if (oai) {
       h2 = conv3(h1, p + ".in_layers.2", 1, 1, 1, E + eoff, n.emb_rows);     // + emb_out (OAI:273)
@@ -554,7 +612,7 @@ struct UNetExec : Exec {
     if (n.has(p + ".skip_connection.weight")) {
       Tensor sk = alloc(x.B, oH, oW, Cout);
       linear_into(xs.p, xs.C, xs.C, x2 ? x2->p : nullptr, x2 ? x2->C : 0, x2 ? x2->C : 0, xs.rows(), n.P(p + ".skip_connection.weight"), Cout,
-                  n.P(p + ".skip_connection.bias"), nullptr, 0, sk.p, Cout);
+                  n.P(p + ".skip_connection.bias"), nullptr, 0, sk.p, Cout, nullptr, xs.amax, x2 ? x2->amax : nullptr);
       residual = sk.p;
     } else {
       CDX_CHECK(!x2 && xs.C == Cout, "resblock %s: identity skip with mismatching channels", p.c_str());
@@ -572,6 +630,8 @@ struct UNetExec : Exec {
       g.Cout = out.p; g.ldc = Cout;
       g.bias = n.P(p + ".out_layers.3.bias");
       g.residual = residual; g.ldr = Cout;
+      g.a_amax = h3.amax;
+      track(out, g, true);
       run(g);
     }
     return out;
@@ -592,6 +652,7 @@ struct UNetExec : Exec {
     {
       Tensor n1 = ln(h, t + ".norm1");
       Tensor a = alloc(B, x.H, x.W, C);
+      a.amax = e.amax_slot();                   // <- max |V| (written by whichever projection produces V)
       bool done = false;
       const bool flash_ok = e.mma_mode == 1 && e.flash_attn && (HW % 128) == 0 && (d == 16 || d == 32 || d == 40 || d == 64 || d == 80);
       if (flash_ok) {
@@ -614,10 +675,13 @@ struct UNetExec : Exec {
           g.Bw = n.P(t + ".attn1.to_q.weight"); g.ldb = C;
           g.Cout = qk_hi; g.ldc = 2 * C; g.Cout_lo = qk_lo;
           g.Ct_hi = vt_hi; g.Ct_lo = vt_lo; g.t_col0 = 2 * C; g.ldt = M;
+          g.a_amax = n1.amax;
+          g.c_amax = a.amax;                    // range of q | k | v: bounds the attention output (a convex combination of V rows)
           run(g);
         } else {
-          linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 2 * C, nullptr, nullptr, 0, qk_hi, 2 * C, qk_lo);
-          linear_into(n.P(t + ".attn1.to_v.weight"), C, C, nullptr, 0, 0, C, n1.p, M, nullptr, nullptr, 0, vt_hi, M, vt_lo);   // V^T = Wv . X^T
+          linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 2 * C, nullptr, nullptr, 0, qk_hi, 2 * C, qk_lo, n1.amax);
+          linear_into(n.P(t + ".attn1.to_v.weight"), C, C, nullptr, 0, 0, C, n1.p, M, nullptr, nullptr, 0, vt_hi, M, vt_lo, nullptr, nullptr,
+                      a.amax);   // V^T = Wv . X^T
         }
         done = flash_attention_tc(e, qk_hi, qk_lo, 2 * C, qk_hi + C, qk_lo + C, 2 * C, vt_hi, vt_lo, a.p, C, B, HW, HW, HW, heads, d, scale, s);
         CDX_CHECK(done, "flash attention rejected an eligible shape (HW=%d d=%d)", HW, d);
@@ -625,15 +689,16 @@ struct UNetExec : Exec {
         // unfused tensor-core attention (mode 2, or shapes the fused kernel does not cover)
         Scope sa(e.arena);
         Tensor qk = alloc(B, x.H, x.W, 2 * C);
-        linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 2 * C, nullptr, nullptr, 0, qk.p, 2 * C);
+        linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 2 * C, nullptr, nullptr, 0, qk.p, 2 * C, nullptr, n1.amax);
         float* vt = (float*)e.arena.alloc((size_t)C * M * sizeof(float));
-        linear_into(n.P(t + ".attn1.to_v.weight"), C, C, nullptr, 0, 0, C, n1.p, M, nullptr, nullptr, 0, vt, M);
+        linear_into(n.P(t + ".attn1.to_v.weight"), C, C, nullptr, 0, 0, C, n1.p, M, nullptr, nullptr, 0, vt, M, nullptr, nullptr, nullptr, a.amax);
         done = attention_tc(e, qk.p, 2 * C, qk.p + C, 2 * C, d, vt, a.p, C, B, HW, HW, heads, d, scale, s);
       }
       if (!done) {
         Scope sa(e.arena);
         Tensor qkv = alloc(B, x.H, x.W, 3 * C);
-        linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 3 * C, nullptr, nullptr, 0, qkv.p, 3 * C);
+        linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 3 * C, nullptr, nullptr, 0, qkv.p, 3 * C, nullptr, n1.amax, nullptr,
+                    a.amax);
         attention(e, qkv.p, 3 * C, qkv.p + C, 3 * C, qkv.p + 2 * C, 3 * C, a.p, C, B, HW, HW, heads, d, d, scale, s);
       }
       h2 = linear(a, t + ".attn1.to_out.0", true, h.p);
@@ -644,6 +709,7 @@ struct UNetExec : Exec {
       Tensor n2 = ln(h2, t + ".norm2");
       const int D = n.ucfg.context_dim;
       Tensor a = alloc(B, x.H, x.W, C);
+      a.amax = kv_amax();                       // <- max |V| of the context projection (lives with the cached K / V in loop mode)
       bool done = false;
       Tensor q;
       if (ctx_pad && (HW % 128) == 0 && (d == 16 || d == 32 || d == 40 || d == 64 || d == 80)) {
@@ -658,10 +724,11 @@ struct UNetExec : Exec {
         float* vt_lo = kv_take(nk);
         float* q_hi = (float*)e.arena.alloc(nq * sizeof(float));
         float* q_lo = (float*)e.arena.alloc(nq * sizeof(float));
-        linear_into(n2.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn2.to_q.weight"), C, nullptr, nullptr, 0, q_hi, C, q_lo);
+        linear_into(n2.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn2.to_q.weight"), C, nullptr, nullptr, 0, q_hi, C, q_lo, n2.amax);
         if (!kv_hit) {
-          linear_into(ctx_pad, D, D, nullptr, 0, 0, Mk, n.P(t + ".attn2.to_k.weight"), C, nullptr, nullptr, 0, k_hi, C, k_lo);
-          linear_into(n.P(t + ".attn2.to_v.weight"), D, D, nullptr, 0, 0, C, ctx_pad, Mk, nullptr, nullptr, 0, vt_hi, Mk, vt_lo);
+          linear_into(ctx_pad, D, D, nullptr, 0, 0, Mk, n.P(t + ".attn2.to_k.weight"), C, nullptr, nullptr, 0, k_hi, C, k_lo, ctx_amax);
+          linear_into(n.P(t + ".attn2.to_v.weight"), D, D, nullptr, 0, 0, C, ctx_pad, Mk, nullptr, nullptr, 0, vt_hi, Mk, vt_lo, nullptr, nullptr,
+                      a.amax);
         }
         done = flash_attention_tc(e, q_hi, q_lo, C, k_hi, k_lo, C, vt_hi, vt_lo, a.p, C, B, HW, ctx_len, ctx_lp, heads, d, scale, s);
         CDX_CHECK(done, "flash cross-attention rejected an eligible shape (HW=%d d=%d L=%d)", HW, d, ctx_len);
@@ -670,7 +737,8 @@ struct UNetExec : Exec {
       if (!done) {
         Scope sa(e.arena);
         float* kv = kv_take((size_t)B * ctx_len * 2 * C);
-        if (!kv_hit) linear_into(ctx, D, D, nullptr, 0, 0, B * ctx_len, n.P(t + ".attn2.to_k.weight"), 2 * C, nullptr, nullptr, 0, kv, 2 * C);
+        if (!kv_hit) linear_into(ctx, D, D, nullptr, 0, 0, B * ctx_len, n.P(t + ".attn2.to_k.weight"), 2 * C, nullptr, nullptr, 0, kv, 2 * C, nullptr,
+                                 ctx_amax, nullptr, a.amax);
         attention(e, q.p, C, kv, 2 * C, kv + C, 2 * C, a.p, C, B, HW, ctx_len, heads, d, d, scale, s);
       }
       h3 = linear(a, t + ".attn2.to_out.0", true, h2.p);
@@ -690,14 +758,20 @@ struct UNetExec : Exec {
         ga.bias = n.P(t + ".ff.net.0.proj.bias");
         ga.geglu = 1;
         ga.Cout = g.p; ga.ldc = 4 * C;
+        ga.a_amax = n3.amax;
+        g.amax = e.amax_slot();
+        ga.c_amax = g.amax;
         run(ga);
       } else {
         Tensor f = linear(n3, t + ".ff.net.0.proj", true);
-        geglu(e, f.p, g.p, M, 4 * C, s);
+        geglu(e, f.p, g.p, M, 4 * C, s);        // (range of g not tracked here: the consumer measures it)
       }
-      h4 = linear(g, t + ".ff.net.2", true, h3.p);
+      h4 = linear(g, t + ".ff.net.2", true, h3.p, true);
     }
-    linear_into(h4.p, C, C, nullptr, 0, 0, M, n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C);
+    out.amax = e.amax_slot();
+    out.stats = e.stat_alloc((size_t)B * C * 2);
+    linear_into(h4.p, C, C, nullptr, 0, 0, M, n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C, nullptr, h4.amax, nullptr,
+                out.amax, out.stats, HW);
     return out;
   }
 
@@ -709,11 +783,17 @@ struct UNetExec : Exec {
     Scope sc(e.arena);
     Tensor xn = gn(x, nullptr, p + ".norm", 1e-5f, false);
     Tensor qkv = alloc(B, x.H, x.W, 3 * C);
-    linear_into(xn.p, C, C, nullptr, 0, 0, M, n.P(p + ".qkv.weight"), 3 * C, n.P(p + ".qkv.bias"), nullptr, 0, qkv.p, 3 * C);
+    qkv.amax = e.amax_slot();
+    linear_into(xn.p, C, C, nullptr, 0, 0, M, n.P(p + ".qkv.weight"), 3 * C, n.P(p + ".qkv.bias"), nullptr, 0, qkv.p, 3 * C, nullptr, xn.amax, nullptr,
+                qkv.amax);
     const float sq = (float)(1.0 / sqrt(sqrt((double)d)));
     Tensor a = alloc(B, x.H, x.W, C);
     attention(e, qkv.p, 3 * C, qkv.p + d, 3 * C, qkv.p + 2 * d, 3 * C, a.p, C, B, HW, HW, heads, d, 3 * d, sq * sq, s);
-    linear_into(a.p, C, C, nullptr, 0, 0, M, n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C);
+    out.amax = e.amax_slot();
+    out.stats = e.stat_alloc((size_t)B * C * 2);
+    // |attention output| <= max |V| <= max |qkv|
+    linear_into(a.p, C, C, nullptr, 0, 0, M, n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C, nullptr, qkv.amax, nullptr,
+                out.amax, out.stats, HW);
     return out;
   }
 
@@ -727,6 +807,7 @@ struct UNetExec : Exec {
     ctx_lp = (L + 3) & ~3;
     const int mc = c.model_channels, half = mc / 2, ted = n.ted;
     Scope top(e.arena);
+    e.pools_reset(s);
     kv_off = 0;
     kv_hit = false;
     if (kv_reuse && context && L > 0) {
@@ -743,6 +824,17 @@ struct UNetExec : Exec {
         kc.cap = need;
       }
       kv_hit = kc.valid && kc.ctx == context && kc.L == L && kc.B == B && !e.dry();
+      if (!kc.amax) {
+        CDX_CUDA(cudaMalloc(&kc.amax, (Net::CtxKV::MAX_LAYERS + 1) * sizeof(float)));
+        CDX_CUDA(cudaMemset(kc.amax, 0, (Net::CtxKV::MAX_LAYERS + 1) * sizeof(float)));
+      }
+      if (!kv_hit && !e.dry()) CDX_CUDA(cudaMemsetAsync(kc.amax, 0, (Net::CtxKV::MAX_LAYERS + 1) * sizeof(float), s));
+    }
+    kv_layer = 0;
+    if (context && L > 0) {
+      // range of the context (A operand of the K / V projections; measured once per loop)
+      ctx_amax = kv_reuse ? (e.dry() ? reinterpret_cast<float*>((uintptr_t)0x100) : n.ctxkv.amax) : e.amax_slot();
+      if (!kv_hit) amax_rows(e, context, (long long)B * L, c.context_dim, c.context_dim, ctx_amax, s);
     }
     if (context && L > 0 && e.mma_mode == 1 && e.flash_attn) {
       // context rows padded to a multiple of 4 per image: TMA needs 16-byte strides for K and V^T of the cross-attention
@@ -840,6 +932,8 @@ struct VaeExec : Exec {
     g.Cout = out.p; g.ldc = Cout;
     g.bias = n.P(p + ".conv2.bias");
     g.residual = residual; g.ldr = Cout;
+    g.a_amax = h3.amax;
+    track(out, g, true);
     run(g);
     return out;
   }
@@ -852,8 +946,9 @@ struct VaeExec : Exec {
     Tensor xn = gn(x, nullptr, p + ".norm", 1e-6f, false);
     Tensor q = linear(xn, p + ".q", true);
     Tensor k = linear(xn, p + ".k", true);
-    Tensor v = linear(xn, p + ".v", true);
+    Tensor v = linear(xn, p + ".v", true, nullptr, true);       // its range bounds the attention output
     Tensor a = alloc(x.B, x.H, x.W, C);
+    a.amax = v.amax;
     const float scale = (float)pow((double)C, -0.5);
     bool done = false;
     if (e.mma_mode == 1 && (HW % 32) == 0 && HW >= 128) {
@@ -864,13 +959,17 @@ struct VaeExec : Exec {
       done = attention_tc(e, q.p, C, k.p, C, C, vt, a.p, C, x.B, HW, HW, 1, C, scale, s);
     }
     if (!done) attention(e, q.p, C, k.p, C, v.p, C, a.p, C, x.B, HW, HW, 1, C, C, scale, s);
-    linear_into(a.p, C, C, nullptr, 0, 0, x.rows(), n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C);
+    out.amax = e.amax_slot();
+    out.stats = e.stat_alloc((size_t)x.B * C * 2);
+    linear_into(a.p, C, C, nullptr, 0, 0, x.rows(), n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C, nullptr, v.amax, nullptr,
+                out.amax, out.stats, HW);
     return out;
   }
 
   void encode(const float* img_nchw, float* moments_nchw, int B, int R) {
     const cdx_vae_config& c = n.vcfg;
     Scope top(e.arena);
+    e.pools_reset(s);
     const std::string E = "encoder.";
     Tensor xin = alloc(B, R, R, c.in_channels);
     nchw_to_nhwc(e, img_nchw, xin.p, B, c.in_channels, R * R, s);
@@ -891,6 +990,7 @@ struct VaeExec : Exec {
   void decode(const float* z_nchw, float* img_nchw, int B, int hsz) {
     const cdx_vae_config& c = n.vcfg;
     Scope top(e.arena);
+    e.pools_reset(s);
     const std::string D = "decoder.";
     Tensor zin = alloc(B, hsz, hsz, c.embed_dim);
     nchw_to_nhwc(e, z_nchw, zin.p, B, c.embed_dim, hsz * hsz, s);
@@ -934,6 +1034,7 @@ void text_encode(Net& n, const int* ids, float* out, int B, int L, cudaStream_t 
   CDX_CHECK(L >= 1 && L <= c.max_len, "text_encode: %d tokens, the position table has %d", L, c.max_len);
   Exec ex(n, s);
   Engine& e = *n.eng;
+  e.pools_reset(s);
   if (c.kind == CDX_TEXT_XTRANSFORMER) {
     // TransformerWrapper.forward(return_embeddings=True) (x_transformer.py:598-626) over AttentionLayers.forward (481-523):
     // x = tok + pos; per layer x += to_out(softmax(q k^T d^-1/2) v) of LN(x), x += W2 gelu(W1 LN(x)); final LN
@@ -951,15 +1052,16 @@ void text_encode(Net& n, const int* ids, float* out, int B, int L, cudaStream_t 
         Tensor n1 = ex.ln(x, pa + ".0");
         Tensor q = ex.linear(n1, pa + ".1.to_q", false);
         Tensor k = ex.linear(n1, pa + ".1.to_k", false);
-        Tensor v = ex.linear(n1, pa + ".1.to_v", false);
+        Tensor v = ex.linear(n1, pa + ".1.to_v", false, nullptr, true);
         Tensor a = ex.alloc(B, L, 1, inner);
+        a.amax = v.amax;                              // |softmax-weighted mean of V rows| <= max |V|
         attention(e, q.p, inner, k.p, inner, v.p, inner, a.p, inner, B, L, L, c.heads, c.dim_head, c.dim_head, scale, s, false);
         Tensor h = ex.linear(a, pa + ".1.to_out", true, x.p);                         // + residual
         Tensor n2 = ex.ln(h, pf + ".0");
-        Tensor f = ex.linear(n2, pf + ".1.net.0.0", true);
-        gelu(e, f.p, f.p, f.numel(), s);
+        Tensor f = ex.linear(n2, pf + ".1.net.0.0", true, nullptr, true);
+        gelu(e, f.p, f.p, f.numel(), s);                 // |gelu(x)| <= |x|: the tracked range stays valid
         const Param& w2 = n.param(pf + ".1.net.2.weight");
-        ex.linear_into(f.p, c.mlp_width, c.mlp_width, nullptr, 0, 0, B * L, n.blob + w2.off, W, n.P(pf + ".1.net.2.bias"), h.p, W, y.p, W);
+        ex.linear_into(f.p, c.mlp_width, c.mlp_width, nullptr, 0, 0, B * L, n.blob + w2.off, W, n.P(pf + ".1.net.2.bias"), h.p, W, y.p, W, nullptr, f.amax);
       }
       x = y;
     }
@@ -980,15 +1082,16 @@ void text_encode(Net& n, const int* ids, float* out, int B, int L, cudaStream_t 
       Tensor n1 = ex.ln(x, p + ".layer_norm1");
       Tensor q = ex.linear(n1, p + ".self_attn.q_proj", true);
       Tensor k = ex.linear(n1, p + ".self_attn.k_proj", true);
-      Tensor v = ex.linear(n1, p + ".self_attn.v_proj", true);
+      Tensor v = ex.linear(n1, p + ".self_attn.v_proj", true, nullptr, true);
       Tensor a = ex.alloc(B, L, 1, W);
+      a.amax = v.amax;
       attention(e, q.p, W, k.p, W, v.p, W, a.p, W, B, L, L, c.heads, d, d, scale, s, true);
       Tensor h = ex.linear(a, p + ".self_attn.out_proj", true, x.p);                 // + residual
       Tensor n2 = ex.ln(h, p + ".layer_norm2");
-      Tensor f = ex.linear(n2, p + ".mlp.fc1", true);
-      quick_gelu(e, f.p, f.p, f.numel(), s);
+      Tensor f = ex.linear(n2, p + ".mlp.fc1", true, nullptr, true);
+      quick_gelu(e, f.p, f.p, f.numel(), s);           // |x sigmoid(1.702 x)| <= |x|
       const Param& w2 = n.param(p + ".mlp.fc2.weight");
-      ex.linear_into(f.p, c.mlp_width, c.mlp_width, nullptr, 0, 0, B * L, n.blob + w2.off, W, n.P(p + ".mlp.fc2.bias"), h.p, W, y.p, W);
+      ex.linear_into(f.p, c.mlp_width, c.mlp_width, nullptr, 0, 0, B * L, n.blob + w2.off, W, n.P(p + ".mlp.fc2.bias"), h.p, W, y.p, W, nullptr, f.amax);
     }
     x = y;
   }

@@ -36,6 +36,11 @@ struct Net {
   float* blob_hi = nullptr;     // rn_tf32(blob)            } pre-split planes for the tcgen05 TS kernel,
   float* blob_lo = nullptr;     // rn_tf32(blob - blob_hi)  } same offsets as `blob`, derived at finalize
   bool planes_valid = false;
+  // fp16-split planes (MODE_H16): hi = fp16(w * 2^w_exp), lo = fp16(w * 2^w_exp - hi), element index = float index into `blob`;
+  // w_exp from the largest |weight| of the GEMM operands (rank >= 2 parameters) so that every scaled weight is < 2^15
+  void* blob_h_hi = nullptr;
+  void* blob_h_lo = nullptr;
+  int w_exp = 0;
   size_t blob_floats = 0;
   bool finalized = false;
   // timestep embedding
@@ -43,7 +48,11 @@ struct Net {
   float* freqs_dev = nullptr;
   // cross-attention K / V of a context that stays fixed over a sampling loop (set up by the loop drivers in cabi.cu):
   // computed by the first U-Net call of the loop, reused by the others (the reference recomputes them every step)
-  struct CtxKV { bool valid = false; const float* ctx = nullptr; int L = 0, B = 0; float* buf = nullptr; size_t cap = 0; } ctxkv;
+  struct CtxKV {
+    static constexpr int MAX_LAYERS = 63;
+    bool valid = false; const float* ctx = nullptr; int L = 0, B = 0; float* buf = nullptr; size_t cap = 0;
+    float* amax = nullptr;     // [0]: max |context|, [1 + layer]: max |V| of that layer's context projection (device)
+  } ctxkv;
   // concatenated ResBlock emb projections: weights [emb_rows][ted] at emb_w_off, biases at emb_b_off
   size_t emb_w_off = 0, emb_b_off = 0;
   int emb_rows = 0, ted = 0;

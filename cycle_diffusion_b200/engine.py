@@ -361,6 +361,24 @@ class UNet(Net):
                                     sched.t_array(), sched.refine_steps, _ptr(extra_noise), _ptr(out), B, Cc, h, w, e.stream))
         return out
 
+    def cycle_lockstep(self, x0, c_src, c_tgt, uc, src_scale, tgt_scale, sched, noise, return_z=False):
+        """Both chains in one loop (one U-Net call + one fused elementwise kernel per step, no z buffer unless asked for):
+        x0 [B,C,h,w] -> translated latent [B,C,h,w] (and z [B, n+1, C,h,w] when return_z).  noise as for latent_encode with
+        n_rec == sched.refine_steps."""
+        e = self.engine
+        x0, c_src, c_tgt, noise = (_f32c(t, e.device) for t in (x0, c_src, c_tgt, noise))
+        uc = _f32c(uc, e.device) if uc is not None else None
+        B, Cc, h, w = x0.shape
+        n = sched.refine_steps
+        assert noise.shape == (n + 1, B, Cc, h, w), f'noise shape {tuple(noise.shape)}'
+        assert c_src.shape == c_tgt.shape
+        out = e.empty(B, Cc, h, w)
+        z = e.empty(B, n + 1, Cc, h, w) if return_z else None
+        check(lib.cdx_cycle_lockstep(self.h, _ptr(x0), _ptr(c_src), _ptr(c_tgt), _ptr(uc), c_src.shape[1], float(src_scale), float(tgt_scale),
+                                     sched.coef_array(), sched.t_array(), n, _ptr(noise), sched.sqrt_a_T, sched.sqrt_1ma_T, _ptr(out), _ptr(z),
+                                     B, Cc, h, w, e.stream))
+        return (out, z) if return_z else out
+
     def pixel_encode(self, x0, sched, noise):
         e = self.engine
         x0, noise = _f32c(x0, e.device), _f32c(noise, e.device)

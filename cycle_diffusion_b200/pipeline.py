@@ -4,9 +4,11 @@ The Diffusers pipeline is NOT part of /root/reference and diffusers is not insta
 *unpinned* (SURVEY.md 8b); the argument list follows diffusers <= 0.2x from the survey.  Semantics are mapped onto the
 reference's sampler: ``strength`` -> ``skip_steps = S - int(S * strength)`` (ddim.py:470), DDIMScheduler ``steps_offset=1``
 == the ``+1`` of util.py:58, ``posterior_sample`` == sample_xt_next (ddim.py:582-601), ``compute_noise`` == compute_eps
-(ddim.py:575-579).  The encode (source prompt, source_guidance_scale) and decode (prompt, guidance_scale) chains are the
-two-phase driver (API-faithful ``encode`` -> z -> ``forward(z)``), which is numerically the same computation as the
-pipeline's lock-step loop because the decode chain only consumes the recovered noise.
+(ddim.py:575-579).  The loop is the engine's lock-step driver (``cdx_cycle_lockstep``): the source chain (source prompt,
+source_guidance_scale) and the target chain (prompt, guidance_scale) advance together, one U-Net call per step on the batch
+[source segments | target segments] and one fused elementwise kernel that recovers the step's noise and consumes it at once --
+no ``z`` buffer exists.  ``two_phase=True`` runs the reference wrapper's encode -> z -> decode instead (same result per sample
+up to split-K summation order; tests/test_cycle_gpu.py compares the two).
 """
 from dataclasses import dataclass
 
@@ -34,7 +36,7 @@ class CycleDiffusionPipeline:
     @torch.no_grad()
     def __call__(self, prompt, source_prompt, image=None, strength=0.8, num_inference_steps=50, guidance_scale=7.5,
                  source_guidance_scale=1, num_images_per_prompt=1, eta=0.1, generator=None, prompt_embeds=None, output_type='pt',
-                 return_dict=True, callback=None, callback_steps=1, cross_attention_kwargs=None, clip_skip=None):
+                 return_dict=True, callback=None, callback_steps=1, cross_attention_kwargs=None, clip_skip=None, two_phase=False):
         if strength < 0 or strength > 1:
             raise ValueError(f'The value of strength should in [0.0, 1.0] but is {strength}')
         if not isinstance(callback_steps, int) or callback_steps <= 0:
@@ -68,8 +70,11 @@ class CycleDiffusionPipeline:
         for i in range(n_rec):
             if sched.refine_steps - 1 - i != 0:
                 noise[1 + i] = rnd(lat_shape)
-        z = g.unet.latent_encode(x0, c_src, uc, source_guidance_scale, sched, n_rec, noise)
-        latents = g.unet.latent_decode(z, c_tgt, uc, guidance_scale, sched)
+        if two_phase:
+            z = g.unet.latent_encode(x0, c_src, uc, source_guidance_scale, sched, n_rec, noise)
+            latents = g.unet.latent_decode(z, c_tgt, uc, guidance_scale, sched)
+        else:
+            latents = g.unet.cycle_lockstep(x0, c_src, c_tgt, uc, source_guidance_scale, guidance_scale, sched, noise)
         if callback is not None:
             callback(n_rec - 1, sched.t_loop[-1], latents)
         img = e.shift_scale(g.decode_first_stage(latents), 1.0, 0.5).clamp(0, 1)

@@ -62,7 +62,14 @@ uint64_t cdx_engine_launch_count(const cdx_engine* e);
 #define CDX_PROF_NTAGS 10
 int cdx_engine_profile(cdx_engine* e, int enable);
 int cdx_engine_profile_read(cdx_engine* e, int tag, double* ms, double* flops, double* bytes, uint64_t* launches);
-/* select the dense-contraction path: 0 = SIMT fp32 FFMA tiles, 1 = tcgen05 3xTF32 split (fp32-faithful) */
+/* select the dense-contraction path:
+ *   0 = SIMT fp32 FFMA tiles (exact fp32)
+ *   1 = tcgen05, fp32-faithful split products (default): weight GEMMs / convs as 3 x kind::f16 over an fp16 hi/lo split of
+ *       power-of-two-scaled operands, attention and activation x activation contractions as 3 x kind::tf32
+ *   2 = as 1 but attention unfused (A/B comparisons)
+ *   3 = as 1 with every contraction as 3 x kind::tf32 (the round-1 scheme)
+ *   4 = FAST PATH, not fp32-faithful: weight GEMMs / convs with the hi*hi term only (plain fp16 inputs, fp32 accumulate);
+ *       reported separately by bench.py together with its measured |delta pixel| */
 int cdx_engine_set_mma_mode(cdx_engine* e, int mode);
 
 /* ---------------------------------------------------------------- networks ----------------- */
@@ -235,6 +242,19 @@ int cdx_latent_decode(cdx_net* unet, const float* z, int n_eps, const float* c, 
                       int ctx_len, float scale, const cdx_ddim_coef* coef, const float* t_host,
                       int n_steps, const float* extra_noise, float* x_out, int B, int C, int h, int w,
                       void* stream);
+/* Both chains in lock-step (the loop shape of Diffusers' CycleDiffusionPipeline.__call__): the source chain
+ * of _ddpm_ddim_encoding (ddim.py:450-501) under c_src / src_scale and the target chain of ddim_sampling_with_eps (ddim.py:395-448)
+ * under c_tgt / tgt_scale advance together, ONE U-Net call per step on the batch [source segments | target segments] (B rows per
+ * segment; a chain contributes [uncond, cond] when its scale is neither 0 nor 1), and the noise recovered at step i is consumed by the
+ * target chain inside the same fused elementwise kernel: no z buffer.  Requires all n_steps noises to be recoverable
+ * (white_box_steps > custom_steps - skip); noise [n_steps+1, B,C,h,w] as for cdx_latent_encode.  z_out (optional, may be NULL)
+ * receives [B, n_steps+1, C,h,w] exactly as cdx_latent_encode would produce it.  Per-sample results equal the two-phase
+ * cdx_latent_encode + cdx_latent_decode up to the summation order of split-K GEMMs (the batch size differs). */
+int cdx_cycle_lockstep(cdx_net* unet, const float* x0, const float* c_src, const float* c_tgt, const float* uc,
+                       int ctx_len, float src_scale, float tgt_scale, const cdx_ddim_coef* coef,
+                       const float* t_host, int n_steps, const float* noise, float sqrt_a_T,
+                       float sqrt_1ma_T, float* x_out, float* z_out, int B, int C, int h, int w,
+                       void* stream);
 /* DDPMDDIMWrapper.encode loop (DW:483-521): coef/t_host have n_rec entries (loop order);
  * noise[0] = x_T draw, noise[1+i] = draw of iteration i; z_out [B, n_rec+1, C,R,R]. */
 int cdx_pixel_encode(cdx_net* unet, const float* x0, const cdx_pixel_coef* coef, const float* t_host,

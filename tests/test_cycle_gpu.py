@@ -204,3 +204,73 @@ def test_pipeline_surface(eng):
     assert isinstance(tup, tuple) and tup[0].shape == (1, 128, 128, 3)
     with pytest.raises(ValueError):
         pipe('a', 'b', image, strength=1.5)
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_lockstep_driver_vs_reference_fixture_and_two_phase(eng, tag):
+    """cdx_cycle_lockstep (one U-Net call + one fused elementwise kernel per step, recovered noise consumed in registers):
+    against the reference-generated fixture (DDIMSampler encode -> decode) and against the engine's own two-phase drivers."""
+    from cycle_diffusion_b200.engine import UNet
+    from cycle_diffusion_b200.schedule import DDIMSchedule
+    g = golden('ddim_cycle_narrow')
+    S, skip, wb, enc_scale, dec_scale, seed = [float(v) for v in g[f'cfg_{tag}']]
+    S, skip, wb, seed = int(S), int(skip), int(wb), int(seed)
+    sd = specs.synth_state_dict(specs.openai_unet_params(NARROW), 11)
+    unet = UNet(eng, NARROW, 'openai').load_state_dict(sd)
+    sched = DDIMSchedule(S, 0.1, skip)
+    n_rec = min(sched.refine_steps, wb - skip - 1)
+    if n_rec != sched.refine_steps:
+        pytest.skip('lock-step needs every step recovered')
+    torch.manual_seed(seed)
+    noise = _encode_noise(sched, n_rec, g['x0'].shape)
+    l0 = eng.launches
+    out, z = unet.cycle_lockstep(g['x0'], g['c_src'], g['c_tgt'], g['uc'], enc_scale, dec_scale, sched, noise, return_z=True)
+    torch.cuda.synchronize()
+    l_lock = eng.launches - l0
+    z2 = unet.latent_encode(g['x0'], g['c_src'], g['uc'], enc_scale, sched, n_rec, noise)
+    out2 = unet.latent_decode(z2, g['c_tgt'], g['uc'], dec_scale, sched)
+    zref = g[f'z_{tag}'].view(z.shape)
+    rz = maxdiff(z.cpu(), zref) / float(zref.abs().max())
+    d_ref = maxdiff(out.cpu(), g[f'tgt_{tag}'])
+    d_two = maxdiff(out.cpu(), out2.cpu())
+    rz_two = maxdiff(z.cpu(), z2.cpu()) / float(zref.abs().max())
+    print(f'lockstep[{tag}]: rel|dz| vs reference {rz:.2e}  |d x| vs reference {d_ref:.2e}  vs two-phase: rel|dz| {rz_two:.2e} |d x| {d_two:.2e}'
+          f'  bit-identical z {bool(torch.equal(z, z2))} x {bool(torch.equal(out, out2))}  launches {l_lock}')
+    assert rz < 2e-4 and d_ref < 1e-3
+    assert rz_two < 2e-5 and d_two < 1e-4
+
+
+def test_pipeline_surface_vs_oracle(eng):
+    """CycleDiffusionPipeline.__call__ (lock-step loop) against the ORACLE's restatement of the same computation
+    (VAE encode -> posterior sample -> DPM-Encoder under the source prompt -> CFG decode under the target prompt -> VAE decode),
+    same generator seed.  (The Diffusers class itself is not in /root/reference: the surface is unpinned, the arithmetic is not.)"""
+    from cycle_diffusion_b200.pipeline import CycleDiffusionPipeline
+    from cycle_diffusion_b200.wrappers import SDStochasticTextWrapper, SyntheticTextEncoder
+    from oracle import dpm_encoder, unet_openai, vae_kl
+    usd = specs.synth_state_dict(specs.openai_unet_params(NARROW), 11)
+    vsd = specs.synth_state_dict(specs.kl_vae_params(VAE_SMALL), 21)
+    sd = {'model.diffusion_model.' + k: v for k, v in usd.items()}
+    sd.update({'first_stage_model.' + k: v for k, v in vsd.items()})
+    cond = SyntheticTextEncoder(48)
+    w = SDStochasticTextWrapper('synthetic', custom_steps=4, eta=0.1, white_box_steps=5, skip_steps=[0], encoder_unconditional_guidance_scales=[1],
+                                decoder_unconditional_guidance_scales=[1], n_trials=1, engine=eng, state_dict=sd, cond_stage=cond,
+                                unet_config=NARROW, vae_config=VAE_SMALL, latent_size=16, resolution=128)
+    pipe = CycleDiffusionPipeline.from_wrapper(w)
+    image = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(4))
+    S, strength, gs, sgs = 8, 0.75, 4.0, 1.0
+    out = pipe(['a dog', 'a red car'], ['a cat', 'a blue car'], image, strength=strength, num_inference_steps=S, guidance_scale=gs,
+               source_guidance_scale=sgs, eta=0.1, generator=torch.Generator().manual_seed(9)).images.cpu()
+    out2 = pipe(['a dog', 'a red car'], ['a cat', 'a blue car'], image, strength=strength, num_inference_steps=S, guidance_scale=gs,
+                source_guidance_scale=sgs, eta=0.1, generator=torch.Generator().manual_seed(9), two_phase=True).images.cpu()
+    skip = S - int(S * strength)
+    ora = dpm_encoder.LatentCycle(lambda x, t, c: unet_openai.unet_forward(usd, NARROW, x, t, c),
+                                  lambda im: vae_kl.encode_moments(vsd, VAE_SMALL, im), lambda zz: vae_kl.decode(vsd, VAE_SMALL, zz), cond,
+                                  custom_steps=S, eta=0.1, white_box_steps=S + 1, skip_steps=[skip], encoder_unconditional_guidance_scales=[sgs],
+                                  decoder_unconditional_guidance_scales=[gs], n_trials=1, channels=4, latent_size=16, resolution=128)
+    torch.manual_seed(9)
+    with torch.no_grad():
+        z_ref = ora.encode(image, ['a cat', 'a blue car'])
+        ref = ora.forward_all(z_ref, ['a dog', 'a red car'])[0].clamp(0, 1)
+    print(f'pipeline vs oracle: |d img| {maxdiff(out, ref):.2e}   lock-step vs two-phase {maxdiff(out, out2):.2e}')
+    assert maxdiff(out, ref) < 1e-3
+    assert maxdiff(out, out2) < 1e-4

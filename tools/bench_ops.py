@@ -22,7 +22,7 @@ LINEARS = [(4096, 320, 320), (4096, 320, 960), (4096, 320, 2560), (4096, 1280, 3
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--mode', type=int, default=1)
+    ap.add_argument("--mode", type=int, default=1, help="1 fp16-split (default), 3 3xTF32, 4 fast path, 0 FFMA")
     ap.add_argument('--batch', type=int, default=8)
     ap.add_argument('--reps', type=int, default=3)
     a = ap.parse_args()
