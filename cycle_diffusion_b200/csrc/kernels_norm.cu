@@ -11,12 +11,31 @@
 // every block folds the channel sums of its image into the 32 group means / rstds (fp64), y = x * sc + sh per channel (the form
 // ATen's CPU kernel uses), optional (1 + scale) / shift of the improved-DDPM scale-shift norm, optional SiLU, and it tracks
 // max |y| for the fp16-split GEMM that consumes y.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace cdx {
 namespace {
 
 constexpr int GN_GROUPS = 32;
+
+// slot <- max(slot, block-wide max of v): one atomic per block at most, and none once the slot already holds a larger value
+// (same-address atomics serialise in L2: one per warp costs more than the kernel itself on the big activations)
+__device__ __forceinline__ void block_amax(float v, float* slot) {
+  __shared__ float s_wmax[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+  if (lane == 0) s_wmax[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < nwarps ? s_wmax[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0 && v > *reinterpret_cast<volatile float*>(slot)) atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(v));
+  }
+}
 
 // per-(image, channel) sums of one source: grid (row chunks, B); thread (tr, tc) owns float4 channel slots tc, tc+ncol, ...
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int C, int HW, int rows_per_chunk, double* __restrict__ stats) {
@@ -145,68 +164,75 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
         *reinterpret_cast<float4*>(dst + (long long)r * C) = act(*reinterpret_cast<const float4*>(src + (long long)r * ldx));
     }
   }
-  if (amax) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if ((threadIdx.x & 31) == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(vmax));
-  }
+  if (amax) block_amax(vmax, amax);
 }
 
-// one warp per row, the row held in registers (NV float4 per lane: C <= 128 NV): one read, one write
+// one warp per row, the row held in registers (NV float4 per lane: C <= 128 NV): one read, one write.  Persistent warps walk the
+// rows two at a time (both rows' loads in flight before either reduction).
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ y, int M, int C,
                                                         float eps, float* __restrict__ amax) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int C4 = C >> 2;
   float vmax = 0.f;
-  if (warp < M) {
-    const float* xr = x + (long long)warp * C;
-    float* yr = y + (long long)warp * C;
-    const int C4 = C >> 2;
-    float4 v[NV];
-    float s = 0.f;
+  float4 g[NV], bt[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c4 = lane + 32 * i;
-      v[i] = c4 < C4 ? *reinterpret_cast<const float4*>(xr + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    g[i] = c4 < C4 ? *reinterpret_cast<const float4*>(gamma + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bt[i] = c4 < C4 ? *reinterpret_cast<const float4*>(beta + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; row0 < M; row0 += nwarps * 2) {
+    float4 v[2][NV];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / (float)C;
-    float q = 0.f;
+    for (int r = 0; r < 2; ++r) {
+      const bool ok = row0 + r < M;
+      const float* xr = x + (long long)(row0 + r) * C;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (lane + 32 * i < C4) {
-        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-        q += (a * a + b * b) + (c * c + d * d);
+      for (int i = 0; i < NV; ++i) {
+        const int c4 = lane + 32 * i;
+        v[r][i] = (ok && c4 < C4) ? *reinterpret_cast<const float4*>(xr + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = 1.f / sqrtf(q / (float)C + eps);
+    for (int r = 0; r < 2; ++r) {
+      if (row0 + r >= M) break;
+      float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c4 = lane + 32 * i;
-      if (c4 < C4) {
-        const float4 g = *reinterpret_cast<const float4*>(gamma + c4 * 4);
-        const float4 b = *reinterpret_cast<const float4*>(beta + c4 * 4);
-        float4 o;
-        o.x = (v[i].x - mean) * rstd * g.x + b.x;
-        o.y = (v[i].y - mean) * rstd * g.y + b.y;
-        o.z = (v[i].z - mean) * rstd * g.z + b.z;
-        o.w = (v[i].w - mean) * rstd * g.w + b.w;
-        vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-        *reinterpret_cast<float4*>(yr + c4 * 4) = o;
+      for (int i = 0; i < NV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / (float)C;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (lane + 32 * i < C4) {
+          const float a = v[r][i].x - mean, b = v[r][i].y - mean, c = v[r][i].z - mean, d = v[r][i].w - mean;
+          q += (a * a + b * b) + (c * c + d * d);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = 1.f / sqrtf(q / (float)C + eps);
+      float* yr = y + (long long)(row0 + r) * C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c4 = lane + 32 * i;
+        if (c4 < C4) {
+          float4 o;
+          o.x = (v[r][i].x - mean) * rstd * g[i].x + bt[i].x;
+          o.y = (v[r][i].y - mean) * rstd * g[i].y + bt[i].y;
+          o.z = (v[r][i].z - mean) * rstd * g[i].z + bt[i].z;
+          o.w = (v[r][i].w - mean) * rstd * g[i].w + bt[i].w;
+          vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+          *reinterpret_cast<float4*>(yr + c4 * 4) = o;
+        }
       }
     }
   }
-  if (amax) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(vmax));
-  }
+  if (amax) block_amax(vmax, amax);
 }
 
 // in-place softmax over rows of length L (row stride ld); one warp per row, three passes (row stays in L1/L2)
@@ -268,8 +294,8 @@ void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, cons
   if (x2 && !st2) st2 = gn_channel_stats(e, x2, C2, B, HW, s);
   if (e.dry()) return;
   ProfScope ps(e, s, PROF_GROUPNORM, 0.0, 2.0 * 4.0 * B * (double)HW * C, 1);   // algorithmic: one read + one write
-  int achunk = cdiv(8LL * e.num_sms, B);
-  if (achunk > HW) achunk = HW;
+  int achunk = cdiv(4LL * e.num_sms, B);      // ~4 blocks per SM in total: the per-block prologue (group statistics, affine table) is amortised
+  if (achunk > HW / 8) achunk = std::max(1, HW / 8);
   const int arows = cdiv(HW, achunk);
   achunk = cdiv(HW, arows);
   gn_apply_kernel<<<dim3(achunk, B), 256, (size_t)C * sizeof(float2), s>>>(x1, C1, x2, C2, gamma, beta, st1, st2, 1.0 / ((double)HW * (C / GN_GROUPS)), eps,
@@ -283,7 +309,7 @@ void layernorm(Engine& e, const float* x, const float* gamma, const float* beta,
   if (e.dry()) return;
   ProfScope ps(e, s, PROF_LAYERNORM, 0.0, 2.0 * 4.0 * (double)M * C, 1);
   const int nv = cdiv(C, 128);
-  const int blocks = cdiv((long long)M * 32, 256);
+  const int blocks = (int)std::min<long long>(cdiv((long long)cdiv(M, 2) * 32, 256), (long long)e.num_sms * 8);
   if (nv <= 3) layernorm_kernel<3><<<blocks, 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f, amax);
   else if (nv <= 6) layernorm_kernel<6><<<blocks, 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f, amax);
   else if (nv <= 10) layernorm_kernel<10><<<blocks, 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f, amax);

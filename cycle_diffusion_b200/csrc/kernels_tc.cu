@@ -317,7 +317,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int j = 0; j < 4; ++j) {
             if (j >= nj) break;
             const uint64_t adv = (uint64_t)((j * 16 * 2) >> 4);
-            if (!p.fast) {
+            if (p.fast != 1) {
               umma_ts_f16(acc, a_lo + j * 8, b_hi + adv, idesc, (kin > 0 || j > 0) ? 1u : 0u);      // small terms first
               umma_ts_f16(acc, a_hi + j * 8, b_lo + adv, idesc, 1u);
               umma_ts_f16(acc, a_hi + j * 8, b_hi + adv, idesc, 1u);
@@ -377,6 +377,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int c = 0; c < 8; ++c) {
             uint32_t v[4];
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(sa + (((uint32_t)c ^ rx) << 4)));
+            if (p.fast == 3) {        // EXPERIMENT: no conversion math (garbage numerics), measures the pipeline without the split ALU work
+              hi[c * 2] = v[0]; hi[c * 2 + 1] = v[1]; lo[c * 2] = v[2]; lo[c * 2 + 1] = v[3];
+              continue;
+            }
 #pragma unroll
             for (int e2 = 0; e2 < 2; ++e2) {
               const float x0 = __uint_as_float(v[2 * e2]) * asc, x1 = __uint_as_float(v[2 * e2 + 1]) * asc;
@@ -1042,7 +1046,8 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
       p.a2_amax = slot;
     }
     p.b_exp = a.b_exp;
-    p.fast = e.tc_kind == 2;
+    p.fast = e.tc_kind == 2 ? 1 : 0;
+    { static const char* dbg = getenv("CDX_TC_SKIP_SPLIT"); if (dbg) p.fast = 3; }
   }
   // side outputs fused into the epilogue: range of C always (the split-K reduce kernel covers the split case); GroupNorm
   // statistics when every 32-row quadrant of a tile lies inside one image and the epilogue is the final one
