@@ -54,9 +54,11 @@ using namespace tc;
 constexpr int TBM = 128, TBN = 128, TBK = 32;
 constexpr double CDX_H16_KC0 = 640.0, CDX_H16_KC1 = 4.2;   // planner cost of one 64-k stage of the fp16-split kernel (cycles)
 constexpr int TILE_BYTES = TBM * TBK * 4;          // 16 KB
-constexpr int NUM_SPLIT_WARPS = 4;
+constexpr int HALO_PLANE = 24 * 1024;             // one 32-channel plane of a conv3x3 halo box (<= 192 pixels x 128 B)
+constexpr int NUM_SPLIT_WARPS = 8;               // two per TMEM lane quadrant (MODE_H16: one per 32-k sub-block of a stage)
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + (NUM_SPLIT_WARPS + NUM_EPI_WARPS) * 32;
+constexpr int FIRST_SPLIT_WARP = 4, FIRST_EPI_WARP = FIRST_SPLIT_WARP + NUM_SPLIT_WARPS;
+constexpr int TC_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;      // 20 warps = 5 warpgroups (setmaxnreg is per warpgroup)
 
 // Operand path of the kernel (template parameter MODE):
 //   MODE_SS   both operands raw fp32 in smem, split in smem into TF32 hi / lo (generic: B may be an activation)
@@ -91,6 +93,11 @@ struct TcParams {
   int bw, bh, bn;           // conv: pixel box of one M tile (bw*bh*bn == 128)
   int tiles_x, tiles_y;     // conv: tiles per row / column
   int cstride, cpad;        // conv: stride (1 or 2: TMA element traversal stride) and low-side padding
+  // MODE_H16 conv3x3 "halo" schedule (stride 1, pad 1, Cin % 64 == 0): the K loop runs (64-channel block, tap) instead of
+  // (tap, channel block); the (bw+2) x (bh+2) x bn pixel halo of a 64-channel block is fetched ONCE (two 32-channel TMA boxes,
+  // OOB zero fill = padding) and the split warps read all nine shifted taps from it, so the activation crosses L2 -> SM once
+  // per tile and channel block instead of nine times (A ingress per stage 32 KB -> ~5 KB; the kernel was L2->SM bound)
+  int halo;
   float* C; int ldc;
   float* C_lo;              // optional: C <- rn_tf32(result), C_lo <- rn_tf32(result - hi)
   float* Ct_hi; float* Ct_lo; int t_col0; long long ldt;   // optional transposed plane output for columns >= t_col0
@@ -128,6 +135,9 @@ struct TcParams {
 __device__ __forceinline__ int h16_exp_of(float amax) {
   const int be = (int)((__float_as_uint(amax) >> 23) & 0xffu);
   if (be == 0 || be == 0xff) return 0;
+  // 2^2 <= amax < 2^15: no rescale.  The split is then exact to 2^-25 absolute (fp16 subnormal spacing of the lo term), i.e.
+  // <= 2^-27 of the tensor's max -- below fp32's own rounding of the products -- and the split warps skip one multiply per element
+  if (be - 127 >= 2 && be - 127 <= 14) return 0;
   return min(max(14 - (be - 127), -100), 100);
 }
 __device__ __forceinline__ int h16_a_exp(const TcParams& p) {
@@ -150,6 +160,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int STAGES = Cfg<MODE>::STAGES;
   constexpr int STAGE_BYTES = Cfg<MODE>::STAGE_BYTES;
   constexpr int TMEM_COLS = Cfg<MODE>::TMEM_COLS;
+  constexpr int SPLIT_ARRIVALS = MODE == MODE_TS ? 4 : NUM_SPLIT_WARPS;   // MODE_TS: only the first four split warps work
   // smem offsets inside a stage
   constexpr int OFF_A = 0;                                   // SS: A_hi (raw in place) ; TS: A_raw ; H16: A_raw k 0..31, then k 32..63
   constexpr int OFF_ALO = TILE_BYTES;                        // SS only
@@ -165,7 +176,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   auto bar_empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto bar_acc_full = [&](int b) { return bars + 8u * (3 * STAGES + b); };
   auto bar_acc_empty = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+  auto bar_halo_full = [&](int h) { return bars + 8u * (3 * STAGES + 4 + h); };
+  auto bar_halo_empty = [&](int h) { return bars + 8u * (3 * STAGES + 6 + h); };
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 8);
+  // halo schedule smem map: B ring of STAGES x (hi 16 KB | lo 16 KB) at the base, then 2 halo buffers x 2 planes of HALO_PLANE bytes
+  const bool halo = H16 && p.halo;
+  const uint32_t b_ring = halo ? base : base + OFF_BHI;
+  const uint32_t b_stride = halo ? 2u * TILE_BYTES : (uint32_t)STAGE_BYTES;
+  const uint32_t halo_base = base + STAGES * 2 * TILE_BYTES;
   float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 512);   // [2][TBN], epilogue warps only
   float4* const s_stage = reinterpret_cast<float4*>(smem_raw + (bars - smem_u32(smem_raw)) + 2048);   // 8 warps x 4 KB
 
@@ -175,12 +193,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full_raw(s), 1);
-      mbar_init(bar_full_split(s), NUM_SPLIT_WARPS);
+      mbar_init(bar_full_split(s), SPLIT_ARRIVALS);
       mbar_init(bar_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full(b), 1);
       mbar_init(bar_acc_empty(b), NUM_EPI_WARPS);
+      mbar_init(bar_halo_full(b), 1);
+      mbar_init(bar_halo_empty(b), SPLIT_ARRIVALS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -193,6 +213,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // register budget per warpgroup (640 threads launch with 96 each): the TMA / MMA warpgroup gives most of its share back,
+  // the epilogue warpgroups (64 fp32 accumulators + a 32-register residual prefetch per thread) take it
+  // (each setmaxnreg sits at the top of its role's branch: ptxas budgets the code it dominates)
 
   // ---- persistent tile loop: every role walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... with GLOBAL k-block and
   // chunk counters, so the smem ring and the two TMEM accumulator buffers keep rolling across tiles and the MMAs of tile
@@ -224,16 +247,48 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     return c;
   };
 
+  if (warp < FIRST_SPLIT_WARP) {
+  // warpgroup 0 (TMA producer, MMA issuer, two warps without a role): all four warps release registers at this one instruction
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // =========================================================================== TMA producer (whole warp, elected issue)
     {
       const int cblocks = p.mode == 1 ? p.Cin / TBK : 0;
-      int gkb = 0;
+      int gkb = 0, ghalo = 0, hl = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc_ = tile_coord(t);
       const int n0 = tc_.n0, m0 = tc_.m0, x0 = tc_.x0, y0 = tc_.y0, b0 = tc_.b0, zb = tc_.zb, zh = tc_.zh;
       for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
+        if (halo) {
+          // stage = (64-channel block cb, tap).  Halo boxes are fetched in channel-block order: the item's first one before its
+          // first stage, the next block's from tap 3 on (by then the split warps are done with the buffer it lands in: this
+          // warp runs at most STAGES stages ahead of the MMAs), so a box is in flight for ~5 stages before its first use
+          const int cb = kb / 9, tap = kb - cb * 9;
+          if (kb == tc_.kb0) hl = cb;
+          const bool need = hl * 9 < tc_.kb1 && (hl == cb || (hl == cb + 1 && tap >= 3));
+          const int hs = ghalo & 1, hcb = hl;
+          if (need) {
+            mbar_wait(bar_halo_empty(hs), ((ghalo >> 1) & 1) ^ 1);
+            ++ghalo;
+            ++hl;
+          }
+          mbar_wait(bar_empty(s), (it & 1) ^ 1);
+          if (!elect_one()) continue;
+          if (need) {
+            const uint32_t hb = halo_base + (uint32_t)hs * 2u * HALO_PLANE;
+            const uint32_t box_bytes = (uint32_t)((p.bw + 2) * (p.bh + 2) * p.bn) * 128u;
+            mbar_expect_tx(bar_halo_full(hs), 2u * box_bytes);
+            tma_load_4d(hb, &mapA, hcb * 64, x0 - 1, y0 - 1, b0, bar_halo_full(hs));                  // OOB -> zeros = padding
+            tma_load_4d(hb + HALO_PLANE, &mapA, hcb * 64 + 32, x0 - 1, y0 - 1, b0, bar_halo_full(hs));
+          }
+          const uint32_t sbh = b_ring + (uint32_t)s * b_stride;
+          const int kB = tap * p.Cin + cb * 64;                      // weight planes stay in (tap, channel) order
+          mbar_expect_tx(bar_full_raw(s), 2 * p.tn_w * BK * 2);
+          tma_load_2d(sbh, &mapB, kB, n0, bar_full_raw(s));
+          tma_load_2d(sbh + TILE_BYTES, &mapBlo, kB, n0, bar_full_raw(s));
+          continue;
+        }
         mbar_wait(bar_empty(s), (it & 1) ^ 1);
         const uint32_t st = base + s * STAGE_BYTES;
         const uint32_t sa = st + OFF_A, sb = st + OFF_BHI;
@@ -306,7 +361,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = base + s * STAGE_BYTES;
         const uint32_t acc = tmem_base + (uint32_t)(buf * TBN);
-        const uint64_t b_hi = make_desc(st + OFF_BHI), b_lo = make_desc(st + OFF_BLO);
+        const uint32_t sbh = H16 ? b_ring + (uint32_t)s * b_stride : st + OFF_BHI;
+        const uint64_t b_hi = make_desc(sbh), b_lo = make_desc(H16 ? sbh + TILE_BYTES : st + OFF_BLO);
         if (!elect_one()) continue;
         if (H16) {
           // A: packed fp16 pairs in TMEM (hi: 32 columns = 64 k, lo: the next 32); a K = 16 MMA consumes 8 columns of A and
@@ -350,64 +406,96 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       gchunk0 += (nkb + KCHUNK - 1) / KCHUNK;
       }
     }
-  } else if (warp < 2 + NUM_SPLIT_WARPS) {
+  }
+  }   // warpgroup 0
+  else if (warp < FIRST_EPI_WARP) {
+    // register pool of the CTA = 640 x 96: warpgroup 0 gives back 40 per thread and the split warpgroups 16, which is exactly
+    // what lets the two epilogue warpgroups grow to 128 (a setmaxnreg.inc that the pool cannot serve spins forever)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     // =========================================================================== split warps
     if (H16) {
-      // thread = one tile row: per stage two sub-blocks of 32 raw floats -> x' = x * 2^ea, hi = fp16(x'), lo = fp16(x' - hi),
-      // packed two per 32-bit TMEM column (even k in the low half)
+      // thread = one tile row of ONE 32-float sub-block of the stage (warps 2..5: sub-block 0, warps 6..9: sub-block 1; the profile
+      // of the 4-warp version showed the split warps issue-bound at ~480 dependent instructions per stage with nothing else
+      // resident on their schedulers): x' = x * 2^ea, hi = fp16(x'), lo = fp16(x' - hi), packed two per 32-bit TMEM column
+      // (even k in the low half)
       const int q = warp & 3;
+      const int sub = (warp - FIRST_SPLIT_WARP) >> 2;
       const int row = q * 32 + lane;
       const uint32_t rbase = (uint32_t)row * 128u;
       const uint32_t rx = (uint32_t)(row & 7);
-      const float asc = exp2i(h16_a_exp(p));
-      int gkb = 0;
+      const int ea = h16_a_exp(p);
+      const float asc = exp2i(ea);
+      // halo schedule: this thread's pixel inside the (bw+2) x (bh+2) x bn halo box at tap (0, 0)
+      const int hrow0 = halo ? ((row / (p.bw * p.bh)) * (p.bh + 2) + (row / p.bw) % p.bh) * (p.bw + 2) + row % p.bw : 0;
+      int gkb = 0, ghalo = 0, cur_h = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc_ = tile_coord(t);
       for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
+        uint32_t sa = base + s * STAGE_BYTES + OFF_A + sub * TILE_BYTES + rbase, rxx = rx;
+        bool halo_done = false;
+        if (halo) {
+          const int cb = kb / 9, tap = kb - cb * 9;
+          if (tap == 0 || kb == tc_.kb0) {
+            cur_h = ghalo & 1;
+            mbar_wait(bar_halo_full(cur_h), (ghalo >> 1) & 1);
+            ++ghalo;
+          }
+          const int dy = tap / 3, dx = tap - dy * 3;
+          const int hp = hrow0 + dy * (p.bw + 2) + dx;
+          sa = halo_base + (uint32_t)(cur_h * 2 + sub) * HALO_PLANE + (uint32_t)hp * 128u;
+          rxx = (uint32_t)(hp & 7);
+          halo_done = tap == 8 || kb == tc_.kb1 - 1;
+        }
         mbar_wait(bar_full_raw(s), it & 1);
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64);
-        const int nsub = (kb * BK + TBK < p.K) ? 2 : 1;
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64 + sub * 16);
+        if (sub == 0 || kb * BK + TBK < p.K) {          // an odd tail stage carries only sub-block 0
+          uint32_t v[32], hi[16], lo[16];
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          if (sub >= nsub) break;
-          const uint32_t sa = base + s * STAGE_BYTES + OFF_A + sub * TILE_BYTES + rbase;
-          uint32_t hi[16], lo[16];
+          for (int c = 0; c < 8; ++c)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3]) : "r"(sa + (((uint32_t)c ^ rxx) << 4)));
+          if (ea != 0) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint32_t v[4];
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(sa + (((uint32_t)c ^ rx) << 4)));
-            if (p.fast == 3) {        // EXPERIMENT: no conversion math (garbage numerics), measures the pipeline without the split ALU work
-              hi[c * 2] = v[0]; hi[c * 2 + 1] = v[1]; lo[c * 2] = v[2]; lo[c * 2 + 1] = v[3];
-              continue;
-            }
-#pragma unroll
-            for (int e2 = 0; e2 < 2; ++e2) {
+            for (int e2 = 0; e2 < 16; ++e2) {
               const float x0 = __uint_as_float(v[2 * e2]) * asc, x1 = __uint_as_float(v[2 * e2 + 1]) * asc;
               const __half2 h = __floats2half2_rn(x0, x1);          // .x (low half) = even k
               const float2 hf = __half22float2(h);
               const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-              hi[c * 2 + e2] = *reinterpret_cast<const uint32_t*>(&h);
-              lo[c * 2 + e2] = *reinterpret_cast<const uint32_t*>(&l);
+              hi[e2] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[e2] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+          } else {
+#pragma unroll
+            for (int e2 = 0; e2 < 16; ++e2) {
+              const float x0 = __uint_as_float(v[2 * e2]), x1 = __uint_as_float(v[2 * e2 + 1]);
+              const __half2 h = __floats2half2_rn(x0, x1);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+              hi[e2] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[e2] = *reinterpret_cast<const uint32_t*>(&l);
             }
           }
-          tmem_st16(ta + sub * 16, hi);
-          tmem_st16(ta + 32 + sub * 16, lo);
+          tmem_st16(ta, hi);
+          tmem_st16(ta + 32, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full_split(s));
+        if (lane == 0) {
+          mbar_arrive(bar_full_split(s));
+          if (halo_done) mbar_arrive(bar_halo_empty(cur_h));      // all nine taps read: the buffer may be refilled
+        }
       }
       }
     } else if (TS) {
       // thread = one tile row: read its 128 raw bytes (8 swizzled 16-byte chunks), store hi / lo into TMEM lane `row`
+      // (the TF32-plane path keeps the one-warp-per-quadrant split: warps 6..9 have nothing to do)
       const int q = warp & 3;                    // TMEM lane quadrant (warps 2..5 -> 2,3,0,1)
       const int row = q * 32 + lane;
       const uint32_t rbase = (uint32_t)row * 128u;
       const uint32_t rx = (uint32_t)(row & 7);
       int gkb = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = warp < FIRST_SPLIT_WARP + 4 ? blockIdx.x : p.total_tiles; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc_ = tile_coord(t);
       for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
@@ -435,7 +523,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       }
     } else {
-      const int st_ = threadIdx.x - 64;        // 0..127
+      const int st_ = threadIdx.x - FIRST_SPLIT_WARP * 32;        // 0..255
       int gkb = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc_ = tile_coord(t);
@@ -464,11 +552,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       }
     }
-  } else {
+  } else if (warp >= FIRST_EPI_WARP) {
     // =========================================================================== drain + epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     // eight warps: two per TMEM lane quadrant, each owning 32 rows x 64 columns (hf = column half) of the tile
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access (warps 6..13 -> 2,3,0,1,2,3,0,1)
-    const int ew = warp - (2 + NUM_SPLIT_WARPS);   // 0..7
+    const int ew = warp - FIRST_EPI_WARP;          // 0..7
     const int hf = ew >> 2;                        // column half
     const int r = q * 32 + lane;                   // tile row owned by this thread
     const int et = hf * 128 + q * 32 + lane;       // 0..255: threads 0..127 stage the tile's bias vector
@@ -954,6 +1043,13 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
     // stride 2 (Downsample convs): TMA traverses every 2nd pixel; box = 2x the number of pixels wanted
     uint32_t bx[4] = {TBK, (uint32_t)(bw * a.stride), (uint32_t)(bh * a.stride), (uint32_t)bn};
     uint32_t es[4] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1};
+    // halo schedule (see TcParams::halo): needs the fp16-split path (decided below), 64-channel blocks and a halo box that fits a plane
+    static const bool no_halo = getenv("CDX_TC_NO_HALO") != nullptr;
+    if (!no_halo && e.tc_kind >= 1 && a.stride == 1 && a.pad == 1 && (Cin % 64) == 0 && (bw + 2) * (bh + 2) * bn * 128 <= HALO_PLANE &&
+        a.Bw_h_hi && a.Bw_h_lo && a16(a.Bw_h_hi) && a16(a.Bw_h_lo) && (a.ldb % 8) == 0) {
+      p.halo = 1;
+      bx[1] = (uint32_t)(bw + 2); bx[2] = (uint32_t)(bh + 2);
+    }
     mA = &get_map(a.A, 4, d, st, bx, es);
     mA2 = mA;
     p.tiles_m = p.tiles_x * p.tiles_y * cdiv(B, bn);
@@ -963,6 +1059,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   const bool ts = a.Bw_hi != nullptr && a.Bw_lo != nullptr && a16(a.Bw_hi) && a16(a.Bw_lo);
   const bool h16 = e.tc_kind >= 1 && a.Bw_h_hi && a.Bw_h_lo && a16(a.Bw_h_hi) && a16(a.Bw_h_lo) && (a.K % TBK) == 0 && (a.ldb % 8) == 0 &&
                    (a.mode == 1 || !a.A2 || (a.C2 % TBK) == 0);
+  if (p.halo && !h16) return false;        // (cannot happen: the halo conditions imply the fp16-split conditions)
   const int bk = h16 ? Cfg<MODE_H16>::BK : TBK;
   const int num_kb = cdiv(a.K, bk);
   // Work partition: tile width w along N (MMA N = valid columns rounded up to 16, so a ragged last tile costs only its
@@ -977,7 +1074,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
     static std::map<std::array<int64_t, 5>, int> plan_cache;      // exact key (no hashing of packed fields: nothing can collide)
     static std::mutex plan_mutex;                                          // engines on different devices may plan concurrently
     std::lock_guard<std::mutex> plan_lock(plan_mutex);
-    const std::array<int64_t, 5> key = {p.tiles_m, a.N, num_kb, ((a.geglu || a.Ct_hi) ? 1 : 0) | (a.out_nchw ? 2 : 0) | (h16 ? 4 : 0), e.num_sms};
+    const std::array<int64_t, 5> key = {p.tiles_m, a.N, num_kb, ((a.geglu || a.Ct_hi) ? 1 : 0) | (a.out_nchw ? 2 : 0) | (h16 ? 4 : 0) | (p.halo ? 8 : 0), e.num_sms};
     // cycles per pipeline stage of a w-wide tile (fitted on B200): TF32 planes 540 + 4.2 w per 32 k; fp16 split per 64 k
     const double kc0 = h16 ? CDX_H16_KC0 : 540.0, kc1 = h16 ? CDX_H16_KC1 : 4.2;
     const int min_kbs = h16 ? 4 : 8;
@@ -1047,7 +1144,6 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
     }
     p.b_exp = a.b_exp;
     p.fast = e.tc_kind == 2 ? 1 : 0;
-    { static const char* dbg = getenv("CDX_TC_SKIP_SPLIT"); if (dbg) p.fast = 3; }
   }
   // side outputs fused into the epilogue: range of C always (the split-K reduce kernel covers the split case); GroupNorm
   // statistics when every 32-row quadrant of a tile lies inside one image and the epilogue is the final one
@@ -1072,7 +1168,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   ensure_attr(e.device);
   ProfScope ps(e, s, a.mode == 1 ? PROF_CONV_TC : PROF_DENSE_TC, 2.0 * a.M * a.N * a.K,
                4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
-  ps.note("M%d N%d K%d w%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, p.tn_w, tiles, p.splits, h16 ? (p.fast ? "H16x1" : "H16") : ts ? "TS" : "SS",
+  ps.note("M%d N%d K%d w%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, p.tn_w, tiles, p.splits, h16 ? (p.fast ? "H16x1" : p.halo ? "H16halo" : "H16") : ts ? "TS" : "SS",
           a.Cout_lo ? " planes" : "", a.geglu ? " geglu" : "", a.residual ? " res" : "");
   if (h16) tc_gemm_kernel<MODE_H16><<<grid, TC_THREADS, Cfg<MODE_H16>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
   else if (ts) tc_gemm_kernel<MODE_TS><<<grid, TC_THREADS, Cfg<MODE_TS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);

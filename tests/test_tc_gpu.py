@@ -54,7 +54,10 @@ def test_linear_tc(eng, M, K, N):
 
 
 @pytest.mark.parametrize('B,Cin,Cout,H', [(1, 32, 128, 16), (2, 64, 64, 16), (1, 320, 320, 32), (4, 128, 256, 64), (3, 96, 160, 8), (8, 64, 32, 4),
-                                           (2, 1280, 1280, 8)])
+                                           (2, 1280, 1280, 8),
+                                           # halo schedule (Cin % 64 == 0, W >= 16): split-K items that start / end inside a channel
+                                           # block, ragged batch, ragged N tile, many channel blocks
+                                           (1, 1280, 640, 16), (8, 640, 640, 32), (3, 192, 96, 32), (1, 1920, 320, 64), (5, 64, 48, 16)])
 def test_conv3x3_tc(eng, B, Cin, Cout, H):
     g = torch.Generator().manual_seed(Cin * 1000 + Cout + H)
     x = torch.randn(B, Cin, H, H, generator=g)
