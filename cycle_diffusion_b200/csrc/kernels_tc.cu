@@ -68,17 +68,22 @@ constexpr int TC_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;      // 20 war
 //             hi + lo carries >= 22 significant bits of x' down to |x'| = 2^-3 and an absolute error <= 2^-25 below that
 //             (2^-40 of the tensor's max), products of 11-bit significands are exact in the fp32 accumulator, and the result is
 //             rescaled by the exact power of two 2^-(ea + eb) in the epilogue.  B planes are pre-scaled fp16 in HBM.
-enum { MODE_SS = 0, MODE_TS = 1, MODE_H16 = 2 };
+//   MODE_H16X2  MODE_H16 on CTA pairs (cta_group::2): a 2-CTA cluster owns a 256-row tile, each CTA splits its own 128 rows into its
+//             own TMEM and holds HALF of the B rows in its smem; the leader issues M = 256 MMAs over both.  B bytes per CTA and stage
+//             halve (ingress, smem fill, tensor-core operand fetch), which buys a 4th pipeline stage in the same shared memory
+enum { MODE_SS = 0, MODE_TS = 1, MODE_H16 = 2, MODE_H16X2 = 3 };
 
 template <int MODE>
 struct Cfg {
   static constexpr bool TS = MODE != MODE_SS;
-  static constexpr bool H16 = MODE == MODE_H16;
+  static constexpr bool CG2 = MODE == MODE_H16X2;
+  static constexpr bool H16 = MODE == MODE_H16 || CG2;
   static constexpr int BK = H16 ? 64 : 32;         // K elements per pipeline stage
   static constexpr int KCHUNK = 256 / BK;          // stages per TMEM accumulation chunk (256 K elements)
-  static constexpr int STAGES = MODE == MODE_TS ? 4 : 3;
+  static constexpr int STAGES = (MODE == MODE_TS || CG2) ? 4 : 3;
+  static constexpr int B_PLANE = CG2 ? TILE_BYTES / 2 : TILE_BYTES;      // smem bytes of one B plane of a stage (CG2: half the rows)
   // SS: A_hi, A_lo, B_hi, B_lo ; TS: A_raw, B_hi, B_lo ; H16: A_raw(k 0..31), A_raw(k 32..63), B_hi, B_lo (fp16, 128 B rows)
-  static constexpr int STAGE_BYTES = MODE == MODE_TS ? 3 * TILE_BYTES : 4 * TILE_BYTES;
+  static constexpr int STAGE_BYTES = MODE == MODE_TS ? 3 * TILE_BYTES : 2 * TILE_BYTES + 2 * B_PLANE;
   static constexpr int TMEM_COLS = TS ? 512 : 256;
   static constexpr int A_COL0 = 256;               // TS / H16: A stage s lives at columns A_COL0 + 64 s (hi) / + 32 (lo)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048 /*barriers + bias staging*/ + 32768 /*epilogue transpose: 8 warps x 4 KB*/ + 1024 /*alignment slack*/;
@@ -155,6 +160,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
   constexpr bool TS = Cfg<MODE>::TS;
   constexpr bool H16 = Cfg<MODE>::H16;
+  constexpr bool CG2 = Cfg<MODE>::CG2;
+  constexpr int B_PLANE = Cfg<MODE>::B_PLANE;
   constexpr int BK = Cfg<MODE>::BK;
   constexpr int KCHUNK = Cfg<MODE>::KCHUNK;
   constexpr int STAGES = Cfg<MODE>::STAGES;
@@ -165,7 +172,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int OFF_A = 0;                                   // SS: A_hi (raw in place) ; TS: A_raw ; H16: A_raw k 0..31, then k 32..63
   constexpr int OFF_ALO = TILE_BYTES;                        // SS only
   constexpr int OFF_BHI = MODE == MODE_TS ? TILE_BYTES : 2 * TILE_BYTES;
-  constexpr int OFF_BLO = MODE == MODE_TS ? 2 * TILE_BYTES : 3 * TILE_BYTES;
+  constexpr int OFF_BLO = MODE == MODE_TS ? 2 * TILE_BYTES : 2 * TILE_BYTES + B_PLANE;
+  // CTA pair: rank in the 2-CTA cluster (0 = leader: issues the MMAs); work items are walked per cluster
+  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
+  const int t_first = CG2 ? (int)cluster_id_x() : (int)blockIdx.x, t_step = CG2 ? (int)nclusters_x() : (int)gridDim.x;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 1024-byte aligned (swizzle atoms)
@@ -182,8 +192,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // halo schedule smem map: B ring of STAGES x (hi 16 KB | lo 16 KB) at the base, then 2 halo buffers x 2 planes of HALO_PLANE bytes
   const bool halo = H16 && p.halo;
   const uint32_t b_ring = halo ? base : base + OFF_BHI;
-  const uint32_t b_stride = halo ? 2u * TILE_BYTES : (uint32_t)STAGE_BYTES;
-  const uint32_t halo_base = base + STAGES * 2 * TILE_BYTES;
+  const uint32_t b_stride = halo ? 2u * B_PLANE : (uint32_t)STAGE_BYTES;
+  const uint32_t halo_base = base + STAGES * 2 * B_PLANE;
   float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 512);   // [2][TBN], epilogue warps only
   float4* const s_stage = reinterpret_cast<float4*>(smem_raw + (bars - smem_u32(smem_raw)) + 2048);   // 8 warps x 4 KB
 
@@ -193,23 +203,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full_raw(s), 1);
-      mbar_init(bar_full_split(s), SPLIT_ARRIVALS);
+      mbar_init(bar_full_split(s), CG2 ? 2 * SPLIT_ARRIVALS : SPLIT_ARRIVALS);     // pair: both CTAs' split warps arrive at the leader
       mbar_init(bar_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full(b), 1);
-      mbar_init(bar_acc_empty(b), NUM_EPI_WARPS);
+      mbar_init(bar_acc_empty(b), CG2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
       mbar_init(bar_halo_full(b), 1);
       mbar_init(bar_halo_empty(b), SPLIT_ARRIVALS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (CG2) cluster_sync_all();          // the peer's barriers must be initialised before any remote arrive / multicast commit
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -227,7 +243,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     c.split = split;
     c.kb0 = split * p.kb_per_split;
     c.kb1 = min(num_kb, c.kb0 + p.kb_per_split);
-    const int tm = t % p.tiles_m;
+    const int tm = CG2 ? 2 * (t % p.tiles_m) + (int)rank : t % p.tiles_m;      // pair: p.tiles_m counts 256-row pair tiles
     const int r = t / p.tiles_m;
     const int tn = r % p.tiles_n, z = r / p.tiles_n;
     c.n0 = tn * p.tn_w;
@@ -255,9 +271,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     {
       const int cblocks = p.mode == 1 ? p.Cin / TBK : 0;
       int gkb = 0, ghalo = 0, hl = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < p.total_tiles; t += t_step) {
       const TileCoord tc_ = tile_coord(t);
       const int n0 = tc_.n0, m0 = tc_.m0, x0 = tc_.x0, y0 = tc_.y0, b0 = tc_.b0, zb = tc_.zb, zh = tc_.zh;
+      // pair: this CTA holds rows [rank * nw/2, +nw/2) of the B tile (the TMA box is tn_w/2 rows; surplus rows of a ragged tile are unused)
+      const int b_rows = CG2 ? p.tn_w / 2 : p.tn_w, b_row0 = CG2 ? (int)rank * (tc_.nw / 2) : 0;
       for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
         if (halo) {
@@ -284,9 +302,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           const uint32_t sbh = b_ring + (uint32_t)s * b_stride;
           const int kB = tap * p.Cin + cb * 64;                      // weight planes stay in (tap, channel) order
-          mbar_expect_tx(bar_full_raw(s), 2 * p.tn_w * BK * 2);
-          tma_load_2d(sbh, &mapB, kB, n0, bar_full_raw(s));
-          tma_load_2d(sbh + TILE_BYTES, &mapBlo, kB, n0, bar_full_raw(s));
+          mbar_expect_tx(bar_full_raw(s), 2 * b_rows * BK * 2);
+          tma_load_2d(sbh, &mapB, kB, n0 + b_row0, bar_full_raw(s));
+          tma_load_2d(sbh + B_PLANE, &mapBlo, kB, n0 + b_row0, bar_full_raw(s));
           continue;
         }
         mbar_wait(bar_empty(s), (it & 1) ^ 1);
@@ -297,7 +315,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (H16) {
           // two 32-float A sub-blocks (each its own tap / source: a stage may straddle) + fp16 B planes of 64 k (128 B rows)
           const int nsub = (k0 + TBK < p.K) ? 2 : 1;               // K % 32 == 0; an odd tail stage carries one sub-block
-          mbar_expect_tx(bar_full_raw(s), nsub * TILE_BYTES + 2 * p.tn_w * BK * 2);
+          mbar_expect_tx(bar_full_raw(s), nsub * TILE_BYTES + 2 * b_rows * BK * 2);
           for (int sub = 0; sub < nsub; ++sub) {
             const int ks = k0 + sub * TBK;
             const uint32_t dst = sa + sub * TILE_BYTES;
@@ -311,8 +329,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               tma_load_4d(dst, &mapA, cb * TBK, x0 * p.cstride + dx - p.cpad, y0 * p.cstride + dy - p.cpad, b0, bar_full_raw(s));
             }
           }
-          tma_load_2d(sb, &mapB, k0, n0, bar_full_raw(s));
-          tma_load_2d(st + OFF_BLO, &mapBlo, k0, n0, bar_full_raw(s));
+          tma_load_2d(sb, &mapB, k0, n0 + b_row0, bar_full_raw(s));
+          tma_load_2d(st + OFF_BLO, &mapBlo, k0, n0 + b_row0, bar_full_raw(s));
           continue;
         }
         mbar_expect_tx(bar_full_raw(s), TILE_BYTES + (TS ? 2 : 1) * p.tn_w * TBK * 4);
@@ -342,68 +360,102 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // =========================================================================== MMA issuer (whole warp, elected issue)
+    // The profile of the previous version showed this warp busy ~75 % of the time with ~150 SASS instructions per stage (div / mod
+    // of the stage counters, descriptor construction, per-MMA branches) around 12 tcgen05.mma: the issue loop, not the tensor pipe,
+    // set the pace.  Counters are now carried incrementally, the smem descriptors are one add per stage, and the reduced-precision
+    // variant has its own copy of the loop.
     {
-      int gkb = 0, gchunk0 = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord tc_ = tile_coord(t);
-      const int nkb = tc_.kb1 - tc_.kb0;
-      // instruction descriptor: D fp32; A / B format tf32 (2) or f16 (0), both K-major; N >> 3; M >> 4
-      const uint32_t idesc = (1u << 4) | (H16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(tc_.nw >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb, ++gkb) {
-        const int s = gkb % STAGES, it = gkb / STAGES;
-        const int lchunk = kb / KCHUNK, kin = kb - lchunk * KCHUNK;
-        const int chunk = gchunk0 + lchunk, buf = chunk & 1;
-        if (kin == 0 && chunk >= 2) {       // the buffer's previous chunk must have been drained
-          mbar_wait(bar_acc_empty(buf), ((chunk >> 1) - 1) & 1);
+      int slot = 0;
+      uint32_t ph = 0;                              // stage slot of the ring and its phase parity
+      int chunk = 0;                                // global chunk counter (TMEM accumulator buffer = chunk & 1)
+      const bool fast = H16 && p.fast == 1;
+      const int kb_half = (H16 && (p.K % BK) != 0) ? num_kb - 1 : -1;   // H16: K % 64 == 32 -> the last stage carries one sub-block
+      const uint64_t desc0 = make_desc(0);
+      for (int t = (CG2 && rank != 0) ? p.total_tiles : t_first; t < p.total_tiles; t += t_step) {      // pair: only the leader issues
+        const TileCoord tc_ = tile_coord(t);
+        // instruction descriptor: D fp32; A / B format tf32 (2) or f16 (0), both K-major; N >> 3; M >> 4 (pair: M = 256)
+        const uint32_t idesc = (1u << 4) | (H16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(tc_.nw >> 3) << 17) | ((uint32_t)((CG2 ? 2 * TBM : TBM) >> 4) << 24);
+        int kin = 0;
+        for (int kb = tc_.kb0; kb < tc_.kb1; ++kb) {
+          const int buf = chunk & 1;
+          if (kin == 0 && chunk >= 2) {       // the buffer's previous chunk must have been drained (pair: by both CTAs)
+            if (CG2) mbar_wait_cluster(bar_acc_empty(buf), ((chunk >> 1) - 1) & 1);
+            else mbar_wait(bar_acc_empty(buf), ((chunk >> 1) - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          if (CG2) mbar_wait_cluster(bar_full_split(slot), ph);
+          else mbar_wait(bar_full_split(slot), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        mbar_wait(bar_full_split(s), it & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = base + s * STAGE_BYTES;
-        const uint32_t acc = tmem_base + (uint32_t)(buf * TBN);
-        const uint32_t sbh = H16 ? b_ring + (uint32_t)s * b_stride : st + OFF_BHI;
-        const uint64_t b_hi = make_desc(sbh), b_lo = make_desc(H16 ? sbh + TILE_BYTES : st + OFF_BLO);
-        if (!elect_one()) continue;
-        if (H16) {
-          // A: packed fp16 pairs in TMEM (hi: 32 columns = 64 k, lo: the next 32); a K = 16 MMA consumes 8 columns of A and
-          // 32 bytes of each B row
-          const uint32_t a_hi = tmem_base + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64), a_lo = a_hi + 32;
-          const int nj = ((tc_.kb0 + kb) * BK + TBK < p.K) ? 4 : 2;     // odd tail stage: only the first sub-block is valid
+          const bool chunk_end = kin == KCHUNK - 1 || kb == tc_.kb1 - 1;
+          const uint32_t acc = tmem_base + (uint32_t)(buf * TBN);
+          const uint32_t st = base + slot * STAGE_BYTES;
+          const uint32_t sbh = H16 ? b_ring + (uint32_t)slot * b_stride : st + OFF_BHI;
+          const uint64_t b_hi = desc0 | (uint64_t)((sbh >> 4) & 0x3FFF);
+          const uint64_t b_lo = H16 ? b_hi + (B_PLANE >> 4) : desc0 | (uint64_t)(((st + OFF_BLO) >> 4) & 0x3FFF);
+          const uint32_t first = kin > 0 ? 1u : 0u;
+          if (elect_one()) {
+            if (H16) {
+              // A: packed fp16 pairs in TMEM (hi: 32 columns = 64 k, lo: the next 32); a K = 16 MMA consumes 8 columns of A and
+              // 32 bytes (2 descriptor units) of each B row
+              const uint32_t a_hi = tmem_base + (uint32_t)(Cfg<MODE>::A_COL0 + slot * 64), a_lo = a_hi + 32;
+              auto umma_ts_f16 = [](uint32_t d, uint32_t a, uint64_t b, uint32_t id, uint32_t accu) {
+                if (CG2) tc::umma2_ts_f16(d, a, b, id, accu);
+                else tc::umma_ts_f16(d, a, b, id, accu);
+              };
+              if (!fast) {
+                umma_ts_f16(acc, a_lo, b_hi, idesc, first);      // small terms first
+                umma_ts_f16(acc, a_hi, b_lo, idesc, 1u);
+                umma_ts_f16(acc, a_hi, b_hi, idesc, 1u);
+                umma_ts_f16(acc, a_lo + 8, b_hi + 2, idesc, 1u);
+                umma_ts_f16(acc, a_hi + 8, b_lo + 2, idesc, 1u);
+                umma_ts_f16(acc, a_hi + 8, b_hi + 2, idesc, 1u);
+                if (kb != kb_half) {
+                  umma_ts_f16(acc, a_lo + 16, b_hi + 4, idesc, 1u);
+                  umma_ts_f16(acc, a_hi + 16, b_lo + 4, idesc, 1u);
+                  umma_ts_f16(acc, a_hi + 16, b_hi + 4, idesc, 1u);
+                  umma_ts_f16(acc, a_lo + 24, b_hi + 6, idesc, 1u);
+                  umma_ts_f16(acc, a_hi + 24, b_lo + 6, idesc, 1u);
+                  umma_ts_f16(acc, a_hi + 24, b_hi + 6, idesc, 1u);
+                }
+              } else {
+                umma_ts_f16(acc, a_hi, b_hi, idesc, first);
+                umma_ts_f16(acc, a_hi + 8, b_hi + 2, idesc, 1u);
+                if (kb != kb_half) {
+                  umma_ts_f16(acc, a_hi + 16, b_hi + 4, idesc, 1u);
+                  umma_ts_f16(acc, a_hi + 24, b_hi + 6, idesc, 1u);
+                }
+              }
+            } else if (TS) {
+              const uint32_t a_hi = tmem_base + (uint32_t)(Cfg<MODE>::A_COL0 + slot * 64), a_lo = a_hi + 32;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j >= nj) break;
-            const uint64_t adv = (uint64_t)((j * 16 * 2) >> 4);
-            if (p.fast != 1) {
-              umma_ts_f16(acc, a_lo + j * 8, b_hi + adv, idesc, (kin > 0 || j > 0) ? 1u : 0u);      // small terms first
-              umma_ts_f16(acc, a_hi + j * 8, b_lo + adv, idesc, 1u);
-              umma_ts_f16(acc, a_hi + j * 8, b_hi + adv, idesc, 1u);
+              for (int j = 0; j < TBK / 8; ++j) {
+                const uint64_t adv = (uint64_t)((j * 8 * 4) >> 4);    // 32 bytes per K chunk of 8 tf32 in smem; 8 columns in TMEM
+                umma_ts(acc, a_lo + j * 8, b_hi + adv, idesc, j > 0 ? 1u : first);      // small terms first
+                umma_ts(acc, a_hi + j * 8, b_lo + adv, idesc, 1u);
+                umma_ts(acc, a_hi + j * 8, b_hi + adv, idesc, 1u);
+              }
             } else {
-              umma_ts_f16(acc, a_hi + j * 8, b_hi + adv, idesc, (kin > 0 || j > 0) ? 1u : 0u);
+              const uint64_t a_hi = desc0 | (uint64_t)(((st + OFF_A) >> 4) & 0x3FFF), a_lo = desc0 | (uint64_t)(((st + OFF_ALO) >> 4) & 0x3FFF);
+#pragma unroll
+              for (int j = 0; j < TBK / 8; ++j) {
+                const uint64_t adv = (uint64_t)((j * 8 * 4) >> 4);
+                umma_ss(acc, a_lo + adv, b_hi + adv, idesc, j > 0 ? 1u : first);
+                umma_ss(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma_ss(acc, a_hi + adv, b_hi + adv, idesc, 1u);
+              }
+            }
+            if (CG2) {
+              umma2_commit_mc(bar_empty(slot));     // both CTAs' stage slots
+              if (chunk_end) umma2_commit_mc(bar_acc_full(buf));
+            } else {
+              umma_commit(bar_empty(slot));       // stage (smem and, for TS, its TMEM A columns) reusable once these MMAs are done
+              if (chunk_end) umma_commit(bar_acc_full(buf));   // chunk complete
             }
           }
-        } else if (TS) {
-          const uint32_t a_hi = tmem_base + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64), a_lo = a_hi + 32;
-#pragma unroll
-          for (int j = 0; j < TBK / 8; ++j) {
-            const uint64_t adv = (uint64_t)((j * 8 * 4) >> 4);    // 32 bytes per K chunk of 8 tf32 in smem; 8 columns in TMEM
-            umma_ts(acc, a_lo + j * 8, b_hi + adv, idesc, (kin > 0 || j > 0) ? 1u : 0u);      // small terms first
-            umma_ts(acc, a_hi + j * 8, b_lo + adv, idesc, 1u);
-            umma_ts(acc, a_hi + j * 8, b_hi + adv, idesc, 1u);
-          }
-        } else {
-          const uint64_t a_hi = make_desc(st + OFF_A), a_lo = make_desc(st + OFF_ALO);
-#pragma unroll
-          for (int j = 0; j < TBK / 8; ++j) {
-            const uint64_t adv = (uint64_t)((j * 8 * 4) >> 4);
-            umma_ss(acc, a_lo + adv, b_hi + adv, idesc, (kin > 0 || j > 0) ? 1u : 0u);
-            umma_ss(acc, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_ss(acc, a_hi + adv, b_hi + adv, idesc, 1u);
-          }
+          __syncwarp();
+          if (chunk_end) { kin = 0; ++chunk; } else ++kin;
+          if (++slot == STAGES) { slot = 0; ph ^= 1u; }
         }
-        umma_commit(bar_empty(s));          // stage (smem and, for TS, its TMEM A columns) reusable once these MMAs are done
-        if (kin == KCHUNK - 1 || kb == nkb - 1) umma_commit(bar_acc_full(buf));   // chunk complete
-      }
-      gchunk0 += (nkb + KCHUNK - 1) / KCHUNK;
       }
     }
   }
@@ -428,7 +480,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // halo schedule: this thread's pixel inside the (bw+2) x (bh+2) x bn halo box at tap (0, 0)
       const int hrow0 = halo ? ((row / (p.bw * p.bh)) * (p.bh + 2) + (row / p.bw) % p.bh) * (p.bw + 2) + row % p.bw : 0;
       int gkb = 0, ghalo = 0, cur_h = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < p.total_tiles; t += t_step) {
       const TileCoord tc_ = tile_coord(t);
       for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
@@ -447,7 +499,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           rxx = (uint32_t)(hp & 7);
           halo_done = tap == 8 || kb == tc_.kb1 - 1;
         }
-        mbar_wait(bar_full_raw(s), it & 1);
+        // halo schedule: the pixels are already in the halo buffer, so load and convert BEFORE waiting for the stage slot (its
+        // barrier only says "TMEM A columns free, B landed"): the split of stage g+1 overlaps the wait for slot g+1
+        if (!halo) mbar_wait(bar_full_raw(s), it & 1);
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64 + sub * 16);
         if (sub == 0 || kb * BK + TBK < p.K) {          // an odd tail stage carries only sub-block 0
           uint32_t v[32], hi[16], lo[16];
@@ -475,14 +529,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               lo[e2] = *reinterpret_cast<const uint32_t*>(&l);
             }
           }
+          if (halo) {
+            mbar_wait(bar_full_raw(s), it & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");     // the MMAs that read these columns are complete
+          }
           tmem_st16(ta, hi);
           tmem_st16(ta + 32, lo);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        } else if (halo) {
+          mbar_wait(bar_full_raw(s), it & 1);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar_full_split(s));
+          if (CG2) mbar_arrive_cluster(mapa_rank(bar_full_split(s), 0));      // the leader's barrier counts both CTAs' split warps
+          else mbar_arrive(bar_full_split(s));
           if (halo_done) mbar_arrive(bar_halo_empty(cur_h));      // all nine taps read: the buffer may be refilled
         }
       }
@@ -495,7 +556,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t rbase = (uint32_t)row * 128u;
       const uint32_t rx = (uint32_t)(row & 7);
       int gkb = 0;
-      for (int t = warp < FIRST_SPLIT_WARP + 4 ? blockIdx.x : p.total_tiles; t < p.total_tiles; t += gridDim.x) {
+      for (int t = warp < FIRST_SPLIT_WARP + 4 ? t_first : p.total_tiles; t < p.total_tiles; t += t_step) {
       const TileCoord tc_ = tile_coord(t);
       for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
@@ -525,7 +586,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else {
       const int st_ = threadIdx.x - FIRST_SPLIT_WARP * 32;        // 0..255
       int gkb = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < p.total_tiles; t += t_step) {
       const TileCoord tc_ = tile_coord(t);
       for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
         const int s = gkb % STAGES, it = gkb / STAGES;
@@ -567,7 +628,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     float omax = 0.f;                              // max |C| stored by this thread (p.c_amax)
     int gchunk0 = 0, tile_it = 0;
 #pragma unroll 1
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
+    for (int t = t_first; t < p.total_tiles; t += t_step, ++tile_it) {
     const TileCoord tc_ = tile_coord(t);
     const int num_chunks = (tc_.kb1 - tc_.kb0 + KCHUNK - 1) / KCHUNK;
     const int n0 = tc_.n0, m0 = tc_.m0, x0 = tc_.x0, y0 = tc_.y0, b0 = tc_.b0, zb = tc_.zb, zh = tc_.zh;
@@ -595,7 +656,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+      if (lane == 0) {
+        if (CG2) mbar_arrive_cluster(mapa_rank(bar_acc_empty(buf), 0));
+        else mbar_arrive(bar_acc_empty(buf));
+      }
     }
     float* const sb = s_bias + (tile_it & 1) * TBN;
     if (et < TBN) sb[et] = bias_v;
@@ -777,10 +841,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (CG2) cluster_sync_all();          // the leader's MMAs read the peer's smem / TMEM: both CTAs stay until both are done
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -866,6 +932,7 @@ void ensure_attr(int device) {
     CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_SS>::SMEM_BYTES));
     CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_TS>::SMEM_BYTES));
     CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_H16>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_H16X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_H16X2>::SMEM_BYTES));
     attr_set[d] = true;
   }
 }
@@ -1062,6 +1129,12 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   if (p.halo && !h16) return false;        // (cannot happen: the halo conditions imply the fp16-split conditions)
   const int bk = h16 ? Cfg<MODE_H16>::BK : TBK;
   const int num_kb = cdiv(a.K, bk);
+  // CTA pairs (MODE_H16X2): two adjacent 128-row tiles share one B tile, half of it in each CTA's shared memory
+  // Measured on B200 (profiles/r02_ops_h16_pair_negative.txt): correct, but 0.6x the single-CTA rate -- the kernel is paced by the
+  // split warps, not by B traffic, and the cross-CTA barrier hops lengthen every stage; kept as an opt-in experiment
+  static const bool use_cg2 = getenv("CDX_TC_PAIR") != nullptr;
+  const bool cg2 = h16 && use_cg2 && (p.tiles_m % 2) == 0 && e.num_sms >= 2;
+  if (cg2) p.tiles_m /= 2;                 // from here on: 256-row pair tiles
   // Work partition: tile width w along N (MMA N = valid columns rounded up to 16, so a ragged last tile costs only its
   // share) and split-K factor S, chosen together against wave quantisation on num_sms persistent CTAs by replaying the
   // kernel's static schedule (CTA c runs items c, c + grid, ...) with a cost model in cycles: one k-block of a w-wide
@@ -1074,7 +1147,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
     static std::map<std::array<int64_t, 5>, int> plan_cache;      // exact key (no hashing of packed fields: nothing can collide)
     static std::mutex plan_mutex;                                          // engines on different devices may plan concurrently
     std::lock_guard<std::mutex> plan_lock(plan_mutex);
-    const std::array<int64_t, 5> key = {p.tiles_m, a.N, num_kb, ((a.geglu || a.Ct_hi) ? 1 : 0) | (a.out_nchw ? 2 : 0) | (h16 ? 4 : 0) | (p.halo ? 8 : 0), e.num_sms};
+    const std::array<int64_t, 5> key = {p.tiles_m, a.N, num_kb, ((a.geglu || a.Ct_hi) ? 1 : 0) | (a.out_nchw ? 2 : 0) | (h16 ? 4 : 0) | (p.halo ? 8 : 0) | (cg2 ? 16 : 0), e.num_sms};
     // cycles per pipeline stage of a w-wide tile (fitted on B200): TF32 planes 540 + 4.2 w per 32 k; fp16 split per 64 k
     const double kc0 = h16 ? CDX_H16_KC0 : 540.0, kc1 = h16 ? CDX_H16_KC1 : 4.2;
     const int min_kbs = h16 ? 4 : 8;
@@ -1084,7 +1157,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
       best_s = it->second & 255;
     } else {
       const int wmin = (a.geglu || a.Ct_hi || a.N <= 64 || fixed_w) ? TBN : 64;
-      const int G = e.num_sms;
+      const int G = cg2 ? e.num_sms / 2 : e.num_sms;      // persistent CTAs (pair mode: clusters)
       double best = 1e30;
       std::vector<double> load((size_t)G);
       for (int w = TBN; w >= wmin; w -= 16) {
@@ -1153,10 +1226,11 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   if (side_done) *side_done = (p.c_amax ? 1 : 0) | (p.c_stats ? 2 : 0);
   if (e.dry()) return true;
   static const int grid_cap = getenv("CDX_TC_GRID") ? atoi(getenv("CDX_TC_GRID")) : 0;      // experiment aid: run on fewer SMs
-  const int grid = std::min(p.total_tiles, grid_cap > 0 ? std::min(grid_cap, e.num_sms) : e.num_sms);
+  const int grid = cg2 ? 2 * std::min(p.total_tiles, (grid_cap > 0 ? std::min(grid_cap, e.num_sms) : e.num_sms) / 2)
+                       : std::min(p.total_tiles, grid_cap > 0 ? std::min(grid_cap, e.num_sms) : e.num_sms);
   if (h16) {
     uint64_t d[2] = {(uint64_t)a.K, (uint64_t)a.N}, st[1] = {(uint64_t)a.ldb * 2};
-    uint32_t bx[2] = {(uint32_t)Cfg<MODE_H16>::BK, (uint32_t)p.tn_w};
+    uint32_t bx[2] = {(uint32_t)Cfg<MODE_H16>::BK, (uint32_t)(cg2 ? p.tn_w / 2 : p.tn_w)};
     mB = &get_map(a.Bw_h_hi, 2, d, st, bx, nullptr, 2);
     mBlo = &get_map(a.Bw_h_lo, 2, d, st, bx, nullptr, 2);
   } else {
@@ -1168,9 +1242,22 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   ensure_attr(e.device);
   ProfScope ps(e, s, a.mode == 1 ? PROF_CONV_TC : PROF_DENSE_TC, 2.0 * a.M * a.N * a.K,
                4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
-  ps.note("M%d N%d K%d w%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, p.tn_w, tiles, p.splits, h16 ? (p.fast ? "H16x1" : p.halo ? "H16halo" : "H16") : ts ? "TS" : "SS",
+  ps.note("M%d N%d K%d w%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, p.tn_w, tiles, p.splits, h16 ? (p.fast ? "H16x1" : p.halo ? (cg2 ? "H16halo-pair" : "H16halo") : (cg2 ? "H16-pair" : "H16")) : ts ? "TS" : "SS",
           a.Cout_lo ? " planes" : "", a.geglu ? " geglu" : "", a.residual ? " res" : "");
-  if (h16) tc_gemm_kernel<MODE_H16><<<grid, TC_THREADS, Cfg<MODE_H16>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
+  if (cg2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg<MODE_H16X2>::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CDX_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MODE_H16X2>, *mA, *mA2, *mB, *mBlo, p));
+  } else if (h16) tc_gemm_kernel<MODE_H16><<<grid, TC_THREADS, Cfg<MODE_H16>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
   else if (ts) tc_gemm_kernel<MODE_TS><<<grid, TC_THREADS, Cfg<MODE_TS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
   else tc_gemm_kernel<MODE_SS><<<grid, TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
   CDX_CUDA(cudaGetLastError());
