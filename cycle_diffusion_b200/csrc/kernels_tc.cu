@@ -466,87 +466,129 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     // =========================================================================== split warps
     if (H16) {
-      // thread = one tile row of ONE 32-float sub-block of the stage (warps 2..5: sub-block 0, warps 6..9: sub-block 1; the profile
-      // of the 4-warp version showed the split warps issue-bound at ~480 dependent instructions per stage with nothing else
-      // resident on their schedulers): x' = x * 2^ea, hi = fp16(x'), lo = fp16(x' - hi), packed two per 32-bit TMEM column
-      // (even k in the low half)
+      // x' = x * 2^ea, hi = fp16(x'), lo = fp16(x' - hi), packed two per 32-bit TMEM column (even k in the low half).  Eight warps,
+      // two per TMEM lane quadrant (the profile of the 4-warp version showed the split warps issue-bound with nothing else resident on
+      // their schedulers).
       const int q = warp & 3;
       const int sub = (warp - FIRST_SPLIT_WARP) >> 2;
       const int row = q * 32 + lane;
-      const uint32_t rbase = (uint32_t)row * 128u;
-      const uint32_t rx = (uint32_t)(row & 7);
       const int ea = h16_a_exp(p);
       const float asc = exp2i(ea);
-      // halo schedule: this thread's pixel inside the (bw+2) x (bh+2) x bn halo box at tap (0, 0)
-      const int hrow0 = halo ? ((row / (p.bw * p.bh)) * (p.bh + 2) + (row / p.bw) % p.bh) * (p.bw + 2) + row % p.bw : 0;
-      int gkb = 0, ghalo = 0, cur_h = 0;
-      for (int t = t_first; t < p.total_tiles; t += t_step) {
-      const TileCoord tc_ = tile_coord(t);
-      for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
-        const int s = gkb % STAGES, it = gkb / STAGES;
-        uint32_t sa = base + s * STAGE_BYTES + OFF_A + sub * TILE_BYTES + rbase, rxx = rx;
-        bool halo_done = false;
-        if (halo) {
+      auto split2 = [&](uint32_t a0, uint32_t a1, uint32_t& h_out, uint32_t& l_out) {
+        float x0 = __uint_as_float(a0), x1 = __uint_as_float(a1);
+        if (ea != 0) { x0 *= asc; x1 *= asc; }
+        const __half2 h = __floats2half2_rn(x0, x1);          // .x (low half) = even k
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        h_out = *reinterpret_cast<const uint32_t*>(&h);
+        l_out = *reinterpret_cast<const uint32_t*>(&l);
+      };
+      if (halo) {
+        // ---- halo schedule.  Every activation element used to be converted once per tap and N tile it takes part in (9 x per tile);
+        // now the halo box of a 64-channel block is converted ONCE, in place, into an fp16 hi plane (plane 0: 64 channels = 128 B per
+        // pixel) and a lo plane (plane 1) -- one pixel per thread -- and the per-tap work of a stage is a copy: 8 x LDS.128 of this
+        // thread's shifted pixel -> one tcgen05.st of 32 columns (warps of sub 0 copy the hi plane, sub 1 the lo plane).
+        const int tid = (int)threadIdx.x - FIRST_SPLIT_WARP * 32;      // 0..255
+        const int npx = (p.bw + 2) * (p.bh + 2) * p.bn;                 // <= 192 (host-checked)
+        const int hrow0 = ((row / (p.bw * p.bh)) * (p.bh + 2) + (row / p.bw) % p.bh) * (p.bw + 2) + row % p.bw;   // pixel at tap (0, 0)
+        int gkb = 0, ghalo = 0, cur_h = 0;
+        for (int t = t_first; t < p.total_tiles; t += t_step) {
+        const TileCoord tc_ = tile_coord(t);
+        for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
+          const int s = gkb % STAGES, it = gkb / STAGES;
           const int cb = kb / 9, tap = kb - cb * 9;
           if (tap == 0 || kb == tc_.kb0) {
             cur_h = ghalo & 1;
             mbar_wait(bar_halo_full(cur_h), (ghalo >> 1) & 1);
             ++ghalo;
+            if (tid < npx) {
+              const uint32_t r0 = halo_base + (uint32_t)(cur_h * 2) * HALO_PLANE + (uint32_t)tid * 128u, r1 = r0 + HALO_PLANE;
+              const uint32_t px = (uint32_t)(tid & 7);
+              uint32_t v[32], lo0[16];
+              // channels 0..31 (raw plane 0) -> hi chunks 0..3 of plane 0 (written now: the whole raw row is in registers), lo kept
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3]) : "r"(r0 + (((uint32_t)c ^ px) << 4)));
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint32_t h[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split2(v[8 * c + 2 * e], v[8 * c + 2 * e + 1], h[e], lo0[4 * c + e]);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(r0 + (((uint32_t)c ^ px) << 4)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+              }
+              // channels 32..63 (raw plane 1) -> hi chunks 4..7 of plane 0, then the whole lo row into plane 1
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3]) : "r"(r1 + (((uint32_t)c ^ px) << 4)));
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split2(v[8 * c + 2 * e], v[8 * c + 2 * e + 1], h[e], l[e]);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(r0 + (((uint32_t)(c + 4) ^ px) << 4)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(r1 + (((uint32_t)(c + 4) ^ px) << 4)), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+              }
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(r1 + (((uint32_t)c ^ px) << 4)), "r"(lo0[4 * c]), "r"(lo0[4 * c + 1]), "r"(lo0[4 * c + 2]), "r"(lo0[4 * c + 3]) : "memory");
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(NUM_SPLIT_WARPS * 32) : "memory");      // every pixel converted before any tap reads it
           }
           const int dy = tap / 3, dx = tap - dy * 3;
           const int hp = hrow0 + dy * (p.bw + 2) + dx;
-          sa = halo_base + (uint32_t)(cur_h * 2 + sub) * HALO_PLANE + (uint32_t)hp * 128u;
-          rxx = (uint32_t)(hp & 7);
-          halo_done = tap == 8 || kb == tc_.kb1 - 1;
-        }
-        // halo schedule: the pixels are already in the halo buffer, so load and convert BEFORE waiting for the stage slot (its
-        // barrier only says "TMEM A columns free, B landed"): the split of stage g+1 overlaps the wait for slot g+1
-        if (!halo) mbar_wait(bar_full_raw(s), it & 1);
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64 + sub * 16);
-        if (sub == 0 || kb * BK + TBK < p.K) {          // an odd tail stage carries only sub-block 0
-          uint32_t v[32], hi[16], lo[16];
+          const uint32_t sa = halo_base + (uint32_t)(cur_h * 2 + sub) * HALO_PLANE + (uint32_t)hp * 128u, hx = (uint32_t)(hp & 7);
+          uint32_t w[32];
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3]) : "r"(sa + (((uint32_t)c ^ rxx) << 4)));
-          if (ea != 0) {
-#pragma unroll
-            for (int e2 = 0; e2 < 16; ++e2) {
-              const float x0 = __uint_as_float(v[2 * e2]) * asc, x1 = __uint_as_float(v[2 * e2 + 1]) * asc;
-              const __half2 h = __floats2half2_rn(x0, x1);          // .x (low half) = even k
-              const float2 hf = __half22float2(h);
-              const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-              hi[e2] = *reinterpret_cast<const uint32_t*>(&h);
-              lo[e2] = *reinterpret_cast<const uint32_t*>(&l);
-            }
-          } else {
-#pragma unroll
-            for (int e2 = 0; e2 < 16; ++e2) {
-              const float x0 = __uint_as_float(v[2 * e2]), x1 = __uint_as_float(v[2 * e2 + 1]);
-              const __half2 h = __floats2half2_rn(x0, x1);
-              const float2 hf = __half22float2(h);
-              const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-              hi[e2] = *reinterpret_cast<const uint32_t*>(&h);
-              lo[e2] = *reinterpret_cast<const uint32_t*>(&l);
-            }
-          }
-          if (halo) {
-            mbar_wait(bar_full_raw(s), it & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");     // the MMAs that read these columns are complete
-          }
-          tmem_st16(ta, hi);
-          tmem_st16(ta + 32, lo);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        } else if (halo) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * c]), "=r"(w[4 * c + 1]), "=r"(w[4 * c + 2]), "=r"(w[4 * c + 3]) : "r"(sa + (((uint32_t)c ^ hx) << 4)));
+          // the stage slot's barrier says "TMEM A columns free, B landed": waited for only now, after the loads were issued
           mbar_wait(bar_full_raw(s), it & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64 + sub * 32), w);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (CG2) mbar_arrive_cluster(mapa_rank(bar_full_split(s), 0));      // the leader's barrier counts both CTAs' split warps
+            else mbar_arrive(bar_full_split(s));
+            if (tap == 8 || kb == tc_.kb1 - 1) {                                 // all taps of this block read: the buffer may be refilled
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy accesses before the next TMA write
+              mbar_arrive(bar_halo_empty(cur_h));
+            }
+          }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          if (CG2) mbar_arrive_cluster(mapa_rank(bar_full_split(s), 0));      // the leader's barrier counts both CTAs' split warps
-          else mbar_arrive(bar_full_split(s));
-          if (halo_done) mbar_arrive(bar_halo_empty(cur_h));      // all nine taps read: the buffer may be refilled
         }
-      }
+      } else {
+        // ---- raw A tiles by TMA: thread = one tile row of ONE 32-float sub-block of the stage (warps of sub 0 / sub 1)
+        const uint32_t rbase = (uint32_t)row * 128u;
+        const uint32_t rx = (uint32_t)(row & 7);
+        int gkb = 0;
+        for (int t = t_first; t < p.total_tiles; t += t_step) {
+        const TileCoord tc_ = tile_coord(t);
+        for (int kb = tc_.kb0; kb < tc_.kb1; ++kb, ++gkb) {
+          const int s = gkb % STAGES, it = gkb / STAGES;
+          const uint32_t sa = base + s * STAGE_BYTES + OFF_A + sub * TILE_BYTES + rbase;
+          mbar_wait(bar_full_raw(s), it & 1);
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<MODE>::A_COL0 + s * 64 + sub * 16);
+          if (sub == 0 || kb * BK + TBK < p.K) {          // an odd tail stage carries only sub-block 0
+            uint32_t v[32], hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3]) : "r"(sa + (((uint32_t)c ^ rx) << 4)));
+#pragma unroll
+            for (int e2 = 0; e2 < 16; ++e2) split2(v[2 * e2], v[2 * e2 + 1], hi[e2], lo[e2]);
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 32, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (CG2) mbar_arrive_cluster(mapa_rank(bar_full_split(s), 0));
+            else mbar_arrive(bar_full_split(s));
+          }
+        }
+        }
       }
     } else if (TS) {
       // thread = one tile row: read its 128 raw bytes (8 swizzled 16-byte chunks), store hi / lo into TMEM lane `row`
@@ -1130,10 +1172,12 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   const int bk = h16 ? Cfg<MODE_H16>::BK : TBK;
   const int num_kb = cdiv(a.K, bk);
   // CTA pairs (MODE_H16X2): two adjacent 128-row tiles share one B tile, half of it in each CTA's shared memory
-  // Measured on B200 (profiles/r02_ops_h16_pair_negative.txt): correct, but 0.6x the single-CTA rate -- the kernel is paced by the
-  // split warps, not by B traffic, and the cross-CTA barrier hops lengthen every stage; kept as an opt-in experiment
-  static const bool use_cg2 = getenv("CDX_TC_PAIR") != nullptr;
-  const bool cg2 = h16 && use_cg2 && (p.tiles_m % 2) == 0 && e.num_sms >= 2;
+  // Measured on B200: the single-CTA kernel saturates the SM's shared-memory pipe (TMA fill of B + tensor-core fetch of B + the
+  // split warps' LDS = ~93 % of its cycles in the ncu capture); the pair halves the first two.  conv3x3 330 -> 420-480 TFLOP/s
+  // (profiles/r02_ops_h16_pair.txt).  The first pair version used cluster-scope acquire / release on the per-stage barriers and
+  // ran at 0.6x: ptxas puts an L1 invalidation (CCTL.IVALL) behind each of them (profiles/r02_ops_h16_pair_negative.txt).
+  static const bool no_cg2 = getenv("CDX_TC_NO_PAIR") != nullptr;
+  const bool cg2 = h16 && !no_cg2 && (p.tiles_m % 2) == 0 && e.num_sms >= 2;
   if (cg2) p.tiles_m /= 2;                 // from here on: 256-row pair tiles
   // Work partition: tile width w along N (MMA N = valid columns rounded up to 16, so a ragged last tile costs only its
   // share) and split-K factor S, chosen together against wave quantisation on num_sms persistent CTAs by replaying the
