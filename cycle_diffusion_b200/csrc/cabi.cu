@@ -114,6 +114,7 @@ struct LatentLoopArgs {
   const float* x0 = nullptr;                       // ENC / LOCK
   const float* c_src = nullptr; const float* c_tgt = nullptr; const float* uc = nullptr; int L = 0;
   float s_scale = 1.f, t_scale = 1.f;
+  const float* s_scale_v = nullptr; const float* t_scale_v = nullptr;     // per-sample scales (device, [B]): ensemble members along B
   const cdx_ddim_coef* coef = nullptr; const float* t_host = nullptr; int n_steps = 0;
   int n_rec = 0; const float* noise = nullptr; float sa = 0.f, s1 = 0.f;      // ENC / LOCK: noise [n_rec+1, B, chw]
   float* z_out = nullptr;                           // ENC: [B, n_rec+1, chw]; LOCK: optional
@@ -127,8 +128,9 @@ void run_latent_loop(Net& unet, const LatentLoopArgs& a, cudaStream_t s) {
   const int B = a.B, chw = a.C * a.h * a.w;
   const size_t n = (size_t)B * chw;
   const bool enc = a.mode & LOOP_ENC, dec = a.mode & LOOP_DEC;
-  const bool cfg_s = enc && a.uc && a.s_scale != 1.0f && a.s_scale != 0.0f;
-  const bool cfg_t = dec && a.uc && a.t_scale != 1.0f && a.t_scale != 0.0f;
+  // (with per-sample scales both segments always run; samples whose scale is 0 / 1 pick their segment's output unchanged)
+  const bool cfg_s = enc && a.uc && (a.s_scale_v || (a.s_scale != 1.0f && a.s_scale != 0.0f));
+  const bool cfg_t = dec && a.uc && (a.t_scale_v || (a.t_scale != 1.0f && a.t_scale != 0.0f));
   const int nseg_src = enc ? (cfg_s ? 2 : 1) : 0, nseg_tgt = dec ? (cfg_t ? 2 : 1) : 0, nseg = nseg_src + nseg_tgt;
   const int nb = nseg * B;
   const int D = unet.ucfg.context_dim;
@@ -150,11 +152,11 @@ void run_latent_loop(Net& unet, const LatentLoopArgs& a, cudaStream_t s) {
     int sg = 0;
     if (enc) {
       if (cfg_s) copy_dd(e, a.uc, ctx_in + (size_t)(sg++) * ctx_n, ctx_n, s);
-      copy_dd(e, (a.uc && a.s_scale == 0.0f) ? a.uc : a.c_src, ctx_in + (size_t)(sg++) * ctx_n, ctx_n, s);
+      copy_dd(e, (a.uc && !a.s_scale_v && a.s_scale == 0.0f) ? a.uc : a.c_src, ctx_in + (size_t)(sg++) * ctx_n, ctx_n, s);
     }
     if (dec) {
       if (cfg_t) copy_dd(e, a.uc, ctx_in + (size_t)(sg++) * ctx_n, ctx_n, s);
-      copy_dd(e, (a.uc && a.t_scale == 0.0f) ? a.uc : a.c_tgt, ctx_in + (size_t)(sg++) * ctx_n, ctx_n, s);
+      copy_dd(e, (a.uc && !a.t_scale_v && a.t_scale == 0.0f) ? a.uc : a.c_tgt, ctx_in + (size_t)(sg++) * ctx_n, ctx_n, s);
     }
   }
   const float* es_uc = cfg_s ? eout : nullptr;
@@ -188,7 +190,7 @@ void run_latent_loop(Net& unet, const LatentLoopArgs& a, cudaStream_t s) {
     if (enc) {
       st.enc = 1;
       st.x0 = a.x0; st.xt = xb[0]; st.xn = xb[1];
-      st.es_c = es_c; st.es_uc = es_uc; st.s_scale = a.s_scale; st.cs = a.coef[i];
+      st.es_c = es_c; st.es_uc = es_uc; st.s_scale = a.s_scale; st.s_scale_v = a.s_scale_v; st.cs = a.coef[i];
       if (a.z_out) { st.z_out = a.z_out + (size_t)(1 + i) * chw; st.z_stride = (long long)(a.n_rec + 1) * chw; }
       st.next = next_kind(i + 1);
       if (st.next) { st.noise_next = a.noise + (size_t)(2 + i) * n; st.cnext = a.coef[i + 1]; }
@@ -196,7 +198,7 @@ void run_latent_loop(Net& unet, const LatentLoopArgs& a, cudaStream_t s) {
     }
     if (dec) {
       st.dec = 1;
-      st.yt = yb[0]; st.et_c = et_c; st.et_uc = et_uc; st.t_scale = a.t_scale; st.ct = a.coef[i];
+      st.yt = yb[0]; st.et_c = et_c; st.et_uc = et_uc; st.t_scale = a.t_scale; st.t_scale_v = a.t_scale_v; st.ct = a.coef[i];
       if (!enc) {
         if (i < a.n_eps) { st.eps_in = a.z_in + (size_t)(1 + i) * chw; st.eps_stride = (long long)(a.n_eps + 1) * chw; }
         else { st.eps_in = a.extra + (size_t)(i - a.n_eps) * n; st.eps_stride = chw; }
@@ -485,6 +487,38 @@ int cdx_cycle_lockstep(cdx_net* un, const float* x0, const float* c_src, const f
     a.x0 = x0; a.c_src = c_src; a.c_tgt = c_tgt; a.uc = uc; a.L = L; a.s_scale = src_scale; a.t_scale = tgt_scale;
     a.coef = coef; a.t_host = t_host; a.n_steps = n_steps; a.n_rec = n_steps; a.noise = noise; a.sa = sqrt_a_T; a.s1 = sqrt_1ma_T;
     a.z_out = z_out; a.x_out = x_out; a.B = B; a.C = C; a.h = h; a.w = w;
+    with_arena(un->owner->e, S(stream), [&] { run_latent_loop(*un->n, a, S(stream)); });
+  });
+}
+
+int cdx_latent_loop_ens(cdx_net* un, int mode, const float* x0, const float* c_src, const float* c_tgt, const float* uc, int L,
+                        const float* src_scales, const float* tgt_scales, const cdx_ddim_coef* coef, const float* t_host, int n_steps, int n_rec,
+                        const float* noise, float sqrt_a_T, float sqrt_1ma_T, const float* z_in, int n_eps, const float* extra_noise,
+                        float* z_out, float* x_out, int B, int C, int h, int w, void* stream) {
+  return guard([&] {
+    CDX_CHECK(un && un->owner && coef && t_host && mode >= LOOP_ENC && mode <= LOOP_LOCK, "latent_loop_ens: bad arguments (mode %d)", mode);
+    const bool enc = mode & LOOP_ENC, dec = mode & LOOP_DEC;
+    CDX_CHECK(n_steps >= 1, "latent_loop_ens: n_steps=%d", n_steps);
+    LatentLoopArgs a;
+    a.mode = mode;
+    a.uc = uc; a.L = L; a.coef = coef; a.t_host = t_host; a.n_steps = n_steps;
+    a.B = B; a.C = C; a.h = h; a.w = w;
+    if (enc) {
+      CDX_CHECK(x0 && c_src && noise && src_scales && uc, "latent_loop_ens: the encode chain needs x0, c_src, uc, noise and per-sample scales");
+      if (mode == LOOP_LOCK) n_rec = n_steps;
+      CDX_CHECK(n_rec >= 0 && n_rec <= n_steps, "latent_loop_ens: n_rec=%d", n_rec);
+      for (int i = 0; i < n_rec; ++i) CDX_CHECK(coef[i].sigma > 0.f, "latent_loop_ens: eta must be > 0 (sigma[%d] == 0), ddim.py:268", i);
+      CDX_CHECK(mode == LOOP_LOCK || z_out, "latent_loop_ens: encode needs z_out");
+      a.x0 = x0; a.c_src = c_src; a.s_scale_v = src_scales; a.n_rec = n_rec; a.noise = noise; a.sa = sqrt_a_T; a.s1 = sqrt_1ma_T; a.z_out = z_out;
+    }
+    if (dec) {
+      CDX_CHECK(c_tgt && tgt_scales && uc && x_out, "latent_loop_ens: the decode chain needs c_tgt, uc, per-sample scales and x_out");
+      a.c_tgt = c_tgt; a.t_scale_v = tgt_scales; a.x_out = x_out;
+      if (!enc) {
+        CDX_CHECK(z_in && n_eps >= 0 && (n_eps >= n_steps || extra_noise), "latent_loop_ens: decode needs z (%d noises for %d steps) or extra noise", n_eps, n_steps);
+        a.z_in = z_in; a.n_eps = n_eps; a.extra = extra_noise;
+      }
+    }
     with_arena(un->owner->e, S(stream), [&] { run_latent_loop(*un->n, a, S(stream)); });
   });
 }

@@ -231,6 +231,9 @@ struct LatentStep {
   int enc = 0;
   const float* x0 = nullptr; const float* xt = nullptr; const float* xn = nullptr;    // x_t and x_{t-1} (already drawn)
   const float* es_c = nullptr; const float* es_uc = nullptr; float s_scale = 1.f;     // eps-hat under the source condition
+  const float* s_scale_v = nullptr; const float* t_scale_v = nullptr;   // optional per-sample guidance scales [B] (ensemble members batched
+                                                                        // along B); scale 1 -> eps-hat(c) and 0 -> eps-hat(uc) EXACTLY,
+                                                                        // as the reference's single-forward branches (ddim.py:550-551)
   cdx_ddim_coef cs{};
   float* z_out = nullptr; long long z_stride = 0;   // optional: eps -> z_out[b*z_stride + r]
   int next = 0;                              // 0 none, 1 posterior sample x_{t-2} from (x0, xn, noise_next), 2 x_{t-2} = x0 (index 0)

@@ -195,6 +195,15 @@ __device__ __forceinline__ float cfg_combine(const float* e_c, const float* e_uc
   return ADD(eu, MUL(scale, SUB(ec, eu)));      // e_t_uncond + s * (e_t - e_t_uncond), ddim.py:559
 }
 
+// per-sample scale (ensemble batching): members whose scale is 1 or 0 take the reference's single-forward value bit for bit
+__device__ __forceinline__ float cfg_combine_v(const float* e_c, const float* e_uc, float scale, size_t i) {
+  const float ec = e_c[i];
+  if (e_uc == nullptr || scale == 1.0f) return ec;
+  const float eu = e_uc[i];
+  if (scale == 0.0f) return eu;
+  return ADD(eu, MUL(scale, SUB(ec, eu)));
+}
+
 __global__ void ddim_posterior_kernel(const float* __restrict__ x0, const float* __restrict__ xt, const float* __restrict__ nz,
                                       cdx_ddim_coef c, float* __restrict__ out, size_t n) {
   GRID_STRIDE(i, n) {
@@ -237,7 +246,7 @@ __global__ void latent_step_kernel(const LatentStep a) {
     const size_t b = i / a.chw, r = i - b * a.chw;
     float eps = 0.f;
     if (a.enc) {
-      const float e_t = cfg_combine(a.es_c, a.es_uc, a.s_scale, i);
+      const float e_t = a.s_scale_v ? cfg_combine_v(a.es_c, a.es_uc, a.s_scale_v[b], i) : cfg_combine(a.es_c, a.es_uc, a.s_scale, i);
       const float xt = a.xt[i], xn = a.xn[i];
       const float pred_x0 = DIV(SUB(xt, MUL(a.cs.sqrt_1m_at_tab, e_t)), a.cs.sqrt_at);          // ddim.py:576
       const float dir = MUL(a.cs.dir_coef, e_t);                                                // :578
@@ -250,7 +259,7 @@ __global__ void latent_step_kernel(const LatentStep a) {
       eps = a.eps_in[b * a.eps_stride + r];
     }
     if (a.dec) {
-      const float e_t = cfg_combine(a.et_c, a.et_uc, a.t_scale, i);
+      const float e_t = a.t_scale_v ? cfg_combine_v(a.et_c, a.et_uc, a.t_scale_v[b], i) : cfg_combine(a.et_c, a.et_uc, a.t_scale, i);
       const float y = a.yt[i];
       const float pred_x0 = DIV(SUB(y, MUL(a.ct.sqrt_1m_at_tab, e_t)), a.ct.sqrt_at);           // ddim.py:634
       const float dir = MUL(a.ct.dir_coef, e_t);                                                // :638

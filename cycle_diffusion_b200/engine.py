@@ -361,6 +361,34 @@ class UNet(Net):
                                     sched.t_array(), sched.refine_steps, _ptr(extra_noise), _ptr(out), B, Cc, h, w, e.stream))
         return out
 
+    # ---- ensemble members batched along B (per-sample guidance scales; cdx_latent_loop_ens)
+    def latent_encode_ens(self, x0, c, uc, scales, sched, n_rec, noise):
+        """latent_encode with one guidance scale per sample: scales [B] -> z [B, n_rec+1, C, h, w]."""
+        e = self.engine
+        x0, c, uc, noise = (_f32c(t, e.device) for t in (x0, c, uc, noise))
+        sc = _f32c(torch.as_tensor(scales, dtype=torch.float32), e.device)
+        B, Cc, h, w = x0.shape
+        assert noise.shape == (n_rec + 1, B, Cc, h, w) and sc.shape == (B,)
+        z = e.empty(B, n_rec + 1, Cc, h, w)
+        check(lib.cdx_latent_loop_ens(self.h, 1, _ptr(x0), _ptr(c), None, _ptr(uc), c.shape[1], _ptr(sc), None, sched.coef_array(), sched.t_array(),
+                                      sched.refine_steps, n_rec, _ptr(noise), sched.sqrt_a_T, sched.sqrt_1ma_T, None, 0, None, _ptr(z), None,
+                                      B, Cc, h, w, e.stream))
+        return z
+
+    def latent_decode_ens(self, z, c, uc, scales, sched, extra_noise=None):
+        """latent_decode with one guidance scale per sample: z [B, n_eps+1, C, h, w], scales [B] -> x0 [B, C, h, w]."""
+        e = self.engine
+        z, c, uc = (_f32c(t, e.device) for t in (z, c, uc))
+        sc = _f32c(torch.as_tensor(scales, dtype=torch.float32), e.device)
+        extra_noise = _f32c(extra_noise, e.device) if extra_noise is not None else None
+        B, n1, Cc, h, w = z.shape
+        assert sc.shape == (B,)
+        out = e.empty(B, Cc, h, w)
+        check(lib.cdx_latent_loop_ens(self.h, 2, None, None, _ptr(c), _ptr(uc), c.shape[1], None, _ptr(sc), sched.coef_array(), sched.t_array(),
+                                      sched.refine_steps, 0, None, 0.0, 0.0, _ptr(z), n1 - 1, _ptr(extra_noise), None, _ptr(out),
+                                      B, Cc, h, w, e.stream))
+        return out
+
     def cycle_lockstep(self, x0, c_src, c_tgt, uc, src_scale, tgt_scale, sched, noise, return_z=False):
         """Both chains in one loop (one U-Net call + one fused elementwise kernel per step, no z buffer unless asked for):
         x0 [B,C,h,w] -> translated latent [B,C,h,w] (and z [B, n+1, C,h,w] when return_z).  noise as for latent_encode with

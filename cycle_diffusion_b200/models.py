@@ -24,8 +24,13 @@ class TextUnsupervisedTranslation(nn.Module):
     def forward(self, sample_id, original_image, encode_text, decode_text):
         self.gan_wrapper.eval()
         assert not self.training
-        z_ensemble = self.gan_wrapper.encode(image=original_image, encode_text=encode_text)
-        img = self.gan_wrapper(z_ensemble=z_ensemble, original_img=original_image, encode_text=encode_text, decode_text=decode_text)
+        w = self.gan_wrapper
+        if getattr(w, 'single_member', None) is not None and w.single_member():
+            # one ensemble member: the reference's encode -> z -> generate (text_unsupervised_translation.py:33-36) as one lock-step loop
+            img = w.cycle(original_image, encode_text, decode_text)
+        else:
+            z_ensemble = w.encode(image=original_image, encode_text=encode_text)
+            img = w(z_ensemble=z_ensemble, original_img=original_image, encode_text=encode_text, decode_text=decode_text)
         losses = dict()
         weighted_loss = torch.zeros_like(sample_id).float()
         return (original_image, img), weighted_loss, losses

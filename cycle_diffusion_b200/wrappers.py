@@ -135,8 +135,11 @@ class _StochasticTextWrapperBase(torch.nn.Module):
     def __init__(self, source_model_type, custom_steps, eta, white_box_steps, skip_steps,
                  encoder_unconditional_guidance_scales=None, decoder_unconditional_guidance_scales=None, n_trials=None, *,
                  engine=None, device=0, state_dict=None, cond_stage=None, ranker=None, unet_config=None, vae_config=None,
-                 latent_size=None, resolution=None, generator=None, seed=1234, tokenizer=None):
+                 latent_size=None, resolution=None, generator=None, seed=1234, tokenizer=None, ensemble_batch=16):
         super().__init__()
+        # ensemble members that share a schedule are batched along the batch dimension, up to this many samples per sampling loop
+        # (cdx_latent_loop_ens); None / 0 = one member at a time, the reference's loop shape
+        self.ensemble_batch = ensemble_batch
         self.encoder_unconditional_guidance_scales = encoder_unconditional_guidance_scales
         self.decoder_unconditional_guidance_scales = decoder_unconditional_guidance_scales
         self.n_trials = n_trials
@@ -196,8 +199,73 @@ class _StochasticTextWrapperBase(torch.nn.Module):
                 noise[1 + i] = torch.randn(shape)
         return noise
 
+    def _chunks(self, members, bsz):
+        per = max(1, (self.ensemble_batch or 1) // max(1, bsz))
+        return [members[i:i + per] for i in range(0, len(members), per)]
+
+    def _generate_batched(self, z_ensemble, decode_text):
+        """generate() with the members of one schedule batched along B: the conditioning is computed once, the context K / V
+        projections once per loop, and (member, scale) pairs share U-Net calls.  Random draws (ddim.py:640) keep the reference order."""
+        g = self.generator
+        bsz = z_ensemble[0].shape[0]
+        c, uc = self._get_condition(decode_text, bsz)
+        nsc = len(self.decoder_unconditional_guidance_scales)
+        imgs = [None] * (len(z_ensemble) * nsc)
+        jobs = {}                                         # skip -> [(output slot, eps_list, scale, extra)]
+        for i, z in enumerate(z_ensemble):
+            skip_steps = self.skip_steps[i % len(self.skip_steps)]
+            if self.white_box_steps != -1:
+                eps_list = z.view(bsz, (self.white_box_steps - skip_steps), g.channels, g.image_size, g.image_size)
+            else:
+                eps_list = z.view(bsz, 1, g.channels, g.image_size, g.image_size)
+            sched = DDIMSchedule(self.custom_steps, self.eta, skip_steps, g.alphas_cumprod)
+            n_extra = sched.refine_steps - (eps_list.shape[1] - 1)
+            for k, scale in enumerate(self.decoder_unconditional_guidance_scales):
+                extra = torch.stack([torch.randn(eps_list[:, 0].shape) for _ in range(n_extra)]) if n_extra > 0 else None
+                jobs.setdefault(skip_steps, []).append((i * nsc + k, eps_list, float(scale), extra))
+        for skip_steps, members in jobs.items():
+            sched = DDIMSchedule(self.custom_steps, self.eta, skip_steps, g.alphas_cumprod)
+            for chunk in self._chunks(members, bsz):
+                zc = torch.cat([m[1].to(self.engine.device) for m in chunk], dim=0)
+                sc = torch.tensor([m[2] for m in chunk for _ in range(bsz)])
+                ex = torch.cat([m[3] for m in chunk], dim=1) if chunk[0][3] is not None else None
+                rep = len(chunk)
+                sample = g.unet.latent_decode_ens(zc, c.repeat(rep, 1, 1), uc.repeat(rep, 1, 1), sc, sched, ex)
+                dec = g.decode_first_stage(sample)
+                for j, m in enumerate(chunk):
+                    imgs[m[0]] = dec[j * bsz:(j + 1) * bsz]
+        return imgs
+
+    def _encode_batched(self, x0, encode_text):
+        g = self.generator
+        bsz = x0.shape[0]
+        c, uc = self._get_condition(encode_text, bsz)
+        assert self.eta > 0                                                       # ddim.py:268
+        jobs, order = {}, 0
+        for _trial in range(self.n_trials):
+            for enc_scale in self.encoder_unconditional_guidance_scales:
+                for skip_steps in self.skip_steps:
+                    sched = DDIMSchedule(self.custom_steps, self.eta, skip_steps, g.alphas_cumprod)
+                    n_rec = max(0, min(sched.refine_steps, self.white_box_steps - skip_steps - 1))
+                    noise = self._encode_noise(sched, n_rec, x0.shape)            # drawn in the reference's member order
+                    jobs.setdefault((skip_steps, n_rec), []).append((order, float(enc_scale), noise))
+                    order += 1
+        z_ensemble = [None] * order
+        for (skip_steps, n_rec), members in jobs.items():
+            sched = DDIMSchedule(self.custom_steps, self.eta, skip_steps, g.alphas_cumprod)
+            for chunk in self._chunks(members, bsz):
+                rep = len(chunk)
+                sc = torch.tensor([m[1] for m in chunk for _ in range(bsz)])
+                nz = torch.cat([m[2] for m in chunk], dim=1)
+                z = g.unet.latent_encode_ens(x0.repeat(rep, 1, 1, 1), c.repeat(rep, 1, 1), uc.repeat(rep, 1, 1), sc, sched, n_rec, nz)
+                for j, m in enumerate(chunk):
+                    z_ensemble[m[0]] = z[j * bsz:(j + 1) * bsz].reshape(bsz, -1)
+        return z_ensemble
+
     def generate(self, z_ensemble, decode_text):
         g = self.generator
+        if self.ensemble_batch and len(z_ensemble) * len(self.decoder_unconditional_guidance_scales) > 1:
+            return self._generate_batched(z_ensemble, decode_text)
         img_ensemble = []
         for i, z in enumerate(z_ensemble):
             skip_steps = self.skip_steps[i % len(self.skip_steps)]
@@ -223,6 +291,8 @@ class _StochasticTextWrapperBase(torch.nn.Module):
         assert image.shape[2] == image.shape[3] == self.resolution
         x0 = g.get_first_stage_encoding(g.encode_first_stage(image))
         bsz = image.shape[0]
+        if self.ensemble_batch and self.n_trials * len(self.encoder_unconditional_guidance_scales) * len(self.skip_steps) > 1:
+            return self._encode_batched(x0, encode_text)
         z_ensemble = []
         for _trial in range(self.n_trials):
             for enc_scale in self.encoder_unconditional_guidance_scales:
@@ -235,6 +305,35 @@ class _StochasticTextWrapperBase(torch.nn.Module):
                     z = g.unet.latent_encode(x0, c, uc, enc_scale, sched, n_rec, noise)
                     z_ensemble.append(z.view(bsz, -1))
         return z_ensemble
+
+    def single_member(self):
+        """True when the ensemble has exactly one member whose every step is recovered (the plain CycleDiffusion cycle)."""
+        if not (self.n_trials == 1 and len(self.skip_steps) == 1 and len(self.encoder_unconditional_guidance_scales) == 1
+                and len(self.decoder_unconditional_guidance_scales) == 1):
+            return False
+        sched = DDIMSchedule(self.custom_steps, self.eta, self.skip_steps[0], self.generator.alphas_cumprod)
+        return self.white_box_steps != -1 and self.white_box_steps - self.skip_steps[0] - 1 >= sched.refine_steps
+
+    def cycle(self, image, encode_text, decode_text):
+        """encode(image, encode_text) followed by forward(z, image, encode_text, decode_text) for a single-member ensemble, on the
+        engine's lock-step driver (cdx_cycle_lockstep): both chains advance together, one U-Net call per step on the batch
+        [source | target uncond | target cond], and the noise recovered at a step is consumed by the target chain at once -- the
+        ``z`` tensor of SDW:169-206 is never materialised.  Same random draws in the same order as encode(); same result per sample
+        as the two calls (tests/test_cycle_gpu.py).  Called by TextUnsupervisedTranslation.forward when single_member()."""
+        assert self.single_member(), 'cycle(): single-member ensembles only (use encode() + forward())'
+        g, e = self.generator, self.engine
+        x = e.shift_scale(image, -0.5, 2.0)
+        assert x.shape[2] == x.shape[3] == self.resolution
+        x0 = g.get_first_stage_encoding(g.encode_first_stage(x))
+        bsz = x.shape[0]
+        c_src, uc = self._get_condition(encode_text, bsz)
+        c_tgt, _ = self._get_condition(decode_text, bsz)
+        assert self.eta > 0
+        sched = DDIMSchedule(self.custom_steps, self.eta, self.skip_steps[0], g.alphas_cumprod)
+        noise = self._encode_noise(sched, sched.refine_steps, x0.shape)
+        sample = g.unet.cycle_lockstep(x0, c_src, c_tgt, uc, self.encoder_unconditional_guidance_scales[0],
+                                       self.decoder_unconditional_guidance_scales[0], sched, noise)
+        return e.shift_scale(g.decode_first_stage(sample), 1.0, 0.5)
 
     def forward(self, z_ensemble, original_img, encode_text, decode_text):
         img_ensemble = self.generate(z_ensemble, decode_text)

@@ -255,6 +255,18 @@ int cdx_cycle_lockstep(cdx_net* unet, const float* x0, const float* c_src, const
                        const float* t_host, int n_steps, const float* noise, float sqrt_a_T,
                        float sqrt_1ma_T, float* x_out, float* z_out, int B, int C, int h, int w,
                        void* stream);
+/* The same three loops with PER-SAMPLE guidance scales (device arrays of B floats): the ensemble driver of the text wrappers
+ * (SDW:146-165 generate, :189-204 encode -- the reference loops trial x encoder-scale x skip, then x decoder-scale, one chain at a
+ * time, recomputing the conditioning and every context K/V projection per member).  Members that share a schedule are batched
+ * along B: mode 1 = encode (x0, c_src, src_scales, noise -> z_out), 2 = decode (z_in, c_tgt, tgt_scales -> x_out), 3 = lock-step.
+ * Both CFG segments run for every member; a member whose scale is 1 (0) takes eps-hat(c) (eps-hat(uc)) unchanged, exactly the
+ * reference's single-forward branch (ddim.py:550-551), so each member equals its own cdx_latent_encode / _decode call.  The context
+ * K / V projections are computed once per loop for the whole batch. */
+int cdx_latent_loop_ens(cdx_net* unet, int mode, const float* x0, const float* c_src, const float* c_tgt, const float* uc,
+                        int ctx_len, const float* src_scales, const float* tgt_scales, const cdx_ddim_coef* coef,
+                        const float* t_host, int n_steps, int n_rec, const float* noise, float sqrt_a_T,
+                        float sqrt_1ma_T, const float* z_in, int n_eps, const float* extra_noise, float* z_out,
+                        float* x_out, int B, int C, int h, int w, void* stream);
 /* DDPMDDIMWrapper.encode loop (DW:483-521): coef/t_host have n_rec entries (loop order);
  * noise[0] = x_T draw, noise[1+i] = draw of iteration i; z_out [B, n_rec+1, C,R,R]. */
 int cdx_pixel_encode(cdx_net* unet, const float* x0, const cdx_pixel_coef* coef, const float* t_host,

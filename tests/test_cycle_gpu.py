@@ -274,3 +274,48 @@ def test_pipeline_surface_vs_oracle(eng):
     print(f'pipeline vs oracle: |d img| {maxdiff(out, ref):.2e}   lock-step vs two-phase {maxdiff(out, out2):.2e}')
     assert maxdiff(out, ref) < 1e-3
     assert maxdiff(out, out2) < 1e-4
+
+
+def test_ensemble_batched_vs_oracle_member_by_member(eng):
+    """the ensemble of SDW:146-165 / 189-204 (n_trials x encoder scales x skips, then x decoder scales) with the members
+    of one schedule batched along B (cdx_latent_loop_ens: per-sample guidance scales, conditioning and context K/V computed once).
+    Every z and every image is compared with the CPU oracle's one-chain-at-a-time restatement, same seeds, same draw order; and with
+    the wrapper's own sequential loops (ensemble_batch=None)."""
+    from cycle_diffusion_b200.wrappers import SDStochasticTextWrapper, SyntheticTextEncoder
+    from oracle import dpm_encoder, unet_openai, vae_kl
+    usd = specs.synth_state_dict(specs.openai_unet_params(NARROW), 11)
+    vsd = specs.synth_state_dict(specs.kl_vae_params(VAE_SMALL), 21)
+    sd = {'model.diffusion_model.' + k: v for k, v in usd.items()}
+    sd.update({'first_stage_model.' + k: v for k, v in vsd.items()})
+    cond = SyntheticTextEncoder(48)
+    kw = dict(custom_steps=6, eta=0.1, white_box_steps=7, skip_steps=[2, 3], encoder_unconditional_guidance_scales=[1.0, 3.0],
+              decoder_unconditional_guidance_scales=[1.0, 3.0], n_trials=2)
+    mk = lambda eb: SDStochasticTextWrapper('synthetic', engine=eng, state_dict=sd, cond_stage=cond, unet_config=NARROW, vae_config=VAE_SMALL,
+                                            latent_size=16, resolution=128, ensemble_batch=eb, **kw)
+    w, w_seq = mk(6), mk(None)
+    image = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(5))
+    src, tgt = ['a photo of a cat', 'a tree'], ['a photo of a dog', 'a tree in winter']
+    torch.manual_seed(77)
+    z_ens = w.encode(image, src)
+    imgs = [eng.shift_scale(i, 1.0, 0.5).cpu() for i in w.generate(z_ens, tgt)]
+    torch.manual_seed(77)
+    z_seq = w_seq.encode(image, src)
+    imgs_seq = [eng.shift_scale(i, 1.0, 0.5).cpu() for i in w_seq.generate(z_seq, tgt)]
+    ora = dpm_encoder.LatentCycle(lambda x, t, c: unet_openai.unet_forward(usd, NARROW, x, t, c),
+                                  lambda im: vae_kl.encode_moments(vsd, VAE_SMALL, im), lambda zz: vae_kl.decode(vsd, VAE_SMALL, zz), cond,
+                                  channels=4, latent_size=16, resolution=128, **kw)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        z_ref = ora.encode(image, src)
+        imgs_ref = ora.forward_all(z_ref, tgt)
+    assert len(z_ens) == len(z_ref) == 8 and len(imgs) == len(imgs_ref) == 16
+    worst_z = worst_i = worst_s = 0.0
+    for a, b, c_ in zip(z_ens, z_ref, z_seq):
+        assert a.shape == b.shape
+        worst_z = max(worst_z, maxdiff(a.cpu(), b) / float(b.abs().max()))
+        worst_s = max(worst_s, maxdiff(a.cpu(), c_.cpu()) / float(b.abs().max()))
+    for a, b, c_ in zip(imgs, imgs_ref, imgs_seq):
+        worst_i = max(worst_i, maxdiff(a, b))
+        worst_s = max(worst_s, maxdiff(a, c_))
+    print(f'ensemble (8 encode x 2 decode members): rel|dz| {worst_z:.2e}  |d img| {worst_i:.2e}  batched vs sequential {worst_s:.2e}')
+    assert worst_z < 2e-4 and worst_i < 1e-3 and worst_s < 1e-3
