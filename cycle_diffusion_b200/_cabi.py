@@ -27,7 +27,7 @@ class VaeConfig(C.Structure):
 
 class TextConfig(C.Structure):
     _fields_ = [('vocab_size', C.c_int), ('width', C.c_int), ('layers', C.c_int), ('heads', C.c_int), ('max_len', C.c_int),
-                ('mlp_width', C.c_int), ('kind', C.c_int), ('dim_head', C.c_int)]
+                ('mlp_width', C.c_int), ('kind', C.c_int), ('dim_head', C.c_int), ('proj_dim', C.c_int), ('patch', C.c_int), ('image_size', C.c_int)]
 
 
 class DdimCoef(C.Structure):
@@ -91,6 +91,11 @@ SIGNATURES = {
                                 _P]),
     'cdx_latent_loop_ens': (_I, [_P, _I, _P, _P, _P, _P, _I, _P, _P, C.POINTER(DdimCoef), C.POINTER(_F), _I, _I, _P, _F, _F, _P, _I, _P, _P, _P,
                                  _I, _I, _I, _I, _P]),
+    'cdx_clip_preprocess': (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    'cdx_clip_image_features': (_I, [_P, _P, _I, _P, _P]),
+    'cdx_text_features': (_I, [_P, _P, _I, _I, _P, _P]),
+    'cdx_dclip_scores': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    'cdx_image_metrics': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     'cdx_pixel_encode': (_I, [_P, _P, C.POINTER(PixelCoef), C.POINTER(_F), _I, _P, _F, _F, _P, _I, _I, _I, _P]),
     'cdx_pixel_decode': (_I, [_P, _P, _I, C.POINTER(PixelCoef), C.POINTER(_F), _I, _P, _P, _I, _I, _I, _P]),
     'cdx_op_conv3x3': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

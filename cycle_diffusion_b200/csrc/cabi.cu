@@ -396,6 +396,38 @@ int cdx_text_encode(cdx_net* n, const int* ids, int B, int L, float* out, void* 
     with_arena(n->owner->e, S(stream), [&] { text_encode(*n->n, ids, out, B, L, S(stream)); });
   });
 }
+#define ENG_CALL_(EH_, ...)                                \
+  return guard([&] {                                       \
+    CDX_CHECK((EH_) != nullptr, "null engine");            \
+    CDX_CUDA(cudaSetDevice(engine_of(EH_).device));        \
+    __VA_ARGS__;                                           \
+  })
+int cdx_text_features(cdx_net* n, const int* ids, int B, int L, float* out, void* stream) {
+  return guard([&] {
+    CDX_CHECK(n && n->owner && ids && out && B > 0, "text_features: bad arguments");
+    with_arena(n->owner->e, S(stream), [&] { text_features(*n->n, ids, out, B, L, S(stream)); });
+  });
+}
+int cdx_clip_image_features(cdx_net* n, const float* pixels, int B, float* out, void* stream) {
+  return guard([&] {
+    CDX_CHECK(n && n->owner && pixels && out && B > 0, "clip_image_features: bad arguments");
+    with_arena(n->owner->e, S(stream), [&] { clip_image_features(*n->n, pixels, out, B, S(stream)); });
+  });
+}
+int cdx_clip_preprocess(cdx_engine* e, const float* img, int B, int R, int size, float* out, void* s) {
+  ENG_CALL_(e, CDX_CHECK(img && out && B > 0 && R > 0 && size > 0, "clip_preprocess: bad arguments"); clip_preprocess(e->e, img, B, R, size, out, S(s)));
+}
+int cdx_dclip_scores(cdx_engine* e, const float* img_f, const float* orig_f, const float* enc_f, const float* dec_f, int B, int D, float* clip_out,
+                     float* dclip_out, void* s) {
+  ENG_CALL_(e, CDX_CHECK(img_f && orig_f && enc_f && dec_f && clip_out && dclip_out && B > 0 && D > 0, "dclip_scores: bad arguments");
+            dclip_scores(e->e, img_f, orig_f, enc_f, dec_f, B, D, clip_out, dclip_out, S(s)));
+}
+int cdx_image_metrics(cdx_engine* eh, const float* a, const float* b, int B, int H, int W, float* out, void* stream) {
+  return guard([&] {
+    CDX_CHECK(eh && a && b && out && B > 0, "image_metrics: bad arguments");
+    with_arena(eh->e, S(stream), [&] { image_metrics(eh->e, a, b, B, H, W, out, S(stream)); });
+  });
+}
 int cdx_vae_decode(cdx_net* n, const float* z, float* img, int B, int h, void* stream) {
   return guard([&] {
     CDX_CHECK(n && n->owner && z && img && B > 0, "vae_decode: bad arguments");

@@ -208,6 +208,15 @@ void embed_tokens(Engine& e, const int* ids, const float* tok, const float* pos,
 void quick_gelu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s);     // x * sigmoid(1.702 x)
 void gelu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s);           // exact erf GELU     // [rows,C] -> [rows,Cp], zero fill
 void copy_rows(Engine& e, const float* src, float* dst, size_t n, cudaStream_t s);
+// ---- Directional-CLIP / metric kernels (kernels_elem.cu)
+void clip_preprocess(Engine& e, const float* img, int B, int R, int size, float* out, cudaStream_t s);
+void patchify(Engine& e, const float* img, float* out, int B, int S, int P, cudaStream_t s);            // [B,3,S,S] -> [B*(S/P)^2, 3*P*P]
+void vit_tokens(Engine& e, const float* patches, const float* cls, const float* pos, float* out, int B, int N, int W, cudaStream_t s);
+void gather_rows(Engine& e, const float* x, const int* row_of_batch, float* out, int B, int L, int W, cudaStream_t s);   // out[b] = x[b, row[b]]
+void eot_rows(Engine& e, const int* ids, int* rows, int B, int L, cudaStream_t s);                      // first argmax of ids per sample
+void dclip_scores(Engine& e, const float* img_f, const float* orig_f, const float* enc_f, const float* dec_f, int B, int D, float* clip_out,
+                  float* dclip_out, cudaStream_t s);
+void image_metrics(Engine& e, const float* a, const float* b, int B, int H, int W, float* out, cudaStream_t s);
 void attention(Engine& e, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
                int B, int Nq, int Nk, int heads, int d, int head_stride, float scale, cudaStream_t s, bool causal = false);
 

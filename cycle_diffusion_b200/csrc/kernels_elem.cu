@@ -340,6 +340,165 @@ __global__ void pixel_step_kernel(const float* __restrict__ xt, const float* __r
     e.launches++;                                                 \
   } while (0)
 
+
+// ------------------------------------------------------------------------------------------------ Directional-CLIP / metrics (8f-3)
+// torch upsample_bicubic2d (aten/src/ATen/native/UpSample.h): A = -0.75, align_corners = False: src = (dst + 0.5) * scale - 0.5,
+// 4 taps at floor(src) - 1 .. + 2 with clamped indices; weights from the cubic convolution polynomials.  Then (x - mean) / std.
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+__device__ __forceinline__ void cubic_coeffs(float t, float w[4]) {
+  const float A = -0.75f;
+  w[0] = cubic2(t + 1.f, A); w[1] = cubic1(t, A); w[2] = cubic1(1.f - t, A); w[3] = cubic2(2.f - t, A);
+}
+__global__ void clip_preprocess_kernel(const float* __restrict__ img, int B, int R, int size, float* __restrict__ out) {
+  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f}, sd[3] = {0.26862954f, 0.26130258f, 0.27577711f};   // clip.py _transform
+  const float scale = (float)R / (float)size;
+  const size_t n = (size_t)B * 3 * size * size;
+  GRID_STRIDE(i, n) {
+    const int x = (int)(i % size), y = (int)((i / size) % size), c = (int)((i / ((size_t)size * size)) % 3), b = (int)(i / ((size_t)3 * size * size));
+    const float sy = ((float)y + 0.5f) * scale - 0.5f, sx = ((float)x + 0.5f) * scale - 0.5f;
+    const float fy = floorf(sy), fx = floorf(sx);
+    float wy[4], wx[4];
+    cubic_coeffs(sy - fy, wy);
+    cubic_coeffs(sx - fx, wx);
+    const float* src = img + ((size_t)b * 3 + c) * R * R;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int yy = min(max((int)fy - 1 + j, 0), R - 1);
+      float row = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int xx = min(max((int)fx - 1 + k, 0), R - 1);
+        row += src[(size_t)yy * R + xx] * wx[k];
+      }
+      acc += row * wy[j];
+    }
+    out[i] = (acc - mean[c]) / sd[c];
+  }
+}
+// patch matrix for the stride-P patch embedding (conv P x P, stride P, no bias == GEMM): row = (b, py, px), col = (c, dy, dx)
+__global__ void patchify_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int S, int P) {
+  const int np = S / P, K = 3 * P * P;
+  const size_t n = (size_t)B * np * np * K;
+  GRID_STRIDE(i, n) {
+    const int col = (int)(i % K);
+    const size_t row = i / K;
+    const int px = (int)(row % np), py = (int)((row / np) % np), b = (int)(row / ((size_t)np * np));
+    const int dx = col % P, dy = (col / P) % P, c = col / (P * P);
+    out[i] = img[(((size_t)b * 3 + c) * S + (py * P + dy)) * S + px * P + dx];
+  }
+}
+// x[b, 0] = class_embedding + pos[0]; x[b, 1 + i] = patch_i + pos[1 + i]      (CLIPVisionEmbeddings.forward)
+__global__ void vit_tokens_kernel(const float* __restrict__ patches, const float* __restrict__ cls, const float* __restrict__ pos,
+                                  float* __restrict__ out, int B, int N, int W) {
+  const size_t n = (size_t)B * (N + 1) * W;
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % W);
+    const int t = (int)((i / W) % (N + 1));
+    const size_t b = i / ((size_t)(N + 1) * W);
+    const float v = t == 0 ? cls[c] : patches[(b * N + (t - 1)) * W + c];
+    out[i] = v + pos[(size_t)t * W + c];
+  }
+}
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ rows, float* __restrict__ out, int B, int L, int W) {
+  const size_t n = (size_t)B * W;
+  GRID_STRIDE(i, n) {
+    const size_t b = i / W;
+    const int c = (int)(i - b * W);
+    const int r = rows ? rows[b] : 0;
+    out[i] = x[(b * L + r) * W + c];
+  }
+}
+__global__ void eot_rows_kernel(const int* __restrict__ ids, int* __restrict__ rows, int B, int L) {      // text.argmax(dim=-1): first maximum
+  GRID_STRIDE(b, (size_t)B) {
+    int best = 0, bv = ids[b * L];
+    for (int l = 1; l < L; ++l) {
+      const int v = ids[b * L + l];
+      if (v > bv) { bv = v; best = l; }
+    }
+    rows[b] = best;
+  }
+}
+// one warp per sample
+__global__ void dclip_scores_kernel(const float* __restrict__ img_f, const float* __restrict__ orig_f, const float* __restrict__ enc_f,
+                                    const float* __restrict__ dec_f, int B, int D, float* __restrict__ clip_out, float* __restrict__ dclip_out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  auto wsum = [&](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  const float *pi = img_f + (size_t)b * D, *po = orig_f + (size_t)b * D, *pe = enc_f + (size_t)b * D, *pd = dec_f + (size_t)b * D;
+  float si = 0.f, so = 0.f, se = 0.f, sd = 0.f;
+  for (int c = lane; c < D; c += 32) { si += pi[c] * pi[c]; so += po[c] * po[c]; se += pe[c] * pe[c]; sd += pd[c] * pd[c]; }
+  const float ni = sqrtf(wsum(si)), no = sqrtf(wsum(so)), ne = sqrtf(wsum(se)), nd = sqrtf(wsum(sd));
+  float clip = 0.f, di2 = 0.f, dt2 = 0.f, dd = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float a = pi[c] / ni, o = po[c] / no, e_ = pe[c] / ne, d = pd[c] / nd;
+    clip += a * d;
+    const float di = a - o, dt = d - e_;
+    di2 += di * di; dt2 += dt * dt; dd += di * dt;
+  }
+  clip = wsum(clip); di2 = wsum(di2); dt2 = wsum(dt2); dd = wsum(dd);
+  if (lane == 0) {
+    clip_out[b] = clip;
+    dclip_out[b] = dd / (sqrtf(di2) * sqrtf(dt2));         // <di / |di|, dt / |dt|>
+  }
+}
+// PSNR / L2 partial sums (fp64) and SSIM over the valid region; grid = (tiles, B); out[b] = {sum sq diff, ssim sum over 3 channels}
+__global__ void image_metrics_kernel(const float* __restrict__ a, const float* __restrict__ b_, int H, int W, double* __restrict__ acc) {
+  const int img = blockIdx.y;
+  const float* A = a + (size_t)img * 3 * H * W;
+  const float* Bp = b_ + (size_t)img * 3 * H * W;
+  __shared__ double gw[11];
+  if (threadIdx.x == 0) {                 // cv2.getGaussianKernel(11, 1.5): exp(-(i-5)^2 / (2 sigma^2)), normalised
+    double s = 0.0;
+    for (int i = 0; i < 11; ++i) { gw[i] = exp(-((double)(i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5)); s += gw[i]; }
+    for (int i = 0; i < 11; ++i) gw[i] /= s;
+  }
+  __syncthreads();
+  const int vh = H - 10, vw = W - 10;
+  const size_t nvalid = (size_t)3 * vh * vw, npix = (size_t)3 * H * W;
+  double sq = 0.0, ss = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const float x = fminf(fmaxf(A[i], 0.f), 1.f), y = fminf(fmaxf(Bp[i], 0.f), 1.f);
+    const float d = x - y;
+    sq += (double)(d * d);                 // fp32 subtract / square as torch does, fp64 accumulation
+  }
+  const double C1 = (0.01 * 255) * (0.01 * 255), C2 = (0.03 * 255) * (0.03 * 255);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvalid; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % vw), y = (int)((i / vw) % vh), c = (int)(i / ((size_t)vw * vh));
+    const float* pa = A + (size_t)c * H * W;
+    const float* pb = Bp + (size_t)c * H * W;
+    double m1 = 0, m2 = 0, s11 = 0, s22 = 0, s12 = 0;
+    for (int dy = 0; dy < 11; ++dy) {
+      for (int dx = 0; dx < 11; ++dx) {
+        const double w = gw[dy] * gw[dx];
+        // (img.numpy() * 255): fp32 product, then astype(float64)
+        const double u = (double)(fminf(fmaxf(pa[(size_t)(y + dy) * W + x + dx], 0.f), 1.f) * 255.f);
+        const double v = (double)(fminf(fmaxf(pb[(size_t)(y + dy) * W + x + dx], 0.f), 1.f) * 255.f);
+        m1 += w * u; m2 += w * v; s11 += w * u * u; s22 += w * v * v; s12 += w * u * v;
+      }
+    }
+    const double v1 = s11 - m1 * m1, v2 = s22 - m2 * m2, cv = s12 - m1 * m2;
+    ss += ((2 * m1 * m2 + C1) * (2 * cv + C2)) / ((m1 * m1 + m2 * m2 + C1) * (v1 + v2 + C2));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { sq += __shfl_xor_sync(0xffffffffu, sq, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(acc + 2 * img, sq); atomicAdd(acc + 2 * img + 1, ss); }
+}
+__global__ void image_metrics_final_kernel(const double* __restrict__ acc, int B, int H, int W, float* __restrict__ out) {
+  GRID_STRIDE(b, (size_t)B) {
+    const double sq = acc[2 * b], ss = acc[2 * b + 1];
+    const float mse = (float)(sq / ((double)3 * H * W));
+    out[3 * b + 0] = mse == 0.f ? 100.f : 10.f * log10f(1.f / mse);
+    out[3 * b + 1] = (float)(ss / ((double)3 * (H - 10) * (W - 10)));
+    out[3 * b + 2] = sqrtf((float)sq);
+  }
+}
+
 void latent_step(Engine& e, const LatentStep& a, cudaStream_t s) { LAUNCH1(latent_step_kernel, a.n, a); }
 void latent_init(Engine& e, const LatentInit& a, cudaStream_t s) { LAUNCH1(latent_init_kernel, a.n, a); }
 void affine(Engine& e, const float* x, float a, float b, float* out, size_t n, cudaStream_t s) { LAUNCH1(affine_kernel, n, x, a, b, out, n); }
@@ -449,4 +608,39 @@ void attention(Engine& e, const float* q, int ldq, const float* k, int ldk, cons
   gemm(e, h, s);
 }
 
+}  // namespace cdx
+
+namespace cdx {
+void clip_preprocess(Engine& e, const float* img, int B, int R, int size, float* out, cudaStream_t s) {
+  LAUNCH1(clip_preprocess_kernel, (size_t)B * 3 * size * size, img, B, R, size, out);
+}
+void patchify(Engine& e, const float* img, float* out, int B, int S, int P, cudaStream_t s) {
+  LAUNCH1(patchify_kernel, (size_t)B * 3 * S * S, img, out, B, S, P);
+}
+void vit_tokens(Engine& e, const float* patches, const float* cls, const float* pos, float* out, int B, int N, int W, cudaStream_t s) {
+  LAUNCH1(vit_tokens_kernel, (size_t)B * (N + 1) * W, patches, cls, pos, out, B, N, W);
+}
+void gather_rows(Engine& e, const float* x, const int* rows, float* out, int B, int L, int W, cudaStream_t s) {
+  LAUNCH1(gather_rows_kernel, (size_t)B * W, x, rows, out, B, L, W);
+}
+void eot_rows(Engine& e, const int* ids, int* rows, int B, int L, cudaStream_t s) { LAUNCH1(eot_rows_kernel, (size_t)B, ids, rows, B, L); }
+void dclip_scores(Engine& e, const float* img_f, const float* orig_f, const float* enc_f, const float* dec_f, int B, int D, float* clip_out,
+                  float* dclip_out, cudaStream_t s) {
+  if (e.dry()) return;
+  dclip_scores_kernel<<<cdiv(B, 4), 128, 0, s>>>(img_f, orig_f, enc_f, dec_f, B, D, clip_out, dclip_out);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+void image_metrics(Engine& e, const float* a, const float* b, int B, int H, int W, float* out, cudaStream_t s) {
+  CDX_CHECK(H > 10 && W > 10, "image_metrics: %dx%d is smaller than the 11x11 SSIM window", H, W);
+  Scope sc(e.arena);
+  double* acc = (double*)e.arena.alloc((size_t)B * 2 * sizeof(double));
+  if (e.dry()) return;
+  CDX_CUDA(cudaMemsetAsync(acc, 0, (size_t)B * 2 * sizeof(double), s));
+  const int tiles = std::min(e.num_sms * 4, cdiv((long long)3 * H * W, 256));
+  image_metrics_kernel<<<dim3(tiles, B), 256, 0, s>>>(a, b, H, W, acc);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+  LAUNCH1(image_metrics_final_kernel, (size_t)B, acc, B, H, W, out);
+}
 }  // namespace cdx

@@ -286,7 +286,8 @@ Net* make_vae(Engine* e, const cdx_vae_config& cfg) {
 // HF CLIPTextModel state_dict order (transformers modeling_clip.py: CLIPTextEmbeddings, CLIPEncoderLayer {self_attn k,v,q,out;
 // layer_norm1; mlp fc1, fc2; layer_norm2}, final_layer_norm)
 Net* make_text(Engine* e, const cdx_text_config& cfg) {
-  CDX_CHECK(cfg.vocab_size > 0 && cfg.width > 0 && cfg.layers > 0 && cfg.heads > 0 && cfg.max_len > 0 && cfg.mlp_width > 0, "text: bad config");
+  CDX_CHECK(cfg.width > 0 && cfg.layers > 0 && cfg.heads > 0 && cfg.mlp_width > 0, "text: bad config");
+  if (cfg.kind != CDX_CLIP_VISION) CDX_CHECK(cfg.vocab_size > 0 && cfg.max_len > 0, "text: bad config");
   CDX_CHECK(cfg.width % cfg.heads == 0 && cfg.width % 4 == 0 && cfg.mlp_width % 4 == 0, "text: width %d / heads %d", cfg.width, cfg.heads);
   Net* n = new Net();
   n->eng = e;
@@ -315,6 +316,30 @@ Net* make_text(Engine* e, const cdx_text_config& cfg) {
     assign_offsets(*n);
     return n;
   }
+  if (cfg.kind == CDX_CLIP_VISION) {
+    // HF CLIPVisionModel(+projection) state_dict order (modeling_clip.py: CLIPVisionEmbeddings {class_embedding, patch_embedding,
+    // position_embedding}, pre_layrnorm [sic], encoder layers as the text tower, post_layernorm) == OpenAI clip VisionTransformer
+    // (clip/model.py: conv1, class_embedding, positional_embedding, ln_pre, transformer, ln_post, proj)
+    CDX_CHECK(cfg.patch > 0 && cfg.image_size % cfg.patch == 0 && cfg.proj_dim > 0 && (3 * cfg.patch * cfg.patch) % 4 == 0, "vision: patch %d size %d", cfg.patch, cfg.image_size);
+    const int np = cfg.image_size / cfg.patch;
+    const std::string V = "vision_model.";
+    v.add(V + "embeddings.class_embedding", {cfg.width});
+    v.add(V + "embeddings.patch_embedding.weight", {cfg.width, 3, cfg.patch, cfg.patch});
+    v.add(V + "embeddings.position_embedding.weight", {np * np + 1, cfg.width});
+    v.norm(V + "pre_layrnorm", cfg.width);
+    for (int l = 0; l < cfg.layers; ++l) {
+      const std::string p = V + "encoder.layers." + std::to_string(l);
+      for (const char* nm : {"k_proj", "v_proj", "q_proj", "out_proj"}) v.lin(p + ".self_attn." + nm, cfg.width, cfg.width);
+      v.norm(p + ".layer_norm1", cfg.width);
+      v.lin(p + ".mlp.fc1", cfg.width, cfg.mlp_width);
+      v.lin(p + ".mlp.fc2", cfg.mlp_width, cfg.width);
+      v.norm(p + ".layer_norm2", cfg.width);
+    }
+    v.norm(V + "post_layernorm", cfg.width);
+    v.lin("visual_projection", cfg.width, cfg.proj_dim, false);
+    assign_offsets(*n);
+    return n;
+  }
   const std::string T = "text_model.";
   v.add(T + "embeddings.token_embedding.weight", {cfg.vocab_size, cfg.width});
   v.add(T + "embeddings.position_embedding.weight", {cfg.max_len, cfg.width});
@@ -327,6 +352,7 @@ Net* make_text(Engine* e, const cdx_text_config& cfg) {
     v.norm(p + ".layer_norm2", cfg.width);
   }
   v.norm(T + "final_layer_norm", cfg.width);
+  if (cfg.proj_dim > 0) v.lin("text_projection", cfg.width, cfg.proj_dim, false);       // CLIPModel.text_projection (clip/model.py text_projection^T)
   assign_offsets(*n);
   return n;
 }
@@ -1026,6 +1052,37 @@ void unet_forward(Net& n, const float* x_nchw, const float* t_dev, const float* 
   }
 }
 
+// CLIPEncoderLayer stack (HF modeling_clip.py; OpenAI clip ResidualAttentionBlock): pre-LN, self-attention (q scaled by d^-1/2; causal
+// for the text tower), quick-GELU MLP.  x [B, L, W] -> returns the last layer's output tensor.
+static Tensor clip_layers(Exec& ex, Net& n, const std::string& prefix, Tensor x, int B, int L, int W, int heads, int layers, int mlp_width,
+                          bool causal, cudaStream_t s) {
+  Engine& e = *n.eng;
+  const int d = W / heads;
+  const float scale = (float)pow((double)d, -0.5);
+  for (int l = 0; l < layers; ++l) {
+    const std::string p = prefix + "encoder.layers." + std::to_string(l);
+    Tensor y = ex.alloc(B, L, 1, W);          // layer output (outlives the layer's temporaries)
+    {
+      Scope sc(e.arena);
+      Tensor n1 = ex.ln(x, p + ".layer_norm1");
+      Tensor q = ex.linear(n1, p + ".self_attn.q_proj", true);
+      Tensor k = ex.linear(n1, p + ".self_attn.k_proj", true);
+      Tensor v = ex.linear(n1, p + ".self_attn.v_proj", true, nullptr, true);
+      Tensor a = ex.alloc(B, L, 1, W);
+      a.amax = v.amax;
+      attention(e, q.p, W, k.p, W, v.p, W, a.p, W, B, L, L, heads, d, d, scale, s, causal);
+      Tensor h = ex.linear(a, p + ".self_attn.out_proj", true, x.p);                 // + residual
+      Tensor n2 = ex.ln(h, p + ".layer_norm2");
+      Tensor f = ex.linear(n2, p + ".mlp.fc1", true, nullptr, true);
+      quick_gelu(e, f.p, f.p, f.numel(), s);           // |x sigmoid(1.702 x)| <= |x|
+      const Param& w2 = n.param(p + ".mlp.fc2.weight");
+      ex.linear_into(f.p, mlp_width, mlp_width, nullptr, 0, 0, B * L, n.blob + w2.off, W, n.P(p + ".mlp.fc2.bias"), h.p, W, y.p, W, nullptr, f.amax);
+    }
+    x = y;
+  }
+  return x;
+}
+
 // CLIPTextTransformer.forward (HF modeling_clip.py; call site ldm/modules/encoders/modules.py:152-157): embeddings, pre-LN
 // encoder layers with causal self-attention (q scaled by d^-1/2) and quick-GELU MLP, final LayerNorm -> last_hidden_state
 void text_encode(Net& n, const int* ids, float* out, int B, int L, cudaStream_t s) {
@@ -1068,35 +1125,57 @@ void text_encode(Net& n, const int* ids, float* out, int B, int L, cudaStream_t 
     layernorm(e, x.p, n.P(T + "norm.weight"), n.P(T + "norm.bias"), out, B * L, W, s);
     return;
   }
-  const int W = c.width, d = W / c.heads;
+  const int W = c.width;
   const std::string T = "text_model.";
   Scope top(e.arena);
   Tensor x = ex.alloc(B, L, 1, W);
   embed_tokens(e, ids, n.P(T + "embeddings.token_embedding.weight"), n.P(T + "embeddings.position_embedding.weight"), x.p, B, L, W, c.vocab_size, s);
-  const float scale = (float)pow((double)d, -0.5);
-  for (int l = 0; l < c.layers; ++l) {
-    const std::string p = T + "encoder.layers." + std::to_string(l);
-    Tensor y = ex.alloc(B, L, 1, W);          // layer output (outlives the layer's temporaries)
-    {
-      Scope sc(e.arena);
-      Tensor n1 = ex.ln(x, p + ".layer_norm1");
-      Tensor q = ex.linear(n1, p + ".self_attn.q_proj", true);
-      Tensor k = ex.linear(n1, p + ".self_attn.k_proj", true);
-      Tensor v = ex.linear(n1, p + ".self_attn.v_proj", true, nullptr, true);
-      Tensor a = ex.alloc(B, L, 1, W);
-      a.amax = v.amax;
-      attention(e, q.p, W, k.p, W, v.p, W, a.p, W, B, L, L, c.heads, d, d, scale, s, true);
-      Tensor h = ex.linear(a, p + ".self_attn.out_proj", true, x.p);                 // + residual
-      Tensor n2 = ex.ln(h, p + ".layer_norm2");
-      Tensor f = ex.linear(n2, p + ".mlp.fc1", true, nullptr, true);
-      quick_gelu(e, f.p, f.p, f.numel(), s);           // |x sigmoid(1.702 x)| <= |x|
-      const Param& w2 = n.param(p + ".mlp.fc2.weight");
-      ex.linear_into(f.p, c.mlp_width, c.mlp_width, nullptr, 0, 0, B * L, n.blob + w2.off, W, n.P(p + ".mlp.fc2.bias"), h.p, W, y.p, W, nullptr, f.amax);
-    }
-    x = y;
-  }
+  x = clip_layers(ex, n, T, x, B, L, W, c.heads, c.layers, c.mlp_width, true, s);
   // final LayerNorm straight into the caller's buffer
   layernorm(e, x.p, n.P(T + "final_layer_norm.weight"), n.P(T + "final_layer_norm.bias"), out, B * L, W, s);
+}
+
+// CLIP.encode_text (clip/model.py:343-356; call site clean_clip.py:24-27): x[arange(B), text.argmax(-1)] of the final-LN states, then
+// @ text_projection
+void text_features(Net& n, const int* ids, float* out, int B, int L, cudaStream_t s) {
+  CDX_CHECK(n.kind == NET_CLIP_TEXT && n.finalized && n.tcfg.kind != CDX_TEXT_XTRANSFORMER && n.tcfg.kind != CDX_CLIP_VISION && n.tcfg.proj_dim > 0,
+            "text_features: needs a CLIP text tower built with proj_dim > 0");
+  Engine& e = *n.eng;
+  const int W = n.tcfg.width;
+  Scope top(e.arena);
+  float* hs = (float*)e.arena.alloc((size_t)B * L * W * sizeof(float));
+  int* rows = (int*)e.arena.alloc((size_t)B * sizeof(int));
+  text_encode(n, ids, hs, B, L, s);
+  eot_rows(e, ids, rows, B, L, s);
+  Exec ex(n, s);
+  Tensor pooled = ex.alloc(B, 1, 1, W);
+  gather_rows(e, hs, rows, pooled.p, B, L, W, s);
+  ex.linear_into(pooled.p, W, W, nullptr, 0, 0, B, n.P("text_projection.weight"), n.tcfg.proj_dim, nullptr, nullptr, 0, out, n.tcfg.proj_dim);
+}
+
+// CLIP.encode_image (clip/model.py VisionTransformer.forward; call site clean_clip.py:28-31): patch embedding as one GEMM, class token
+// + positions, ln_pre, the layer stack (full attention), ln_post of the class token, @ proj.  pixels [B,3,S,S] already preprocessed.
+void clip_image_features(Net& n, const float* pixels, float* out, int B, cudaStream_t s) {
+  CDX_CHECK(n.kind == NET_CLIP_TEXT && n.finalized && n.tcfg.kind == CDX_CLIP_VISION, "clip_image_features: not a finalized CLIP vision tower");
+  const cdx_text_config& c = n.tcfg;
+  Engine& e = *n.eng;
+  e.pools_reset(s);
+  Exec ex(n, s);
+  const int W = c.width, P = c.patch, S = c.image_size, np = S / P, N = np * np, K = 3 * P * P;
+  const std::string V = "vision_model.";
+  Scope top(e.arena);
+  float* pm = (float*)e.arena.alloc((size_t)B * N * K * sizeof(float));
+  patchify(e, pixels, pm, B, S, P, s);
+  float* pe = (float*)e.arena.alloc((size_t)B * N * W * sizeof(float));
+  ex.linear_into(pm, K, K, nullptr, 0, 0, B * N, n.P(V + "embeddings.patch_embedding.weight"), W, nullptr, nullptr, 0, pe, W);
+  Tensor x = ex.alloc(B, N + 1, 1, W);
+  vit_tokens(e, pe, n.P(V + "embeddings.class_embedding"), n.P(V + "embeddings.position_embedding.weight"), x.p, B, N, W, s);
+  Tensor x1 = ex.ln(x, V + "pre_layrnorm");
+  Tensor y = clip_layers(ex, n, V, x1, B, N + 1, W, c.heads, c.layers, c.mlp_width, false, s);
+  Tensor cls = ex.alloc(B, 1, 1, W);
+  gather_rows(e, y.p, nullptr, cls.p, B, N + 1, W, s);
+  Tensor pooled = ex.ln(cls, V + "post_layernorm");
+  ex.linear_into(pooled.p, W, W, nullptr, 0, 0, B, n.P("visual_projection.weight"), c.proj_dim, nullptr, nullptr, 0, out, c.proj_dim, nullptr, pooled.amax);
 }
 
 void vae_encode(Net& n, const float* img, float* moments, int B, int R, cudaStream_t s) {

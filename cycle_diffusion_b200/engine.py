@@ -176,6 +176,32 @@ class Engine:
         check(lib.cdx_op_linear(self.h, _ptr(x), _ptr(w), _ptr(bias), _ptr(y), M, K, N, self.stream))
         return y
 
+    # ---- Directional-CLIP ranking / evaluation metrics
+    def clip_preprocess(self, img, size=224):
+        """clean_clip.py:14-17 on a float batch in [0,1]: bicubic resize to size x size + CLIP normalisation."""
+        x = _f32c(img, self.device)
+        B, Cc, R, R2 = x.shape
+        assert Cc == 3 and R == R2, 'square RGB batches (the reference feeds R x R sampler outputs)'
+        out = self.empty(B, 3, size, size)
+        check(lib.cdx_clip_preprocess(self.h, _ptr(x), B, R, size, _ptr(out), self.stream))
+        return out
+
+    def dclip_scores(self, img_f, orig_f, enc_f, dec_f):
+        fs = [_f32c(t, self.device) for t in (img_f, orig_f, enc_f, dec_f)]
+        B, D = fs[0].shape
+        clip, dclip = self.empty(B), self.empty(B)
+        check(lib.cdx_dclip_scores(self.h, *[_ptr(t) for t in fs], B, D, _ptr(clip), _ptr(dclip), self.stream))
+        return clip, dclip
+
+    def image_metrics(self, a, b):
+        """-> [B, 3] = (psnr, ssim, l2) per image pair (evaluation/translate_text.py:76-89)."""
+        a, b = _f32c(a, self.device), _f32c(b, self.device)
+        B, Cc, H, W = a.shape
+        assert Cc == 3 and a.shape == b.shape
+        out = self.empty(B, 3)
+        check(lib.cdx_image_metrics(self.h, _ptr(a), _ptr(b), B, H, W, _ptr(out), self.stream))
+        return out
+
     def op_groupnorm(self, x_nhwc, gamma, beta, eps, silu):
         x, gamma, beta = (_f32c(t, self.device) for t in (x_nhwc, gamma, beta))
         B, H, W, Cc = x.shape
@@ -478,8 +504,9 @@ class TextEncoder(Net):
         c = TextConfig()
         c.vocab_size, c.width, c.layers = cfg['vocab_size'], cfg['width'], cfg['layers']
         c.heads, c.max_len, c.mlp_width = cfg['heads'], cfg['max_len'], cfg['mlp_width']
-        c.kind = 2 if cfg.get('kind', 'clip') == 'xtransformer' else 1
+        c.kind = {'clip': 1, 'xtransformer': 2, 'clip_vision': 3}[cfg.get('kind', 'clip')]
         c.dim_head = cfg.get('dim_head', cfg['width'] // cfg['heads'])
+        c.proj_dim, c.patch, c.image_size = cfg.get('proj_dim', 0), cfg.get('patch', 0), cfg.get('image_size', 0)
         h = C.c_void_p()
         check(lib.cdx_text_create(engine.h if engine is not None else None, C.byref(c), C.byref(h)))
         super().__init__(engine, h)
@@ -502,3 +529,31 @@ class TextEncoder(Net):
 
     __call__ = forward
 
+    def features(self, input_ids):
+        """CLIP.encode_text: ids [B, L] -> [B, proj_dim] (final-LN state at the EOT token @ text_projection); needs cfg['proj_dim']."""
+        e = self.engine
+        ids = input_ids.to(device=e.device, dtype=torch.int32).contiguous()
+        B, L = ids.shape
+        out = torch.empty(B, self.cfg['proj_dim'], device=e.device, dtype=torch.float32)
+        check(lib.cdx_text_features(self.h, _ptr(ids), B, L, _ptr(out), e.stream))
+        return out
+
+
+class ClipVision(TextEncoder):
+    """CLIP ViT image tower (cfg: width, layers, heads, mlp_width, patch, image_size, proj_dim): CLIP.encode_image."""
+
+    def __init__(self, engine, cfg):
+        cfg = dict(cfg, kind='clip_vision', vocab_size=cfg.get('vocab_size', 0), max_len=cfg.get('max_len', 0))
+        super().__init__(engine, cfg)
+
+    def forward(self, pixels):
+        """pixels [B,3,S,S] (already preprocessed) -> image features [B, proj_dim]."""
+        e = self.engine
+        x = _f32c(pixels, e.device)
+        B, _, S, S2 = x.shape
+        assert S == S2 == self.cfg['image_size'], f'{tuple(x.shape)} vs image_size {self.cfg["image_size"]}'
+        out = torch.empty(B, self.cfg['proj_dim'], device=e.device, dtype=torch.float32)
+        check(lib.cdx_clip_image_features(self.h, _ptr(x), B, _ptr(out), e.stream))
+        return out
+
+    __call__ = forward

@@ -317,3 +317,30 @@ def synth_state_dict(params, seed, gain=1.0):
             t = (torch.rand(shape, generator=g) * 2.0 - 1.0) * b
         sd[name] = t.contiguous()
     return sd
+
+
+def clip_b32_vision_config():
+    """OpenAI CLIP ViT-B/32 image tower (clip/model.py build_model; what clean_clip.py:10 loads)."""
+    return dict(kind='clip_vision', width=768, layers=12, heads=12, mlp_width=3072, patch=32, image_size=224, proj_dim=512)
+
+
+def clip_b32_text_config():
+    return dict(kind='clip', vocab_size=49408, width=512, layers=12, heads=8, max_len=77, mlp_width=2048, proj_dim=512)
+
+
+def clip_vision_params(cfg):
+    """(name, shape, kind) in the engine's inventory order for the CLIP image tower (csrc/nets.cu make_text, CDX_CLIP_VISION)."""
+    W, P, n = cfg['width'], cfg['patch'], (cfg['image_size'] // cfg['patch']) ** 2
+    V = 'vision_model.'
+    out = [(V + 'embeddings.class_embedding', (W,), 'b'), (V + 'embeddings.patch_embedding.weight', (W, 3, P, P), 'w'),
+           (V + 'embeddings.position_embedding.weight', (n + 1, W), 'w'), (V + 'pre_layrnorm.weight', (W,), 'nw'), (V + 'pre_layrnorm.bias', (W,), 'nb')]
+    for l in range(cfg['layers']):
+        p = f'{V}encoder.layers.{l}'
+        for nm in ('k_proj', 'v_proj', 'q_proj', 'out_proj'):
+            out += [(f'{p}.self_attn.{nm}.weight', (W, W), 'w'), (f'{p}.self_attn.{nm}.bias', (W,), 'b')]
+        out += [(f'{p}.layer_norm1.weight', (W,), 'nw'), (f'{p}.layer_norm1.bias', (W,), 'nb'),
+                (f'{p}.mlp.fc1.weight', (cfg['mlp_width'], W), 'w'), (f'{p}.mlp.fc1.bias', (cfg['mlp_width'],), 'b'),
+                (f'{p}.mlp.fc2.weight', (W, cfg['mlp_width']), 'w'), (f'{p}.mlp.fc2.bias', (W,), 'b'),
+                (f'{p}.layer_norm2.weight', (W,), 'nw'), (f'{p}.layer_norm2.bias', (W,), 'nb')]
+    out += [(V + 'post_layernorm.weight', (W,), 'nw'), (V + 'post_layernorm.bias', (W,), 'nb'), ('visual_projection.weight', (cfg['proj_dim'], W), 'w')]
+    return out

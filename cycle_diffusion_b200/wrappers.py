@@ -343,8 +343,10 @@ class _StochasticTextWrapperBase(torch.nn.Module):
         if len(img_ensemble) == 1:
             return img_ensemble[0]
         if self.directional_clip is None:
-            raise NotImplementedError('ranking an ensemble needs ranker=<callable(img, original_img, encode_text, decode_text) '
-                                      '-> (_, score[B])> (DirectionalCLIP is outside the engine, SURVEY.md 8f-3)')
+            raise NotImplementedError('ranking an ensemble needs ranker=<callable(img, original_img, encode_text, decode_text) -> (_, score[B])>, '
+                                      'e.g. cycle_diffusion_b200.clip_rank.DirectionalCLIP(engine, clip_state_dict, tokenizer) (SURVEY.md 8f-3)')
+        if hasattr(self.directional_clip, 'rank'):        # in-engine DirectionalCLIP (clip_rank.py): scores, argmax and gather stay on the device
+            return self.directional_clip.rank(img_ensemble, original_img, encode_text, decode_text)[0]
         scores = []
         for img in img_ensemble:
             _, s = self.directional_clip(img, original_img, encode_text, decode_text)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CDX_ABI_VERSION 1
+#define CDX_ABI_VERSION 2
 
 #define CDX_OK 0
 #define CDX_E_INVALID (-1)   /* bad argument / precondition (the reference's assert) */
@@ -103,9 +103,15 @@ typedef struct cdx_text_config { /* CLIP ViT-L/14 text tower as FrozenCLIPEmbedd
                    (encoders/modules.py:79-98 -> x_transformer.py TransformerWrapper(Encoder(dim, depth))): pre-LN blocks of
                    bias-free q/k/v (heads x dim_head), full attention, exact-GELU feed-forward; 30522 BERT word pieces */
   int dim_head; /* XTRANSFORMER: per-head width (x_transformer DEFAULT_DIM_HEAD = 64; heads * dim_head may differ from width) */
+  /* DirectionalCLIP towers (model/energy/clean_clip.py:7-41 runs OpenAI CLIP ViT-B/32 encode_image / encode_text):
+     proj_dim > 0 adds the projection head (text: `text_projection.weight` [proj, width], applied to the EOT token's final-LN
+     state; vision: `visual_projection.weight`).  kind CDX_CLIP_VISION: the ViT image tower, `patch` x `patch` patches of an
+     `image_size`^2 input (HF CLIPVisionModel names under `vision_model.`; vocab_size / max_len unused) */
+  int proj_dim, patch, image_size;
 } cdx_text_config;
 #define CDX_TEXT_CLIP 1
 #define CDX_TEXT_XTRANSFORMER 2
+#define CDX_CLIP_VISION 3
 
 /* Build the host-side execution plan and parameter inventory (no GPU work). */
 int cdx_unet_create(cdx_engine* e, const cdx_unet_config* cfg, cdx_net** out);
@@ -267,6 +273,23 @@ int cdx_latent_loop_ens(cdx_net* unet, int mode, const float* x0, const float* c
                         const float* t_host, int n_steps, int n_rec, const float* noise, float sqrt_a_T,
                         float sqrt_1ma_T, const float* z_in, int n_eps, const float* extra_noise, float* z_out,
                         float* x_out, int B, int C, int h, int w, void* stream);
+/* ---- Directional-CLIP ranking and the evaluation metrics on the device
+ * clip_preprocess: clean_clip.py:14-17 = Resize(size, bicubic) + CenterCrop(size) + Normalize(mean, std) on a float image batch in
+ *   [0,1] (square inputs; torch bicubic, A = -0.75, align_corners = False, no antialias -- the tensor path of the torchvision release
+ *   the reference pins).  img [B,3,R,R] -> out [B,3,size,size].
+ * cdx_clip_image_features: CLIP.encode_image = ViT tower -> ln_post(class token) @ proj  -> [B, proj_dim] (net kind CDX_CLIP_VISION).
+ * cdx_text_features: CLIP.encode_text = final-LN state at the EOT token (argmax of the ids) @ text_projection -> [B, proj_dim].
+ * cdx_dclip_scores: clean_clip.py:24-39: L2-normalise the four feature sets, clip = <img, dec_text>, dclip = <unit(img - orig),
+ *   unit(dec_text - enc_text)>.  All [B, D] device arrays; clip_out / dclip_out [B].
+ * cdx_image_metrics: evaluation/translate_text.py:76-89 per image pair after clamp(0,1): PSNR = 10 log10(1 / mse) (100 when equal;
+ *   evaluation/utils.py:60-66), L2 = sqrt(sum sq diff), SSIM of the x255 images (11x11 Gaussian sigma 1.5, valid region, per channel,
+ *   mean of 3; evaluation/utils.py:35-57).  a, b [B,3,H,W] -> out [B,3] = {psnr, ssim, l2} (fp32). */
+int cdx_clip_preprocess(cdx_engine* e, const float* img, int B, int R, int size, float* out, void* stream);
+int cdx_clip_image_features(cdx_net* vision, const float* pixels, int B, float* out, void* stream);
+int cdx_text_features(cdx_net* text, const int* ids_dev, int B, int L, float* out, void* stream);
+int cdx_dclip_scores(cdx_engine* e, const float* img_f, const float* orig_f, const float* enc_f, const float* dec_f, int B, int D,
+                     float* clip_out, float* dclip_out, void* stream);
+int cdx_image_metrics(cdx_engine* e, const float* a, const float* b, int B, int H, int W, float* out, void* stream);
 /* DDPMDDIMWrapper.encode loop (DW:483-521): coef/t_host have n_rec entries (loop order);
  * noise[0] = x_T draw, noise[1+i] = draw of iteration i; z_out [B, n_rec+1, C,R,R]. */
 int cdx_pixel_encode(cdx_net* unet, const float* x0, const cdx_pixel_coef* coef, const float* t_host,

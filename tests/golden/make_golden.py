@@ -358,6 +358,62 @@ def golden_bert_text():
     save('bert_text', **out)
 
 
+def golden_clip_rank():
+    """Directional-CLIP ranking.  Features / scores: the installed transformers CLIPModel (the HF restatement of the
+    OpenAI CLIP model clean_clip.py:10 loads) on a reduced ViT config with synthetic weights loaded strict; preprocessing as the
+    reference's tensor path (bicubic, no antialias).  Metrics: the reference's OWN evaluation/utils.py functions."""
+    from transformers import CLIPConfig, CLIPModel, CLIPTextConfig, CLIPVisionConfig
+    import torch.nn.functional as F
+    vc = dict(kind='clip_vision', width=64, layers=2, heads=4, mlp_width=256, patch=8, image_size=32, proj_dim=48)
+    tc = dict(kind='clip', vocab_size=600, width=96, layers=2, heads=4, max_len=77, mlp_width=384, proj_dim=48)
+    cfg = CLIPConfig(text_config=CLIPTextConfig(vocab_size=tc['vocab_size'], hidden_size=tc['width'], intermediate_size=tc['mlp_width'],
+                                                num_hidden_layers=tc['layers'], num_attention_heads=tc['heads'], max_position_embeddings=77,
+                                                hidden_act='quick_gelu', layer_norm_eps=1e-5, projection_dim=48, eos_token_id=2).to_dict(),
+                     vision_config=CLIPVisionConfig(hidden_size=vc['width'], intermediate_size=vc['mlp_width'], num_hidden_layers=vc['layers'],
+                                                    num_attention_heads=vc['heads'], image_size=32, patch_size=8, hidden_act='quick_gelu',
+                                                    layer_norm_eps=1e-5, projection_dim=48).to_dict(), projection_dim=48)
+    m = CLIPModel(cfg).eval()
+    sd = dict(specs.synth_state_dict(specs.clip_vision_params(vc), 31, gain=2.0))
+    sd.update(specs.synth_state_dict(specs.clip_text_params(tc) + [('text_projection.weight', (48, tc['width']), 'w')], 32, gain=2.0))
+    want = {k for k in m.state_dict() if not k.endswith('position_ids') and k != 'logit_scale'}
+    assert want == set(sd), sorted(want ^ set(sd))[:8]
+    m.load_state_dict(sd, strict=False)
+    g = torch.Generator().manual_seed(17)
+    img, orig = torch.rand(3, 3, 80, 80, generator=g), torch.rand(3, 3, 80, 80, generator=g)
+    ids_e, ids_d = torch.randint(3, 599, (3, 77), generator=g), torch.randint(3, 599, (3, 77), generator=g)
+    for t in (ids_e, ids_d):                     # CLIP tokenisation: the EOT token has the LARGEST id and sits at a different place per prompt
+        for b, pos in enumerate((5, 19, 76)):
+            t[b, pos] = 599
+    mean = torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(1, 3, 1, 1)
+    std = torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(1, 3, 1, 1)
+    pre = lambda x: (F.interpolate(x, size=(32, 32), mode='bicubic', align_corners=False) - mean) / std
+    with torch.no_grad():
+        pi, po = pre(img), pre(orig)
+        fi = m.vision_model(pixel_values=pi).pooler_output @ m.visual_projection.weight.t()        # == get_image_features
+        fo = m.vision_model(pixel_values=po).pooler_output @ m.visual_projection.weight.t()
+        # (transformers pools at eos_token_id; the OpenAI model pools at argmax(ids) -- same position here by construction)
+        te = m.text_model(input_ids=ids_e).last_hidden_state[torch.arange(3), ids_e.argmax(-1)] @ m.text_projection.weight.t()
+        td = m.text_model(input_ids=ids_d).last_hidden_state[torch.arange(3), ids_d.argmax(-1)] @ m.text_projection.weight.t()
+        n = lambda t: t / t.norm(dim=-1, keepdim=True)
+        fi_, fo_, te_, td_ = n(fi), n(fo), n(te), n(td)
+        clip = torch.einsum('bz,bz->b', fi_, td_)
+        dclip = torch.einsum('bz,bz->b', n(fi_ - fo_), n(td_ - te_))
+    # metrics from the reference's own functions (evaluation/utils.py; call site evaluation/translate_text.py:76-89)
+    sys.path.insert(0, REF)
+    from evaluation.utils import calculate_psnr, calculate_ssim
+    a = (torch.rand(2, 3, 48, 40, generator=g) * 1.2 - 0.1)
+    b = (a + 0.1 * torch.randn(2, 3, 48, 40, generator=g))
+    met = []
+    for x, y in zip(a, b):
+        x, y = x.clamp(0, 1), y.clamp(0, 1)
+        met.append([calculate_psnr(x, y).item(),
+                    calculate_ssim((x.numpy() * 255).transpose((1, 2, 0)), (y.numpy() * 255).transpose((1, 2, 0))),
+                    torch.sqrt(((x - y) ** 2).sum(2).sum(1).sum(0)).item()])
+    save('clip_rank', img=img, orig=orig, ids_e=ids_e, ids_d=ids_d, pre_img=pi, f_img=fi, f_orig=fo, f_enc=te, f_dec=td, clip=clip, dclip=dclip,
+         met_a=a, met_b=b, met=np.asarray(met, dtype=np.float64))
+    print(f'clip_rank: clip {clip.tolist()} dclip {dclip.tolist()} metrics {met}')
+
+
 if __name__ == '__main__':
     _shim_omegaconf()
     sys.path.insert(0, os.path.join(REF, 'model/lib/stable_diffusion'))
@@ -370,3 +426,4 @@ if __name__ == '__main__':
     golden_pixel_cycle()
     golden_clip_text()
     golden_bert_text()
+    golden_clip_rank()

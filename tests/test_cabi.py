@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(_cabi.lib, s), f'{s} declared in cdx.h but not exported by libcdx.so'
         assert s in _cabi.SIGNATURES, f'{s} has no ctypes signature'
     assert sorted(_cabi.SIGNATURES) == syms
-    assert _cabi.lib.cdx_abi_version() == 1
+    assert _cabi.lib.cdx_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='needs a box without CUDA')
@@ -60,3 +60,15 @@ def test_inventory_only_net_rejects_compute():
     net = UNet(None, NARROW, 'openai')
     with pytest.raises(AssertionError):
         net.finalize()
+
+
+def test_clip_rank_tower_inventories_match_specs():
+    """the CLIP image tower / projected text tower inventories of csrc/nets.cu equal specs.py (CPU, no GPU work)."""
+    from cycle_diffusion_b200 import specs
+    from cycle_diffusion_b200.engine import ClipVision, TextEncoder
+    vc = specs.clip_b32_vision_config()
+    assert [(a, tuple(b)) for a, b in ClipVision(None, vc).inventory()] == [(a, tuple(b)) for a, b, _ in specs.clip_vision_params(vc)]
+    tc = specs.clip_b32_text_config()
+    inv = TextEncoder(None, tc).inventory()
+    assert [(a, tuple(b)) for a, b in inv[:-1]] == [(a, tuple(b)) for a, b, _ in specs.clip_text_params(tc)]
+    assert inv[-1] == ('text_projection.weight', (512, 512))

@@ -133,3 +133,26 @@ def test_bert_text_oracle_vs_reference_fixture(tag):
     with torch.no_grad():
         y = bert_text.text_forward(sd, cfg, g[f'tok_{tag}'])
     assert maxdiff(y, g[f'out_{tag}']) <= 2e-5
+
+
+def test_clip_rank_oracle_vs_third_party_and_reference_metrics():
+    """oracle.clip_rank against the installed transformers CLIPModel (features, scores) and against the reference's own
+    evaluation/utils.py (PSNR / SSIM / L2), fixture tests/golden/clip_rank.npz."""
+    from cycle_diffusion_b200 import specs
+    from oracle import clip_rank
+    g = golden('clip_rank')
+    vc = dict(kind='clip_vision', width=64, layers=2, heads=4, mlp_width=256, patch=8, image_size=32, proj_dim=48)
+    tc = dict(kind='clip', vocab_size=600, width=96, layers=2, heads=4, max_len=77, mlp_width=384, proj_dim=48)
+    sd = dict(specs.synth_state_dict(specs.clip_vision_params(vc), 31, gain=2.0))
+    sd.update(specs.synth_state_dict(specs.clip_text_params(tc) + [('text_projection.weight', (48, tc['width']), 'w')], 32, gain=2.0))
+    with torch.no_grad():
+        pre = clip_rank.preprocess(g['img'], 32)
+        assert maxdiff(pre, g['pre_img']) < 1e-5
+        assert maxdiff(clip_rank.image_features(sd, vc, pre), g['f_img']) < 2e-5 * float(g['f_img'].abs().max()) + 1e-6
+        assert maxdiff(clip_rank.text_features(sd, tc, g['ids_e'].long()), g['f_enc']) < 2e-5 * float(g['f_enc'].abs().max()) + 1e-6
+        clip, dclip = clip_rank.directional_clip(sd, vc, tc, g['img'], g['orig'], g['ids_e'].long(), g['ids_d'].long())
+    assert maxdiff(clip, g['clip']) < 1e-5 and maxdiff(dclip, g['dclip']) < 1e-4
+    for i in range(2):
+        m = clip_rank.metrics(g['met_a'][i], g['met_b'][i])
+        ref = g['met'][i].tolist()
+        assert abs(m[0] - ref[0]) < 1e-4 and abs(m[1] - ref[1]) < 1e-9 and abs(m[2] - ref[2]) < 1e-4, (m, ref)
