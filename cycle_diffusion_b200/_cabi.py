@@ -22,7 +22,7 @@ class UnetConfig(C.Structure):
 
 class VaeConfig(C.Structure):
     _fields_ = [('ch', C.c_int), ('n_mult', C.c_int), ('ch_mult', C.c_int * 8), ('num_res_blocks', C.c_int),
-                ('in_channels', C.c_int), ('out_ch', C.c_int), ('z_channels', C.c_int), ('embed_dim', C.c_int)]
+                ('in_channels', C.c_int), ('out_ch', C.c_int), ('z_channels', C.c_int), ('embed_dim', C.c_int), ('vq', C.c_int), ('n_embed', C.c_int)]
 
 
 class TextConfig(C.Structure):

@@ -148,7 +148,7 @@ void run_latent_loop(Net& unet, const LatentLoopArgs& a, cudaStream_t s) {
   const int loop_steps = enc && !dec ? a.n_rec : a.n_steps;
   float* tdev = (float*)e.arena.alloc((size_t)std::max(loop_steps, 1) * nb * sizeof(float));
   upload_timesteps(e, a.t_host, loop_steps, nb, tdev, s);
-  {   // cat([uc, c]) per chain: uncond first (ddim.py:555-557)
+  if (ctx_n) {   // cat([uc, c]) per chain: uncond first (ddim.py:555-557); unconditional models (L == 0) carry no context
     int sg = 0;
     if (enc) {
       if (cfg_s) copy_dd(e, a.uc, ctx_in + (size_t)(sg++) * ctx_n, ctx_n, s);
@@ -479,7 +479,7 @@ int cdx_latent_encode(cdx_net* un, const float* x0, const float* c, const float*
                       const float* t_host, int n_steps, int n_rec, const float* noise, float sqrt_a_T, float sqrt_1ma_T, float* z_out, int B,
                       int C, int h, int w, void* stream) {
   return guard([&] {
-    CDX_CHECK(un && un->owner && x0 && c && coef && t_host && noise && z_out, "latent_encode: null argument");
+    CDX_CHECK(un && un->owner && x0 && (c || L == 0) && coef && t_host && noise && z_out, "latent_encode: null argument");
     CDX_CHECK(n_steps >= 1 && n_rec >= 0 && n_rec <= n_steps, "latent_encode: n_steps=%d n_rec=%d", n_steps, n_rec);
     for (int i = 0; i < n_rec; ++i) CDX_CHECK(coef[i].sigma > 0.f, "latent_encode: eta must be > 0 (sigma[%d] == 0), ddim.py:268", i);
     LatentLoopArgs a;
@@ -494,7 +494,7 @@ int cdx_latent_encode(cdx_net* un, const float* x0, const float* c, const float*
 int cdx_latent_decode(cdx_net* un, const float* z, int n_eps, const float* c, const float* uc, int L, float scale, const cdx_ddim_coef* coef,
                       const float* t_host, int n_steps, const float* extra_noise, float* x_out, int B, int C, int h, int w, void* stream) {
   return guard([&] {
-    CDX_CHECK(un && un->owner && z && c && coef && t_host && x_out, "latent_decode: null argument");
+    CDX_CHECK(un && un->owner && z && (c || L == 0) && coef && t_host && x_out, "latent_decode: null argument");
     CDX_CHECK(n_steps >= 1 && n_eps >= 0, "latent_decode: n_steps=%d n_eps=%d", n_steps, n_eps);
     CDX_CHECK(n_eps >= n_steps || extra_noise != nullptr, "latent_decode: %d steps but only %d recovered noises and no extra noise", n_steps, n_eps);
     LatentLoopArgs a;

@@ -208,6 +208,8 @@ void embed_tokens(Engine& e, const int* ids, const float* tok, const float* pos,
 void quick_gelu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s);     // x * sigmoid(1.702 x)
 void gelu(Engine& e, const float* x, float* y, size_t n, cudaStream_t s);           // exact erf GELU     // [rows,C] -> [rows,Cp], zero fill
 void copy_rows(Engine& e, const float* src, float* dst, size_t n, cudaStream_t s);
+// taming VectorQuantizer2.forward on NHWC latents: per pixel the first argmin_k of (|z|^2 + |e_k|^2) - 2 z.e_k, output z + (e_k - z)
+void vq_quantize(Engine& e, const float* z, const float* codebook, float* out, size_t npix, int dim, int n_embed, cudaStream_t s);
 // ---- Directional-CLIP / metric kernels (kernels_elem.cu)
 void clip_preprocess(Engine& e, const float* img, int B, int R, int size, float* out, cudaStream_t s);
 void patchify(Engine& e, const float* img, float* out, int B, int S, int P, cudaStream_t s);            // [B,3,S,S] -> [B*(S/P)^2, 3*P*P]

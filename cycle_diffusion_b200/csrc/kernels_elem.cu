@@ -611,6 +611,39 @@ void attention(Engine& e, const float* q, int ldq, const float* k, int ldk, cons
 }  // namespace cdx
 
 namespace cdx {
+namespace {
+// one warp per latent pixel; lanes stride over the codebook, (distance, index) min-reduced with ties to the LOWER index (torch.argmin)
+__global__ void vq_quantize_kernel(const float* __restrict__ z, const float* __restrict__ cb, float* __restrict__ out, size_t npix, int dim, int n_embed) {
+  const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= npix) return;
+  const float* zp = z + pix * dim;
+  float zz = 0.f;
+  for (int c = 0; c < dim; ++c) zz += zp[c] * zp[c];
+  float best = 3.4e38f;
+  int bi = 0x7fffffff;
+  for (int k = lane; k < n_embed; k += 32) {
+    const float* e = cb + (size_t)k * dim;
+    float ee = 0.f, dot = 0.f;
+    for (int c = 0; c < dim; ++c) { ee += e[c] * e[c]; dot += zp[c] * e[c]; }
+    const float d = (zz + ee) - 2.f * dot;
+    if (d < best) { best = d; bi = k; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  for (int c = lane; c < dim; c += 32) out[pix * dim + c] = zp[c] + (cb[(size_t)bi * dim + c] - zp[c]);      // z + (z_q - z).detach()
+}
+}  // namespace
+void vq_quantize(Engine& e, const float* z, const float* codebook, float* out, size_t npix, int dim, int n_embed, cudaStream_t s) {
+  if (e.dry()) return;
+  vq_quantize_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, s>>>(z, codebook, out, npix, dim, n_embed);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
 void clip_preprocess(Engine& e, const float* img, int B, int R, int size, float* out, cudaStream_t s) {
   LAUNCH1(clip_preprocess_kernel, (size_t)B * 3 * size * size, img, B, R, size, out);
 }

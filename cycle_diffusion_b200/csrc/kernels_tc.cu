@@ -964,6 +964,19 @@ __global__ void amax_rows_kernel(const float* __restrict__ x, long long rows, in
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(m));
 }
 
+// any C / stride (few-channel tensors: a 3-channel VQ latent)
+__global__ void amax_rows_scalar_kernel(const float* __restrict__ x, long long rows, int C, long long ld, float* __restrict__ slot) {
+  float m = 0.f;
+  const long long total = rows * (long long)C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    m = fmaxf(m, fabsf(x[r * ld + (i - r * C)]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(m));
+}
+
 // cudaFuncSetAttribute is per DEVICE: remember which devices of this process have it (engines on several devices share the library)
 void ensure_attr(int device) {
   static bool attr_set[64] = {};
@@ -1001,7 +1014,14 @@ void split_planes_h16(Engine& e, const float* w, void* hi, void* lo, size_t n, i
 
 void amax_rows(Engine& e, const float* x, long long rows, int C, long long ld, float* slot, cudaStream_t s) {
   if (e.dry()) return;
-  CDX_CHECK((C & 3) == 0 && (ld & 3) == 0 && a16(x), "amax_rows: C=%d ld=%lld must be multiples of 4 (16-byte rows)", C, ld);
+  if ((C & 3) || (ld & 3) || !a16(x)) {
+    const long long total = rows * (long long)C;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e.num_sms * 8);
+    amax_rows_scalar_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, rows, C, ld, slot);
+    CDX_CUDA(cudaGetLastError());
+    e.launches++;
+    return;
+  }
   const long long total = rows * (long long)(C >> 2);
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e.num_sms * 8);
   amax_rows_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, rows, C, ld, slot);

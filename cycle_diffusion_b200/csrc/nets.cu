@@ -115,7 +115,7 @@ void build_unet_inventory(Net& n) {
     v.add(p + ".proj_out.weight", {ch, ch, 1});
     v.add(p + ".proj_out.bias", {ch});
   };
-  auto attention_layer = [&](const std::string& p, int ch) { oai ? st(p, ch) : attn(p, ch); };
+  auto attention_layer = [&](const std::string& p, int ch) { (oai && c.context_dim > 0) ? st(p, ch) : attn(p, ch); };
 
   v.lin("time_embed.0", mc, ted);
   v.lin("time_embed.2", ted, ted);
@@ -204,7 +204,7 @@ void build_vae_inventory(Net& n) {
   attn(E + "mid.attn_1", block_in);
   res(E + "mid.block_2", block_in, block_in);
   v.norm(E + "norm_out", block_in);
-  v.conv(E + "conv_out", block_in, 2 * c.z_channels, 3);
+  v.conv(E + "conv_out", block_in, (c.vq ? 1 : 2) * c.z_channels, 3);
 
   block_in = ch * c.ch_mult[L - 1];
   v.conv(D + "conv_in", c.z_channels, block_in, 3);
@@ -221,7 +221,8 @@ void build_vae_inventory(Net& n) {
   }
   v.norm(D + "norm_out", block_in);
   v.conv(D + "conv_out", block_in, c.out_ch, 3);
-  v.conv("quant_conv", 2 * c.z_channels, 2 * c.embed_dim, 1);
+  if (c.vq) v.add("quantize.embedding.weight", {c.n_embed, c.embed_dim});
+  v.conv("quant_conv", (c.vq ? 1 : 2) * c.z_channels, (c.vq ? 1 : 2) * c.embed_dim, 1);
   v.conv("post_quant_conv", c.embed_dim, c.z_channels, 1);
 }
 
@@ -255,8 +256,8 @@ Net* make_unet(Engine* e, const cdx_unet_config& cfg) {
   CDX_CHECK(cfg.kind == CDX_UNET_OPENAI || cfg.kind == CDX_UNET_IDDPM, "unet: bad kind %d", cfg.kind);
   CDX_CHECK(cfg.n_mult >= 1 && cfg.n_mult <= 8 && cfg.n_attn >= 0 && cfg.n_attn <= 8, "unet: bad level counts");
   CDX_CHECK(cfg.model_channels % 32 == 0, "unet: model_channels must be a multiple of 32 (GroupNorm32)");
-  if (cfg.kind == CDX_UNET_OPENAI) CDX_CHECK(cfg.num_heads > 0 && cfg.context_dim > 0, "unet: heads/context_dim");
-  else CDX_CHECK(cfg.num_head_channels > 0, "unet: num_head_channels");
+  if (cfg.kind == CDX_UNET_OPENAI && cfg.context_dim > 0) CDX_CHECK(cfg.num_heads > 0, "unet: heads");
+  else CDX_CHECK(cfg.num_head_channels > 0 || cfg.num_heads > 0, "unet: num_head_channels / num_heads");
   Net* n = new Net();
   n->eng = e;
   n->kind = cfg.kind == CDX_UNET_OPENAI ? NET_UNET_OPENAI : NET_UNET_IDDPM;
@@ -274,6 +275,7 @@ Net* make_unet(Engine* e, const cdx_unet_config& cfg) {
 Net* make_vae(Engine* e, const cdx_vae_config& cfg) {
   CDX_CHECK(cfg.n_mult >= 1 && cfg.n_mult <= 8, "vae: bad level count");
   CDX_CHECK(cfg.ch % 32 == 0, "vae: ch must be a multiple of 32");
+  CDX_CHECK(!cfg.vq || cfg.n_embed > 0, "vae: vq needs n_embed");
   Net* n = new Net();
   n->eng = e;
   n->kind = NET_VAE;
@@ -471,7 +473,7 @@ struct Exec {
   void track(Tensor& t, GemmArgs& g, bool stats) {
     t.amax = e.amax_slot();
     g.c_amax = t.amax;
-    if (stats) {
+    if (stats && (t.C % 4) == 0) {          // (few-channel outputs -- a 3-channel VQ latent -- are never GroupNorm inputs)
       t.stats = e.stat_alloc((size_t)t.B * t.C * 2);
       g.c_stats = t.stats;
       g.rows_per_batch = t.H * t.W;
@@ -803,7 +805,7 @@ struct UNetExec : Exec {
 
   // i-DDPM AttentionBlock + QKVAttentionLegacy (IU:304-310, 342-363): qkv channels are [head][q|k|v][d]
   Tensor attention_block(const Tensor& x, const std::string& p) {
-    const int C = x.C, d = n.ucfg.num_head_channels, heads = C / d;
+    const int C = x.C, d = n.ucfg.num_head_channels > 0 ? n.ucfg.num_head_channels : C / n.ucfg.num_heads, heads = C / d;
     const int M = x.rows(), HW = x.H * x.W, B = x.B;
     Tensor out = alloc(B, x.H, x.W, C);
     Scope sc(e.arena);
@@ -823,7 +825,7 @@ struct UNetExec : Exec {
     return out;
   }
 
-  Tensor attn_layer(const Tensor& x, const std::string& p) { return oai ? spatial_transformer(x, p) : attention_block(x, p); }
+  Tensor attn_layer(const Tensor& x, const std::string& p) { return (oai && n.ucfg.context_dim > 0) ? spatial_transformer(x, p) : attention_block(x, p); }
 
   void forward(const float* x_nchw, const float* t_dev, const float* context, int L, float* out_nchw, int B, int H, int W) {
     const cdx_unet_config& c = n.ucfg;
@@ -1020,6 +1022,11 @@ struct VaeExec : Exec {
     const std::string D = "decoder.";
     Tensor zin = alloc(B, hsz, hsz, c.embed_dim);
     nchw_to_nhwc(e, z_nchw, zin.p, B, c.embed_dim, hsz * hsz, s);
+    if (c.vq) {       // VQModelInterface.decode: quantise first (autoencoder.py:272-281)
+      Tensor zq = alloc(B, hsz, hsz, c.embed_dim);
+      vq_quantize(e, zin.p, n.P("quantize.embedding.weight"), zq.p, (size_t)B * hsz * hsz, c.embed_dim, c.n_embed, s);
+      zin = zq;
+    }
     Tensor h = linear(zin, "post_quant_conv", true);
     h = conv3(h, D + "conv_in");
     h = resnet(h, D + "mid.block_1");
@@ -1040,11 +1047,11 @@ void unet_forward(Net& n, const float* x_nchw, const float* t_dev, const float* 
                   cudaStream_t s, bool reuse_ctx) {
   CDX_CHECK(n.kind == NET_UNET_OPENAI || n.kind == NET_UNET_IDDPM, "unet_forward on a non-U-Net");
   CDX_CHECK(n.finalized, "unet_forward before finalize");
-  if (n.kind == NET_UNET_OPENAI) CDX_CHECK(ctx != nullptr && ctx_len > 0, "unet_forward: the SD/LDM U-Net needs a context");
+  if (n.kind == NET_UNET_OPENAI && n.ucfg.context_dim > 0) CDX_CHECK(ctx != nullptr && ctx_len > 0, "unet_forward: the SD/LDM U-Net needs a context");
   const int down = 1 << (n.ucfg.n_mult - 1);
   CDX_CHECK(H % down == 0 && W % down == 0, "unet_forward: %dx%d not divisible by %d", H, W, down);
   UNetExec ex(n, s);
-  ex.kv_reuse = reuse_ctx && n.kind == NET_UNET_OPENAI;
+  ex.kv_reuse = reuse_ctx && n.kind == NET_UNET_OPENAI && n.ucfg.context_dim > 0;
   ex.forward(x_nchw, t_dev, ctx, ctx_len, out_nchw, B, H, W);
   if (ex.kv_reuse && !n.eng->dry()) {
     n.ctxkv.valid = true;

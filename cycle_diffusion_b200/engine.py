@@ -365,12 +365,13 @@ class UNet(Net):
     def latent_encode(self, x0, c, uc, scale, sched, n_rec, noise):
         """-> z [B, n_rec+1, C, h, w]; noise [n_rec+1, B, C, h, w] in the reference's draw order."""
         e = self.engine
-        x0, c, noise = _f32c(x0, e.device), _f32c(c, e.device), _f32c(noise, e.device)
+        x0, noise = _f32c(x0, e.device), _f32c(noise, e.device)
+        c = _f32c(c, e.device) if c is not None else None            # None: unconditional model (no context)
         uc = _f32c(uc, e.device) if uc is not None else None
         B, Cc, h, w = x0.shape
         assert noise.shape == (n_rec + 1, B, Cc, h, w), f'noise shape {tuple(noise.shape)}'
         z = e.empty(B, n_rec + 1, Cc, h, w)
-        check(lib.cdx_latent_encode(self.h, _ptr(x0), _ptr(c), _ptr(uc), c.shape[1], float(scale), sched.coef_array(), sched.t_array(),
+        check(lib.cdx_latent_encode(self.h, _ptr(x0), _ptr(c), _ptr(uc), c.shape[1] if c is not None else 0, float(scale), sched.coef_array(), sched.t_array(),
                                     sched.refine_steps, n_rec, _ptr(noise), sched.sqrt_a_T, sched.sqrt_1ma_T, _ptr(z), B, Cc, h, w,
                                     e.stream))
         return z
@@ -378,14 +379,27 @@ class UNet(Net):
     def latent_decode(self, z, c, uc, scale, sched, extra_noise=None):
         """z [B, n_eps+1, C, h, w] -> x0 [B, C, h, w]."""
         e = self.engine
-        z, c = _f32c(z, e.device), _f32c(c, e.device)
+        z = _f32c(z, e.device)
+        c = _f32c(c, e.device) if c is not None else None
         uc = _f32c(uc, e.device) if uc is not None else None
         extra_noise = _f32c(extra_noise, e.device) if extra_noise is not None else None
         B, n1, Cc, h, w = z.shape
         out = e.empty(B, Cc, h, w)
-        check(lib.cdx_latent_decode(self.h, _ptr(z), n1 - 1, _ptr(c), _ptr(uc), c.shape[1], float(scale), sched.coef_array(),
+        check(lib.cdx_latent_decode(self.h, _ptr(z), n1 - 1, _ptr(c), _ptr(uc), c.shape[1] if c is not None else 0, float(scale), sched.coef_array(),
                                     sched.t_array(), sched.refine_steps, _ptr(extra_noise), _ptr(out), B, Cc, h, w, e.stream))
         return out
+
+    def latent_refine(self, x0, c, uc, scale, S, refine_steps, noise, alphas_cumprod=None):
+        """DDIMSampler.refine / _refine (ddim.py:114-168, 339-393) as the latentdiff wrappers call it (eta = 1): re-noise x0 to the
+        level of step `refine_steps - 1` of the S-step eta-1 schedule and run the last `refine_steps` stochastic DDIM steps with
+        fresh noise.  noise [refine_steps + 1, B, C, h, w]: the x_t draw (ddim.py:349), then one per step (p_sample_ddim)."""
+        from .schedule import DDIMSchedule
+        assert 0 < refine_steps < S                                   # ddim.py:364
+        sched = DDIMSchedule(S, 1.0, S - refine_steps, alphas_cumprod)
+        noise = _f32c(noise, self.engine.device)
+        assert noise.shape[0] == refine_steps + 1
+        xt = self.engine.q_sample(x0, noise[0], sched.sqrt_a_T, sched.sqrt_1ma_T)
+        return self.latent_decode(xt.unsqueeze(1).contiguous(), c, uc, scale, sched, extra_noise=noise[1:].contiguous())
 
     # ---- ensemble members batched along B (per-sample guidance scales; cdx_latent_loop_ens)
     def latent_encode_ens(self, x0, c, uc, scales, sched, n_rec, noise):
@@ -470,6 +484,7 @@ class VAE(Net):
         c.num_res_blocks = cfg['num_res_blocks']
         c.in_channels, c.out_ch = cfg['in_channels'], cfg['out_ch']
         c.z_channels, c.embed_dim = cfg['z_channels'], cfg['embed_dim']
+        c.vq, c.n_embed = int(bool(cfg.get('vq', False))), cfg.get('n_embed', 0)
         h = C.c_void_p()
         check(lib.cdx_vae_create(engine.h if engine is not None else None, C.byref(c), C.byref(h)))
         super().__init__(engine, h)
@@ -480,7 +495,7 @@ class VAE(Net):
         img = _f32c(img, e.device)
         B, _, R, R2 = img.shape
         assert R == R2
-        out = e.empty(B, 2 * self.cfg['embed_dim'], R // self.down, R // self.down)
+        out = e.empty(B, (1 if self.cfg.get('vq') else 2) * self.cfg['embed_dim'], R // self.down, R // self.down)      # vq: h itself
         check(lib.cdx_vae_encode(self.h, _ptr(img), _ptr(out), B, R, e.stream))
         return out
 

@@ -58,7 +58,7 @@ def _norm(out, name, c):
 def openai_unet_params(cfg, prefix=''):
     """Ordered (name, shape, kind) list of the SD/LDM UNetModel (spatial-transformer variant)."""
     mc, mult, nrb, ar = cfg['model_channels'], cfg['channel_mult'], cfg['num_res_blocks'], cfg['attention_resolutions']
-    ctx, ted = cfg['context_dim'], 4 * cfg['model_channels']
+    ctx, ted = cfg.get('context_dim', 0), 4 * cfg['model_channels']
     out = []
 
     def res(p, cin, cout):
@@ -71,6 +71,13 @@ def openai_unet_params(cfg, prefix=''):
             _conv(out, p + '.skip_connection', cin, cout, 1)
 
     def st(p, c):
+        if not ctx:                      # use_spatial_transformer=False: AttentionBlock (openaimodel.py:278-315), conv1d weights
+            _norm(out, p + '.norm', c)
+            out.append((p + '.qkv.weight', (3 * c, c, 1), 'w'))
+            out.append((p + '.qkv.bias', (3 * c,), 'b'))
+            out.append((p + '.proj_out.weight', (c, c, 1), 'w'))
+            out.append((p + '.proj_out.bias', (c,), 'b'))
+            return
         _norm(out, p + '.norm', c)
         _conv(out, p + '.proj_in', c, c, 1)
         t = p + '.transformer_blocks.0'
@@ -224,7 +231,8 @@ def kl_vae_params(cfg, prefix=''):
     attn(E + 'mid.attn_1', block_in)
     res(E + 'mid.block_2', block_in, block_in)
     _norm(out, E + 'norm_out', block_in)
-    _conv(out, E + 'conv_out', block_in, 2 * zc, 3)
+    vq = bool(cfg.get('vq'))
+    _conv(out, E + 'conv_out', block_in, (1 if vq else 2) * zc, 3)
 
     D = prefix + 'decoder.'
     block_in = ch * mult[-1]
@@ -241,7 +249,9 @@ def kl_vae_params(cfg, prefix=''):
             _conv(out, f'{D}up.{lvl}.upsample.conv', block_in, block_in, 3)
     _norm(out, D + 'norm_out', block_in)
     _conv(out, D + 'conv_out', block_in, cfg['out_ch'], 3)
-    _conv(out, prefix + 'quant_conv', 2 * zc, 2 * ed, 1)
+    if vq:                                                   # VQModel: quantize.embedding (taming VectorQuantizer2), single-width quant_conv
+        out.append((prefix + 'quantize.embedding.weight', (cfg['n_embed'], ed), 'w'))
+    _conv(out, prefix + 'quant_conv', (1 if vq else 2) * zc, (1 if vq else 2) * ed, 1)
     _conv(out, prefix + 'post_quant_conv', ed, zc, 1)
     return out
 
@@ -344,3 +354,16 @@ def clip_vision_params(cfg):
                 (f'{p}.layer_norm2.weight', (W,), 'nw'), (f'{p}.layer_norm2.bias', (W,), 'nb')]
     out += [(V + 'post_layernorm.weight', (W,), 'nw'), (V + 'post_layernorm.bias', (W,), 'nb'), ('visual_projection.weight', (cfg['proj_dim'], W), 'w')]
     return out
+
+
+def ldm_uncond_unet_config():
+    """Unconditional LDM U-Net of the ffhq256 / celeba256 zoo entries the reference's LatentDiffStochastic configs load
+    (models/ldm/ffhq256/config.yaml upstream; the yaml is not in the tree -- values from the CompVis release): no context,
+    AttentionBlock with 32 channels per head."""
+    return dict(in_channels=3, out_channels=3, model_channels=224, attention_resolutions=(8, 4, 2), num_res_blocks=2,
+                channel_mult=(1, 2, 3, 4), num_head_channels=32, context_dim=0)
+
+
+def vq_f4_config():
+    """VQModelInterface first stage of the same models: embed_dim 3, 8192 codes, ch 128, ch_mult (1,2,4)."""
+    return dict(ch=128, ch_mult=(1, 2, 4), num_res_blocks=2, in_channels=3, out_ch=3, z_channels=3, embed_dim=3, vq=True, n_embed=8192)

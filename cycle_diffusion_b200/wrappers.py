@@ -108,6 +108,8 @@ class _LatentGenerator:
         return self.vae.encode_moments(image)                              # moments of the DiagonalGaussianDistribution
 
     def get_first_stage_encoding(self, moments):
+        if self.vae.cfg.get('vq'):                                         # VQModelInterface: the encoder output itself (ddpm.py:536-543, tensor branch)
+            return self.engine.affine(moments, self.scale_factor, 0.0)
         noise = None
         if self.sample_posterior:                                          # ddpm.py:536-543; distributions.py:36 draws on the CPU
             B, C2, h, w = moments.shape
@@ -380,6 +382,94 @@ class LatentDiffStochasticTextWrapper(_StochasticTextWrapperBase):
         return os.path.join(cls.CKPT_DIR, str(source_model_type), 'model.ckpt')
 
 
+class LatentDiffStochasticWrapper(torch.nn.Module):
+    """Unconditional latent-diffusion models (ffhq256 -> celeba256; VQ-f4 first stage, U-Net without context), SURVEY 8f-4.
+
+    ref model/gan_wrapper/latentdiff_stochastic_wrapper.py:185-316: ``encode(image, class_label=None) -> z [B, white_box_steps*C*h*w]``,
+    ``forward(z, class_label=None) -> img in [0,1]``, optional eta = 1 refinement pass after the decode (convsample_ddim :57-79 ->
+    DDIMSampler.refine, ddim.py:114-168, 339-393).  The class-conditional branch (enforce_class_input: ClassEmbedder cross-attention
+    conditioning, cin256) is not built."""
+
+    @staticmethod
+    def default_checkpoint(source_model_type):
+        """latentdiff_stochastic_wrapper.py:16: ``ckpts/ldm_models/ldm/<source_model_type>/model.ckpt``."""
+        return os.path.join('ckpts', 'ldm_models', 'ldm', str(source_model_type), 'model.ckpt')
+
+    def __init__(self, source_model_type, custom_steps, eta, white_box_steps, refine_steps=0, enforce_class_input=None,
+                 unconditional_guidance_scale=None, *, engine=None, device=0, state_dict=None, unet_config=None, vae_config=None,
+                 latent_size=64, resolution=256, generator=None, seed=1234, alphas_cumprod=None, scale_factor=1.0):
+        super().__init__()
+        if enforce_class_input:
+            raise NotImplementedError('class-conditional latent diffusion (ClassEmbedder conditioning) is not built; unconditional models only')
+        self.enforce_class_input = enforce_class_input
+        self.unconditional_guidance_scale = unconditional_guidance_scale
+        self.refine_steps = refine_steps
+        self.eta, self.custom_steps, self.white_box_steps = eta, custom_steps, white_box_steps
+        self.vanilla = False
+        if generator is not None:
+            self.generator, self.engine = generator, generator.engine
+        else:
+            self.engine = engine or Engine(device)
+            ucfg, vcfg = unet_config or specs.ldm_uncond_unet_config(), vae_config or specs.vq_f4_config()
+            unet, vae = UNet(self.engine, ucfg, 'openai'), VAE(self.engine, vcfg)
+            if state_dict == 'synthetic':
+                unet.load_state_dict(specs.synth_state_dict(specs.openai_unet_params(ucfg), seed))
+                vae.load_state_dict(specs.synth_state_dict(specs.kl_vae_params(vcfg), seed + 1))
+            else:
+                sd = _load_sd(state_dict, self.default_checkpoint(source_model_type), None, seed)
+                unet.load_state_dict(sd, prefix='model.diffusion_model.', strict=False)
+                vae.load_state_dict(sd, prefix='first_stage_model.', strict=False)
+            self.generator = _LatentGenerator(self.engine, unet, vae, None, ucfg['in_channels'], latent_size, scale_factor, False)
+            # ffhq256 / celeba256 LDMs: linear_start 0.0015, linear_end 0.0195 (upstream config.yaml; pass alphas_cumprod to override)
+            from .schedule import ldm_alphas_cumprod
+            self.generator.alphas_cumprod = alphas_cumprod if alphas_cumprod is not None else ldm_alphas_cumprod(1000, 0.0015, 0.0195)
+        self.resolution = resolution
+        g = self.generator
+        self.latent_dim = g.image_size ** 2 * g.channels * self.white_box_steps
+        self._dummy = torch.nn.Parameter(torch.zeros(1, device=self.engine.device), requires_grad=False)
+
+    def _sched(self):
+        return DDIMSchedule(self.custom_steps, self.eta, 0, self.generator.alphas_cumprod)
+
+    def generate(self, z, class_label):
+        g = self.generator
+        bsz = z.shape[0]
+        eps_list = z.view(bsz, self.white_box_steps, g.channels, g.image_size, g.image_size)
+        sched = self._sched()
+        n_extra = sched.refine_steps - (eps_list.shape[1] - 1)
+        extra = torch.stack([torch.randn(eps_list[:, 0].shape) for _ in range(n_extra)]) if n_extra > 0 else None      # ddim.py:640
+        sample = g.unet.latent_decode(eps_list, None, None, 1.0, sched, extra)
+        if self.refine_steps > 0:                                     # refine_eta = 1 (latentdiff_stochastic_wrapper.py:68-77)
+            noise = torch.stack([torch.randn(sample.shape) for _ in range(self.refine_steps + 1)])
+            sample = g.unet.latent_refine(sample, None, None, 1.0, self.custom_steps, self.refine_steps, noise, g.alphas_cumprod)
+        return g.decode_first_stage(sample)
+
+    def encode(self, image, class_label=None):
+        g, e = self.generator, self.engine
+        bsz = image.shape[0]
+        image = e.shift_scale(image, -0.5, 2.0)
+        assert image.shape[2] == image.shape[3] == self.resolution
+        x0 = g.get_first_stage_encoding(g.encode_first_stage(image))
+        assert self.eta > 0
+        sched = self._sched()
+        n_rec = max(0, min(sched.refine_steps, self.white_box_steps - 1))
+        noise = torch.zeros((n_rec + 1,) + tuple(x0.shape))
+        noise[0] = torch.randn(x0.shape)
+        for i in range(n_rec):
+            if sched.refine_steps - 1 - i != 0:                        # ddim.py:583-584: the last step returns x0 without a draw
+                noise[1 + i] = torch.randn(x0.shape)
+        z = g.unet.latent_encode(x0, None, None, 1.0, sched, n_rec, noise).view(bsz, -1)
+        assert z.shape[1] == self.latent_dim
+        return z
+
+    def forward(self, z, class_label=None):
+        return self.engine.shift_scale(self.generate(z, class_label), 1.0, 0.5)
+
+    @property
+    def device(self):
+        return self.engine.device
+
+
 class DDPMDDIMWrapper(torch.nn.Module):
     """Pixel-space DPM-Encoder / decoder (improved-DDPM U-Net for AFHQ / FFHQ)."""
 
@@ -477,7 +567,9 @@ def get_gan_wrapper(args, target=False, **extra):
                 elif (not target) and kw.startswith('source_'):
                     kwargs[kw] = arg
     kwargs.update(extra)
-    if gan_type == "DDPM_DDIM":
+    if gan_type == "LatentDiffStochastic":
+        return LatentDiffStochasticWrapper(**kwargs)
+    elif gan_type == "DDPM_DDIM":
         return DDPMDDIMWrapper(**kwargs)
     elif gan_type == "LatentDiffStochasticText":
         return LatentDiffStochasticTextWrapper(**kwargs)

@@ -85,7 +85,9 @@ typedef struct cdx_unet_config {
   int attention_ds[8];     /* downsample factors at which attention runs (OAI:541 / IU:506) */
   int num_heads;           /* OPENAI: heads (d_head = ch / heads, legacy=False, OAI:542-549) */
   int num_head_channels;   /* IDDPM: channels per head (IU:287-293) */
-  int context_dim;         /* OPENAI: cross-attention context width (768 SD, 1280 LDM) */
+  int context_dim;         /* OPENAI: cross-attention context width (768 SD, 1280 LDM); 0 = the unconditional LDM U-Net
+                              (use_spatial_transformer=False, OAI:560-577): attention layers are AttentionBlock + QKVAttentionLegacy
+                              (OAI:278-351) with num_head_channels (or num_heads) and the forward takes no context */
 } cdx_unet_config;
 
 typedef struct cdx_vae_config { /* AutoencoderKL ddconfig, v1-inference.yaml:51-65 */
@@ -94,6 +96,11 @@ typedef struct cdx_vae_config { /* AutoencoderKL ddconfig, v1-inference.yaml:51-
   int ch_mult[8];
   int num_res_blocks;
   int in_channels, out_ch, z_channels, embed_dim;
+  /* vq != 0: VQModelInterface first stage of the unconditional LDMs (ldm/models/autoencoder.py:14-21, 258-282): encoder
+     -> quant_conv gives h [B, embed_dim, h, w] (no moments, no quantisation on the way in); decode = nearest code of the n_embed x
+     embed_dim codebook `quantize.embedding.weight` (taming VectorQuantizer2.forward: argmin of |z|^2 + |e|^2 - 2 z.e, straight-through
+     value z + (z_q - z)) -> post_quant_conv -> decoder */
+  int vq, n_embed;
 } cdx_vae_config;
 
 typedef struct cdx_text_config { /* CLIP ViT-L/14 text tower as FrozenCLIPEmbedder uses it: HF CLIPTextModel

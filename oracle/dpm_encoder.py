@@ -117,6 +117,27 @@ def latent_decode(unet_fn, x_T, eps_list, c, uc, S, eta, skip_steps, scale, alph
     return img
 
 
+def latent_refine(unet_fn, x0, c, uc, S, refine_steps, scale=1.0, alphas_cumprod=None):
+    """DDIMSampler.refine -> _refine (ddim.py:114-168, 339-393) as latentdiff_stochastic_wrapper.py:68-77 calls it (eta = 1): x_t at
+    ddim_alphas[refine_steps - 1] from a fresh draw, then p_sample_ddim over the last `refine_steps` timesteps, fresh noise per step."""
+    tab = DDIMTables(S, 1.0, alphas_cumprod)
+    assert refine_steps < tab.timesteps.shape[0]
+    at = tab.alphas[refine_steps - 1]
+    img = at.sqrt() * x0 + (1 - at).sqrt() * torch.randn(x0.shape)
+    time_range = np.flip(tab.timesteps)[-refine_steps:]
+    b = x0.shape[0]
+    for i, step in enumerate(time_range):
+        index = refine_steps - i - 1
+        ts = torch.full((b,), int(step), dtype=torch.long)
+        e_t = _guided_eps(unet_fn, img, ts, c, uc, scale)
+        a_t, a_prev, sigma_t, sqrt_1m_at = _coeffs(tab, index, b)
+        pred_x0 = (img - sqrt_1m_at * e_t) / a_t.sqrt()
+        dir_xt = (1. - a_prev - sigma_t ** 2).sqrt() * e_t
+        noise = sigma_t * torch.randn(img.shape) * 1.0
+        img = a_prev.sqrt() * pred_x0 + dir_xt + noise
+    return img
+
+
 class LatentCycle:
     """SDStochasticTextWrapper / LatentDiffStochasticTextWrapper restated (SDW:100-253, LDW:102-252).
 

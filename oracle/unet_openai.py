@@ -93,6 +93,25 @@ def _spatial_transformer(sd, p, x, context, heads):
     return x + x_in
 
 
+def _attention_block(sd, p, x, cfg):
+    """AttentionBlock._forward + QKVAttentionLegacy (openaimodel.py:304-315, 318-351): the use_spatial_transformer=False attention of
+    the unconditional LDM U-Nets; qkv channels are [head][q|k|v][d]."""
+    b, c, hh, ww = x.shape
+    d = cfg['num_head_channels'] if cfg.get('num_head_channels', 0) > 0 else c // cfg['num_heads']
+    heads = c // d
+    xf = x.reshape(b, c, -1)
+    qkv = F.conv1d(_gn(sd, p + '.norm', xf, 1e-5), sd[p + '.qkv.weight'], sd[p + '.qkv.bias'])
+    bs, width, length = qkv.shape
+    ch = width // (3 * heads)
+    q, k, v = qkv.reshape(bs * heads, ch * 3, length).split(ch, dim=1)
+    scale = 1 / math.sqrt(math.sqrt(ch))
+    weight = torch.einsum('bct,bcs->bts', q * scale, k * scale)
+    weight = torch.softmax(weight.float(), dim=-1)
+    a = torch.einsum('bts,bcs->bct', weight, v).reshape(bs, -1, length)
+    h = F.conv1d(a, sd[p + '.proj_out.weight'], sd[p + '.proj_out.bias'])
+    return (xf + h).reshape(b, c, hh, ww)
+
+
 def plan(cfg):
     """Block list mirroring UNetModel.__init__ (openaimodel.py:516-686).
 
@@ -122,7 +141,7 @@ def plan(cfg):
 def unet_forward(sd, cfg, x, timesteps, context, prefix=''):
     """x [B,Cin,h,w] fp32, timesteps [B] (long or float), context [B,77,D] -> [B,Cout,h,w]."""
     P = prefix
-    heads = cfg['num_heads']
+    heads = cfg.get('num_heads', 0)
     inp, mid, outb = plan(cfg)
     emb = _lin(sd, P + 'time_embed.2', F.silu(_lin(sd, P + 'time_embed.0', timestep_embedding(timesteps, cfg['model_channels']))))
 
@@ -134,7 +153,7 @@ def unet_forward(sd, cfg, x, timesteps, context, prefix=''):
             elif kind == 'res':
                 h = _resblock(sd, p, h, emb)
             elif kind == 'st':
-                h = _spatial_transformer(sd, p, h, context, heads)
+                h = _spatial_transformer(sd, p, h, context, heads) if cfg.get('context_dim', 0) else _attention_block(sd, p, h, cfg)
             elif kind == 'down':
                 h = _conv(sd, p + '.op', h, stride=2, padding=1)
             elif kind == 'up':

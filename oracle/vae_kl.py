@@ -72,10 +72,26 @@ def encode_moments(sd, cfg, x, prefix=''):
     return _conv(sd, prefix + 'quant_conv', h, padding=0)
 
 
+def vq_quantize(sd, z, prefix=''):
+    """taming.modules.vqvae.quantize.VectorQuantizer2.forward (third party, absent from the tree; the published algorithm): nearest
+    code by  |z|^2 + |e|^2 - 2 z.e , straight-through value  z + (z_q - z).  z [B, e_dim, h, w] -> same shape."""
+    emb = sd[prefix + 'quantize.embedding.weight']
+    zp = z.permute(0, 2, 3, 1).contiguous()
+    zf = zp.view(-1, emb.shape[1])
+    d = torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(emb ** 2, dim=1) - 2 * torch.einsum('bd,dn->bn', zf, emb.t())
+    idx = torch.argmin(d, dim=1)
+    zq = emb[idx].view(zp.shape)
+    zq = zp + (zq - zp)
+    return zq.permute(0, 3, 1, 2).contiguous()
+
+
 def decode(sd, cfg, z, prefix=''):
-    """z [B,embed_dim,h,w] (already divided by scale_factor) -> image [B,3,8h,8w]."""
+    """z [B,embed_dim,h,w] (already divided by scale_factor) -> image [B,3,8h,8w].  cfg['vq']: VQModelInterface.decode
+    (ldm/models/autoencoder.py:272-281) quantises first."""
     P = prefix + 'decoder.'
     nres = len(cfg['ch_mult'])
+    if cfg.get('vq'):
+        z = vq_quantize(sd, z, prefix)
     h = _conv(sd, prefix + 'post_quant_conv', z, padding=0)
     h = _conv(sd, P + 'conv_in', h)
     h = _resnet(sd, P + 'mid.block_1', h)

@@ -414,6 +414,77 @@ def golden_clip_rank():
     print(f'clip_rank: clip {clip.tolist()} dclip {dclip.tolist()} metrics {met}')
 
 
+UNCOND_SMALL = dict(in_channels=3, out_channels=3, model_channels=32, attention_resolutions=(2, 4), num_res_blocks=1,
+                    channel_mult=(1, 2, 2), num_head_channels=16, context_dim=0)
+VQ_SMALL = dict(ch=32, ch_mult=(1, 2, 4), num_res_blocks=1, in_channels=3, out_ch=3, z_channels=3, embed_dim=3, vq=True, n_embed=256)
+
+
+def golden_ldm_uncond():
+    """the unconditional LDM path of LatentDiffStochasticWrapper.  (i) the reference UNetModel built with
+    use_spatial_transformer=False (AttentionBlock + QKVAttentionLegacy); (ii) the reference VAE Encoder / Decoder with double_z=False
+    around the VQ 1x1 convs, quantiser restated (taming is absent from the tree); (iii) DDIMSampler: ddpm_ddim_encoding with no
+    conditioning -> sample_with_eps -> refine(eta=1), the call sequence of latentdiff_stochastic_wrapper.py:57-79, 164-170."""
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from ldm.modules.diffusionmodules.model import Encoder, Decoder
+    from ldm.models.diffusion.ddim import DDIMSampler
+
+    class CPUSampler(DDIMSampler):
+        def register_buffer(self, name, attr):
+            setattr(self, name, attr)
+
+    cfg = UNCOND_SMALL
+    sd = specs.synth_state_dict(specs.openai_unet_params(cfg), 41)
+    with _quiet():
+        unet = UNetModel(image_size=16, in_channels=3, out_channels=3, model_channels=cfg['model_channels'],
+                         attention_resolutions=list(cfg['attention_resolutions']), num_res_blocks=cfg['num_res_blocks'],
+                         channel_mult=list(cfg['channel_mult']), num_head_channels=cfg['num_head_channels'], use_spatial_transformer=False,
+                         use_checkpoint=False).eval()
+    unet.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(241)
+    x = torch.randn(2, 3, 16, 16, generator=g)
+    t = torch.tensor([801, 41], dtype=torch.long)
+    with torch.no_grad():
+        y = unet(x, t)
+    out = dict(x=x, t=t, y=y, wsum=sd_checksum(sd))
+    # (ii) VQ first stage
+    vc = VQ_SMALL
+    vsd = specs.synth_state_dict(specs.kl_vae_params(vc), 42)
+    dd = dict(double_z=False, z_channels=3, resolution=64, in_channels=3, out_ch=3, ch=vc['ch'], ch_mult=list(vc['ch_mult']),
+              num_res_blocks=vc['num_res_blocks'], attn_resolutions=[], dropout=0.0)
+    with _quiet():
+        enc, dec = Encoder(**dd).eval(), Decoder(**dd).eval()
+    enc.load_state_dict({k[len('encoder.'):]: v for k, v in vsd.items() if k.startswith('encoder.')}, strict=True)
+    dec.load_state_dict({k[len('decoder.'):]: v for k, v in vsd.items() if k.startswith('decoder.')}, strict=True)
+    img = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    zz = torch.randn(2, 3, 16, 16, generator=g) * 0.5
+    import torch.nn.functional as F
+    with torch.no_grad():
+        h = F.conv2d(enc(img), vsd['quant_conv.weight'], vsd['quant_conv.bias'])                 # VQModelInterface.encode
+        emb = vsd['quantize.embedding.weight']
+        zp = zz.permute(0, 2, 3, 1).contiguous()
+        zf = zp.view(-1, 3)
+        d = torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(emb ** 2, dim=1) - 2 * torch.einsum('bd,dn->bn', zf, emb.t())
+        zq = emb[torch.argmin(d, dim=1)].view(zp.shape)
+        zq = (zp + (zq - zp)).permute(0, 3, 1, 2).contiguous()
+        rec = dec(F.conv2d(zq, vsd['post_quant_conv.weight'], vsd['post_quant_conv.bias']))     # VQModelInterface.decode
+    out.update(img=img, h=h, zz=zz, rec=rec)
+    # (iii) sampler sequence
+    model = _LatentStandIn(unet)
+    model.apply_model = lambda xx, tt, cc: unet(xx, tt)
+    x0 = torch.randn(2, 3, 16, 16, generator=g) * 0.7
+    S, wb, r = 8, 9, 3
+    torch.manual_seed(4242)
+    with torch.no_grad(), _quiet():
+        z_list = CPUSampler(model).ddpm_ddim_encoding(S, batch_size=2, shape=(3, 16, 16), eta=0.1, white_box_steps=wb, verbose=False, x0=x0)
+        z = torch.stack(z_list, dim=1).view(2, -1)
+        eps_list = z.view(2, wb, 3, 16, 16)
+        dec_, _ = CPUSampler(model).sample_with_eps(S, eps_list[:, 1:], batch_size=2, shape=(3, 16, 16), eta=0.1, verbose=False, x_T=eps_list[:, 0])
+        ref_, _ = CPUSampler(model).refine(S, refine_steps=r, batch_size=2, shape=(3, 16, 16), eta=1, verbose=False, x0=dec_)
+    print(f'ldm_uncond: unet |y|max {y.abs().max():.3f}  cycle |dec - x0| {(dec_ - x0).abs().max():.2e}  |refined - dec| {(ref_ - dec_).abs().max():.3f}')
+    out.update(x0=x0, z=z, dec=dec_, refined=ref_, cyc=np.asarray([S, wb, r, 4242], dtype=np.int64))
+    save('ldm_uncond', **out)
+
+
 if __name__ == '__main__':
     _shim_omegaconf()
     sys.path.insert(0, os.path.join(REF, 'model/lib/stable_diffusion'))
@@ -427,3 +498,4 @@ if __name__ == '__main__':
     golden_clip_text()
     golden_bert_text()
     golden_clip_rank()
+    golden_ldm_uncond()

@@ -72,3 +72,14 @@ def test_clip_rank_tower_inventories_match_specs():
     inv = TextEncoder(None, tc).inventory()
     assert [(a, tuple(b)) for a, b in inv[:-1]] == [(a, tuple(b)) for a, b, _ in specs.clip_text_params(tc)]
     assert inv[-1] == ('text_projection.weight', (512, 512))
+
+
+def test_uncond_ldm_inventories_match_specs():
+    """the context-free OPENAI U-Net (AttentionBlock) and the VQ-f4 first stage inventories equal specs.py."""
+    from cycle_diffusion_b200 import specs
+    from cycle_diffusion_b200.engine import UNet, VAE
+    for cfg in (specs.ldm_uncond_unet_config(), dict(in_channels=3, out_channels=3, model_channels=32, attention_resolutions=(2, 4), num_res_blocks=1,
+                                                     channel_mult=(1, 2, 2), num_head_channels=16, context_dim=0)):
+        assert [(a, tuple(b)) for a, b in UNet(None, cfg, 'openai').inventory()] == [(a, tuple(b)) for a, b, _ in specs.openai_unet_params(cfg)]
+    vc = specs.vq_f4_config()
+    assert [(a, tuple(b)) for a, b in VAE(None, vc).inventory()] == [(a, tuple(b)) for a, b, _ in specs.kl_vae_params(vc)]

@@ -156,3 +156,29 @@ def test_clip_rank_oracle_vs_third_party_and_reference_metrics():
         m = clip_rank.metrics(g['met_a'][i], g['met_b'][i])
         ref = g['met'][i].tolist()
         assert abs(m[0] - ref[0]) < 1e-4 and abs(m[1] - ref[1]) < 1e-9 and abs(m[2] - ref[2]) < 1e-4, (m, ref)
+
+
+UNCOND_SMALL = dict(in_channels=3, out_channels=3, model_channels=32, attention_resolutions=(2, 4), num_res_blocks=1,
+                    channel_mult=(1, 2, 2), num_head_channels=16, context_dim=0)
+VQ_SMALL = dict(ch=32, ch_mult=(1, 2, 4), num_res_blocks=1, in_channels=3, out_ch=3, z_channels=3, embed_dim=3, vq=True, n_embed=256)
+
+
+def test_ldm_uncond_oracle_vs_reference_fixture():
+    """unconditional LDM pieces (AttentionBlock U-Net, VQ first stage, encode -> decode -> eta-1 refine) of the oracle
+    against the fixture produced by the reference's own UNetModel / Encoder / Decoder / DDIMSampler."""
+    g = golden('ldm_uncond')
+    usd = specs.synth_state_dict(specs.openai_unet_params(UNCOND_SMALL), 41)
+    vsd = specs.synth_state_dict(specs.kl_vae_params(VQ_SMALL), 42)
+    assert abs(wsum(usd)[1] - float(g['wsum'][1])) < 1e-6 * float(g['wsum'][1])
+    fn = lambda x, t, c: unet_openai.unet_forward(usd, UNCOND_SMALL, x, t, None)
+    with torch.no_grad():
+        assert maxdiff(fn(g['x'], g['t'].long(), None), g['y']) < 2e-5 * float(g['y'].abs().max())
+        assert maxdiff(vae_kl.encode_moments(vsd, VQ_SMALL, g['img']), g['h']) < 2e-5 * float(g['h'].abs().max())
+        assert maxdiff(vae_kl.decode(vsd, VQ_SMALL, g['zz']), g['rec']) < 2e-5 * float(g['rec'].abs().max())
+        S, wb, r, seed = [int(v) for v in g['cyc']]
+        torch.manual_seed(seed)
+        z = torch.stack(dpm_encoder.latent_encode(fn, g['x0'], None, None, S, 0.1, 0, wb, 1.0), dim=1)
+        dec = dpm_encoder.latent_decode(fn, z[:, 0], z[:, 1:], None, None, S, 0.1, 0, 1.0)
+        ref = dpm_encoder.latent_refine(fn, dec, None, None, S, r)
+    assert maxdiff(z.reshape(2, -1), g['z']) < 2e-4 * float(g['z'].abs().max())
+    assert maxdiff(dec, g['dec']) < 1e-4 and maxdiff(ref, g['refined']) < 1e-4
