@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, 'libcdx.so')
 
 CDX_UNET_OPENAI = 1
 CDX_UNET_IDDPM = 2
+CDX_UNET_DDPM = 3
 
 
 class UnetConfig(C.Structure):

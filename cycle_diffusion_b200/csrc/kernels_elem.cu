@@ -112,13 +112,14 @@ __global__ void transpose_kernel(const float* __restrict__ x, float* __restrict_
     if (r < R && c < Cc) yb[(size_t)c * R + r] = tile[threadIdx.x][j];
   }
 }
-__global__ void temb_kernel(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ emb, int B, int half) {
+// [cos | sin] (util.py:152-172, nn.py:103-122) or, sin_first, [sin | cos] (ddpm/diffusion.py:6-25)
+__global__ void temb_kernel(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ emb, int B, int half, int sin_first) {
   const int n = B * half;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int b = i / half, j = i - b * half;
     const float a = MUL(t[b], freqs[j]);
-    emb[(size_t)b * 2 * half + j] = cosf(a);
-    emb[(size_t)b * 2 * half + half + j] = sinf(a);
+    emb[(size_t)b * 2 * half + (sin_first ? half : 0) + j] = cosf(a);
+    emb[(size_t)b * 2 * half + (sin_first ? 0 : half) + j] = sinf(a);
   }
 }
 // OIHW (3x3) -> O,kh,kw,I
@@ -534,9 +535,9 @@ void nhwc_to_nchw(Engine& e, const float* x, float* y, int B, int C, int HW, cud
   CDX_CUDA(cudaGetLastError());
   e.launches++;
 }
-void timestep_embedding(Engine& e, const float* t, const float* freqs, float* emb, int B, int half, cudaStream_t s) {
+void timestep_embedding(Engine& e, const float* t, const float* freqs, float* emb, int B, int half, cudaStream_t s, bool sin_first) {
   if (e.dry()) return;
-  temb_kernel<<<cdiv(B * half, 256), 256, 0, s>>>(t, freqs, emb, B, half);
+  temb_kernel<<<cdiv(B * half, 256), 256, 0, s>>>(t, freqs, emb, B, half, sin_first ? 1 : 0);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
 }

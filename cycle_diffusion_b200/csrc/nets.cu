@@ -170,6 +170,68 @@ void build_unet_inventory(Net& n) {
   n.emb_rows = emb_rows;
 }
 
+// Ho et al. DDPM (ddpm/diffusion.py:192-297): temb.dense, conv_in, down.{l}.block / attn / downsample, mid, up.{l}.block / attn /
+// upsample (num_res_blocks + 1 blocks per level, skip widths as built at :262-271), norm_out, conv_out
+void build_ddpm_inventory(Net& n) {
+  const cdx_unet_config& c = n.ucfg;
+  Inv v(n);
+  const int ch = c.model_channels, ted = 4 * ch, L = c.n_mult;
+  n.ted = ted;
+  int emb_rows = 0;
+  auto res = [&](const std::string& p, int cin, int cout) {
+    v.norm(p + ".norm1", cin);
+    v.conv(p + ".conv1", cin, cout, 3);
+    v.lin(p + ".temb_proj", ted, cout, true, 1);
+    n.emb_off[p] = emb_rows;
+    emb_rows += cout;
+    v.norm(p + ".norm2", cout);
+    v.conv(p + ".conv2", cout, cout, 3);
+    if (cin != cout) v.conv(p + ".nin_shortcut", cin, cout, 1);
+  };
+  auto attn = [&](const std::string& p, int cch) {
+    v.norm(p + ".norm", cch);
+    for (const char* nm : {"q", "k", "v", "proj_out"}) v.conv(p + "." + nm, cch, cch, 1);
+  };
+  v.lin("temb.dense.0", ch, ted);
+  v.lin("temb.dense.1", ted, ted);
+  v.conv("conv_in", c.in_channels, ch, 3);
+  int ds = 1, block_in = ch;
+  for (int lvl = 0; lvl < L; ++lvl) {
+    block_in = ch * (lvl == 0 ? 1 : c.channel_mult[lvl - 1]);
+    const int block_out = ch * c.channel_mult[lvl];
+    const std::string D = "down." + std::to_string(lvl);
+    for (int b = 0; b < c.num_res_blocks; ++b) {
+      res(D + ".block." + std::to_string(b), block_in, block_out);
+      block_in = block_out;
+    }
+    // (ModuleList order inside a level: all blocks, then all attns, then the downsample -- names carry the indices)
+    if (contains(c.attention_ds, c.n_attn, ds))
+      for (int b = 0; b < c.num_res_blocks; ++b) attn(D + ".attn." + std::to_string(b), block_out);
+    if (lvl != L - 1) { v.conv(D + ".downsample.conv", block_in, block_in, 3); ds *= 2; }
+  }
+  res("mid.block_1", block_in, block_in);
+  attn("mid.attn_1", block_in);
+  res("mid.block_2", block_in, block_in);
+  // decoder levels are built top-down (reversed) but registered with insert(0): state_dict order is up.0 first; inventory order is free
+  std::vector<std::pair<int, int>> geom((size_t)L);     // per level: (block_in at entry, ds)
+  for (int lvl = L - 1; lvl >= 0; --lvl) {
+    const int block_out = ch * c.channel_mult[lvl];
+    const std::string U = "up." + std::to_string(lvl);
+    int skip_in = block_out;
+    for (int b = 0; b <= c.num_res_blocks; ++b) {
+      if (b == c.num_res_blocks) skip_in = ch * (lvl == 0 ? 1 : c.channel_mult[lvl - 1]);
+      res(U + ".block." + std::to_string(b), block_in + skip_in, block_out);
+      block_in = block_out;
+    }
+    if (contains(c.attention_ds, c.n_attn, ds))
+      for (int b = 0; b <= c.num_res_blocks; ++b) attn(U + ".attn." + std::to_string(b), block_out);
+    if (lvl != 0) { v.conv(U + ".upsample.conv", block_in, block_in, 3); ds /= 2; }
+  }
+  v.norm("norm_out", block_in);
+  v.conv("conv_out", block_in, c.out_channels, 3);
+  n.emb_rows = emb_rows;
+}
+
 void build_vae_inventory(Net& n) {
   const cdx_vae_config& c = n.vcfg;
   Inv v(n);
@@ -253,16 +315,17 @@ const Param& Net::param(const std::string& name) const {
 }
 
 Net* make_unet(Engine* e, const cdx_unet_config& cfg) {
-  CDX_CHECK(cfg.kind == CDX_UNET_OPENAI || cfg.kind == CDX_UNET_IDDPM, "unet: bad kind %d", cfg.kind);
+  CDX_CHECK(cfg.kind == CDX_UNET_OPENAI || cfg.kind == CDX_UNET_IDDPM || cfg.kind == CDX_UNET_DDPM, "unet: bad kind %d", cfg.kind);
   CDX_CHECK(cfg.n_mult >= 1 && cfg.n_mult <= 8 && cfg.n_attn >= 0 && cfg.n_attn <= 8, "unet: bad level counts");
   CDX_CHECK(cfg.model_channels % 32 == 0, "unet: model_channels must be a multiple of 32 (GroupNorm32)");
   if (cfg.kind == CDX_UNET_OPENAI && cfg.context_dim > 0) CDX_CHECK(cfg.num_heads > 0, "unet: heads");
-  else CDX_CHECK(cfg.num_head_channels > 0 || cfg.num_heads > 0, "unet: num_head_channels / num_heads");
+  else if (cfg.kind != CDX_UNET_DDPM) CDX_CHECK(cfg.num_head_channels > 0 || cfg.num_heads > 0, "unet: num_head_channels / num_heads");
   Net* n = new Net();
   n->eng = e;
-  n->kind = cfg.kind == CDX_UNET_OPENAI ? NET_UNET_OPENAI : NET_UNET_IDDPM;
+  n->kind = cfg.kind == CDX_UNET_OPENAI ? NET_UNET_OPENAI : cfg.kind == CDX_UNET_IDDPM ? NET_UNET_IDDPM : NET_UNET_DDPM;
   n->ucfg = cfg;
-  build_unet_inventory(*n);
+  if (cfg.kind == CDX_UNET_DDPM) build_ddpm_inventory(*n);
+  else build_unet_inventory(*n);
   assign_offsets(*n);
   // default sinusoid frequencies (util.py:161-163); the host normally overrides them with torch's own values
   const int half = cfg.model_channels / 2;
@@ -414,7 +477,7 @@ void net_load_param(Net& n, const char* name, const float* data, bool on_device,
 
 void net_finalize(Net& n) {
   for (const Param& p : n.params) CDX_CHECK(p.loaded, "finalize: parameter '%s' was never loaded", p.name.c_str());
-  if (n.kind != NET_VAE) {
+  if (n.kind != NET_VAE && !n.freqs_host.empty()) {
     if (!n.freqs_dev) CDX_CUDA(cudaMalloc(&n.freqs_dev, n.freqs_host.size() * sizeof(float)));
     CDX_CUDA(cudaMemcpy(n.freqs_dev, n.freqs_host.data(), n.freqs_host.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
@@ -572,6 +635,35 @@ struct Exec {
     layernorm(e, x.p, n.P(name + ".weight"), n.P(name + ".bias"), y.p, x.rows(), x.C, s, y.amax);
     return y;
   }
+
+  // AttnBlock (AEM:178-202): single head, d = C, scale C^-1/2
+  Tensor attn(const Tensor& x, const std::string& p) {
+    const int C = x.C, HW = x.H * x.W;
+    Tensor out = alloc(x.B, x.H, x.W, C);
+    Scope sc(e.arena);
+    Tensor xn = gn(x, nullptr, p + ".norm", 1e-6f, false);
+    Tensor q = linear(xn, p + ".q", true);
+    Tensor k = linear(xn, p + ".k", true);
+    Tensor v = linear(xn, p + ".v", true, nullptr, true);       // its range bounds the attention output
+    Tensor a = alloc(x.B, x.H, x.W, C);
+    a.amax = v.amax;
+    const float scale = (float)pow((double)C, -0.5);
+    bool done = false;
+    if (e.mma_mode == 1 && (HW % 32) == 0 && HW >= 128) {
+      // tensor-core path: S = q k^T, row softmax, O = P V with V transposed to [C, B*HW] (both P.V operands K-major)
+      Scope sa(e.arena);
+      float* vt = (float*)e.arena.alloc((size_t)C * x.rows() * sizeof(float));
+      nhwc_to_nchw(e, v.p, vt, 1, C, x.rows(), s);
+      done = attention_tc(e, q.p, C, k.p, C, C, vt, a.p, C, x.B, HW, HW, 1, C, scale, s);
+    }
+    if (!done) attention(e, q.p, C, k.p, C, v.p, C, a.p, C, x.B, HW, HW, 1, C, C, scale, s);
+    out.amax = e.amax_slot();
+    out.stats = e.stat_alloc((size_t)x.B * C * 2);
+    linear_into(a.p, C, C, nullptr, 0, 0, x.rows(), n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C, nullptr, v.amax, nullptr,
+                out.amax, out.stats, HW);
+    return out;
+  }
+
 };
 
 // ------------------------------------------------------------------------------------------------ U-Nets
@@ -827,6 +919,89 @@ struct UNetExec : Exec {
 
   Tensor attn_layer(const Tensor& x, const std::string& p) { return (oai && n.ucfg.context_dim > 0) ? spatial_transformer(x, p) : attention_block(x, p); }
 
+  // ResnetBlock.forward (ddpm/diffusion.py:117-139): conv1(swish(norm1 x)) + temb_proj(swish temb); conv2(swish(norm2 h)); + shortcut
+  Tensor ddpm_resblock(const Tensor& x, const Tensor* x2, const std::string& p) {
+    const int Cout = n.dim0(p + ".conv1.weight");
+    Tensor out = alloc(x.B, x.H, x.W, Cout);
+    Scope sc(e.arena);
+    Tensor h1 = gn(x, x2, p + ".norm1", 1e-6f, true);
+    Tensor h2 = conv3(h1, p + ".conv1", 1, 1, 1, E + n.emb_off.at(p), n.emb_rows);
+    Tensor h3 = gn(h2, nullptr, p + ".norm2", 1e-6f, true);
+    const float* residual;
+    if (n.has(p + ".nin_shortcut.weight")) {
+      Tensor sk = alloc(x.B, x.H, x.W, Cout);
+      linear_into(x.p, x.C, x.C, x2 ? x2->p : nullptr, x2 ? x2->C : 0, x2 ? x2->C : 0, x.rows(), n.P(p + ".nin_shortcut.weight"), Cout,
+                  n.P(p + ".nin_shortcut.bias"), nullptr, 0, sk.p, Cout, nullptr, x.amax, x2 ? x2->amax : nullptr);
+      residual = sk.p;
+    } else {
+      CDX_CHECK(!x2 && x.C == Cout, "ddpm resblock %s: identity skip with mismatching channels", p.c_str());
+      residual = x.p;
+    }
+    const Param& w = n.param(p + ".conv2.weight");
+    GemmArgs g;
+    g.mode = 1;
+    g.M = h3.rows(); g.N = Cout; g.K = 9 * h3.C;
+    g.A = h3.p; g.lda = h3.C; g.C1 = h3.C;
+    g.Hin = h3.H; g.Win = h3.W; g.Hout = h3.H; g.Wout = h3.W;
+    g.Bw = n.blob + w.off; g.ldb = 9 * h3.C;
+    g.Cout = out.p; g.ldc = Cout;
+    g.bias = n.P(p + ".conv2.bias");
+    g.residual = residual; g.ldr = Cout;
+    g.a_amax = h3.amax;
+    track(out, g, true);
+    run(g);
+    return out;
+  }
+
+  // DDPM.forward (ddpm/diffusion.py:299-337)
+  void forward_ddpm(const float* x_nchw, const float* t_dev, float* out_nchw, int B, int H, int W) {
+    const cdx_unet_config& c = n.ucfg;
+    const int ch = c.model_channels, half = ch / 2, ted = n.ted, L = c.n_mult;
+    Scope top(e.arena);
+    e.pools_reset(s);
+    Tensor temb = alloc(B, 1, 1, ch);
+    timestep_embedding(e, t_dev, n.freqs_dev, temb.p, B, half, s, true);          // [sin | cos]
+    Tensor e1 = linear(temb, "temb.dense.0", true);
+    silu(e, e1.p, e1.p, e1.numel(), s);
+    Tensor emb = linear(e1, "temb.dense.1", true);
+    silu(e, emb.p, emb.p, emb.numel(), s);   // every ResnetBlock applies the swish before its temb_proj (:125)
+    Tensor Eall = alloc(B, 1, 1, n.emb_rows);
+    linear_into(emb.p, ted, ted, nullptr, 0, 0, B, n.blob + n.emb_w_off, n.emb_rows, n.blob + n.emb_b_off, nullptr, 0, Eall.p, n.emb_rows);
+    E = Eall.p;
+    Tensor xin = alloc(B, H, W, c.in_channels);
+    nchw_to_nhwc(e, x_nchw, xin.p, B, c.in_channels, H * W, s);
+    std::vector<Tensor> hs;
+    hs.push_back(conv3(xin, "conv_in"));
+    int ds = 1;
+    for (int lvl = 0; lvl < L; ++lvl) {
+      const std::string D = "down." + std::to_string(lvl);
+      const bool at = contains(c.attention_ds, c.n_attn, ds);
+      for (int b = 0; b < c.num_res_blocks; ++b) {
+        Tensor h = ddpm_resblock(hs.back(), nullptr, D + ".block." + std::to_string(b));
+        if (at) h = attn(h, D + ".attn." + std::to_string(b));
+        hs.push_back(h);
+      }
+      if (lvl != L - 1) { hs.push_back(conv3(hs.back(), D + ".downsample.conv", 2, 0)); ds *= 2; }      // pad (0,1,0,1), :60-64
+    }
+    Tensor h = hs.back();
+    h = ddpm_resblock(h, nullptr, "mid.block_1");
+    h = attn(h, "mid.attn_1");
+    h = ddpm_resblock(h, nullptr, "mid.block_2");
+    for (int lvl = L - 1; lvl >= 0; --lvl) {
+      const std::string U = "up." + std::to_string(lvl);
+      const bool at = contains(c.attention_ds, c.n_attn, ds);
+      for (int b = 0; b <= c.num_res_blocks; ++b) {
+        const Tensor skip = hs.back();
+        hs.pop_back();
+        h = ddpm_resblock(h, &skip, U + ".block." + std::to_string(b));
+        if (at) h = attn(h, U + ".attn." + std::to_string(b));
+      }
+      if (lvl != 0) { h = conv3(h, U + ".upsample.conv", 1, 1, 2); ds /= 2; }
+    }
+    Tensor ho = gn(h, nullptr, "norm_out", 1e-6f, true);
+    conv3(ho, "conv_out", 1, 1, 1, nullptr, 0, nullptr, out_nchw);
+  }
+
   void forward(const float* x_nchw, const float* t_dev, const float* context, int L, float* out_nchw, int B, int H, int W) {
     const cdx_unet_config& c = n.ucfg;
     ctx = context;
@@ -966,34 +1141,6 @@ struct VaeExec : Exec {
     return out;
   }
 
-  // AttnBlock (AEM:178-202): single head, d = C, scale C^-1/2
-  Tensor attn(const Tensor& x, const std::string& p) {
-    const int C = x.C, HW = x.H * x.W;
-    Tensor out = alloc(x.B, x.H, x.W, C);
-    Scope sc(e.arena);
-    Tensor xn = gn(x, nullptr, p + ".norm", 1e-6f, false);
-    Tensor q = linear(xn, p + ".q", true);
-    Tensor k = linear(xn, p + ".k", true);
-    Tensor v = linear(xn, p + ".v", true, nullptr, true);       // its range bounds the attention output
-    Tensor a = alloc(x.B, x.H, x.W, C);
-    a.amax = v.amax;
-    const float scale = (float)pow((double)C, -0.5);
-    bool done = false;
-    if (e.mma_mode == 1 && (HW % 32) == 0 && HW >= 128) {
-      // tensor-core path: S = q k^T, row softmax, O = P V with V transposed to [C, B*HW] (both P.V operands K-major)
-      Scope sa(e.arena);
-      float* vt = (float*)e.arena.alloc((size_t)C * x.rows() * sizeof(float));
-      nhwc_to_nchw(e, v.p, vt, 1, C, x.rows(), s);
-      done = attention_tc(e, q.p, C, k.p, C, C, vt, a.p, C, x.B, HW, HW, 1, C, scale, s);
-    }
-    if (!done) attention(e, q.p, C, k.p, C, v.p, C, a.p, C, x.B, HW, HW, 1, C, C, scale, s);
-    out.amax = e.amax_slot();
-    out.stats = e.stat_alloc((size_t)x.B * C * 2);
-    linear_into(a.p, C, C, nullptr, 0, 0, x.rows(), n.P(p + ".proj_out.weight"), C, n.P(p + ".proj_out.bias"), x.p, C, out.p, C, nullptr, v.amax, nullptr,
-                out.amax, out.stats, HW);
-    return out;
-  }
-
   void encode(const float* img_nchw, float* moments_nchw, int B, int R) {
     const cdx_vae_config& c = n.vcfg;
     Scope top(e.arena);
@@ -1045,13 +1192,14 @@ struct VaeExec : Exec {
 
 void unet_forward(Net& n, const float* x_nchw, const float* t_dev, const float* ctx, int ctx_len, float* out_nchw, int B, int H, int W,
                   cudaStream_t s, bool reuse_ctx) {
-  CDX_CHECK(n.kind == NET_UNET_OPENAI || n.kind == NET_UNET_IDDPM, "unet_forward on a non-U-Net");
+  CDX_CHECK(n.kind == NET_UNET_OPENAI || n.kind == NET_UNET_IDDPM || n.kind == NET_UNET_DDPM, "unet_forward on a non-U-Net");
   CDX_CHECK(n.finalized, "unet_forward before finalize");
   if (n.kind == NET_UNET_OPENAI && n.ucfg.context_dim > 0) CDX_CHECK(ctx != nullptr && ctx_len > 0, "unet_forward: the SD/LDM U-Net needs a context");
   const int down = 1 << (n.ucfg.n_mult - 1);
   CDX_CHECK(H % down == 0 && W % down == 0, "unet_forward: %dx%d not divisible by %d", H, W, down);
   UNetExec ex(n, s);
   ex.kv_reuse = reuse_ctx && n.kind == NET_UNET_OPENAI && n.ucfg.context_dim > 0;
+  if (n.kind == NET_UNET_DDPM) { ex.forward_ddpm(x_nchw, t_dev, out_nchw, B, H, W); return; }
   ex.forward(x_nchw, t_dev, ctx, ctx_len, out_nchw, B, H, W);
   if (ex.kv_reuse && !n.eng->dry()) {
     n.ctxkv.valid = true;

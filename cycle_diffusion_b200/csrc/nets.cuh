@@ -22,7 +22,7 @@ struct Param {
   bool loaded = false;
 };
 
-enum NetKind { NET_UNET_OPENAI = 1, NET_UNET_IDDPM = 2, NET_VAE = 3, NET_CLIP_TEXT = 4 };
+enum NetKind { NET_UNET_OPENAI = 1, NET_UNET_IDDPM = 2, NET_VAE = 3, NET_CLIP_TEXT = 4, NET_UNET_DDPM = 5 };
 
 struct Net {
   Engine* eng = nullptr;

@@ -323,7 +323,7 @@ class UNet(Net):
         self.cfg = dict(cfg)
         self.kind = kind
         c = UnetConfig()
-        c.kind = _cabi.CDX_UNET_OPENAI if kind == 'openai' else _cabi.CDX_UNET_IDDPM
+        c.kind = {'openai': _cabi.CDX_UNET_OPENAI, 'iddpm': _cabi.CDX_UNET_IDDPM, 'ddpm': _cabi.CDX_UNET_DDPM}[kind]
         c.in_channels, c.out_channels = cfg['in_channels'], cfg['out_channels']
         c.model_channels, c.num_res_blocks = cfg['model_channels'], cfg['num_res_blocks']
         c.n_mult = len(cfg['channel_mult'])
@@ -340,7 +340,10 @@ class UNet(Net):
             # sinusoid frequencies with the reference expression (util.py:161-163 / nn.py:112-114), evaluated by torch on
             # the host so that they are bit-identical to what the reference / oracle computes on this machine
             half = cfg['model_channels'] // 2
-            freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+            if kind == 'ddpm':          # get_timestep_embedding, ddpm/diffusion.py:15-18: log(10000) / (half - 1)
+                freqs = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+            else:
+                freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
             arr = (C.c_float * half)(*freqs.tolist())
             check(lib.cdx_unet_set_time_freqs(self.h, arr, half))
 

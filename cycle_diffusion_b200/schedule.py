@@ -69,7 +69,7 @@ class DDIMSchedule:
 class PixelSchedule:
     """Per-step scalars of DDPMDDIMWrapper.encode / generate (ddpm_ddim_wrapper.py:392-523)."""
 
-    def __init__(self, sample_type, custom_steps, es_steps, eta=None, t_0=None, beta_start=1e-4, beta_end=2e-2, T=1000):
+    def __init__(self, sample_type, custom_steps, es_steps, eta=None, t_0=None, beta_start=1e-4, beta_end=2e-2, T=1000, var_type='fixedsmall'):
         if sample_type == 'ddim':
             assert eta > 0                                              # DW:333-334
         elif sample_type == 'ddpm':
@@ -82,7 +82,12 @@ class PixelSchedule:
         self.b = torch.from_numpy(betas64).float()                                   # DW:350-352
         ac = np.cumprod(1.0 - betas64, axis=0)
         ac_prev = np.append(1.0, ac[:-1])
-        self.logvar = np.log(np.maximum(betas64 * (1.0 - ac_prev) / (1.0 - ac), 1e-20))   # DW:356-373 (fp64)
+        post_var = betas64 * (1.0 - ac_prev) / (1.0 - ac)
+        if var_type == 'fixedlarge':                                                  # DW:362-363 (Ho-et-al checkpoints may use it)
+            self.logvar = np.log(np.append(post_var[1], betas64[1:]))
+        else:
+            assert var_type == 'fixedsmall'
+            self.logvar = np.log(np.maximum(post_var, 1e-20))                         # DW:356-373 (fp64)
         if (t_0 + 1) % custom_steps == 0:                                             # DW:393-400
             seq_inv = range(0, t_0 + 1, (t_0 + 1) // custom_steps)
             assert len(seq_inv) == custom_steps

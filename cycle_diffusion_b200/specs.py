@@ -367,3 +367,68 @@ def ldm_uncond_unet_config():
 def vq_f4_config():
     """VQModelInterface first stage of the same models: embed_dim 3, 8192 codes, ch 128, ch_mult (1,2,4)."""
     return dict(ch=128, ch_mult=(1, 2, 4), num_res_blocks=2, in_channels=3, out_ch=3, z_channels=3, embed_dim=3, vq=True, n_embed=8192)
+
+
+def ddpm_config(image_size=256, ch=128, ch_mult=(1, 1, 2, 2, 4, 4), attn_resolutions=(16,), num_res_blocks=2):
+    """Ho et al. DDPM U-Net as the CelebA-HQ / LSUN checkpoints are built (ddpm/diffusion.py:192-297; the DDIM repo's celeba_hq.yml /
+    bedroom.yml: ch 128, ch_mult (1,1,2,2,4,4), 2 res blocks, attention at 16x16, resamp_with_conv).  ``attention_resolutions`` holds
+    the downsample FACTORS at which attention runs (image_size / resolution), like the other U-Net configs here."""
+    return dict(image_size=image_size, in_channels=3, out_channels=3, model_channels=ch, num_res_blocks=num_res_blocks, channel_mult=tuple(ch_mult),
+                attention_resolutions=tuple(image_size // r for r in attn_resolutions))
+
+
+def ddpm_unet_params(cfg):
+    """(name, shape, kind) of ddpm/diffusion.py DDPM in the engine's inventory order (csrc/nets.cu build_ddpm_inventory)."""
+    ch, mult, nrb, ar = cfg['model_channels'], cfg['channel_mult'], cfg['num_res_blocks'], cfg['attention_resolutions']
+    ted = 4 * ch
+    out = []
+
+    def res(p, cin, cout):
+        _norm(out, p + '.norm1', cin)
+        _conv(out, p + '.conv1', cin, cout, 3)
+        _lin(out, p + '.temb_proj', ted, cout)
+        _norm(out, p + '.norm2', cout)
+        _conv(out, p + '.conv2', cout, cout, 3)
+        if cin != cout:
+            _conv(out, p + '.nin_shortcut', cin, cout, 1)
+
+    def attn(p, c):
+        _norm(out, p + '.norm', c)
+        for nm in ('q', 'k', 'v', 'proj_out'):
+            _conv(out, f'{p}.{nm}', c, c, 1)
+
+    _lin(out, 'temb.dense.0', ch, ted)
+    _lin(out, 'temb.dense.1', ted, ted)
+    _conv(out, 'conv_in', cfg['in_channels'], ch, 3)
+    in_mult = (1,) + tuple(mult)
+    ds, block_in = 1, ch
+    for lvl in range(len(mult)):
+        block_in, block_out = ch * in_mult[lvl], ch * mult[lvl]
+        for b in range(nrb):
+            res(f'down.{lvl}.block.{b}', block_in, block_out)
+            block_in = block_out
+        if ds in ar:
+            for b in range(nrb):
+                attn(f'down.{lvl}.attn.{b}', block_out)
+        if lvl != len(mult) - 1:
+            _conv(out, f'down.{lvl}.downsample.conv', block_in, block_in, 3)
+            ds *= 2
+    res('mid.block_1', block_in, block_in)
+    attn('mid.attn_1', block_in)
+    res('mid.block_2', block_in, block_in)
+    for lvl in reversed(range(len(mult))):
+        block_out, skip_in = ch * mult[lvl], ch * mult[lvl]
+        for b in range(nrb + 1):
+            if b == nrb:
+                skip_in = ch * in_mult[lvl]
+            res(f'up.{lvl}.block.{b}', block_in + skip_in, block_out)
+            block_in = block_out
+        if ds in ar:
+            for b in range(nrb + 1):
+                attn(f'up.{lvl}.attn.{b}', block_out)
+        if lvl != 0:
+            _conv(out, f'up.{lvl}.upsample.conv', block_in, block_in, 3)
+            ds //= 2
+    _norm(out, 'norm_out', block_in)
+    _conv(out, 'conv_out', block_in, cfg['out_channels'], 3)
+    return out

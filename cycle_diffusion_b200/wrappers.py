@@ -475,8 +475,12 @@ class DDPMDDIMWrapper(torch.nn.Module):
 
     def __init__(self, source_model_type, sample_type, custom_steps, es_steps, source_model_path=None, refine_steps=0,
                  refine_iterations=1, eta=None, t_0=None, enforce_class_input=None, *, engine=None, device=0, state_dict=None,
-                 image_size=None, unet=None, seed=4321):
+                 image_size=None, unet=None, seed=4321, dataset=None, var_type='fixedsmall'):
         super().__init__()
+        # DW:360-369: the model family follows config.data.dataset -- CelebA_HQ / LSUN checkpoints are Ho et al. DDPM U-Nets
+        # (models/ddpm/diffusion.py), AFHQ / FFHQ ones improved-DDPM U-Nets.  `dataset` (or a source_model_type that names one) selects it.
+        name = (dataset or str(source_model_type)).lower()
+        self.model_family = 'ddpm' if any(k in name for k in ('celeba', 'lsun', 'bedroom', 'church')) else 'iddpm'
         self.enforce_class_input = enforce_class_input
         self.custom_steps, self.refine_steps, self.refine_iterations = custom_steps, refine_steps, refine_iterations
         self.sample_type, self.eta = sample_type, eta
@@ -496,14 +500,19 @@ class DDPMDDIMWrapper(torch.nn.Module):
             self.generator, self.engine = unet, unet.engine
         else:
             self.engine = engine or Engine(device)
-            cfg = specs.iddpm_config(image_size)
-            self.generator = UNet(self.engine, cfg, 'iddpm')
-            sd = _load_sd(state_dict if state_dict is not None else source_model_path, source_model_path or '', specs.iddpm_unet_params(cfg), seed)
+            if self.model_family == 'ddpm':
+                cfg = specs.ddpm_config(image_size)
+                params = specs.ddpm_unet_params(cfg)
+            else:
+                cfg = specs.iddpm_config(image_size)
+                params = specs.iddpm_unet_params(cfg)
+            self.generator = UNet(self.engine, cfg, self.model_family)
+            sd = _load_sd(state_dict if state_dict is not None else source_model_path, source_model_path or '', params, seed)
             self.generator.load_state_dict(sd)
         self.resolution = image_size
         self.channels = 3
         self.latent_dim = self.resolution ** 2 * self.channels * self.es_steps
-        self.sched = PixelSchedule(sample_type, custom_steps, es_steps, eta, self.t_0)
+        self.sched = PixelSchedule(sample_type, custom_steps, es_steps, eta, self.t_0, var_type=var_type)     # config.model.var_type, DW:362-367
         self._dummy = torch.nn.Parameter(torch.zeros(1, device=self.engine.device), requires_grad=False)
 
     def generate(self, z, class_label):

@@ -75,6 +75,9 @@ int cdx_engine_set_mma_mode(cdx_engine* e, int mode);
 /* ---------------------------------------------------------------- networks ----------------- */
 #define CDX_UNET_OPENAI 1 /* SD v1 / LDM text2img U-Net: OAI:413-742 + attention.py:152-261 */
 #define CDX_UNET_IDDPM 2  /* improved-DDPM pixel U-Net: IU:401-668 */
+#define CDX_UNET_DDPM 3   /* Ho et al. DDPM pixel U-Net (CelebA-HQ / LSUN checkpoints, DW:360-369): models/ddpm/diffusion.py:192-337 --
+                             ResnetBlock + single-head AttnBlock (GroupNorm eps 1e-6, swish), [sin | cos] timestep embedding, conv
+                             down / up sampling (asymmetric pad), num_res_blocks + 1 decoder blocks per level */
 
 typedef struct cdx_unet_config {
   int kind;                /* CDX_UNET_* */

@@ -485,6 +485,30 @@ def golden_ldm_uncond():
     save('ldm_uncond', **out)
 
 
+DDPM_SMALL = dict(image_size=32, in_channels=3, out_channels=3, model_channels=32, num_res_blocks=2, channel_mult=(1, 2, 2), attention_resolutions=(2,))
+
+
+def golden_unet_ddpm():
+    """the reference's own Ho-et-al ``DDPM`` class (models/ddpm/diffusion.py) on a reduced config, synthetic weights strict."""
+    sys.path.insert(0, os.path.join(REF, 'model/lib/ddpm_ddim'))
+    from models.ddpm.diffusion import DDPM
+    from types import SimpleNamespace as NS
+    cfg = DDPM_SMALL
+    conf = NS(model=NS(ch=32, out_ch=3, ch_mult=(1, 2, 2), num_res_blocks=2, attn_resolutions=[16], dropout=0.0, in_channels=3, resamp_with_conv=True),
+              data=NS(image_size=32))
+    m = DDPM(conf).eval()
+    sd = specs.synth_state_dict(specs.ddpm_unet_params(cfg), 61)
+    assert set(m.state_dict()) == set(sd), sorted(set(m.state_dict()) ^ set(sd))[:8]
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(261)
+    x = torch.randn(2, 3, 32, 32, generator=g)
+    t = torch.tensor([999., 3.])
+    with torch.no_grad():
+        y = m(x, t)
+    print(f'unet_ddpm: |y|max {y.abs().max():.3f}')
+    save('unet_ddpm', x=x, t=t, y=y, wsum=sd_checksum(sd))
+
+
 if __name__ == '__main__':
     _shim_omegaconf()
     sys.path.insert(0, os.path.join(REF, 'model/lib/stable_diffusion'))
@@ -499,3 +523,4 @@ if __name__ == '__main__':
     golden_bert_text()
     golden_clip_rank()
     golden_ldm_uncond()
+    golden_unet_ddpm()

@@ -83,3 +83,12 @@ def test_uncond_ldm_inventories_match_specs():
         assert [(a, tuple(b)) for a, b in UNet(None, cfg, 'openai').inventory()] == [(a, tuple(b)) for a, b, _ in specs.openai_unet_params(cfg)]
     vc = specs.vq_f4_config()
     assert [(a, tuple(b)) for a, b in VAE(None, vc).inventory()] == [(a, tuple(b)) for a, b, _ in specs.kl_vae_params(vc)]
+
+
+def test_ddpm_unet_inventory_matches_specs():
+    """Ho-et-al DDPM U-Net inventory (csrc/nets.cu build_ddpm_inventory) equals specs.ddpm_unet_params."""
+    from cycle_diffusion_b200 import specs
+    from cycle_diffusion_b200.engine import UNet
+    for cfg in (specs.ddpm_config(256), dict(image_size=32, in_channels=3, out_channels=3, model_channels=32, num_res_blocks=2, channel_mult=(1, 2, 2),
+                                             attention_resolutions=(2,))):
+        assert [(a, tuple(b)) for a, b in UNet(None, cfg, 'ddpm').inventory()] == [(a, tuple(b)) for a, b, _ in specs.ddpm_unet_params(cfg)]

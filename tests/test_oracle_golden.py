@@ -182,3 +182,16 @@ def test_ldm_uncond_oracle_vs_reference_fixture():
         ref = dpm_encoder.latent_refine(fn, dec, None, None, S, r)
     assert maxdiff(z.reshape(2, -1), g['z']) < 2e-4 * float(g['z'].abs().max())
     assert maxdiff(dec, g['dec']) < 1e-4 and maxdiff(ref, g['refined']) < 1e-4
+
+
+DDPM_SMALL = dict(image_size=32, in_channels=3, out_channels=3, model_channels=32, num_res_blocks=2, channel_mult=(1, 2, 2), attention_resolutions=(2,))
+
+
+def test_unet_ddpm_oracle_vs_reference_fixture():
+    """oracle.unet_ddpm against the reference's own Ho-et-al DDPM class (tests/golden/unet_ddpm.npz)."""
+    from oracle import unet_ddpm
+    g = golden('unet_ddpm')
+    sd = specs.synth_state_dict(specs.ddpm_unet_params(DDPM_SMALL), 61)
+    with torch.no_grad():
+        y = unet_ddpm.unet_forward(sd, DDPM_SMALL, g['x'], g['t'])
+    assert maxdiff(y, g['y']) < 2e-5 * float(g['y'].abs().max())
