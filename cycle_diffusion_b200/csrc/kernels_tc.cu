@@ -163,7 +163,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr bool CG2 = Cfg<MODE>::CG2;
   constexpr int B_PLANE = Cfg<MODE>::B_PLANE;
   constexpr int BK = Cfg<MODE>::BK;
-  constexpr int KCHUNK = Cfg<MODE>::KCHUNK;
+  // stages per TMEM accumulation chunk: 256 K elements; a work item of at most 512 K elements is ONE chunk (its truncation error stays
+  // ~2e-6 relative, and the short-K projections -- epilogue-bound -- save a drain round trip per tile)
+  const int KCHUNK = p.kb_per_split <= 2 * Cfg<MODE>::KCHUNK ? 2 * Cfg<MODE>::KCHUNK : Cfg<MODE>::KCHUNK;
   constexpr int STAGES = Cfg<MODE>::STAGES;
   constexpr int STAGE_BYTES = Cfg<MODE>::STAGE_BYTES;
   constexpr int TMEM_COLS = Cfg<MODE>::TMEM_COLS;

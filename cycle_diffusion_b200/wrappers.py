@@ -475,10 +475,15 @@ class DDPMDDIMWrapper(torch.nn.Module):
 
     def __init__(self, source_model_type, sample_type, custom_steps, es_steps, source_model_path=None, refine_steps=0,
                  refine_iterations=1, eta=None, t_0=None, enforce_class_input=None, *, engine=None, device=0, state_dict=None,
-                 image_size=None, unet=None, seed=4321, dataset=None, var_type='fixedsmall'):
+                 image_size=None, unet=None, seed=4321, dataset=None, var_type='fixedsmall', rng='cpu'):
         super().__init__()
         # DW:360-369: the model family follows config.data.dataset -- CelebA_HQ / LSUN checkpoints are Ho et al. DDPM U-Nets
         # (models/ddpm/diffusion.py), AFHQ / FFHQ ones improved-DDPM U-Nets.  `dataset` (or a source_model_type that names one) selects it.
+        # rng='cpu': every draw comes from the torch CPU generator in the reference's order (reproduces the reference CPU path under a
+        # seed); rng='cuda': drawn on the engine's device (the reference's own GPU runs do this; avoids es_steps x image of host randn +
+        # H2D per batch -- 1.5 GB at 250 steps, batch 8, 256^2)
+        assert rng in ('cpu', 'cuda')
+        self.rng = rng
         name = (dataset or str(source_model_type)).lower()
         self.model_family = 'ddpm' if any(k in name for k in ('celeba', 'lsun', 'bedroom', 'church')) else 'iddpm'
         self.enforce_class_input = enforce_class_input
@@ -515,6 +520,9 @@ class DDPMDDIMWrapper(torch.nn.Module):
         self.sched = PixelSchedule(sample_type, custom_steps, es_steps, eta, self.t_0, var_type=var_type)     # config.model.var_type, DW:362-367
         self._dummy = torch.nn.Parameter(torch.zeros(1, device=self.engine.device), requires_grad=False)
 
+    def _randn(self, shape):
+        return torch.randn(shape, device=self.engine.device) if self.rng == 'cuda' else torch.randn(shape)
+
     def generate(self, z, class_label):
         bsz = z.shape[0]
         eps_list = z.view(bsz, self.es_steps, self.channels, self.resolution, self.resolution)
@@ -522,7 +530,7 @@ class DDPMDDIMWrapper(torch.nn.Module):
             assert class_label is not None
             raise NotImplementedError()
         shape = eps_list[:, 0].shape
-        last = torch.randn(shape).unsqueeze(0)       # denoising_step draws once more; the draw is multiplied by 0 (DU:115,131)
+        last = self._randn(shape).unsqueeze(0)       # denoising_step draws once more; the draw is multiplied by 0 (DU:115,131)
         x = self.generator.pixel_decode(eps_list, self.sched, last_noise=last)
         if self.refine_steps != 0:
             assert self.refine_steps < self.custom_steps
@@ -532,8 +540,8 @@ class DDPMDDIMWrapper(torch.nn.Module):
             t_loop = [float(i) for i, _ in pairs]
             at = PixelSchedule._extract(self.sched.cumprod, self.refine_steps - 1)               # DW:436-437
             for _ in range(self.refine_iterations):
-                xt = self.engine.q_sample(x, torch.randn(shape), at.sqrt().item(), (1 - at).sqrt().item())
-                noises = torch.stack([torch.randn(shape) for _ in pairs])
+                xt = self.engine.q_sample(x, self._randn(shape), at.sqrt().item(), (1 - at).sqrt().item())
+                noises = torch.stack([self._randn(shape) for _ in pairs])
                 x = self.generator.pixel_decode(xt.view(bsz, 1, *shape[1:]), ref, coefs=coefs, t_loop=t_loop, last_noise=noises)
         return x
 
@@ -546,7 +554,10 @@ class DDPMDDIMWrapper(torch.nn.Module):
             raise NotImplementedError()
         bsz = image.shape[0]
         n_rec = self.es_steps - 1
-        noise = torch.stack([torch.randn(image.shape) for _ in range(n_rec + 1)])     # sample_xt, then one per sample_xt_next
+        if self.rng == 'cuda':
+            noise = torch.randn((n_rec + 1,) + tuple(image.shape), device=e.device)
+        else:
+            noise = torch.stack([torch.randn(image.shape) for _ in range(n_rec + 1)])     # sample_xt, then one per sample_xt_next
         z = self.generator.pixel_encode(image, self.sched, noise).view(bsz, -1)
         assert z.shape[1] == self.latent_dim
         return z
