@@ -323,6 +323,8 @@ void gemm(Engine& e, const GemmArgs& a, cudaStream_t s) {
       return;
     }
   }
+  CDX_CHECK(!a.gn_ab && !(a.mode == 1 && a.A2), "gemm: a fused-GroupNorm / concat conv3x3 reached the FFMA back end (M=%d N=%d): the caller must ask conv_halo_eligible()",
+            a.M, a.N);
   if (a.c_amax || a.c_stats) {
     GemmArgs b = a;
     b.c_amax = nullptr; b.c_stats = nullptr;

@@ -103,6 +103,9 @@ struct TcParams {
   // OOB zero fill = padding) and the split warps read all nine shifted taps from it, so the activation crosses L2 -> SM once
   // per tile and channel block instead of nine times (A ingress per stage 32 KB -> ~5 KB; the kernel was L2->SM bound)
   int halo;
+  // halo schedule, optional: the A operand is silu?(x * a + o), (a, o) = gn_ab[b * Cin + c] (GroupNorm of the input applied during the
+  // halo conversion; out-of-image pixels stay 0).  Needs bn == 1.  C1 < Cin: channels >= C1 come from the second source (mapA2)
+  const float2* gn_ab; int gn_silu;
   float* C; int ldc;
   float* C_lo;              // optional: C <- rn_tf32(result), C_lo <- rn_tf32(result - hi)
   float* Ct_hi; float* Ct_lo; int t_col0; long long ldt;   // optional transposed plane output for columns >= t_col0
@@ -146,6 +149,7 @@ __device__ __forceinline__ int h16_exp_of(float amax) {
   return min(max(14 - (be - 127), -100), 100);
 }
 __device__ __forceinline__ int h16_a_exp(const TcParams& p) {
+  if (p.gn_ab) return 0;         // normalised (+SiLU) activations are O(1..100): inside the no-rescale range by construction
   float m = p.a_amax ? *p.a_amax : 0.f;
   if (p.a2_amax) m = fmaxf(m, *p.a2_amax);
   return h16_exp_of(m);
@@ -198,6 +202,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t halo_base = base + STAGES * 2 * B_PLANE;
   float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 512);   // [2][TBN], epilogue warps only
   float4* const s_stage = reinterpret_cast<float4*>(smem_raw + (bars - smem_u32(smem_raw)) + 2048);   // 8 warps x 4 KB
+  float2* const s_gn = reinterpret_cast<float2*>(smem_raw + (bars - smem_u32(smem_raw)) + 1536);      // 64 (a, o) pairs of the fused GroupNorm
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -299,8 +304,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint32_t hb = halo_base + (uint32_t)hs * 2u * HALO_PLANE;
             const uint32_t box_bytes = (uint32_t)((p.bw + 2) * (p.bh + 2) * p.bn) * 128u;
             mbar_expect_tx(bar_halo_full(hs), 2u * box_bytes);
-            tma_load_4d(hb, &mapA, hcb * 64, x0 - 1, y0 - 1, b0, bar_halo_full(hs));                  // OOB -> zeros = padding
-            tma_load_4d(hb + HALO_PLANE, &mapA, hcb * 64 + 32, x0 - 1, y0 - 1, b0, bar_halo_full(hs));
+            const int hc = hcb * 64;                                   // channel concat: blocks >= C1 come from the second source
+            const CUtensorMap* hm = hc < p.C1 ? &mapA : &mapA2;
+            const int hcc = hc < p.C1 ? hc : hc - p.C1;
+            tma_load_4d(hb, hm, hcc, x0 - 1, y0 - 1, b0, bar_halo_full(hs));                  // OOB -> zeros = padding
+            tma_load_4d(hb + HALO_PLANE, hm, hcc + 32, x0 - 1, y0 - 1, b0, bar_halo_full(hs));
           }
           const uint32_t sbh = b_ring + (uint32_t)s * b_stride;
           const int kB = tap * p.Cin + cb * 64;                      // weight planes stay in (tap, channel) order
@@ -503,6 +511,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             cur_h = ghalo & 1;
             mbar_wait(bar_halo_full(cur_h), (ghalo >> 1) & 1);
             ++ghalo;
+            bool inside = true;
+            if (p.gn_ab) {
+              // fused GroupNorm (+SiLU): this block's 64 (a, o) pairs of the tile's image -> shared memory (bn == 1), and whether
+              // this thread's halo pixel lies inside the image (padding pixels must stay 0 AFTER the activation)
+              if (tid < 64) s_gn[tid] = p.gn_ab[(long long)tc_.b0 * p.Cin + cb * 64 + tid];
+              asm volatile("bar.sync 3, %0;" ::"n"(NUM_SPLIT_WARPS * 32) : "memory");
+              const int hx = tc_.x0 - 1 + tid % (p.bw + 2), hy = tc_.y0 - 1 + (tid / (p.bw + 2)) % (p.bh + 2);
+              inside = hx >= 0 && hx < p.W && hy >= 0 && hy < p.H && tc_.b0 < p.B;
+            }
+            auto gn_act = [&](uint32_t& bits, int c) {
+              const float2 ao = s_gn[c];
+              float t = fmaf(__uint_as_float(bits), ao.x, ao.y);
+              if (p.gn_silu) t = __fdividef(t, 1.f + __expf(-t));
+              bits = inside ? __float_as_uint(t) : 0u;
+            };
             if (tid < npx) {
               const uint32_t r0 = halo_base + (uint32_t)(cur_h * 2) * HALO_PLANE + (uint32_t)tid * 128u, r1 = r0 + HALO_PLANE;
               const uint32_t px = (uint32_t)(tid & 7);
@@ -511,6 +534,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
               for (int c = 0; c < 8; ++c)
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3]) : "r"(r0 + (((uint32_t)c ^ px) << 4)));
+              if (p.gn_ab) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) gn_act(v[c], c);
+              }
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 uint32_t h[4];
@@ -522,6 +549,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
               for (int c = 0; c < 8; ++c)
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3]) : "r"(r1 + (((uint32_t)c ^ px) << 4)));
+              if (p.gn_ab) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) gn_act(v[c], 32 + c);
+              }
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 uint32_t h[4], l[4];
@@ -1106,6 +1137,21 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
   return true;
 }
 
+bool conv_halo_eligible(const Engine& e, int B, int H, int W, int C1, int C2, int Cout, bool out_nchw) {
+  // Measured on B200 (profiles/r02_gn_fusion_negative.txt): parity holds (89 GPU tests), GroupNorm time 1.73 -> 1.01 ms per SD
+  // U-Net call, but conv3x3 8.6 -> 13.8 ms: every N tile of a conv re-applies the norm and the SiLU (two MUFU ops per element) while
+  // converting its halo, which puts the split warps back on the critical path.  Opt-in (CDX_GN_FUSION=1) until the conversion is
+  // shared between the N tiles of a row block.
+  static const bool no_fuse = getenv("CDX_GN_FUSION") == nullptr;
+  const long long M = (long long)B * H * W;
+  if (no_fuse || e.mma_mode != 1 || e.tc_kind < 1 || !pow2(H) || !pow2(W) || (C1 % 64) || (C2 % 64) || M < 64) return false;
+  if ((Cout < 32 && M < 2048) || (!out_nchw && (Cout & 3))) return false;       // (the shapes gemm_tc leaves to the FFMA tiles)
+  const int bw = W < 16 ? W : 16;
+  const int bh = H < TBM / bw ? H : TBM / bw;
+  const int bn = TBM / (bw * bh);
+  return bn == 1 && (bw + 2) * (bh + 2) * 128 <= HALO_PLANE;
+}
+
 bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   // ---- eligibility (everything else takes the FFMA tiles)
   if (a.batch * a.heads != 1 || a.b_kn) return false;
@@ -1156,9 +1202,12 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
     }
     p.tiles_m = cdiv(a.M, TBM);
   } else {
-    const int Cin = a.C1;
-    if (a.A2 || (a.stride != 1 && a.stride != 2) || a.up != 1) return false;
+    const int Cin = a.C1 + (a.A2 ? a.C2 : 0);
+    if ((a.stride != 1 && a.stride != 2) || a.up != 1) return false;
     if (Cin % TBK) return false;
+    // a channel-concat input or a fused GroupNorm exists only on the halo schedule; the caller asks conv_halo_eligible() first
+    const bool needs_halo = a.A2 != nullptr || a.gn_ab != nullptr;
+    CDX_CHECK(!a.A2 || a.gn_ab, "conv3x3: a channel-concat input is only supported together with the fused GroupNorm");
     if (a.Hin != a.Hout * a.stride || a.Win != a.Wout * a.stride || !pow2(a.Hout) || !pow2(a.Wout)) return false;
     const int B = a.M / (a.Hout * a.Wout);
     int bw = a.Wout < 16 ? a.Wout : 16;
@@ -1169,20 +1218,31 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
     p.bw = bw; p.bh = bh; p.bn = bn;
     p.cstride = a.stride; p.cpad = a.pad;
     p.tiles_x = a.Wout / bw; p.tiles_y = a.Hout / bh;
-    uint64_t d[4] = {(uint64_t)Cin, (uint64_t)a.Win, (uint64_t)a.Hin, (uint64_t)B};
+    uint64_t d[4] = {(uint64_t)a.C1, (uint64_t)a.Win, (uint64_t)a.Hin, (uint64_t)B};
     uint64_t st[3] = {(uint64_t)a.lda * 4, (uint64_t)a.lda * 4 * a.Win, (uint64_t)a.lda * 4 * a.Win * a.Hin};
     // stride 2 (Downsample convs): TMA traverses every 2nd pixel; box = 2x the number of pixels wanted
     uint32_t bx[4] = {TBK, (uint32_t)(bw * a.stride), (uint32_t)(bh * a.stride), (uint32_t)bn};
     uint32_t es[4] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1};
     // halo schedule (see TcParams::halo): needs the fp16-split path (decided below), 64-channel blocks and a halo box that fits a plane
     static const bool no_halo = getenv("CDX_TC_NO_HALO") != nullptr;
-    if (!no_halo && e.tc_kind >= 1 && a.stride == 1 && a.pad == 1 && (Cin % 64) == 0 && (bw + 2) * (bh + 2) * bn * 128 <= HALO_PLANE &&
-        a.Bw_h_hi && a.Bw_h_lo && a16(a.Bw_h_hi) && a16(a.Bw_h_lo) && (a.ldb % 8) == 0) {
+    if ((!no_halo || needs_halo) && e.tc_kind >= 1 && a.stride == 1 && a.pad == 1 && (a.C1 % 64) == 0 && (!a.A2 || (a.C2 % 64) == 0) &&
+        (bw + 2) * (bh + 2) * bn * 128 <= HALO_PLANE && a.Bw_h_hi && a.Bw_h_lo && a16(a.Bw_h_hi) && a16(a.Bw_h_lo) && (a.ldb % 8) == 0 &&
+        (!a.gn_ab || bn == 1)) {
       p.halo = 1;
       bx[1] = (uint32_t)(bw + 2); bx[2] = (uint32_t)(bh + 2);
     }
+    CDX_CHECK(p.halo || !needs_halo, "conv3x3: a concat input / fused GroupNorm needs the halo schedule (C1=%d C2=%d %dx%d): check conv_halo_eligible() first",
+              a.C1, a.C2, a.Hout, a.Wout);
+    p.C1 = a.C1;
+    p.gn_ab = reinterpret_cast<const float2*>(a.gn_ab); p.gn_silu = a.gn_silu;
     mA = &get_map(a.A, 4, d, st, bx, es);
     mA2 = mA;
+    if (a.A2) {
+      CDX_CHECK(a16(a.A2) && (a.lda2 & 3) == 0, "conv3x3: misaligned second source");
+      uint64_t d2[4] = {(uint64_t)a.C2, (uint64_t)a.Win, (uint64_t)a.Hin, (uint64_t)B};
+      uint64_t st2[3] = {(uint64_t)a.lda2 * 4, (uint64_t)a.lda2 * 4 * a.Win, (uint64_t)a.lda2 * 4 * a.Win * a.Hin};
+      mA2 = &get_map(a.A2, 4, d2, st2, bx, es);
+    }
     p.tiles_m = p.tiles_x * p.tiles_y * cdiv(B, bn);
   }
   // ---- operand path: fp16-split (MODE_H16) when the engine selects it, the weights have fp16 planes and the geometry allows it
@@ -1190,6 +1250,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   const bool ts = a.Bw_hi != nullptr && a.Bw_lo != nullptr && a16(a.Bw_hi) && a16(a.Bw_lo);
   const bool h16 = e.tc_kind >= 1 && a.Bw_h_hi && a.Bw_h_lo && a16(a.Bw_h_hi) && a16(a.Bw_h_lo) && (a.K % TBK) == 0 && (a.ldb % 8) == 0 &&
                    (a.mode == 1 || !a.A2 || (a.C2 % TBK) == 0);
+  CDX_CHECK(!(a.mode == 1 && (a.A2 || a.gn_ab)) || h16, "conv3x3: concat / fused GroupNorm input without the fp16-split path");
   if (p.halo && !h16) return false;        // (cannot happen: the halo conditions imply the fp16-split conditions)
   const int bk = h16 ? Cfg<MODE_H16>::BK : TBK;
   const int num_kb = cdiv(a.K, bk);
@@ -1270,13 +1331,13 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   if (h16) {
     p.a_amax = a.a_amax;
     p.a2_amax = a.A2 ? a.a2_amax : nullptr;
-    if (!p.a_amax) {
+    if (!p.a_amax && !p.gn_ab) {
       float* slot = e.amax_slot();
       if (a.mode == 1) amax_rows(e, a.A, (long long)(a.M / (a.Hout * a.Wout)) * a.Hin * a.Win, a.C1, a.lda, slot, s);
       else amax_rows(e, a.A, a.M, a.C1, a.lda, slot, s);
       p.a_amax = slot;
     }
-    if (a.A2 && !p.a2_amax) {
+    if (a.A2 && !p.a2_amax && !p.gn_ab && a.mode == 0) {
       float* slot = e.amax_slot();
       amax_rows(e, a.A2, a.M, a.C2, a.lda2, slot, s);
       p.a2_amax = slot;

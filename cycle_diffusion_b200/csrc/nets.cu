@@ -636,6 +636,61 @@ struct Exec {
     return y;
   }
 
+  // GroupNorm(32)(+ scale-shift) + SiLU + conv3x3 (stride 1, pad 1) of x (optionally the channel concat [x | x2]): the ResBlock pattern
+  // of all four network families (OAI:255-275, IU:241-261, AEM:121-141, ddpm/diffusion.py:117-139).  When the conv can take the halo
+  // schedule the norm and the activation are applied INSIDE the conv kernel while it converts the halo box that TMA staged in shared
+  // memory: the normalised tensor never exists in HBM (one read of x instead of read + write + read), and the concat is never
+  // materialised either.  Otherwise: the standalone GroupNorm kernel, then the conv.  `into` (optional): preallocated output.
+  Tensor gn_silu_conv3(const Tensor& x, const Tensor* x2, const std::string& norm, float eps, const std::string& conv, const float* scale = nullptr,
+                       const float* shift = nullptr, int ld_ss = 0, const float* rowvec = nullptr, int ld_rowvec = 0, const float* residual = nullptr,
+                       Tensor* into = nullptr, float* out_nchw = nullptr) {
+    const Param& w = n.param(conv + ".weight");
+    const int Cout = (int)w.dims[0], Cin = x.C + (x2 ? x2->C : 0);
+    CDX_CHECK((int)w.dims[1] == Cin, "conv %s: input has %d channels, weight expects %d", conv.c_str(), Cin, (int)w.dims[1]);
+    const bool fused = !w.cin_pad && n.planes_valid && conv_halo_eligible(e, x.B, x.H, x.W, x.C, x2 ? x2->C : 0, Cout, out_nchw != nullptr);
+    if (!fused) {
+      Tensor h = gn(x, x2, norm, eps, true, scale, shift, ld_ss);
+      if (!into) return conv3(h, conv, 1, 1, 1, rowvec, ld_rowvec, residual, out_nchw);
+      GemmArgs g;
+      g.mode = 1;
+      g.M = h.rows(); g.N = Cout; g.K = 9 * h.C;
+      g.A = h.p; g.lda = h.C; g.C1 = h.C;
+      g.Hin = h.H; g.Win = h.W; g.Hout = h.H; g.Wout = h.W; g.stride = 1; g.pad = 1; g.up = 1;
+      g.Bw = n.blob + w.off; g.ldb = 9 * h.C;
+      g.Cout = into->p; g.ldc = Cout;
+      g.bias = n.P(conv + ".bias");
+      g.rowvec = rowvec; g.ld_rowvec = ld_rowvec; g.rows_per_batch = h.H * h.W;
+      g.residual = residual; g.ldr = Cout;
+      g.a_amax = h.amax;
+      track(*into, g, true);
+      run(g);
+      return *into;
+    }
+    const float* ab = gn_affine(e, x.p, x.C, x2 ? x2->p : nullptr, x2 ? x2->C : 0, n.P(norm + ".weight"), n.P(norm + ".bias"), eps, scale, shift, ld_ss,
+                                x.B, x.H * x.W, s, x.stats, x2 ? x2->stats : nullptr);
+    Tensor y;
+    if (out_nchw) { y.p = out_nchw; y.B = x.B; y.H = x.H; y.W = x.W; y.C = Cout; }
+    else if (into) y = *into;
+    else y = alloc(x.B, x.H, x.W, Cout);
+    GemmArgs g;
+    g.mode = 1;
+    g.M = x.rows(); g.N = Cout; g.K = 9 * Cin;
+    g.A = x.p; g.lda = x.C; g.C1 = x.C;
+    if (x2) { g.A2 = x2->p; g.lda2 = x2->C; g.C2 = x2->C; }
+    g.gn_ab = ab; g.gn_silu = 1;
+    g.Hin = x.H; g.Win = x.W; g.Hout = x.H; g.Wout = x.W; g.stride = 1; g.pad = 1; g.up = 1;
+    g.Bw = n.blob + w.off; g.ldb = 9 * Cin;
+    g.Cout = y.p; g.ldc = Cout;
+    g.bias = n.P(conv + ".bias");
+    g.rowvec = rowvec; g.ld_rowvec = ld_rowvec; g.rows_per_batch = x.H * x.W;
+    g.residual = residual; g.ldr = Cout;
+    if (out_nchw) { g.out_nchw = 1; g.rows_per_img = x.H * x.W; }
+    else track(y, g, true);
+    run(g);
+    if (into) *into = y;
+    return y;
+  }
+
   // AttnBlock (AEM:178-202): single head, d = C, scale C^-1/2
   Tensor attn(const Tensor& x, const std::string& p) {
     const int C = x.C, HW = x.H * x.W;
@@ -702,9 +757,9 @@ struct UNetExec : Exec {
     const int oW = updown == 1 ? x.W / 2 : (updown == 2 ? x.W * 2 : x.W);
     Tensor out = alloc(x.B, oH, oW, Cout);
     Scope sc(e.arena);
-    Tensor h1 = gn(x, x2, p + ".in_layers.0", 1e-5f, true);
     Tensor xs = x;    // skip-path input after x_upd
-    Tensor h2;
+    Tensor h1, h2;
+    if (updown != 0) h1 = gn(x, x2, p + ".in_layers.0", 1e-5f, true);
     if (updown == 1) {
       CDX_CHECK(!x2, "res down with concat input");
       Tensor hp = alloc(x.B, oH, oW, x.C);
@@ -721,13 +776,10 @@ struct UNetExec : Exec {
       xs.amax = x.amax;
       h2 = conv3(h1, p + ".in_layers.2", 1, 1, 2);
     } else if (oai) {
-      h2 = conv3(h1, p + ".in_layers.2", 1, 1, 1, E + eoff, n.emb_rows);     // + emb_out (OAI:273)
+      h2 = gn_silu_conv3(x, x2, p + ".in_layers.0", 1e-5f, p + ".in_layers.2", nullptr, nullptr, 0, E + eoff, n.emb_rows);     // + emb_out (OAI:273)
     } else {
-      h2 = conv3(h1, p + ".in_layers.2");
+      h2 = gn_silu_conv3(x, x2, p + ".in_layers.0", 1e-5f, p + ".in_layers.2");
     }
-    if (!oai && updown == 0) { /* nothing: scale-shift handled in the norm below */ }
-    Tensor h3 = oai ? gn(h2, nullptr, p + ".out_layers.0", 1e-5f, true)
-                    : gn(h2, nullptr, p + ".out_layers.0", 1e-5f, true, E + eoff, E + eoff + Cout, n.emb_rows);   // IU:253-257
     const float* residual;
     if (n.has(p + ".skip_connection.weight")) {
       Tensor sk = alloc(x.B, oH, oW, Cout);
@@ -738,22 +790,9 @@ struct UNetExec : Exec {
       CDX_CHECK(!x2 && xs.C == Cout, "resblock %s: identity skip with mismatching channels", p.c_str());
       residual = xs.p;
     }
-    // conv3 allocates its own output on the arena; write into `out` by running the GEMM directly
-    {
-      const Param& w = n.param(p + ".out_layers.3.weight");
-      GemmArgs g;
-      g.mode = 1;
-      g.M = h3.rows(); g.N = Cout; g.K = 9 * h3.C;
-      g.A = h3.p; g.lda = h3.C; g.C1 = h3.C;
-      g.Hin = h3.H; g.Win = h3.W; g.Hout = h3.H; g.Wout = h3.W; g.stride = 1; g.pad = 1; g.up = 1;
-      g.Bw = n.blob + w.off; g.ldb = 9 * h3.C;
-      g.Cout = out.p; g.ldc = Cout;
-      g.bias = n.P(p + ".out_layers.3.bias");
-      g.residual = residual; g.ldr = Cout;
-      g.a_amax = h3.amax;
-      track(out, g, true);
-      run(g);
-    }
+    // out_layers: GroupNorm (i-DDPM: scale-shift norm, IU:253-257) + SiLU + conv3x3 + residual, written into `out`
+    if (oai) gn_silu_conv3(h2, nullptr, p + ".out_layers.0", 1e-5f, p + ".out_layers.3", nullptr, nullptr, 0, nullptr, 0, residual, &out);
+    else gn_silu_conv3(h2, nullptr, p + ".out_layers.0", 1e-5f, p + ".out_layers.3", E + eoff, E + eoff + Cout, n.emb_rows, nullptr, 0, residual, &out);
     return out;
   }
 
@@ -924,9 +963,7 @@ struct UNetExec : Exec {
     const int Cout = n.dim0(p + ".conv1.weight");
     Tensor out = alloc(x.B, x.H, x.W, Cout);
     Scope sc(e.arena);
-    Tensor h1 = gn(x, x2, p + ".norm1", 1e-6f, true);
-    Tensor h2 = conv3(h1, p + ".conv1", 1, 1, 1, E + n.emb_off.at(p), n.emb_rows);
-    Tensor h3 = gn(h2, nullptr, p + ".norm2", 1e-6f, true);
+    Tensor h2 = gn_silu_conv3(x, x2, p + ".norm1", 1e-6f, p + ".conv1", nullptr, nullptr, 0, E + n.emb_off.at(p), n.emb_rows);
     const float* residual;
     if (n.has(p + ".nin_shortcut.weight")) {
       Tensor sk = alloc(x.B, x.H, x.W, Cout);
@@ -937,19 +974,7 @@ struct UNetExec : Exec {
       CDX_CHECK(!x2 && x.C == Cout, "ddpm resblock %s: identity skip with mismatching channels", p.c_str());
       residual = x.p;
     }
-    const Param& w = n.param(p + ".conv2.weight");
-    GemmArgs g;
-    g.mode = 1;
-    g.M = h3.rows(); g.N = Cout; g.K = 9 * h3.C;
-    g.A = h3.p; g.lda = h3.C; g.C1 = h3.C;
-    g.Hin = h3.H; g.Win = h3.W; g.Hout = h3.H; g.Wout = h3.W;
-    g.Bw = n.blob + w.off; g.ldb = 9 * h3.C;
-    g.Cout = out.p; g.ldc = Cout;
-    g.bias = n.P(p + ".conv2.bias");
-    g.residual = residual; g.ldr = Cout;
-    g.a_amax = h3.amax;
-    track(out, g, true);
-    run(g);
+    gn_silu_conv3(h2, nullptr, p + ".norm2", 1e-6f, p + ".conv2", nullptr, nullptr, 0, nullptr, 0, residual, &out);
     return out;
   }
 
@@ -998,8 +1023,7 @@ struct UNetExec : Exec {
       }
       if (lvl != 0) { h = conv3(h, U + ".upsample.conv", 1, 1, 2); ds /= 2; }
     }
-    Tensor ho = gn(h, nullptr, "norm_out", 1e-6f, true);
-    conv3(ho, "conv_out", 1, 1, 1, nullptr, 0, nullptr, out_nchw);
+    gn_silu_conv3(h, nullptr, "norm_out", 1e-6f, "conv_out", nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, out_nchw);
   }
 
   void forward(const float* x_nchw, const float* t_dev, const float* context, int L, float* out_nchw, int B, int H, int W) {
@@ -1104,8 +1128,7 @@ struct UNetExec : Exec {
         ++bo;
       }
     }
-    Tensor ho = gn(h, nullptr, "out.0", 1e-5f, true);
-    conv3(ho, "out.2", 1, 1, 1, nullptr, 0, nullptr, out_nchw);
+    gn_silu_conv3(h, nullptr, "out.0", 1e-5f, "out.2", nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, out_nchw);
   }
 };
 
@@ -1117,27 +1140,13 @@ struct VaeExec : Exec {
     const int Cout = n.dim0(p + ".conv1.weight");
     Tensor out = alloc(x.B, x.H, x.W, Cout);
     Scope sc(e.arena);
-    Tensor h1 = gn(x, nullptr, p + ".norm1", 1e-6f, true);
-    Tensor h2 = conv3(h1, p + ".conv1");
-    Tensor h3 = gn(h2, nullptr, p + ".norm2", 1e-6f, true);
+    Tensor h2 = gn_silu_conv3(x, nullptr, p + ".norm1", 1e-6f, p + ".conv1");
     const float* residual = x.p;
     if (n.has(p + ".nin_shortcut.weight")) {
       Tensor sk = linear(x, p + ".nin_shortcut", true);
       residual = sk.p;
     }
-    const Param& w = n.param(p + ".conv2.weight");
-    GemmArgs g;
-    g.mode = 1;
-    g.M = h3.rows(); g.N = Cout; g.K = 9 * h3.C;
-    g.A = h3.p; g.lda = h3.C; g.C1 = h3.C;
-    g.Hin = h3.H; g.Win = h3.W; g.Hout = h3.H; g.Wout = h3.W;
-    g.Bw = n.blob + w.off; g.ldb = 9 * h3.C;
-    g.Cout = out.p; g.ldc = Cout;
-    g.bias = n.P(p + ".conv2.bias");
-    g.residual = residual; g.ldr = Cout;
-    g.a_amax = h3.amax;
-    track(out, g, true);
-    run(g);
+    gn_silu_conv3(h2, nullptr, p + ".norm2", 1e-6f, p + ".conv2", nullptr, nullptr, 0, nullptr, 0, residual, &out);
     return out;
   }
 
@@ -1156,8 +1165,7 @@ struct VaeExec : Exec {
     h = resnet(h, E + "mid.block_1");
     h = attn(h, E + "mid.attn_1");
     h = resnet(h, E + "mid.block_2");
-    Tensor ho = gn(h, nullptr, E + "norm_out", 1e-6f, true);
-    Tensor m = conv3(ho, E + "conv_out");
+    Tensor m = gn_silu_conv3(h, nullptr, E + "norm_out", 1e-6f, E + "conv_out");
     Tensor q = linear(m, "quant_conv", true);
     nhwc_to_nchw(e, q.p, moments_nchw, B, q.C, q.H * q.W, s);
   }
@@ -1183,8 +1191,7 @@ struct VaeExec : Exec {
       for (int b = 0; b <= c.num_res_blocks; ++b) h = resnet(h, D + "up." + std::to_string(lvl) + ".block." + std::to_string(b));
       if (lvl != 0) h = conv3(h, D + "up." + std::to_string(lvl) + ".upsample.conv", 1, 1, 2);
     }
-    Tensor ho = gn(h, nullptr, D + "norm_out", 1e-6f, true);
-    conv3(ho, D + "conv_out", 1, 1, 1, nullptr, 0, nullptr, img_nchw);
+    gn_silu_conv3(h, nullptr, D + "norm_out", 1e-6f, D + "conv_out", nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, img_nchw);
   }
 };
 
