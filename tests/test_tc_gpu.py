@@ -221,3 +221,36 @@ def test_fast_path_is_reduced_precision_and_marked():
     r_full = rel(e.op_linear(x.cuda(), w.cuda(), None).cpu(), ref)
     print(f'fast path rel {r_fast:.2e} vs faithful {r_full:.2e}')
     assert r_full < 2e-5 and 1e-5 < r_fast < 5e-3
+
+
+def test_gn_fusion_opt_in_keeps_parity():
+    """The opt-in experiment CDX_GN_FUSION=1 (GroupNorm + SiLU applied inside the conv3x3 halo conversion, two-source halo; measured slower,
+    profiles/r02_gn_fusion_negative.txt) stays correct: the 320-channel U-Net fixture in a fresh process with the switch on."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import torch\n"
+            "from cycle_diffusion_b200 import specs\n"
+            "from cycle_diffusion_b200.engine import Engine, UNet\n"
+            "from tests.common import WIDE, golden, maxdiff\n"
+            "g = golden('unet_sd_wide')\n"
+            "eng = Engine(0)\n"
+            "net = UNet(eng, WIDE, 'openai').load_state_dict(specs.synth_state_dict(specs.openai_unet_params(WIDE), int(g['seed'])))\n"
+            "eng.profile(True)\n"
+            "y = net(g['x'], g['t'], g['ctx']).cpu()\n"
+            "fam = eng.profile_read()\n"
+            "print('REL', maxdiff(y, g['y']) / float(g['y'].abs().max()), 'GN_LAUNCHES', fam.get('groupnorm', {}).get('launches', 0))\n")
+    outs = {}
+    for flag in ('0', '1'):
+        env = dict(os.environ)
+        env.pop('CDX_GN_FUSION', None)
+        if flag == '1':
+            env['CDX_GN_FUSION'] = '1'
+        r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=root, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        line = [l for l in r.stdout.splitlines() if l.startswith('REL')][-1].split()
+        outs[flag] = (float(line[1]), int(float(line[3])))
+    print(f'gn fusion off: rel {outs["0"][0]:.2e}, {outs["0"][1]} GroupNorm launches; on: rel {outs["1"][0]:.2e}, {outs["1"][1]} launches')
+    assert outs['0'][0] < 2e-4 and outs['1'][0] < 2e-4
+    assert outs['1'][1] < outs['0'][1]          # the fused convs really took their norms
