@@ -107,6 +107,10 @@ struct TcParams {
   // halo conversion; out-of-image pixels stay 0).  Needs bn == 1.  C1 < Cin: channels >= C1 come from the second source (mapA2)
   const float2* gn_ab; int gn_silu;
   float* C; int ldc;
+  // dense mode, final epilogue: tiles leave through TMA (mapC / mapClo: 32 x 32 float boxes of C / C_lo, mapR: of the residual); the
+  // epilogue warps stage 32-column blocks in the map's swizzle and one lane issues the bulk store (no per-row address arithmetic,
+  // predicates or 16-byte global stores on the warps that also drain TMEM)
+  int epi_tma;
   float* C_lo;              // optional: C <- rn_tf32(result), C_lo <- rn_tf32(result - hi)
   float* Ct_hi; float* Ct_lo; int t_col0; long long ldt;   // optional transposed plane output for columns >= t_col0
   const float* bias;
@@ -161,7 +165,9 @@ struct TileCoord { int n0, nend, nw, m0, x0, y0, b0, zb, zh, kb0, kb1, split; };
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
-               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
+               const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapClo, const __grid_constant__ CUtensorMap mapR,
+               const TcParams p) {
   constexpr bool TS = Cfg<MODE>::TS;
   constexpr bool H16 = Cfg<MODE>::H16;
   constexpr bool CG2 = Cfg<MODE>::CG2;
@@ -195,6 +201,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   auto bar_halo_full = [&](int h) { return bars + 8u * (3 * STAGES + 4 + h); };
   auto bar_halo_empty = [&](int h) { return bars + 8u * (3 * STAGES + 6 + h); };
   const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 8);
+  auto bar_res = [&](int w) { return bars + 256u + 8u * w; };       // per epilogue warp: its residual box has landed
   // halo schedule smem map: B ring of STAGES x (hi 16 KB | lo 16 KB) at the base, then 2 halo buffers x 2 planes of HALO_PLANE bytes
   const bool halo = H16 && p.halo;
   const uint32_t b_ring = halo ? base : base + OFF_BHI;
@@ -219,6 +226,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_init(bar_halo_full(b), 1);
       mbar_init(bar_halo_empty(b), SPLIT_ARRIVALS);
     }
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(bar_res(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -701,6 +709,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // MODE_H16: the accumulator holds 2^(ea + eb) times the product -> exact power-of-two rescale folded into alpha
     const float alpha = H16 ? p.alpha * exp2i(-h16_a_exp(p)) * exp2i(-p.b_exp) : p.alpha;
     float omax = 0.f;                              // max |C| stored by this thread (p.c_amax)
+    float4* const stg = s_stage + ew * 256;        // this warp's 4 KB staging block: [32 rows][8 float4], chunk index XOR (row & 7)
+    const uint32_t stg_addr = smem_u32(stg);
+    uint32_t res_ph = 0;
     int gchunk0 = 0, tile_it = 0;
 #pragma unroll 1
     for (int t = t_first; t < p.total_tiles; t += t_step, ++tile_it) {
@@ -711,6 +722,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // all rows through shared memory; double-buffered by tile parity so a fast warp cannot overwrite a slow warp's tile
     float bias_v = 0.f;
     if (et < TBN && p.bias && p.splits == 1 && n0 + et < p.N) bias_v = __ldg(p.bias + n0 + et);
+    // TMA epilogue (p.epi_tma): this warp's 32 rows x 64 columns leave as one or two 32 x 32 boxes; it needs whole rows and whole
+    // 32-column blocks (anything else takes the per-row path below).  The residual box of the first block is requested before the
+    // drain, so it is in shared memory by the time the accumulator is
+    const int wcols = p.geglu ? HN : min(max(tc_.nend - (n0 + hf * HN), 0), HN);
+    const bool tma_tile = p.epi_tma && m0 + TBM <= p.M && (wcols & 31) == 0 && !(p.Ct_hi && n0 >= p.t_col0);
+    const int tparts = p.geglu ? 1 : wcols >> 5;
+    const int tcol0 = p.geglu ? (n0 >> 1) + hf * 32 : n0 + hf * HN, trow0 = m0 + q * 32;
+    if (p.epi_tma) {
+      if (lane == 0) {
+        bulk_wait_read0();                         // the previous tile's stores have left the staging buffer
+        if (tma_tile && p.residual && tparts > 0) {
+          mbar_expect_tx(bar_res(ew), 4096);
+          tma_load_2d(stg_addr, &mapR, tcol0, trow0, bar_res(ew));
+        }
+      }
+      __syncwarp();
+    }
     float acc[HN];
 #pragma unroll
     for (int j = 0; j < HN; ++j) acc[j] = 0.f;
@@ -777,6 +805,108 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
       }
+    } else if (tma_tile) {
+      if (tparts > 0) {
+#pragma unroll
+        for (int j = 0; j < HN; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(sb + hf * HN + j);
+          acc[j + 0] = alpha * acc[j + 0] + bv.x;
+          acc[j + 1] = alpha * acc[j + 1] + bv.y;
+          acc[j + 2] = alpha * acc[j + 2] + bv.z;
+          acc[j + 3] = alpha * acc[j + 3] + bv.w;
+        }
+        if (p.rowvec) {
+          const float* rv = p.rowvec + (m / p.rows_per_batch) * p.ld_rowvec + n0 + hf * HN;
+#pragma unroll
+          for (int j = 0; j < HN; j += 4) {
+            if (j < wcols) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(rv + j));
+              acc[j + 0] += bv.x; acc[j + 1] += bv.y; acc[j + 2] += bv.z; acc[j + 3] += bv.w;
+            }
+          }
+        }
+        if (p.geglu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float gt = acc[32 + j];
+            acc[j] *= 0.5f * gt * (1.f + erff(gt * 0.70710678118654752440f));     // exact-erf GELU as F.gelu
+          }
+        }
+#pragma unroll
+        for (int part = 0; part < HN / 32; ++part) {
+          if (part < tparts) {
+            if (p.residual) {
+              mbar_wait(bar_res(ew), res_ph);
+              res_ph ^= 1u;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float4 v = stg[lane * 8 + (c ^ (lane & 7))];
+                acc[part * 32 + 4 * c + 0] += v.x; acc[part * 32 + 4 * c + 1] += v.y;
+                acc[part * 32 + 4 * c + 2] += v.z; acc[part * 32 + 4 * c + 3] += v.w;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float4 o = make_float4(acc[part * 32 + 4 * c], acc[part * 32 + 4 * c + 1], acc[part * 32 + 4 * c + 2], acc[part * 32 + 4 * c + 3]);
+              if (p.C_lo) {
+                o.x = __uint_as_float(rn_tf32(__float_as_uint(o.x))); o.y = __uint_as_float(rn_tf32(__float_as_uint(o.y)));
+                o.z = __uint_as_float(rn_tf32(__float_as_uint(o.z))); o.w = __uint_as_float(rn_tf32(__float_as_uint(o.w)));
+              }
+              omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+              stg[lane * 8 + (c ^ (lane & 7))] = o;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk store
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(stg_addr, &mapC, tcol0 + part * 32, trow0);
+              bulk_commit();
+            }
+            if (p.c_stats) {
+              // GroupNorm statistics of the tensor being written: lane = column of the staged block (conflict-free: the swizzle
+              // permutes the eight 16-byte chunks per row), summed over the warp's 32 rows, which lie inside one image
+              const float* const sf = reinterpret_cast<const float*>(stg);
+              float cs = 0.f, cq = 0.f;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                const float v = sf[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
+                cs += v; cq += v * v;
+              }
+              double* st = p.c_stats + ((long long)(trow0 / p.rows_per_batch) * p.N + (tcol0 + part * 32 + lane)) * 2;
+              atomicAdd(st, (double)cs);
+              atomicAdd(st + 1, (double)cq);
+            }
+            if (p.C_lo) {
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                float4 o = make_float4(acc[part * 32 + 4 * c], acc[part * 32 + 4 * c + 1], acc[part * 32 + 4 * c + 2], acc[part * 32 + 4 * c + 3]);
+                o.x = __uint_as_float(rn_tf32(__float_as_uint(o.x - __uint_as_float(rn_tf32(__float_as_uint(o.x))))));
+                o.y = __uint_as_float(rn_tf32(__float_as_uint(o.y - __uint_as_float(rn_tf32(__float_as_uint(o.y))))));
+                o.z = __uint_as_float(rn_tf32(__float_as_uint(o.z - __uint_as_float(rn_tf32(__float_as_uint(o.z))))));
+                o.w = __uint_as_float(rn_tf32(__float_as_uint(o.w - __uint_as_float(rn_tf32(__float_as_uint(o.w))))));
+                stg[lane * 8 + (c ^ (lane & 7))] = o;
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(stg_addr, &mapClo, tcol0 + part * 32, trow0);
+                bulk_commit();
+              }
+            }
+            if (part + 1 < tparts) {
+              if (lane == 0) {
+                bulk_wait_read0();
+                if (p.residual) {
+                  mbar_expect_tx(bar_res(ew), 4096);
+                  tma_load_2d(stg_addr, &mapR, tcol0 + (part + 1) * 32, trow0, bar_res(ew));
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
     } else {
       const bool fin = p.splits == 1;                // otherwise: raw partial sums to ws[split][M][N]
       // the thread-per-row accumulator layout would store 16 B to 32 different rows per instruction (32 L1 wavefronts
@@ -788,7 +918,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const float* const rsd = fin ? p.residual : nullptr;
       float* const dst_lo = (fin && p.C_lo) ? p.C_lo + zb * p.sC_b + zh * p.sC_h : nullptr;
       const int m32 = row_ok ? (int)m : -1;
-      float4* const stg = s_stage + ew * 256;         // [32 rows][8 float4], chunk index XOR (row & 7)
       const int g = lane & 7, rsub = lane >> 3;
       // GEGLU tiles are [32 value | 32 gate | 32 value | 32 gate]: this thread's 64 columns are 32 values + their gates
       const int nparts = p.geglu ? 1 : HN / 32;
@@ -908,6 +1037,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
     }   // tile loop
+    if (p.epi_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // bulk stores done before the CTA retires
     if (p.c_amax && p.splits == 1) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
@@ -1103,7 +1233,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     p.splits = 1; p.kb_per_split = cdiv(d, TBK);
     p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(Nk, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
-    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
+    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, mA, mA, mA, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -1130,7 +1260,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     p.splits = 1; p.kb_per_split = cdiv(Nk, TBK);
     p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(d, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
-    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, p);
+    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, mA, mA, mA, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -1366,6 +1496,21 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
     mB = &get_map(ts ? a.Bw_hi : a.Bw, 2, d, st, bx);
     mBlo = ts ? &get_map(a.Bw_lo, 2, d, st, bx) : mB;
   }
+  // TMA epilogue (TcParams::epi_tma): dense layers whose epilogue is the final one and needs no per-column statistics
+  const CUtensorMap *mC = mA, *mClo = mA, *mR = mA;
+  static const bool no_epi_tma = getenv("CDX_TC_NO_EPI_TMA") != nullptr;
+  if (!no_epi_tma && a.mode == 0 && !a.out_nchw && p.splits == 1 && a.M >= TBM) {
+    const uint64_t nc = (uint64_t)(a.geglu ? a.N / 2 : a.N);
+    uint64_t d[2] = {nc, (uint64_t)a.M}, st[1] = {(uint64_t)a.ldc * 4};
+    uint32_t bx[2] = {32, 32};
+    mC = &get_map(a.Cout, 2, d, st, bx);
+    if (p.C_lo) mClo = &get_map(p.C_lo, 2, d, st, bx);
+    if (a.residual) {
+      uint64_t sr[1] = {(uint64_t)a.ldr * 4};
+      mR = &get_map(a.residual, 2, d, sr, bx);
+    }
+    p.epi_tma = 1;
+  }
   ensure_attr(e.device);
   ProfScope ps(e, s, a.mode == 1 ? PROF_CONV_TC : PROF_DENSE_TC, 2.0 * a.M * a.N * a.K,
                4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
@@ -1383,10 +1528,10 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CDX_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MODE_H16X2>, *mA, *mA2, *mB, *mBlo, p));
-  } else if (h16) tc_gemm_kernel<MODE_H16><<<grid, TC_THREADS, Cfg<MODE_H16>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
-  else if (ts) tc_gemm_kernel<MODE_TS><<<grid, TC_THREADS, Cfg<MODE_TS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
-  else tc_gemm_kernel<MODE_SS><<<grid, TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, p);
+    CDX_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MODE_H16X2>, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, p));
+  } else if (h16) tc_gemm_kernel<MODE_H16><<<grid, TC_THREADS, Cfg<MODE_H16>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, p);
+  else if (ts) tc_gemm_kernel<MODE_TS><<<grid, TC_THREADS, Cfg<MODE_TS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, p);
+  else tc_gemm_kernel<MODE_SS><<<grid, TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, p);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
   if (p.splits > 1) {

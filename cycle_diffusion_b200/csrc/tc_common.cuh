@@ -66,6 +66,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
                "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// smem -> global tile store through the tensor map (bulk async group of the issuing thread); the smem tile is in the map's
+// swizzled layout, rows / columns outside the tensor are clipped by the hardware
+__device__ __forceinline__ void tma_store_2d(uint32_t src, const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // D[tmem] (+)= A[smem] . B[smem]
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
