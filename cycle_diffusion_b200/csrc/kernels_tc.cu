@@ -41,6 +41,7 @@
 #include <vector>
 #include <cstdlib>
 #include <cmath>
+#include <type_traits>
 
 #include <cuda_fp16.h>
 
@@ -107,8 +108,8 @@ struct TcParams {
   // halo conversion; out-of-image pixels stay 0).  Needs bn == 1.  C1 < Cin: channels >= C1 come from the second source (mapA2)
   const float2* gn_ab; int gn_silu;
   float* C; int ldc;
-  // dense mode, final epilogue: tiles leave through TMA (mapC / mapClo: 32 x 32 float boxes of C / C_lo, mapR: of the residual); the
-  // epilogue warps stage 32-column blocks in the map's swizzle and one lane issues the bulk store (no per-row address arithmetic,
+  // dense mode, final epilogue: tiles leave through TMA (mapC / mapClo: 32 x 32 float boxes of C / C_lo, mapR: of the residual;
+  // map*16: 16-column boxes for the tail of a ragged tile); the epilogue warps stage column blocks in the map's swizzle and one lane issues the bulk store (no per-row address arithmetic,
   // predicates or 16-byte global stores on the warps that also drain TMEM)
   int epi_tma;
   float* C_lo;              // optional: C <- rn_tf32(result), C_lo <- rn_tf32(result - hi)
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
                const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapClo, const __grid_constant__ CUtensorMap mapR,
+               const __grid_constant__ CUtensorMap mapC16, const __grid_constant__ CUtensorMap mapClo16, const __grid_constant__ CUtensorMap mapR16,
                const TcParams p) {
   constexpr bool TS = Cfg<MODE>::TS;
   constexpr bool H16 = Cfg<MODE>::H16;
@@ -722,19 +724,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // all rows through shared memory; double-buffered by tile parity so a fast warp cannot overwrite a slow warp's tile
     float bias_v = 0.f;
     if (et < TBN && p.bias && p.splits == 1 && n0 + et < p.N) bias_v = __ldg(p.bias + n0 + et);
-    // TMA epilogue (p.epi_tma): this warp's 32 rows x 64 columns leave as one or two 32 x 32 boxes; it needs whole rows and whole
-    // 32-column blocks (anything else takes the per-row path below).  The residual box of the first block is requested before the
-    // drain, so it is in shared memory by the time the accumulator is
-    const int wcols = p.geglu ? HN : min(max(tc_.nend - (n0 + hf * HN), 0), HN);
-    const bool tma_tile = p.epi_tma && m0 + TBM <= p.M && (wcols & 31) == 0 && !(p.Ct_hi && n0 >= p.t_col0);
-    const int tparts = p.geglu ? 1 : wcols >> 5;
+    // TMA epilogue (p.epi_tma): this warp's 32 rows x 64 columns leave as one or two boxes of 32 (the last one possibly 16) columns;
+    // it needs whole rows and whole 16-column blocks (anything else takes the per-row path below).  The residual box of the first
+    // slot is requested before the drain, so it is in shared memory by the time the accumulator is
+    const int wcols = p.geglu ? HN / 2 : min(max(tc_.nend - (n0 + hf * HN), 0), HN);       // columns this warp stores
+    const bool tma_tile = p.epi_tma && m0 + TBM <= p.M && (wcols & 15) == 0 && !(p.Ct_hi && n0 >= p.t_col0);
+    const int tparts = (wcols + 31) >> 5;
     const int tcol0 = p.geglu ? (n0 >> 1) + hf * 32 : n0 + hf * HN, trow0 = m0 + q * 32;
     if (p.epi_tma) {
       if (lane == 0) {
-        bulk_wait_read0();                         // the previous tile's stores have left the staging buffer
-        if (tma_tile && p.residual && tparts > 0) {
-          mbar_expect_tx(bar_res(ew), 4096);
-          tma_load_2d(stg_addr, &mapR, tcol0, trow0, bar_res(ew));
+        bulk_wait_read0();                         // the previous tile's stores have left the staging block
+        if (tma_tile && p.residual && wcols > 0) {
+          mbar_expect_tx(bar_res(ew), wcols >= 32 ? 4096 : 2048);
+          tma_load_2d(stg_addr, wcols >= 32 ? &mapR : &mapR16, tcol0, trow0, bar_res(ew));
         }
       }
       __syncwarp();
@@ -832,79 +834,100 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             acc[j] *= 0.5f * gt * (1.f + erff(gt * 0.70710678118654752440f));     // exact-erf GELU as F.gelu
           }
         }
+        // The warp's 64 columns leave as two slots of 32 (4 KB box, 128 B swizzle: [32 rows][8 chunks], chunk ^ (row & 7)); a ragged
+        // tile's last slot may be 16 wide (2 KB box of the 64 B-swizzle maps: [32 rows][4 chunks], index ^ ((row >> 1) & 3)).
+        // Measured: 16-column boxes everywhere cost 10-15 % on the 128-wide tiles (twice the bulk operations, half-line writes)
+        auto epi_block = [&](auto partc, auto ncc) {
+          constexpr int part = decltype(partc)::value;
+          constexpr int NC = decltype(ncc)::value;          // 16-byte chunks per row: 8 or 4
+          auto sidx = [&](int row, int c) { return NC == 8 ? row * 8 + (c ^ (row & 7)) : (row * 4 + c) ^ ((row >> 1) & 3); };
+          if (p.residual) {
+            mbar_wait(bar_res(ew), res_ph);
+            res_ph ^= 1u;
 #pragma unroll
-        for (int part = 0; part < HN / 32; ++part) {
-          if (part < tparts) {
-            if (p.residual) {
-              mbar_wait(bar_res(ew), res_ph);
-              res_ph ^= 1u;
+            for (int c = 0; c < NC; ++c) {
+              const float4 v = stg[sidx(lane, c)];
+              acc[part * 32 + 4 * c + 0] += v.x; acc[part * 32 + 4 * c + 1] += v.y;
+              acc[part * 32 + 4 * c + 2] += v.z; acc[part * 32 + 4 * c + 3] += v.w;
+            }
+          }
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float4 v = stg[lane * 8 + (c ^ (lane & 7))];
-                acc[part * 32 + 4 * c + 0] += v.x; acc[part * 32 + 4 * c + 1] += v.y;
-                acc[part * 32 + 4 * c + 2] += v.z; acc[part * 32 + 4 * c + 3] += v.w;
-              }
+          for (int c = 0; c < NC; ++c) {
+            float4 o = make_float4(acc[part * 32 + 4 * c], acc[part * 32 + 4 * c + 1], acc[part * 32 + 4 * c + 2], acc[part * 32 + 4 * c + 3]);
+            if (p.C_lo) {
+              o.x = __uint_as_float(rn_tf32(__float_as_uint(o.x))); o.y = __uint_as_float(rn_tf32(__float_as_uint(o.y)));
+              o.z = __uint_as_float(rn_tf32(__float_as_uint(o.z))); o.w = __uint_as_float(rn_tf32(__float_as_uint(o.w)));
             }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              float4 o = make_float4(acc[part * 32 + 4 * c], acc[part * 32 + 4 * c + 1], acc[part * 32 + 4 * c + 2], acc[part * 32 + 4 * c + 3]);
-              if (p.C_lo) {
-                o.x = __uint_as_float(rn_tf32(__float_as_uint(o.x))); o.y = __uint_as_float(rn_tf32(__float_as_uint(o.y)));
-                o.z = __uint_as_float(rn_tf32(__float_as_uint(o.z))); o.w = __uint_as_float(rn_tf32(__float_as_uint(o.w)));
-              }
-              omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-              stg[lane * 8 + (c ^ (lane & 7))] = o;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk store
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(stg_addr, &mapC, tcol0 + part * 32, trow0);
-              bulk_commit();
-            }
-            if (p.c_stats) {
-              // GroupNorm statistics of the tensor being written: lane = column of the staged block (conflict-free: the swizzle
-              // permutes the eight 16-byte chunks per row), summed over the warp's 32 rows, which lie inside one image
-              const float* const sf = reinterpret_cast<const float*>(stg);
-              float cs = 0.f, cq = 0.f;
+            omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+            stg[sidx(lane, c)] = o;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk store
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(stg_addr, NC == 8 ? &mapC : &mapC16, tcol0 + part * 32, trow0);
+            bulk_commit();
+          }
+          if (p.c_stats) {
+            // GroupNorm statistics of the tensor being written, from the staged block (the warp's 32 rows lie inside one image)
+            const float* const sf = reinterpret_cast<const float*>(stg);
+            float cs = 0.f, cq = 0.f;
+            if (NC == 8) {                       // lane -> column, all 32 rows (the swizzle permutes chunks: no bank conflict)
 #pragma unroll
               for (int rr = 0; rr < 32; ++rr) {
-                const float v = sf[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
+                const float v = sf[(sidx(rr, lane >> 2) << 2) | (lane & 3)];
                 cs += v; cq += v * v;
               }
-              double* st = p.c_stats + ((long long)(trow0 / p.rows_per_batch) * p.N + (tcol0 + part * 32 + lane)) * 2;
+            } else {                             // lane & 15 -> column, half-warp -> 16 rows (opposite row parity: different banks)
+              const int hh = lane >> 4;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int rr = hh * 16 + (i ^ hh);
+                const float v = sf[(sidx(rr, (lane & 15) >> 2) << 2) | (lane & 3)];
+                cs += v; cq += v * v;
+              }
+              cs += __shfl_xor_sync(0xffffffffu, cs, 16);
+              cq += __shfl_xor_sync(0xffffffffu, cq, 16);
+            }
+            if (NC == 8 || lane < 16) {
+              double* st = p.c_stats + ((long long)(trow0 / p.rows_per_batch) * p.N + (tcol0 + part * 32 + (NC == 8 ? lane : (lane & 15)))) * 2;
               atomicAdd(st, (double)cs);
               atomicAdd(st + 1, (double)cq);
             }
-            if (p.C_lo) {
-              if (lane == 0) bulk_wait_read0();
-              __syncwarp();
+          }
+          if (p.C_lo) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                float4 o = make_float4(acc[part * 32 + 4 * c], acc[part * 32 + 4 * c + 1], acc[part * 32 + 4 * c + 2], acc[part * 32 + 4 * c + 3]);
-                o.x = __uint_as_float(rn_tf32(__float_as_uint(o.x - __uint_as_float(rn_tf32(__float_as_uint(o.x))))));
-                o.y = __uint_as_float(rn_tf32(__float_as_uint(o.y - __uint_as_float(rn_tf32(__float_as_uint(o.y))))));
-                o.z = __uint_as_float(rn_tf32(__float_as_uint(o.z - __uint_as_float(rn_tf32(__float_as_uint(o.z))))));
-                o.w = __uint_as_float(rn_tf32(__float_as_uint(o.w - __uint_as_float(rn_tf32(__float_as_uint(o.w))))));
-                stg[lane * 8 + (c ^ (lane & 7))] = o;
-              }
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(stg_addr, &mapClo, tcol0 + part * 32, trow0);
-                bulk_commit();
-              }
+            for (int c = 0; c < NC; ++c) {
+              float4 o = make_float4(acc[part * 32 + 4 * c], acc[part * 32 + 4 * c + 1], acc[part * 32 + 4 * c + 2], acc[part * 32 + 4 * c + 3]);
+              o.x = __uint_as_float(rn_tf32(__float_as_uint(o.x - __uint_as_float(rn_tf32(__float_as_uint(o.x))))));
+              o.y = __uint_as_float(rn_tf32(__float_as_uint(o.y - __uint_as_float(rn_tf32(__float_as_uint(o.y))))));
+              o.z = __uint_as_float(rn_tf32(__float_as_uint(o.z - __uint_as_float(rn_tf32(__float_as_uint(o.z))))));
+              o.w = __uint_as_float(rn_tf32(__float_as_uint(o.w - __uint_as_float(rn_tf32(__float_as_uint(o.w))))));
+              stg[sidx(lane, c)] = o;
             }
-            if (part + 1 < tparts) {
-              if (lane == 0) {
-                bulk_wait_read0();
-                if (p.residual) {
-                  mbar_expect_tx(bar_res(ew), 4096);
-                  tma_load_2d(stg_addr, &mapR, tcol0 + (part + 1) * 32, trow0, bar_res(ew));
-                }
-              }
-              __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(stg_addr, NC == 8 ? &mapClo : &mapClo16, tcol0 + part * 32, trow0);
+              bulk_commit();
             }
           }
+        };
+        using std::integral_constant;
+        if (wcols >= 32) epi_block(integral_constant<int, 0>{}, integral_constant<int, 8>{});
+        else epi_block(integral_constant<int, 0>{}, integral_constant<int, 4>{});
+        if (wcols > 32) {
+          if (lane == 0) {
+            bulk_wait_read0();                     // slot 0 has left the staging block
+            if (p.residual) {
+              mbar_expect_tx(bar_res(ew), wcols == 64 ? 4096 : 2048);
+              tma_load_2d(stg_addr, wcols == 64 ? &mapR : &mapR16, tcol0 + 32, trow0, bar_res(ew));
+            }
+          }
+          __syncwarp();
+          if (wcols == 64) epi_block(integral_constant<int, 1>{}, integral_constant<int, 8>{});
+          else epi_block(integral_constant<int, 1>{}, integral_constant<int, 4>{});
         }
       }
     } else {
@@ -1233,7 +1256,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     p.splits = 1; p.kb_per_split = cdiv(d, TBK);
     p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(Nk, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
-    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, mA, mA, mA, p);
+    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, mA, mA, mA, mA, mA, mA, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -1260,7 +1283,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     p.splits = 1; p.kb_per_split = cdiv(Nk, TBK);
     p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(d, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
-    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, mA, mA, mA, p);
+    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, mA, mA, mA, mA, mA, mA, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -1497,17 +1520,23 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
     mBlo = ts ? &get_map(a.Bw_lo, 2, d, st, bx) : mB;
   }
   // TMA epilogue (TcParams::epi_tma): dense layers whose epilogue is the final one and needs no per-column statistics
-  const CUtensorMap *mC = mA, *mClo = mA, *mR = mA;
+  const CUtensorMap *mC = mA, *mClo = mA, *mR = mA, *mC16 = mA, *mClo16 = mA, *mR16 = mA;
   static const bool no_epi_tma = getenv("CDX_TC_NO_EPI_TMA") != nullptr;
   if (!no_epi_tma && a.mode == 0 && !a.out_nchw && p.splits == 1 && a.M >= TBM) {
     const uint64_t nc = (uint64_t)(a.geglu ? a.N / 2 : a.N);
     uint64_t d[2] = {nc, (uint64_t)a.M}, st[1] = {(uint64_t)a.ldc * 4};
-    uint32_t bx[2] = {32, 32};
+    uint32_t bx[2] = {32, 32}, bx16[2] = {16, 32};
+    const bool tail16 = (p.tn_w & 31) != 0 || ((a.N % p.tn_w) & 31) != 0;      // some warp stores a 16-column tail slot
     mC = &get_map(a.Cout, 2, d, st, bx);
-    if (p.C_lo) mClo = &get_map(p.C_lo, 2, d, st, bx);
+    if (tail16) mC16 = &get_map(a.Cout, 2, d, st, bx16, nullptr, 4, 64);
+    if (p.C_lo) {
+      mClo = &get_map(p.C_lo, 2, d, st, bx);
+      if (tail16) mClo16 = &get_map(p.C_lo, 2, d, st, bx16, nullptr, 4, 64);
+    }
     if (a.residual) {
       uint64_t sr[1] = {(uint64_t)a.ldr * 4};
       mR = &get_map(a.residual, 2, d, sr, bx);
+      if (tail16) mR16 = &get_map(a.residual, 2, d, sr, bx16, nullptr, 4, 64);
     }
     p.epi_tma = 1;
   }
@@ -1528,10 +1557,10 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CDX_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MODE_H16X2>, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, p));
-  } else if (h16) tc_gemm_kernel<MODE_H16><<<grid, TC_THREADS, Cfg<MODE_H16>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, p);
-  else if (ts) tc_gemm_kernel<MODE_TS><<<grid, TC_THREADS, Cfg<MODE_TS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, p);
-  else tc_gemm_kernel<MODE_SS><<<grid, TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, p);
+    CDX_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MODE_H16X2>, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p));
+  } else if (h16) tc_gemm_kernel<MODE_H16><<<grid, TC_THREADS, Cfg<MODE_H16>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  else if (ts) tc_gemm_kernel<MODE_TS><<<grid, TC_THREADS, Cfg<MODE_TS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  else tc_gemm_kernel<MODE_SS><<<grid, TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
   if (p.splits > 1) {

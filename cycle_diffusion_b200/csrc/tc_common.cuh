@@ -75,6 +75,7 @@ __device__ __forceinline__ void tma_store_2d(uint32_t src, const CUtensorMap* ma
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores of this thread have finished READING their shared-memory source (it may be overwritten)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the newest
 // D[tmem] (+)= A[smem] . B[smem]
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -236,13 +237,15 @@ struct MapKey {
   uint32_t box[4], es[4];
   int rank;
   int esize;
+  int swz;
   bool operator<(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
 };
 
-// fp32 (esize 4) or fp16 (esize 2), 128B swizzle, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
+// fp32 (esize 4) or fp16 (esize 2), 128B swizzle (swz 128) or 64B swizzle (swz 64: boxes with a 64-byte inner extent -- with the
+// 128B mode the hardware pads such a box to 128-byte rows in shared memory), zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
 // `estr` (optional): element traversal strides; with stride s along a dim, box[i] = n*s loads n elements.
 inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
-                                  const uint32_t* estr = nullptr, int esize = 4) {
+                                  const uint32_t* estr = nullptr, int esize = 4, int swz = 128) {
   // node-based map: returned references stay valid; on overflow the live generation is parked in `old` (and the generation
   // before it dropped), so a reference handed out earlier in the same call can never dangle
   static std::map<MapKey, CUtensorMap> cache, old;
@@ -253,6 +256,7 @@ inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dim
   k.ptr = ptr;
   k.rank = rank;
   k.esize = esize;
+  k.swz = swz;
   for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.es[i] = estr ? estr[i] : 1; }
   for (int i = 0; i < rank - 1; ++i) k.strides[i] = strides[i];
   auto it = cache.find(k);
@@ -270,7 +274,7 @@ inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dim
   EncodeTiledFn enc = get_encode();
   if (!enc) throw Error(CDX_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUresult r = enc(&m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char b[256];
     snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u", (int)r, rank,
