@@ -55,7 +55,8 @@ using namespace tc;
 constexpr int TBM = 128, TBN = 128, TBK = 32;
 constexpr double CDX_H16_KC0 = 640.0, CDX_H16_KC1 = 4.2;   // planner cost of one 64-k stage of the fp16-split kernel (cycles)
 constexpr int TILE_BYTES = TBM * TBK * 4;          // 16 KB
-constexpr int HALO_PLANE = 24 * 1024;             // one 32-channel plane of a conv3x3 halo box (<= 192 pixels x 128 B)
+constexpr int HALO_PLANE_1CTA = 24 * 1024;        // one 32-channel plane of a conv3x3 halo box (<= 192 pixels x 128 B)
+constexpr int HALO_PLANE_PAIR = 25 * 1024;        // pair kernel (its B ring is half the size): 200 pixels = the two 10 x 10 halos of an 8 x 8 tile
 constexpr int NUM_SPLIT_WARPS = 8;               // two per TMEM lane quadrant (MODE_H16: one per 32-k sub-block of a stage)
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int FIRST_SPLIT_WARP = 4, FIRST_EPI_WARP = FIRST_SPLIT_WARP + NUM_SPLIT_WARPS;
@@ -83,6 +84,7 @@ struct Cfg {
   static constexpr int KCHUNK = 256 / BK;          // stages per TMEM accumulation chunk (256 K elements)
   static constexpr int STAGES = (MODE == MODE_TS || CG2) ? 4 : 3;
   static constexpr int B_PLANE = CG2 ? TILE_BYTES / 2 : TILE_BYTES;      // smem bytes of one B plane of a stage (CG2: half the rows)
+  static constexpr int HALO_PLANE = CG2 ? HALO_PLANE_PAIR : HALO_PLANE_1CTA;
   // SS: A_hi, A_lo, B_hi, B_lo ; TS: A_raw, B_hi, B_lo ; H16: A_raw(k 0..31), A_raw(k 32..63), B_hi, B_lo (fp16, 128 B rows)
   static constexpr int STAGE_BYTES = MODE == MODE_TS ? 3 * TILE_BYTES : 2 * TILE_BYTES + 2 * B_PLANE;
   static constexpr int TMEM_COLS = TS ? 512 : 256;
@@ -174,6 +176,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr bool H16 = Cfg<MODE>::H16;
   constexpr bool CG2 = Cfg<MODE>::CG2;
   constexpr int B_PLANE = Cfg<MODE>::B_PLANE;
+  constexpr int HALO_PLANE = Cfg<MODE>::HALO_PLANE;
   constexpr int BK = Cfg<MODE>::BK;
   // stages per TMEM accumulation chunk: 256 K elements; a work item of at most 512 K elements is ONE chunk (its truncation error stays
   // ~2e-6 relative, and the short-K projections -- epilogue-bound -- save a drain round trip per tile)
@@ -509,7 +512,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // pixel) and a lo plane (plane 1) -- one pixel per thread -- and the per-tap work of a stage is a copy: 8 x LDS.128 of this
         // thread's shifted pixel -> one tcgen05.st of 32 columns (warps of sub 0 copy the hi plane, sub 1 the lo plane).
         const int tid = (int)threadIdx.x - FIRST_SPLIT_WARP * 32;      // 0..255
-        const int npx = (p.bw + 2) * (p.bh + 2) * p.bn;                 // <= 192 (host-checked)
+        const int npx = (p.bw + 2) * (p.bh + 2) * p.bn;                 // <= 200 <= 256 threads (host-checked against the plane size)
         const int hrow0 = ((row / (p.bw * p.bh)) * (p.bh + 2) + (row / p.bw) % p.bh) * (p.bw + 2) + row % p.bw;   // pixel at tap (0, 0)
         int gkb = 0, ghalo = 0, cur_h = 0;
         for (int t = t_first; t < p.total_tiles; t += t_step) {
@@ -1302,7 +1305,7 @@ bool conv_halo_eligible(const Engine& e, int B, int H, int W, int C1, int C2, in
   const int bw = W < 16 ? W : 16;
   const int bh = H < TBM / bw ? H : TBM / bw;
   const int bn = TBM / (bw * bh);
-  return bn == 1 && (bw + 2) * (bh + 2) * 128 <= HALO_PLANE;
+  return bn == 1 && (bw + 2) * (bh + 2) * 128 <= HALO_PLANE_1CTA;
 }
 
 bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
@@ -1378,8 +1381,12 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
     uint32_t es[4] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1};
     // halo schedule (see TcParams::halo): needs the fp16-split path (decided below), 64-channel blocks and a halo box that fits a plane
     static const bool no_halo = getenv("CDX_TC_NO_HALO") != nullptr;
+    // (the pair kernel has room for a 25 KB plane: the 8 x 8 level, two images per tile, joins the halo schedule when the launch pairs)
+    static const bool no_pair = getenv("CDX_TC_NO_PAIR") != nullptr;
+    const bool will_pair = !no_pair && ((p.tiles_x * p.tiles_y * cdiv(B, bn)) % 2) == 0 && e.num_sms >= 2;
+    const int plane_cap = will_pair ? HALO_PLANE_PAIR : HALO_PLANE_1CTA;
     if ((!no_halo || needs_halo) && e.tc_kind >= 1 && a.stride == 1 && a.pad == 1 && (a.C1 % 64) == 0 && (!a.A2 || (a.C2 % 64) == 0) &&
-        (bw + 2) * (bh + 2) * bn * 128 <= HALO_PLANE && a.Bw_h_hi && a.Bw_h_lo && a16(a.Bw_h_hi) && a16(a.Bw_h_lo) && (a.ldb % 8) == 0 &&
+        (bw + 2) * (bh + 2) * bn * 128 <= plane_cap && a.Bw_h_hi && a.Bw_h_lo && a16(a.Bw_h_hi) && a16(a.Bw_h_lo) && (a.ldb % 8) == 0 &&
         (!a.gn_ab || bn == 1)) {
       p.halo = 1;
       bx[1] = (uint32_t)(bw + 2); bx[2] = (uint32_t)(bh + 2);
@@ -1414,6 +1421,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   // ran at 0.6x: ptxas puts an L1 invalidation (CCTL.IVALL) behind each of them (profiles/r02_ops_h16_pair_negative.txt).
   static const bool no_cg2 = getenv("CDX_TC_NO_PAIR") != nullptr;
   const bool cg2 = h16 && !no_cg2 && (p.tiles_m % 2) == 0 && e.num_sms >= 2;
+  CDX_CHECK(!p.halo || cg2 || (p.bw + 2) * (p.bh + 2) * p.bn * 128 <= HALO_PLANE_1CTA, "conv3x3: halo plane sized for the pair kernel on a single-CTA launch");
   if (cg2) p.tiles_m /= 2;                 // from here on: 256-row pair tiles
   // Work partition: tile width w along N (MMA N = valid columns rounded up to 16, so a ragged last tile costs only its
   // share) and split-K factor S, chosen together against wave quantisation on num_sms persistent CTAs by replaying the

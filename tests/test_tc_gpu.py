@@ -57,7 +57,9 @@ def test_linear_tc(eng, M, K, N):
                                            (2, 1280, 1280, 8),
                                            # halo schedule (Cin % 64 == 0, W >= 16): split-K items that start / end inside a channel
                                            # block, ragged batch, ragged N tile, many channel blocks
-                                           (1, 1280, 640, 16), (8, 640, 640, 32), (3, 192, 96, 32), (1, 1920, 320, 64), (5, 64, 48, 16)])
+                                           (1, 1280, 640, 16), (8, 640, 640, 32), (3, 192, 96, 32), (1, 1920, 320, 64), (5, 64, 48, 16),
+                                           # 8 x 8 level on CTA pairs: two images per 128-row tile, 200-pixel halo plane; ragged batch / N
+                                           (8, 1280, 1280, 8), (4, 128, 64, 8), (12, 192, 80, 8), (7, 64, 48, 8)])
 def test_conv3x3_tc(eng, B, Cin, Cout, H):
     g = torch.Generator().manual_seed(Cin * 1000 + Cout + H)
     x = torch.randn(B, Cin, H, H, generator=g)
