@@ -700,7 +700,38 @@ int cdx_op_attention(cdx_engine* eh, const float* q, const float* k, const float
     with_arena(e, s, [&] {
       Scope sc(e.arena);
       bool done = false;
-      if (e.mma_mode == 1 && Nq == Nk && (Nq % 32) == 0 && Nq >= 128 && (d % 4) == 0) {
+      if (e.mma_mode == 1 && e.flash_attn && e.tc_kind >= 1 && (Nq % 128) == 0 && (C % 8) == 0 && (d == 16 || d == 32 || d == 40 || d == 64 || d == 80)) {
+        // the SpatialTransformer's fp16-split path on loose q / k / v: ranges measured here, keys padded to a multiple of 8 per image
+        e.pools_reset(s);
+        const int Nks = (Nk + 7) & ~7, M = B * Nq, Mk = B * Nks;
+        float *qa = e.amax_slot(), *ka = e.amax_slot(), *va = e.amax_slot();
+        amax_rows(e, q, M, C, C, qa, s);
+        amax_rows(e, k, (long long)B * Nk, C, C, ka, s);
+        amax_rows(e, v, (long long)B * Nk, C, C, va, s);
+        const float *kp = k, *vp = v;
+        if (Nks != Nk) {
+          float* kb = (float*)e.arena.alloc((size_t)Mk * C * sizeof(float));
+          float* vb = (float*)e.arena.alloc((size_t)Mk * C * sizeof(float));
+          if (!e.dry()) {
+            CDX_CUDA(cudaMemsetAsync(kb, 0, (size_t)Mk * C * 4, s));
+            CDX_CUDA(cudaMemsetAsync(vb, 0, (size_t)Mk * C * 4, s));
+            CDX_CUDA(cudaMemcpy2DAsync(kb, (size_t)Nks * C * 4, k, (size_t)Nk * C * 4, (size_t)Nk * C * 4, B, cudaMemcpyDeviceToDevice, s));
+            CDX_CUDA(cudaMemcpy2DAsync(vb, (size_t)Nks * C * 4, v, (size_t)Nk * C * 4, (size_t)Nk * C * 4, B, cudaMemcpyDeviceToDevice, s));
+          }
+          kp = kb; vp = vb;
+        }
+        void* qh = e.arena.alloc((size_t)M * C * 2);
+        void* ql = e.arena.alloc((size_t)M * C * 2);
+        void* kh = e.arena.alloc((size_t)Mk * C * 2);
+        void* kl = e.arena.alloc((size_t)Mk * C * 2);
+        void* vh = e.arena.alloc((size_t)Mk * C * 2);
+        void* vl = e.arena.alloc((size_t)Mk * C * 2);
+        split_rows_h16(e, q, M, C, C, qh, ql, C, qa, s);
+        split_rows_h16(e, kp, Mk, C, C, kh, kl, C, ka, s);
+        split_transpose_h16(e, vp, Mk, C, C, vh, vl, va, s);
+        done = flash_attention_h16(e, qh, ql, C, kh, kl, C, vh, vl, qa, ka, va, out, C, B, Nq, Nk, Nks, heads, d, scale, s);
+      }
+      if (!done && e.mma_mode == 1 && Nq == Nk && (Nq % 32) == 0 && Nq >= 128 && (d % 4) == 0) {
         // same operand preparation as the SpatialTransformer: q|k side by side, V transposed, TF32 planes
         const int M = B * Nq;
         float* qk = (float*)e.arena.alloc((size_t)M * 2 * C * sizeof(float));

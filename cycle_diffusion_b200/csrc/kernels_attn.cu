@@ -20,6 +20,8 @@
 //             adds in registers (the tensor core's accumulation truncates, see kernels_tc.cu; accumulating per block in
 //             registers also makes the online-softmax rescale free).  Final O / l -> global.
 // TMEM columns (<= 512): [S x SB][P hi|lo x PB][O x PB][Q_hi][Q_lo], see ACfg.
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace cdx {
@@ -30,7 +32,10 @@ using namespace tc;
 constexpr int AQ = 128;        // queries per CTA
 constexpr int AKV = 64;        // keys per block
 
-template <int D>
+// F16: operands are fp16 hi / lo planes (x * 2^e split as in kernels_tc.cu's MODE_H16) and the three product terms run as
+// kind::f16 MMAs (K = 16 per instruction): half the tensor-pipe time and half the operand bytes of the TF32 planes.  P is split as
+// fp16(p * 2^10): the scale keeps the lo term out of fp16's subnormal range and cancels in O / l.
+template <int D, bool F16>
 struct ACfg {
   // softmax warps per TMEM lane quadrant (each takes AKV / NSUB score columns and NV / NSUB output columns of its 32 rows):
   // 4 (16 softmax warps) hides the tcgen05.ld / MUFU / barrier latencies of the softmax chain better than 2 (a profile of the
@@ -38,12 +43,17 @@ struct ACfg {
   // max exchange and keeps 2
   static constexpr int NSUB = (D <= 40) ? 4 : 2;
   static constexpr int THREADS = 128 + 4 * NSUB * 32;       // TMA warp, three MMA issuer warps (QK, PV even / odd blocks), softmax warps
-  static constexpr int KB2 = (D + 31) / 32;                 // 32-float k-blocks covering the head dim
+  static constexpr int KD = F16 ? (D + 15) / 16 * 16 : D;    // head dim as the QK MMAs see it (F16: zero-padded to K = 16 steps by the TMA fill)
+  static constexpr int KW = F16 ? 64 : 32;                  // elements per 128-byte k-block row
+  static constexpr int KB2 = (D + KW - 1) / KW;             // 128-byte k-blocks covering the head dim
+  static constexpr int NG = F16 ? KD / 16 : D / 8;          // 8-column TMEM groups of a Q plane == MMA K steps of Q.K^T
+  static constexpr int QC = F16 ? KD / 2 : D;               // TMEM columns of one Q plane
+  static constexpr int PW = F16 ? AKV / 2 : AKV;            // TMEM columns of one P plane
   static constexpr int NV = (D + 15) / 16 * 16;             // PV MMA N (rows of the V^T tile)
   static constexpr int KTILE = AKV * 128;                   // one k-block tile of K: 64 rows x 128 B
   static constexpr int K_STAGE = 2 * KB2 * KTILE;           // hi + lo
-  static constexpr int VTILE = NV * 128;                    // one 32-key block of V^T: NV rows x 128 B
-  static constexpr int V_STAGE = 2 * 2 * VTILE;             // (2 key sub-blocks) x (hi + lo)
+  static constexpr int VTILE = NV * 128;                    // one 128-byte block of V^T (32 keys; F16: 64 keys): NV rows x 128 B
+  static constexpr int V_STAGE = (F16 ? 1 : 2) * 2 * VTILE; // (key sub-blocks) x (hi + lo)
   static constexpr int Q_STAGE = KB2 * AQ * 128;            // one plane of Q (== K_STAGE)
   // ring depths: the prefetch distance must cover the TMA latency (a first profile with 2-deep rings had the MMA thread
   // spinning on k_full); the Q staging buffer is the LAST K stage, which is first needed KS-1 blocks into the loop
@@ -63,11 +73,11 @@ struct ACfg {
   static constexpr int SB = (D <= 40) ? 1 : 2;
   static constexpr int PB = (D <= 40) ? 2 : 1;            // P buffers == O buffers
   static constexpr int COL_S = 0;
-  static constexpr int COL_P = SB * AKV;                    // buffer b: hi at COL_P + b*128, lo at + 64
-  static constexpr int COL_O = COL_P + PB * 2 * AKV;        // buffer b at COL_O + b*NV
-  static constexpr int COL_QH = COL_O + PB * NV, COL_QL = COL_QH + D;
+  static constexpr int COL_P = SB * AKV;                    // buffer b: hi at COL_P + b*2*PW, lo at + PW
+  static constexpr int COL_O = COL_P + PB * 2 * PW;         // buffer b at COL_O + b*NV
+  static constexpr int COL_QH = COL_O + PB * NV, COL_QL = COL_QH + QC;
   static_assert(D % 8 == 0 && D >= 16 && D <= 80, "head dim must be a multiple of 8 in [16, 80]");
-  static_assert(COL_QL + D <= 512, "TMEM overflow");
+  static_assert(COL_QL + QC <= 512, "TMEM overflow");
   static_assert(SMEM_BYTES <= 232448, "smem overflow");
   static_assert(NV % 16 == 0, "NV");
 };
@@ -76,6 +86,7 @@ struct AttnParams {
   int N, Nk, heads, d, B;   // N queries, Nk keys (cross-attention: Nk != N; keys >= Nk in the last block are masked)
   float scale_log2e;      // scale * log2(e): scores are kept in the log2 domain
   float* out; int ldo;
+  const float *q_amax, *k_amax, *v_amax;   // F16: tracked max |q|, |k|, |v| (the planes hold x * 2^h16_exp_of(amax))
 };
 
 #define TMEM_LD(NUM, ...) asm volatile("tcgen05.ld.sync.aligned.32x32b.x" #NUM ".b32 " __VA_ARGS__)
@@ -108,13 +119,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int D>
-__global__ void __launch_bounds__(ACfg<D>::THREADS, 1)
+template <int D, bool F16>
+__global__ void __launch_bounds__(ACfg<D, F16>::THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_constant__ CUtensorMap mapQl,
                   const __grid_constant__ CUtensorMap mapKh, const __grid_constant__ CUtensorMap mapKl,
                   const __grid_constant__ CUtensorMap mapVh, const __grid_constant__ CUtensorMap mapVl, const AttnParams p) {
-  using C = ACfg<D>;
-  constexpr int KB2 = C::KB2, NV = C::NV, NSUB = C::NSUB;
+  using C = ACfg<D, F16>;
+  constexpr int KB2 = C::KB2, NV = C::NV, NSUB = C::NSUB, KW = C::KW, PW = C::PW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + C::OFF_BAR;
@@ -179,12 +190,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       // Q: hi plane, then (after the softmax warps moved it to TMEM) lo plane through the same staging buffer
       if (elect_one()) {
         mbar_expect_tx(bar_q_full, C::Q_STAGE);
-        for (int kb = 0; kb < KB2; ++kb) tma_load_4d(sq + kb * AQ * 128, &mapQh, kb * 32, h, q0, b, bar_q_full);
+        for (int kb = 0; kb < KB2; ++kb) tma_load_4d(sq + kb * AQ * 128, &mapQh, kb * KW, h, q0, b, bar_q_full);
       }
       mbar_wait(bar_q_free, 0);
       if (elect_one()) {
         mbar_expect_tx(bar_q_full, C::Q_STAGE);
-        for (int kb = 0; kb < KB2; ++kb) tma_load_4d(sq + kb * AQ * 128, &mapQl, kb * 32, h, q0, b, bar_q_full);
+        for (int kb = 0; kb < KB2; ++kb) tma_load_4d(sq + kb * AQ * 128, &mapQl, kb * KW, h, q0, b, bar_q_full);
       }
       for (int j = 0; j < nb; ++j) {
         const int s = j % KS, it = j / KS;
@@ -195,8 +206,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         if (elect_one()) {
           mbar_expect_tx(bar_k_full(s), C::K_STAGE);
           for (int kb = 0; kb < KB2; ++kb) {
-            tma_load_4d(sk + kb * C::KTILE, &mapKh, kb * 32, h, j * AKV, b, bar_k_full(s));
-            tma_load_4d(sk + (KB2 + kb) * C::KTILE, &mapKl, kb * 32, h, j * AKV, b, bar_k_full(s));
+            tma_load_4d(sk + kb * C::KTILE, &mapKh, kb * KW, h, j * AKV, b, bar_k_full(s));
+            tma_load_4d(sk + (KB2 + kb) * C::KTILE, &mapKl, kb * KW, h, j * AKV, b, bar_k_full(s));
           }
         }
         // V^T block j: [NV channel rows x 64 keys] as two 32-key tiles, hi + lo
@@ -205,9 +216,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         const uint32_t sv = base + C::OFF_V + sv_ * C::V_STAGE;
         if (elect_one()) {
           mbar_expect_tx(bar_v_full(sv_), C::V_STAGE);
-          for (int kk = 0; kk < 2; ++kk) {
-            tma_load_4d(sv + kk * C::VTILE, &mapVh, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(sv_));
-            tma_load_4d(sv + (2 + kk) * C::VTILE, &mapVl, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(sv_));
+          if (F16) {
+            tma_load_4d(sv, &mapVh, j * AKV, b, h * p.d, 0, bar_v_full(sv_));
+            tma_load_4d(sv + C::VTILE, &mapVl, j * AKV, b, h * p.d, 0, bar_v_full(sv_));
+          } else {
+            for (int kk = 0; kk < 2; ++kk) {
+              tma_load_4d(sv + kk * C::VTILE, &mapVh, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(sv_));
+              tma_load_4d(sv + (2 + kk) * C::VTILE, &mapVl, j * AKV + kk * 32, b, h * p.d, 0, bar_v_full(sv_));
+            }
           }
         }
       }
@@ -215,7 +231,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
   } else if (warp == 1) {
     // =========================================================================== MMA issuer of the Q.K^T stream (whole warp, elected issue)
     {
-      const uint32_t idesc_qk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AKV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
+      const uint32_t idesc_qk = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(AKV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
       const uint32_t q_hi = tmem_base + C::COL_QH, q_lo = tmem_base + C::COL_QL;
 
       auto issue_qk = [&](int j) {
@@ -224,14 +240,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         const uint32_t s_acc = tmem_base + C::COL_S + sb * AKV;
         if (!elect_one()) return;
 #pragma unroll
-        for (int c = 0; c < D / 8; ++c) {      // K chunks of 8 floats along the head dim
+        for (int c = 0; c < C::NG; ++c) {      // K steps along the head dim: 8 floats, or 16 halves (= 8 TMEM columns of Q, 32 B of a K row)
           const int kb = c >> 2;
           const uint64_t adv = (uint64_t)(((c & 3) * 32) >> 4);
           const uint64_t k_hi = make_desc(sk + kb * C::KTILE) + adv;
           const uint64_t k_lo = make_desc(sk + (KB2 + kb) * C::KTILE) + adv;
-          umma_ts(s_acc, q_lo + c * 8, k_hi, idesc_qk, c > 0 ? 1u : 0u);
-          umma_ts(s_acc, q_hi + c * 8, k_lo, idesc_qk, 1u);
-          umma_ts(s_acc, q_hi + c * 8, k_hi, idesc_qk, 1u);
+          if (F16) {
+            umma_ts_f16(s_acc, q_lo + c * 8, k_hi, idesc_qk, c > 0 ? 1u : 0u);
+            umma_ts_f16(s_acc, q_hi + c * 8, k_lo, idesc_qk, 1u);
+            umma_ts_f16(s_acc, q_hi + c * 8, k_hi, idesc_qk, 1u);
+          } else {
+            umma_ts(s_acc, q_lo + c * 8, k_hi, idesc_qk, c > 0 ? 1u : 0u);
+            umma_ts(s_acc, q_hi + c * 8, k_lo, idesc_qk, 1u);
+            umma_ts(s_acc, q_hi + c * 8, k_hi, idesc_qk, 1u);
+          }
         }
         umma_commit(bar_s_full(sb));
         umma_commit(bar_k_empty(ks));
@@ -254,7 +276,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
     // With two P/O buffers the even and the odd key blocks are independent streams: one issuer warp each.
     constexpr int NPV = (PB == 2) ? 2 : 1;
     if (warp - 2 < NPV) {
-      const uint32_t idesc_pv = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(NV >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
       for (int j = warp - 2; j < nb; j += NPV) {
         const int vs = j % VS, pb = j % PB;
         mbar_wait(bar_v_full(vs), (j / VS) & 1);
@@ -262,9 +284,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         if (j >= PB) mbar_wait(bar_o_empty(pb), ((j / PB) - 1) & 1);                  // O buffer of block j-PB has been accumulated
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sv = base + C::OFF_V + vs * C::V_STAGE;
-        const uint32_t p_hi = tmem_base + C::COL_P + pb * 2 * AKV, p_lo = p_hi + AKV;
+        const uint32_t p_hi = tmem_base + C::COL_P + pb * 2 * PW, p_lo = p_hi + PW;
         const uint32_t o_acc = tmem_base + C::COL_O + pb * NV;
         if (!elect_one()) continue;
+        if (F16) {
+#pragma unroll
+          for (int c = 0; c < AKV / 16; ++c) {   // K steps of 16 keys: 8 TMEM columns of P, 32 B of a V^T row
+            const uint64_t adv = (uint64_t)((c * 32) >> 4);
+            const uint64_t v_hi = make_desc(sv) + adv;
+            const uint64_t v_lo = make_desc(sv + C::VTILE) + adv;
+            umma_ts_f16(o_acc, p_lo + c * 8, v_hi, idesc_pv, c > 0 ? 1u : 0u);
+            umma_ts_f16(o_acc, p_hi + c * 8, v_lo, idesc_pv, 1u);
+            umma_ts_f16(o_acc, p_hi + c * 8, v_hi, idesc_pv, 1u);
+          }
+        } else {
 #pragma unroll
         for (int c = 0; c < AKV / 8; ++c) {    // K chunks of 8 keys
           const int kk = c >> 2;
@@ -274,6 +307,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           umma_ts(o_acc, p_lo + c * 8, v_hi, idesc_pv, c > 0 ? 1u : 0u);
           umma_ts(o_acc, p_hi + c * 8, v_lo, idesc_pv, 1u);
           umma_ts(o_acc, p_hi + c * 8, v_hi, idesc_pv, 1u);
+        }
         }
         umma_commit(bar_pv_done(pb));
         umma_commit(bar_v_empty(vs));
@@ -297,7 +331,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         mbar_wait(bar_q_full, plane);
         const uint32_t col = tmem_base + lane_base + (plane == 0 ? C::COL_QH : C::COL_QL);
 #pragma unroll
-        for (int c8 = 0; c8 < D / 8; ++c8) {         // 8 floats = two 16-byte chunks
+        for (int c8 = 0; c8 < C::NG; ++c8) {         // 8 TMEM columns = two 16-byte chunks of the row
           const int kb = c8 >> 2, ch = (c8 & 3) * 2;
           const uint32_t a = base + C::OFF_Q + kb * AQ * 128 + rbase;
           uint32_t v[8];
@@ -312,6 +346,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       }
     }
 
+    // F16: the planes carry 2^eq q, 2^ek k, 2^ev v -> scores rescaled by the exact 2^-(eq+ek), output by 2^-ev; P is handed to the
+    // tensor core as p * 2^10 (folded into the exponent; the row sum carries the same factor, so O / l is unchanged)
+    float scale_l2 = p.scale_log2e, oscale = 1.f;
+    if (F16) {
+      scale_l2 = scale_l2 * exp2i(-h16_exp_of(*p.q_amax)) * exp2i(-h16_exp_of(*p.k_amax));
+      oscale = exp2i(-h16_exp_of(*p.v_amax));
+    }
+    constexpr float PEXP = F16 ? 10.f : 0.f;
     float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
     float o[HO];
 #pragma unroll
@@ -369,13 +411,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xa + (uint32_t)((hf + o2) % NSUB) * 512u) : "memory");
         mx = fmaxf(mx, other);
       }
-      mx *= p.scale_log2e;
+      mx *= scale_l2;
       const float m_new = fmaxf(m_run, mx);
       const float corr = ex2_approx(m_run - m_new);      // 0 on the first block (m_run = -inf)
+      const float nm = PEXP - m_new;
       float psum = 0.f;
 #pragma unroll
       for (int c = 0; c < HC; ++c) {
-        sc[c] = ex2_approx(fmaf(sc[c], p.scale_log2e, -m_new));
+        sc[c] = ex2_approx(fmaf(sc[c], scale_l2, nm));
         psum += sc[c];
       }
       l_run = l_run * corr + psum;
@@ -385,6 +428,25 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       if (PB == 1 && j >= 1) accumulate_o(j - 1, corr_prev);     // single P buffer: PV_{j-1} must be done before P_j is written
 
       // P -> hi / lo planes in TMEM (hi rounded to nearest; lo is left to the tensor core's own truncation: |lo| <= 2^-12 p)
+      if (F16) {
+        // fp16 hi / lo, two keys per TMEM column (even key in the low half), both rounded to nearest
+#pragma unroll
+        for (int c8 = 0; c8 < HC / 16; ++c8) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float x0 = sc[c8 * 16 + 2 * e], x1 = sc[c8 * 16 + 2 * e + 1];
+            const __half2 hh = __floats2half2_rn(x0, x1);
+            const float2 hf2 = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(x0 - hf2.x, x1 - hf2.y);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          const uint32_t pcol = tmem_base + lane_base + C::COL_P + (j % PB) * 2 * PW + (hf * HC) / 2 + c8 * 8;
+          tmem_st8(pcol, hi);
+          tmem_st8(pcol + PW, lo);
+        }
+      } else {
 #pragma unroll
       for (int c8 = 0; c8 < HC / 8; ++c8) {
         uint32_t hi[8], lo[8];
@@ -396,6 +458,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         const uint32_t pcol = tmem_base + lane_base + C::COL_P + (j % PB) * 2 * AKV + hf * HC + c8 * 8;
         tmem_st8(pcol, hi);
         tmem_st8(pcol + AKV, lo);
+      }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -420,7 +483,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lv) : "r"(xl + (uint32_t)o2 * 512u) : "memory");
       l_tot += lv;
     }
-    const float inv_l = 1.f / l_tot;
+    const float inv_l = oscale / l_tot;
     float* dst = p.out + ((long long)b * p.N + q0 + row) * p.ldo + h * p.d + hf * HO;
 #pragma unroll
     for (int c = 0; c < HO; c += 4) {
@@ -440,17 +503,69 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
   }
 }
 
-template <int D>
+template <int D, bool F16>
 void launch_flash(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& kh, const CUtensorMap& kl, const CUtensorMap& vh,
                   const CUtensorMap& vl, const AttnParams& p, cudaStream_t s) {
   static bool attr[64] = {};          // per device (cudaFuncSetAttribute is device state); engines are single-threaded per device
   int dev = 0;
   CDX_CUDA(cudaGetDevice(&dev));
   if (!attr[dev & 63]) {
-    CDX_CUDA(cudaFuncSetAttribute(flash_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<D>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(flash_attn_kernel<D, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<D, F16>::SMEM_BYTES));
     attr[dev & 63] = true;
   }
-  flash_attn_kernel<D><<<dim3(p.N / AQ, p.heads, p.B), ACfg<D>::THREADS, ACfg<D>::SMEM_BYTES, s>>>(qh, ql, kh, kl, vh, vl, p);
+  flash_attn_kernel<D, F16><<<dim3(p.N / AQ, p.heads, p.B), ACfg<D, F16>::THREADS, ACfg<D, F16>::SMEM_BYTES, s>>>(qh, ql, kh, kl, vh, vl, p);
+}
+
+
+// x * 2^e -> fp16 hi / lo planes, e = h16_exp_of(*amax) (the exponent the attention kernel derives from the same slot).
+// src [rows, ld] (cols % 4 == 0) -> hi / lo [rows, ldh]
+__global__ void split_rows_h16_kernel(const float* __restrict__ src, long long rows, int cols, long long ld, __half* __restrict__ hi,
+                                      __half* __restrict__ lo, long long ldh, const float* __restrict__ amax) {
+  const float sc = exp2i(h16_exp_of(*amax));
+  const int c4n = cols >> 2;
+  const long long total = rows * (long long)c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4n;
+    const int c = (int)(i - r * c4n) * 4;
+    float4 v = *reinterpret_cast<const float4*>(src + r * ld + c);
+    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    uint2 ph, pl;
+    ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+    pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(hi + r * ldh + c) = ph;
+    *reinterpret_cast<uint2*>(lo + r * ldh + c) = pl;
+  }
+}
+
+// the same split, transposed: src [R, ld] columns 0..C-1 -> hi / lo [C, R] (V^T: both P.V operands K-major for tcgen05).
+// 64 (rows) x 32 (columns) tiles through shared memory; R % 2 == 0
+__global__ void __launch_bounds__(256) split_transpose_h16_kernel(const float* __restrict__ src, int R, int Cc, long long ld, __half* __restrict__ hi,
+                                                                   __half* __restrict__ lo, const float* __restrict__ amax) {
+  __shared__ float tile[64][33];
+  const float sc = exp2i(h16_exp_of(*amax));
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    tile[ty + 8 * k][tx] = (r < R && c < Cc) ? src[(long long)r * ld + c] * sc : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k, r = r0 + 2 * tx;            // one warp: 64 consecutive rows of one output row = 128 B
+    if (c < Cc && r < R) {
+      const float x0 = tile[2 * tx][ty + 8 * k], x1 = tile[2 * tx + 1][ty + 8 * k];
+      const __half2 h = __floats2half2_rn(x0, x1);
+      const float2 f = __half22float2(h);
+      const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+      *reinterpret_cast<__half2*>(hi + (long long)c * R + r) = h;
+      *reinterpret_cast<__half2*>(lo + (long long)c * R + r) = l;
+    }
+  }
 }
 
 }  // namespace
@@ -484,13 +599,76 @@ bool flash_attention_tc(Engine& e, const float* q_hi, const float* q_lo, int ldq
   p.N = N; p.Nk = Nk; p.heads = heads; p.d = d; p.B = B;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = out; p.ldo = ldo;
+  p.q_amax = p.k_amax = p.v_amax = nullptr;
   ProfScope ps(e, s, PROF_BATCHED_TC, 4.0 * N * (double)Nk * d * B * heads, 4.0 * B * heads * (2.0 * N * d + 2.0 * (double)Nk * d), 1);
   switch (d) {
-    case 16: launch_flash<16>(qh, ql, kh, kl, vh, vl, p, s); break;
-    case 32: launch_flash<32>(qh, ql, kh, kl, vh, vl, p, s); break;
-    case 40: launch_flash<40>(qh, ql, kh, kl, vh, vl, p, s); break;
-    case 64: launch_flash<64>(qh, ql, kh, kl, vh, vl, p, s); break;
-    case 80: launch_flash<80>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 16: launch_flash<16, false>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 32: launch_flash<32, false>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 40: launch_flash<40, false>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 64: launch_flash<64, false>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 80: launch_flash<80, false>(qh, ql, kh, kl, vh, vl, p, s); break;
+    default: return false;
+  }
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+  return true;
+}
+
+void split_rows_h16(Engine& e, const float* src, long long rows, int cols, long long ld, void* hi, void* lo, long long ldh, const float* amax,
+                    cudaStream_t s) {
+  CDX_CHECK((cols & 3) == 0 && (ld & 3) == 0 && (ldh & 3) == 0 && a16(src) && a16(hi) && a16(lo), "split_rows_h16: cols / strides must be multiples of 4");
+  if (e.dry()) return;
+  const long long total = rows * (long long)(cols >> 2);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e.num_sms * 16);
+  split_rows_h16_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(src, rows, cols, ld, (__half*)hi, (__half*)lo, ldh, amax);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+
+void split_transpose_h16(Engine& e, const float* src, int R, int Cc, long long ld, void* hi, void* lo, const float* amax, cudaStream_t s) {
+  CDX_CHECK((R & 1) == 0 && a16(hi) && a16(lo), "split_transpose_h16: even row count");
+  if (e.dry()) return;
+  split_transpose_h16_kernel<<<dim3((unsigned)((R + 63) / 64), (unsigned)((Cc + 31) / 32)), 256, 0, s>>>(src, R, Cc, ld, (__half*)hi, (__half*)lo, amax);
+  CDX_CUDA(cudaGetLastError());
+  e.launches++;
+}
+
+// fp16-split variant: q / k planes [rows, ld] halves (head h at column h*d), V^T planes [heads*d, B*Nks] halves, each tensor's
+// planes scaled by 2^h16_exp_of(*amax) of its slot (split_rows_h16 / split_transpose_h16 above).  ld and Nks multiples of 8.
+bool flash_attention_h16(Engine& e, const void* q_hi, const void* q_lo, int ldq, const void* k_hi, const void* k_lo, int ldk, const void* vt_hi,
+                         const void* vt_lo, const float* q_amax, const float* k_amax, const float* v_amax, float* out, int ldo, int B, int N,
+                         int Nk, int Nks, int heads, int d, float scale, cudaStream_t s) {
+  if ((N % AQ) || (ldq & 7) || (ldk & 7) || (ldo & 3) || (Nks & 7) || Nk < 1 || Nk > Nks) return false;
+  if (!(d == 16 || d == 32 || d == 40 || d == 64 || d == 80)) return false;
+  if (!a16(q_hi) || !a16(q_lo) || !a16(k_hi) || !a16(k_lo) || !a16(vt_hi) || !a16(vt_lo) || !a16(out)) return false;
+  if (e.dry()) return true;
+  const int NV = (d + 15) / 16 * 16;
+  uint64_t dq[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
+  uint64_t sq[3] = {(uint64_t)d * 2, (uint64_t)ldq * 2, (uint64_t)N * ldq * 2};
+  uint64_t dk[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)Nks, (uint64_t)B};
+  uint64_t sk[3] = {(uint64_t)d * 2, (uint64_t)ldk * 2, (uint64_t)Nks * ldk * 2};
+  uint32_t bq[4] = {64, 1, AQ, 1}, bk[4] = {64, 1, AKV, 1};
+  uint64_t dv[4] = {(uint64_t)Nks, (uint64_t)B, (uint64_t)heads * d, 1};
+  uint64_t sv[3] = {(uint64_t)Nks * 2, (uint64_t)B * Nks * 2, (uint64_t)B * Nks * 2 * heads * d};
+  uint32_t bv[4] = {64, 1, (uint32_t)NV, 1};
+  const CUtensorMap& qh = get_map(q_hi, 4, dq, sq, bq, nullptr, 2);
+  const CUtensorMap& ql = get_map(q_lo, 4, dq, sq, bq, nullptr, 2);
+  const CUtensorMap& kh = get_map(k_hi, 4, dk, sk, bk, nullptr, 2);
+  const CUtensorMap& kl = get_map(k_lo, 4, dk, sk, bk, nullptr, 2);
+  const CUtensorMap& vh = get_map(vt_hi, 4, dv, sv, bv, nullptr, 2);
+  const CUtensorMap& vl = get_map(vt_lo, 4, dv, sv, bv, nullptr, 2);
+  AttnParams p;
+  p.N = N; p.Nk = Nk; p.heads = heads; p.d = d; p.B = B;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = out; p.ldo = ldo;
+  p.q_amax = q_amax; p.k_amax = k_amax; p.v_amax = v_amax;
+  ProfScope ps(e, s, PROF_BATCHED_TC, 4.0 * N * (double)Nk * d * B * heads, 2.0 * B * heads * (2.0 * N * d + 2.0 * (double)Nk * d) + 4.0 * B * heads * (double)N * d, 1);
+  switch (d) {
+    case 16: launch_flash<16, true>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 32: launch_flash<32, true>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 40: launch_flash<40, true>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 64: launch_flash<64, true>(qh, ql, kh, kl, vh, vl, p, s); break;
+    case 80: launch_flash<80, true>(qh, ql, kh, kl, vh, vl, p, s); break;
     default: return false;
   }
   CDX_CUDA(cudaGetLastError());

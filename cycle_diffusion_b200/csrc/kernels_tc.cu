@@ -146,22 +146,12 @@ struct TcParams {
                             // every 32-row quadrant of a tile to lie inside one image (checked on the host)
 };
 
-// exponent e such that amax * 2^e lies in [2^14, 2^15): |x * 2^e| < 2^15 for every |x| <= amax (0 for an all-zero tensor)
-__device__ __forceinline__ int h16_exp_of(float amax) {
-  const int be = (int)((__float_as_uint(amax) >> 23) & 0xffu);
-  if (be == 0 || be == 0xff) return 0;
-  // 2^2 <= amax < 2^15: no rescale.  The split is then exact to 2^-25 absolute (fp16 subnormal spacing of the lo term), i.e.
-  // <= 2^-27 of the tensor's max -- below fp32's own rounding of the products -- and the split warps skip one multiply per element
-  if (be - 127 >= 2 && be - 127 <= 14) return 0;
-  return min(max(14 - (be - 127), -100), 100);
-}
 __device__ __forceinline__ int h16_a_exp(const TcParams& p) {
   if (p.gn_ab) return 0;         // normalised (+SiLU) activations are O(1..100): inside the no-rescale range by construction
   float m = p.a_amax ? *p.a_amax : 0.f;
   if (p.a2_amax) m = fmaxf(m, *p.a2_amax);
   return h16_exp_of(m);
 }
-__device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(min(max(e, -126), 127) + 127) << 23); }
 
 struct TileCoord { int n0, nend, nw, m0, x0, y0, b0, zb, zh, kb0, kb1, split; };
 

@@ -814,7 +814,23 @@ struct UNetExec : Exec {
       a.amax = e.amax_slot();                   // <- max |V| (written by whichever projection produces V)
       bool done = false;
       const bool flash_ok = e.mma_mode == 1 && e.flash_attn && (HW % 128) == 0 && (d == 16 || d == 32 || d == 40 || d == 64 || d == 80);
-      if (flash_ok) {
+      if (flash_ok && e.tc_kind >= 1 && (C % 8) == 0) {
+        // fp16-split fused attention: ONE plain fp32 q|k|v projection (its range tracked by the epilogue), then one pass that
+        // writes the fp16 hi / lo planes of q|k and of V^T (both P.V operands K-major for tcgen05) with the tensor's exponent
+        Scope sa(e.arena);
+        float* qkv = (float*)e.arena.alloc((size_t)M * 3 * C * sizeof(float));
+        linear_into(n1.p, C, C, nullptr, 0, 0, M, n.P(t + ".attn1.to_q.weight"), 3 * C, nullptr, nullptr, 0, qkv, 3 * C, nullptr, n1.amax, nullptr,
+                    a.amax);                    // range of q | k | v (v bounds the attention output: a convex combination of V rows)
+        void* qk_hi = e.arena.alloc((size_t)M * 2 * C * 2);
+        void* qk_lo = e.arena.alloc((size_t)M * 2 * C * 2);
+        void* vt_hi = e.arena.alloc((size_t)C * M * 2);
+        void* vt_lo = e.arena.alloc((size_t)C * M * 2);
+        split_rows_h16(e, qkv, M, 2 * C, 3 * C, qk_hi, qk_lo, 2 * C, a.amax, s);
+        split_transpose_h16(e, qkv + 2 * C, M, C, 3 * C, vt_hi, vt_lo, a.amax, s);
+        done = flash_attention_h16(e, qk_hi, qk_lo, 2 * C, (const char*)qk_hi + (size_t)C * 2, (const char*)qk_lo + (size_t)C * 2, 2 * C, vt_hi, vt_lo,
+                                   a.amax, a.amax, a.amax, a.p, C, B, HW, HW, HW, heads, d, scale, s);
+        CDX_CHECK(done, "flash attention (fp16-split) rejected an eligible shape (HW=%d d=%d)", HW, d);
+      } else if (flash_ok) {
         // fused tensor-core attention: q|k projection and V^T (= Wv . X^T, a swapped-role GEMM, so that both P.V operands
         // are K-major for tcgen05) are written by their GEMM epilogues directly as TF32 hi / lo planes
         Scope sa(e.arena);
@@ -871,7 +887,33 @@ struct UNetExec : Exec {
       a.amax = kv_amax();                       // <- max |V| of the context projection (lives with the cached K / V in loop mode)
       bool done = false;
       Tensor q;
-      if (ctx_pad && (HW % 128) == 0 && (d == 16 || d == 32 || d == 40 || d == 64 || d == 80)) {
+      if (ctx_pad && e.tc_kind >= 1 && (C % 8) == 0 && (HW % 128) == 0 && (d == 16 || d == 32 || d == 40 || d == 64 || d == 80)) {
+        // fp16-split fused attention over the zero-padded context (ctx_lp rows per image, keys >= ctx_len masked in the kernel):
+        // q projected as plain fp32 (range tracked), K | V from one fused projection of the context; fp16 planes by the split pass.
+        // K and V share the layer's slot (one exponent for both); in loop mode planes and slot are computed by the first call only
+        Scope sa(e.arena);
+        const int Mk = B * ctx_lp;
+        const size_t nk = (size_t)Mk * C;
+        float* k_hi = kv_take(nk / 2);
+        float* k_lo = kv_take(nk / 2);
+        float* vt_hi = kv_take(nk / 2);
+        float* vt_lo = kv_take(nk / 2);
+        Tensor qf = linear(n2, t + ".attn2.to_q", false, nullptr, true);
+        void* q_hi = e.arena.alloc((size_t)M * C * 2);
+        void* q_lo = e.arena.alloc((size_t)M * C * 2);
+        split_rows_h16(e, qf.p, M, C, C, q_hi, q_lo, C, qf.amax, s);
+        if (!kv_hit) {
+          Scope sk(e.arena);
+          float* kvf = (float*)e.arena.alloc((size_t)Mk * 2 * C * sizeof(float));
+          linear_into(ctx_pad, D, D, nullptr, 0, 0, Mk, n.P(t + ".attn2.to_k.weight"), 2 * C, nullptr, nullptr, 0, kvf, 2 * C, nullptr, ctx_amax, nullptr,
+                      a.amax);
+          split_rows_h16(e, kvf, Mk, C, 2 * C, k_hi, k_lo, C, a.amax, s);
+          split_transpose_h16(e, kvf + C, Mk, C, 2 * C, vt_hi, vt_lo, a.amax, s);
+        }
+        done = flash_attention_h16(e, q_hi, q_lo, C, k_hi, k_lo, C, vt_hi, vt_lo, qf.amax, a.amax, a.amax, a.p, C, B, HW, ctx_len, ctx_lp, heads, d,
+                                   scale, s);
+        CDX_CHECK(done, "flash cross-attention (fp16-split) rejected an eligible shape (HW=%d d=%d L=%d)", HW, d, ctx_len);
+      } else if (ctx_pad && (HW % 128) == 0 && (d == 16 || d == 32 || d == 40 || d == 64 || d == 80)) {
         // fused tensor-core attention over the zero-padded context (ctx_lp rows per image, keys >= ctx_len masked in the
         // kernel): q = n2.Wq^T, K = ctx.Wk^T, V^T = Wv.ctx^T (swapped-role GEMM), all written as TF32 planes
         Scope sa(e.arena);
@@ -1031,7 +1073,7 @@ struct UNetExec : Exec {
     ctx = context;
     ctx_len = L;
     ctx_pad = nullptr;
-    ctx_lp = (L + 3) & ~3;
+    ctx_lp = (L + 7) & ~7;                // (fp16 planes: 16-byte TMA strides need 8 keys)
     const int mc = c.model_channels, half = mc / 2, ted = n.ted;
     Scope top(e.arena);
     e.pools_reset(s);
@@ -1064,7 +1106,7 @@ struct UNetExec : Exec {
       if (!kv_hit) amax_rows(e, context, (long long)B * L, c.context_dim, c.context_dim, ctx_amax, s);
     }
     if (context && L > 0 && e.mma_mode == 1 && e.flash_attn) {
-      // context rows padded to a multiple of 4 per image: TMA needs 16-byte strides for K and V^T of the cross-attention
+      // context rows padded to a multiple of 8 per image: TMA needs 16-byte strides for K and V^T of the cross-attention
       const size_t D = (size_t)c.context_dim;
       float* cp = (float*)e.arena.alloc((size_t)B * ctx_lp * D * sizeof(float));
       if (!e.dry() && !kv_hit) {

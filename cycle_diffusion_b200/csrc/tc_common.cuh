@@ -210,6 +210,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
+// exponent e such that amax * 2^e lies in [2^14, 2^15): |x * 2^e| < 2^15 for every |x| <= amax (0 for an all-zero tensor)
+__device__ __forceinline__ int h16_exp_of(float amax) {
+  const int be = (int)((__float_as_uint(amax) >> 23) & 0xffu);
+  if (be == 0 || be == 0xff) return 0;
+  // 2^2 <= amax < 2^15: no rescale.  The split is then exact to 2^-25 absolute (fp16 subnormal spacing of the lo term), i.e.
+  // <= 2^-27 of the tensor's max -- below fp32's own rounding of the products -- and the split warps skip one multiply per element
+  if (be - 127 >= 2 && be - 127 <= 14) return 0;
+  return min(max(14 - (be - 127), -100), 100);
+}
+__device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(min(max(e, -126), 127) + 127) << 23); }
 __device__ __forceinline__ uint32_t rn_tf32(uint32_t bits) { return (bits + 0x1000u) & 0xFFFFE000u; }
 
 
