@@ -116,10 +116,11 @@ def test_cycle_tc_vs_reference_fixture(eng):
     assert rz < 2e-4 and maxdiff(tgt, g['tgt_a']) < 1e-3 and maxdiff(own, g['x0']) < 1e-3
 
 
-@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('mode', [1, 2, 3])
 @pytest.mark.parametrize('B,N,heads,d', [(1, 4096, 8, 40), (2, 1024, 8, 80), (2, 256, 2, 16), (1, 128, 4, 64), (1, 256, 3, 32), (3, 384, 2, 40)])
 def test_attention_tc(B, N, heads, d, mode):
-    """mode 1: fused flash kernel (tcgen05, S/P never leave the SM); mode 2: unfused tcgen05 QK^T / softmax / PV^T."""
+    """mode 1: fused flash kernel on fp16-split operands (tcgen05 kind::f16, S/P never leave the SM); mode 2: unfused tcgen05
+    QK^T / softmax / PV^T; mode 3: the fused kernel on TF32 planes (round-1 scheme, kept for --mma 3)."""
     from cycle_diffusion_b200.engine import Engine
     e = Engine(0)
     e.set_mma_mode(mode)
@@ -160,6 +161,29 @@ def test_attention_tc_vae_shape():
     print(f'attention d=512 N=4096: max abs err {err:.2e}  families {sorted(fam)}')
     assert 'batched_tc' in fam and 'batched_ffma' not in fam, sorted(fam)
     assert err < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('sq,sk,sv', [(1e3, 1e-3, 1.0), (1e-4, 1e4, 3e4), (1.0, 1.0, 1e-10), (2e-3, 5e2, 1e6)])
+def test_attention_h16_is_scale_invariant(sq, sk, sv):
+    """The fp16-split attention rescales q, k and v by exact powers of two from their measured ranges: operands far outside
+    fp16's own range must give the same relative accuracy as O(1) data (same scores, output proportional to sv)."""
+    from cycle_diffusion_b200.engine import Engine
+    e = Engine(0)
+    e.set_mma_mode(1)
+    B, N, heads, d = 2, 256, 4, 40
+    g = torch.Generator().manual_seed(77)
+    C = heads * d
+    q, k, v = (torch.randn(B, N, C, generator=g) for _ in range(3))
+    q, k, v = q * 1.5 * sq, k * sk, v * sv
+    scale = d ** -0.5
+    sp = lambda t: t.double().reshape(B, -1, heads, d).permute(0, 2, 1, 3)
+    attn = (torch.einsum('bhid,bhjd->bhij', sp(q), sp(k)) * scale).softmax(-1)
+    ref = torch.einsum('bhij,bhjd->bhid', attn, sp(v)).permute(0, 2, 1, 3).reshape(B, N, C)
+    y = e.op_attention(q.cuda(), k.cuda(), v.cuda(), heads, scale).cpu().double()
+    r = float((y - ref).abs().max() / ref.abs().max())
+    print(f'attention scales q{sq:g} k{sk:g} v{sv:g}: rel err {r:.2e}')
+    assert r < 2e-5
 
 
 @pytest.mark.gpu
