@@ -126,6 +126,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
                   const __grid_constant__ CUtensorMap mapVh, const __grid_constant__ CUtensorMap mapVl, const AttnParams p) {
   using C = ACfg<D, F16>;
   constexpr int KB2 = C::KB2, NV = C::NV, NSUB = C::NSUB, KW = C::KW, PW = C::PW;
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + C::OFF_BAR;
@@ -182,6 +183,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();                     // everything above touched shared memory / TMEM only
 
   if (warp == 0) {
     // =========================================================================== TMA producer (whole warp, elected issue)
@@ -513,7 +515,7 @@ void launch_flash(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMa
     CDX_CUDA(cudaFuncSetAttribute(flash_attn_kernel<D, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<D, F16>::SMEM_BYTES));
     attr[dev & 63] = true;
   }
-  flash_attn_kernel<D, F16><<<dim3(p.N / AQ, p.heads, p.B), ACfg<D, F16>::THREADS, ACfg<D, F16>::SMEM_BYTES, s>>>(qh, ql, kh, kl, vh, vl, p);
+  launch_ex(flash_attn_kernel<D, F16>, dim3(p.N / AQ, p.heads, p.B), dim3(ACfg<D, F16>::THREADS), ACfg<D, F16>::SMEM_BYTES, s, 1, qh, ql, kh, kl, vh, vl, p);
 }
 
 
@@ -521,6 +523,8 @@ void launch_flash(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMa
 // src [rows, ld] (cols % 4 == 0) -> hi / lo [rows, ldh]
 __global__ void split_rows_h16_kernel(const float* __restrict__ src, long long rows, int cols, long long ld, __half* __restrict__ hi,
                                       __half* __restrict__ lo, long long ldh, const float* __restrict__ amax) {
+  pdl_trigger();
+  pdl_wait();
   const float sc = exp2i(h16_exp_of(*amax));
   const int c4n = cols >> 2;
   const long long total = rows * (long long)c4n;
@@ -545,6 +549,8 @@ __global__ void split_rows_h16_kernel(const float* __restrict__ src, long long r
 __global__ void __launch_bounds__(256) split_transpose_h16_kernel(const float* __restrict__ src, int R, int Cc, long long ld, __half* __restrict__ hi,
                                                                    __half* __restrict__ lo, const float* __restrict__ amax) {
   __shared__ float tile[64][33];
+  pdl_trigger();
+  pdl_wait();
   const float sc = exp2i(h16_exp_of(*amax));
   const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
@@ -620,7 +626,7 @@ void split_rows_h16(Engine& e, const float* src, long long rows, int cols, long 
   if (e.dry()) return;
   const long long total = rows * (long long)(cols >> 2);
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e.num_sms * 16);
-  split_rows_h16_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(src, rows, cols, ld, (__half*)hi, (__half*)lo, ldh, amax);
+  launch_ex(split_rows_h16_kernel, dim3((unsigned)(blocks > 0 ? blocks : 1)), dim3(256), 0, s, 1, src, rows, cols, ld, (__half*)hi, (__half*)lo, ldh, amax);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
 }
@@ -628,7 +634,7 @@ void split_rows_h16(Engine& e, const float* src, long long rows, int cols, long 
 void split_transpose_h16(Engine& e, const float* src, int R, int Cc, long long ld, void* hi, void* lo, const float* amax, cudaStream_t s) {
   CDX_CHECK((R & 1) == 0 && a16(hi) && a16(lo), "split_transpose_h16: even row count");
   if (e.dry()) return;
-  split_transpose_h16_kernel<<<dim3((unsigned)((R + 63) / 64), (unsigned)((Cc + 31) / 32)), 256, 0, s>>>(src, R, Cc, ld, (__half*)hi, (__half*)lo, amax);
+  launch_ex(split_transpose_h16_kernel, dim3((unsigned)((R + 63) / 64), (unsigned)((Cc + 31) / 32)), dim3(256), 0, s, 1, src, R, Cc, ld, (__half*)hi, (__half*)lo, amax);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
 }

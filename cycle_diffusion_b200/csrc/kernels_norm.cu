@@ -13,7 +13,7 @@
 // max |y| for the fp16-split GEMM that consumes y.
 #include <algorithm>
 
-#include "common.cuh"
+#include "tc_common.cuh"      // pdl_trigger / pdl_wait / launch_ex
 
 namespace cdx {
 namespace {
@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        float eps, int silu,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        int ld_ss, float* __restrict__ y, int HW, int rows_per_chunk, float* __restrict__ amax) {
+  tc::pdl_trigger();
+  tc::pdl_wait();
   const int C = C1 + C2;
   const int cpg = C / GN_GROUPS;
   const int C4 = C >> 2;
@@ -218,6 +220,8 @@ template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ y, int M, int C,
                                                         float eps, float* __restrict__ amax) {
+  tc::pdl_trigger();
+  tc::pdl_wait();
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int C4 = C >> 2;
@@ -343,8 +347,8 @@ void groupnorm(Engine& e, const float* x1, int C1, const float* x2, int C2, cons
   if (achunk > HW / 8) achunk = std::max(1, HW / 8);
   const int arows = cdiv(HW, achunk);
   achunk = cdiv(HW, arows);
-  gn_apply_kernel<<<dim3(achunk, B), 256, (size_t)C * sizeof(float2), s>>>(x1, C1, x2, C2, gamma, beta, st1, st2, 1.0 / ((double)HW * (C / GN_GROUPS)), eps,
-                                                                          silu ? 1 : 0, scale, shift, ld_ss, y, HW, arows, amax);
+  tc::launch_ex(gn_apply_kernel, dim3((unsigned)achunk, (unsigned)B), dim3(256), (size_t)C * sizeof(float2), s, 1, x1, C1, x2, C2, gamma, beta, st1, st2,
+                1.0 / ((double)HW * (C / GN_GROUPS)), eps, silu ? 1 : 0, scale, shift, ld_ss, y, HW, arows, amax);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
 }
@@ -369,10 +373,10 @@ void layernorm(Engine& e, const float* x, const float* gamma, const float* beta,
   ProfScope ps(e, s, PROF_LAYERNORM, 0.0, 2.0 * 4.0 * (double)M * C, 1);
   const int nv = cdiv(C, 128);
   const int blocks = (int)std::min<long long>(cdiv((long long)cdiv(M, 2) * 32, 256), (long long)e.num_sms * 8);
-  if (nv <= 3) layernorm_kernel<3><<<blocks, 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f, amax);
-  else if (nv <= 6) layernorm_kernel<6><<<blocks, 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f, amax);
-  else if (nv <= 10) layernorm_kernel<10><<<blocks, 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f, amax);
-  else layernorm_kernel<16><<<blocks, 256, 0, s>>>(x, gamma, beta, y, M, C, 1e-5f, amax);
+  if (nv <= 3) tc::launch_ex(layernorm_kernel<3>, dim3((unsigned)blocks), dim3(256), 0, s, 1, x, gamma, beta, y, M, C, 1e-5f, amax);
+  else if (nv <= 6) tc::launch_ex(layernorm_kernel<6>, dim3((unsigned)blocks), dim3(256), 0, s, 1, x, gamma, beta, y, M, C, 1e-5f, amax);
+  else if (nv <= 10) tc::launch_ex(layernorm_kernel<10>, dim3((unsigned)blocks), dim3(256), 0, s, 1, x, gamma, beta, y, M, C, 1e-5f, amax);
+  else tc::launch_ex(layernorm_kernel<16>, dim3((unsigned)blocks), dim3(256), 0, s, 1, x, gamma, beta, y, M, C, 1e-5f, amax);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
 }

@@ -184,6 +184,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
   const int t_first = CG2 ? (int)cluster_id_x() : (int)blockIdx.x, t_step = CG2 ? (int)nclusters_x() : (int)gridDim.x;
 
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 1024-byte aligned (swizzle atoms)
   const uint32_t bars = base + STAGES * STAGE_BYTES;
@@ -239,6 +240,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();                     // everything above touched shared memory / TMEM only
   // register budget per warpgroup (640 threads launch with 96 each): the TMA / MMA warpgroup gives most of its share back,
   // the epilogue warpgroups (64 fp32 accumulators + a 32-register residual prefetch per thread) take it
   // (each setmaxnreg sits at the top of its role's branch: ptxas budgets the code it dominates)
@@ -1073,6 +1075,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
 // C = alpha * sum_s ws[s] (+bias) (+row vector) (+residual): fixed summation order, so split-K stays deterministic
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, TcParams p, int h16) {
+  pdl_trigger();
+  pdl_wait();
   const long long total4 = (long long)p.M * p.N / 4;
   const float alpha = h16 ? p.alpha * exp2i(-h16_a_exp(p)) * exp2i(-p.b_exp) : p.alpha;
   float omax = 0.f;
@@ -1249,7 +1253,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     p.splits = 1; p.kb_per_split = cdiv(d, TBK);
     p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(Nk, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
-    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, mA, mA, mA, mA, mA, mA, p);
+    launch_ex(tc_gemm_kernel<MODE_SS>, dim3((unsigned)std::min(p.total_tiles, e.num_sms)), dim3(TC_THREADS), Cfg<MODE_SS>::SMEM_BYTES, s, 1, mA, mA, mB, mB, mA, mA, mA, mA, mA, mA, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -1276,7 +1280,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     p.splits = 1; p.kb_per_split = cdiv(Nk, TBK);
     p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(d, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
-    tc_gemm_kernel<MODE_SS><<<std::min(p.total_tiles, e.num_sms), TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(mA, mA, mB, mB, mA, mA, mA, mA, mA, mA, p);
+    launch_ex(tc_gemm_kernel<MODE_SS>, dim3((unsigned)std::min(p.total_tiles, e.num_sms)), dim3(TC_THREADS), Cfg<MODE_SS>::SMEM_BYTES, s, 1, mA, mA, mB, mB, mA, mA, mA, mA, mA, mA, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -1543,28 +1547,16 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
                4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
   ps.note("M%d N%d K%d w%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, p.tn_w, tiles, p.splits, h16 ? (p.fast ? "H16x1" : p.halo ? (cg2 ? "H16halo-pair" : "H16halo") : (cg2 ? "H16-pair" : "H16")) : ts ? "TS" : "SS",
           a.Cout_lo ? " planes" : "", a.geglu ? " geglu" : "", a.residual ? " res" : "");
-  if (cg2) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid, 1, 1);
-    cfg.blockDim = dim3(TC_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = Cfg<MODE_H16X2>::SMEM_BYTES;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CDX_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MODE_H16X2>, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p));
-  } else if (h16) tc_gemm_kernel<MODE_H16><<<grid, TC_THREADS, Cfg<MODE_H16>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
-  else if (ts) tc_gemm_kernel<MODE_TS><<<grid, TC_THREADS, Cfg<MODE_TS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
-  else tc_gemm_kernel<MODE_SS><<<grid, TC_THREADS, Cfg<MODE_SS>::SMEM_BYTES, s>>>(*mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  if (cg2) launch_ex(tc_gemm_kernel<MODE_H16X2>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_H16X2>::SMEM_BYTES, s, 2, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  else if (h16) launch_ex(tc_gemm_kernel<MODE_H16>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_H16>::SMEM_BYTES, s, 1, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  else if (ts) launch_ex(tc_gemm_kernel<MODE_TS>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_TS>::SMEM_BYTES, s, 1, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  else launch_ex(tc_gemm_kernel<MODE_SS>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_SS>::SMEM_BYTES, s, 1, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
   if (p.splits > 1) {
     const long long total4 = (long long)a.M * a.N / 4;
     const int blocks = (int)std::min<long long>((total4 + 255) / 256, (long long)e.num_sms * 8);
-    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(p.ws, p.splits, p, h16 ? 1 : 0);
+    launch_ex(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, s, 1, p.ws, p.splits, p, h16 ? 1 : 0);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }

@@ -6,6 +6,8 @@
 #include <map>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
+#include <utility>
 
 #include "common.cuh"
 
@@ -76,6 +78,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // all bulk stores of this thread have finished READING their shared-memory source (it may be overwritten)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the newest
+// Programmatic dependent launch (launch attribute set by launch_ex below unless CDX_PDL=0; both instructions are no-ops without it):
+// pdl_trigger() lets the next kernel of the stream start launching CTAs once every CTA of this grid has issued it, pdl_wait() blocks
+// until the preceding grid has completed and flushed.  Rule in this code base: trigger at kernel entry, wait after the setup that
+// touches no global memory and BEFORE the first global access of any thread (reads of a predecessor's output, and writes of buffers a
+// predecessor may still read: the workspace arena is reused in stream order)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // D[tmem] (+)= A[smem] . B[smem]
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -293,6 +302,32 @@ inline const CUtensorMap& get_map(const void* ptr, int rank, const uint64_t* dim
     throw Error(CDX_E_CUDA, b);
   }
   return cache.emplace(k, m).first->second;
+}
+
+inline bool pdl_enabled() {
+  static const bool on = getenv("CDX_PDL") == nullptr || atoi(getenv("CDX_PDL")) != 0;      // default on; CDX_PDL=0 disables
+  return on;
+}
+// one launch path for the kernels that take part in programmatic dependent launch (and / or need a cluster dimension)
+template <typename... KArgs, typename... Args>
+inline void launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, unsigned cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  CDX_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
 }
 
 inline bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
