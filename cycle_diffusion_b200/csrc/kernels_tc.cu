@@ -155,7 +155,10 @@ __device__ __forceinline__ int h16_a_exp(const TcParams& p) {
 
 struct TileCoord { int n0, nend, nw, m0, x0, y0, b0, zb, zh, kb0, kb1, split; };
 
-template <int MODE>
+// EPI: the TMA-store epilogue of the dense layers is compiled in (TcParams::epi_tma selects it per launch).  A separate instantiation,
+// because the extra live state of that path costs the conv launches' epilogue registers (ptxas: 92 -> 304 bytes of spill stores in
+// the shared body; the short-K convs of the pixel U-Net slowed by 8 %)
+template <int MODE, bool EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
@@ -723,10 +726,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // it needs whole rows and whole 16-column blocks (anything else takes the per-row path below).  The residual box of the first
     // slot is requested before the drain, so it is in shared memory by the time the accumulator is
     const int wcols = p.geglu ? HN / 2 : min(max(tc_.nend - (n0 + hf * HN), 0), HN);       // columns this warp stores
-    const bool tma_tile = p.epi_tma && m0 + TBM <= p.M && (wcols & 15) == 0 && !(p.Ct_hi && n0 >= p.t_col0);
+    const bool tma_tile = EPI && p.epi_tma && m0 + TBM <= p.M && (wcols & 15) == 0 && !(p.Ct_hi && n0 >= p.t_col0);
     const int tparts = (wcols + 31) >> 5;
     const int tcol0 = p.geglu ? (n0 >> 1) + hf * 32 : n0 + hf * HN, trow0 = m0 + q * 32;
-    if (p.epi_tma) {
+    if (EPI && p.epi_tma) {
       if (lane == 0) {
         bulk_wait_read0();                         // the previous tile's stores have left the staging block
         if (tma_tile && p.residual && wcols > 0) {
@@ -1055,7 +1058,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
     }   // tile loop
-    if (p.epi_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // bulk stores done before the CTA retires
+    if (EPI && p.epi_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // bulk stores done before the CTA retires
     if (p.c_amax && p.splits == 1) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
@@ -1167,10 +1170,12 @@ void ensure_attr(int device) {
   std::lock_guard<std::mutex> lock(mtx);
   const int d = device & 63;
   if (!attr_set[d]) {
-    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_SS>::SMEM_BYTES));
-    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_TS>::SMEM_BYTES));
-    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_H16>::SMEM_BYTES));
-    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_H16X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_H16X2>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_SS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_SS>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_TS>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_H16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_H16>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_H16X2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_H16X2>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_H16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_H16>::SMEM_BYTES));
+    CDX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_H16X2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE_H16X2>::SMEM_BYTES));
     attr_set[d] = true;
   }
 }
@@ -1253,7 +1258,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     p.splits = 1; p.kb_per_split = cdiv(d, TBK);
     p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(Nk, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
-    launch_ex(tc_gemm_kernel<MODE_SS>, dim3((unsigned)std::min(p.total_tiles, e.num_sms)), dim3(TC_THREADS), Cfg<MODE_SS>::SMEM_BYTES, s, 1, mA, mA, mB, mB, mA, mA, mA, mA, mA, mA, p);
+    launch_ex(tc_gemm_kernel<MODE_SS, false>, dim3((unsigned)std::min(p.total_tiles, e.num_sms)), dim3(TC_THREADS), Cfg<MODE_SS>::SMEM_BYTES, s, 1, mA, mA, mB, mB, mA, mA, mA, mA, mA, mA, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -1280,7 +1285,7 @@ bool attention_tc(Engine& e, const float* q, int ldq, const float* k, int ldk, i
     p.splits = 1; p.kb_per_split = cdiv(Nk, TBK);
     p.tn_w = TBN;
     p.tiles_m = cdiv(Nq, TBM); p.tiles_n = cdiv(d, TBN); p.total_tiles = p.tiles_m * p.tiles_n * B * heads;
-    launch_ex(tc_gemm_kernel<MODE_SS>, dim3((unsigned)std::min(p.total_tiles, e.num_sms)), dim3(TC_THREADS), Cfg<MODE_SS>::SMEM_BYTES, s, 1, mA, mA, mB, mB, mA, mA, mA, mA, mA, mA, p);
+    launch_ex(tc_gemm_kernel<MODE_SS, false>, dim3((unsigned)std::min(p.total_tiles, e.num_sms)), dim3(TC_THREADS), Cfg<MODE_SS>::SMEM_BYTES, s, 1, mA, mA, mB, mB, mA, mA, mA, mA, mA, mA, p);
     CDX_CUDA(cudaGetLastError());
     e.launches++;
   }
@@ -1524,7 +1529,7 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
   // TMA epilogue (TcParams::epi_tma): dense layers whose epilogue is the final one and needs no per-column statistics
   const CUtensorMap *mC = mA, *mClo = mA, *mR = mA, *mC16 = mA, *mClo16 = mA, *mR16 = mA;
   static const bool no_epi_tma = getenv("CDX_TC_NO_EPI_TMA") != nullptr;
-  if (!no_epi_tma && a.mode == 0 && !a.out_nchw && p.splits == 1 && a.M >= TBM) {
+  if (!no_epi_tma && h16 && a.mode == 0 && !a.out_nchw && p.splits == 1 && a.M >= TBM) {       // (compiled into the fp16-split kernels only)
     const uint64_t nc = (uint64_t)(a.geglu ? a.N / 2 : a.N);
     uint64_t d[2] = {nc, (uint64_t)a.M}, st[1] = {(uint64_t)a.ldc * 4};
     uint32_t bx[2] = {32, 32}, bx16[2] = {16, 32};
@@ -1547,10 +1552,12 @@ bool gemm_tc(Engine& e, const GemmArgs& a, cudaStream_t s, int* side_done) {
                4.0 * ((double)a.M * a.K / (a.mode == 1 ? 9 : 1) + (double)a.N * a.K + (double)a.M * a.N), 1);
   ps.note("M%d N%d K%d w%d tiles%d S%d %s%s%s%s", a.M, a.N, a.K, p.tn_w, tiles, p.splits, h16 ? (p.fast ? "H16x1" : p.halo ? (cg2 ? "H16halo-pair" : "H16halo") : (cg2 ? "H16-pair" : "H16")) : ts ? "TS" : "SS",
           a.Cout_lo ? " planes" : "", a.geglu ? " geglu" : "", a.residual ? " res" : "");
-  if (cg2) launch_ex(tc_gemm_kernel<MODE_H16X2>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_H16X2>::SMEM_BYTES, s, 2, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
-  else if (h16) launch_ex(tc_gemm_kernel<MODE_H16>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_H16>::SMEM_BYTES, s, 1, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
-  else if (ts) launch_ex(tc_gemm_kernel<MODE_TS>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_TS>::SMEM_BYTES, s, 1, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
-  else launch_ex(tc_gemm_kernel<MODE_SS>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_SS>::SMEM_BYTES, s, 1, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  if (cg2 && p.epi_tma) launch_ex(tc_gemm_kernel<MODE_H16X2, true>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_H16X2>::SMEM_BYTES, s, 2, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  else if (cg2) launch_ex(tc_gemm_kernel<MODE_H16X2, false>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_H16X2>::SMEM_BYTES, s, 2, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  else if (h16 && p.epi_tma) launch_ex(tc_gemm_kernel<MODE_H16, true>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_H16>::SMEM_BYTES, s, 1, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  else if (h16) launch_ex(tc_gemm_kernel<MODE_H16, false>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_H16>::SMEM_BYTES, s, 1, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  else if (ts) launch_ex(tc_gemm_kernel<MODE_TS, false>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_TS>::SMEM_BYTES, s, 1, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
+  else launch_ex(tc_gemm_kernel<MODE_SS, false>, dim3((unsigned)grid), dim3(TC_THREADS), Cfg<MODE_SS>::SMEM_BYTES, s, 1, *mA, *mA2, *mB, *mBlo, *mC, *mClo, *mR, *mC16, *mClo16, *mR16, p);
   CDX_CUDA(cudaGetLastError());
   e.launches++;
   if (p.splits > 1) {
