@@ -1,37 +1,36 @@
-// kernels_tc.cu -- tcgen05 / TMEM / TMA back end for the dense contractions: fp32-faithful 3xTF32.
+// kernels_tc.cu -- tcgen05 / TMEM / TMA back end for the dense contractions (conv3x3, conv1x1 / Linear, batched attention products):
+// fp32-faithful products from three tensor-core terms.
 //
-// Why 3xTF32: the path's acceptance bar is parity with the reference's fp32 CPU path (|d pixel| <= 1e-3 through
-// 50-250 sequential U-Net calls with a 1/sigma_t amplification), which plain TF32/BF16 tensor-core math cannot hold
-// (SURVEY.md section 7).  Every fp32 operand x is split as  hi = rn_tf32(x)  and  lo = rn_tf32(x - hi)  (x - hi is
-// exact in fp32) and the product is accumulated as  lo*hi + hi*lo + hi*hi  in the fp32 TMEM accumulator (the dropped
-// lo*lo term is < 2^-22 relative).  Three tcgen05.mma.kind::tf32 per 8-wide K chunk.
+// Why three terms: the path's acceptance bar is parity with the reference's fp32 CPU path (|d pixel| <= 1e-3 through 50-250 sequential
+// U-Net calls with a 1/sigma_t amplification), which plain TF32/BF16/FP16 tensor-core math cannot hold (the
+// single-term fast path ends at 6e-3).  Every fp32 operand is split into hi + lo and the product is accumulated as
+// lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator (the dropped lo*lo term is < 2^-22 relative):
+//   MODE_H16 / MODE_H16X2 (default)  x' = x * 2^e (e from the tensor's tracked range), hi = fp16(x'), lo = fp16(x' - hi): three
+//                         tcgen05.mma.kind::f16 per 16-wide K step, exact power-of-two rescale in the epilogue;
+//   MODE_TS / MODE_SS     hi = rn_tf32(x), lo = rn_tf32(x - hi): three kind::tf32 per 8-wide K step (round-1 scheme: --mma 3, and the
+//                         activation x activation products, where neither operand has pre-split planes).
 //
-// Tensor-core accumulation truncates (measured: the error of one long accumulation grows linearly with K, 5.8e-5
-// relative at K = 11520), so the K loop is cut into chunks of 8 blocks (256 elements): each chunk accumulates in one of
-// two TMEM buffers and is drained by the epilogue warps into fp32 registers with round-to-nearest adds while the next
-// chunk already runs in the other buffer.  Measured error after both fixes: ~1.3e-6 relative, independent of K.
+// Tensor-core accumulation truncates (measured: the error of one long accumulation grows linearly with K, 5.8e-5 relative at
+// K = 11520), so the K loop is cut into chunks of 256 elements (one chunk if K <= 512): each chunk accumulates in one of two TMEM
+// buffers and is drained by the epilogue warps into fp32 registers with round-to-nearest adds while the next chunk already runs in the
+// other buffer.  Measured error after both fixes: ~1.3e-6 relative, independent of K.
 //
-// One 128 x 128 output tile per CTA, K walked in 32-float (128-byte) blocks, 320 threads:
-//   warp 0      TMA producer (cp.async.bulk.tensor, 128B-swizzled smem).  A is a 2D [M,K] row matrix (dense / 1x1 conv /
-//               Linear, optionally two channel-concatenated sources), or for conv3x3 a 4D box {32 ch, bw, bh, bn} of
-//               the NHWC activation shifted by the tap (dy-1, dx-1): TMA's out-of-bounds zero fill *is* the conv's
-//               zero padding, so im2col is never materialised and the halo costs nothing; or (batched mode) 4D maps
-//               over (k, head, row, batch) for the attention contractions.
-//   warp 1      MMA issuer: one lane issues 12 tcgen05.mma per K block, tcgen05.commit hands the stage back.
-//   warps 2-5   split warps.
-//   warps 6-13  drain + epilogue (two warps per TMEM lane quadrant, 32 rows x 64 columns each): tcgen05.ld 32x32b.x32 per
-//               chunk -> RN add into 64 fp32 registers per thread; at the
-//               end alpha, +bias, +per-sample row vector (timestep embedding), +residual -> 128-bit global stores.
-//
-// Two variants of the operand path (template parameter TS):
-//   TS = false  "SS": A and B raw tiles land in smem, the split warps rewrite both as hi (in place) + lo (twin buffer),
-//               both operands are read from smem by the MMA.  3 stages x 64 KB.  Generic (B may be an activation).
-//   TS = true   "TS": weights are pre-split once at load time into hi / lo planes in HBM, so B_hi and B_lo arrive
-//               straight from TMA; the split warps read the raw A row from smem, and store hi / lo with tcgen05.st into
-//               TMEM, from where the MMA takes the A operand.  No smem writes by the SM and no smem reads of A by the
-//               tensor core: the ncu profile of the SS variant showed shared-memory bandwidth (LSU split traffic +
-//               tensor-core operand fetch ~ 84 % of smem cycles, tensor pipe 33 % active) as the limiter.
-//               4 stages x 48 KB; TMEM: 2 x 128 accumulator columns + 4 x 64 A columns = 512.
+// Persistent kernel, one CTA (MODE_H16X2: one 2-CTA cluster = 256 rows, cta_group::2) per SM walks work items (tile, K split) of
+// 128 (256) rows x w <= 128 columns, K in 128-byte blocks.  640 threads = 5 warpgroups with setmaxnreg budgets:
+//   warp 0      TMA producer (cp.async.bulk.tensor, 128B-swizzled smem).  A is a 2D [M,K] row matrix (dense / 1x1 conv / Linear,
+//               optionally two channel-concatenated sources), or for conv3x3 a 4D box of the NHWC activation -- per tap {32 ch, bw, bh,
+//               bn} shifted by (dy-1, dx-1), or on the HALO schedule the (bw+2) x (bh+2) pixel halo of a 64-channel block fetched
+//               once: TMA's out-of-bounds zero fill *is* the conv's zero padding, im2col is never materialised; or (batched mode) 4D
+//               maps over (k, head, row, batch) for the attention contractions.  B: pre-split weight planes (fp16 or TF32) by TMA.
+//   warp 1      MMA issuer: one lane issues the three-term MMAs of a K block (A operand from TMEM), tcgen05.commit hands the stage
+//               back (pair: multicast to both CTAs' barriers).  Warps 2-3 idle (they only return their registers).
+//   warps 4-11  split warps: raw fp32 A rows (or, halo schedule, the halo converted once in place into fp16 hi / lo planes and then
+//               copied per tap) -> hi / lo -> tcgen05.st into the TMEM A ring.
+//   warps 12-19 drain + epilogue (two warps per TMEM lane quadrant, 32 rows x 64 columns each): tcgen05.ld per chunk -> RN add into
+//               64 fp32 registers per thread; then alpha / rescale, +bias, +per-sample row vector (timestep embedding), GEGLU,
+//               +residual, range / GroupNorm side outputs, and the store: TMA boxes staged in the map's swizzle for the dense layers
+//               (template parameter EPI), a swizzled smem transpose with 128-bit global stores otherwise.
+// DESIGN.md 5.1 has the measured history of each of these choices (profiles/r01_*, r02_*).
 #include <algorithm>
 
 #include <mutex>
