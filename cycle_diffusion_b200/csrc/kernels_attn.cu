@@ -1,24 +1,27 @@
-// kernels_attn.cu -- fused self-attention on tcgen05 (flash-style, fp32-faithful 3xTF32).
+// kernels_attn.cu -- fused self- / cross-attention on tcgen05 (flash-style, fp32-faithful three-term products).
 //
 //   out[b, q, h*d + c] = sum_j softmax_j( scale * <Q[b,q,h,:], K[b,j,h,:]> ) * V[b,j,h,c]
 // replaces CrossAttention.forward's two einsums + softmax (ldm/modules/attention.py:178-192), which materialise a
 // [B*heads, N, N] fp32 score matrix (4.3 GB per layer at N=4096, B=8) -- here scores never leave the SM.
 //
-// Inputs are the TF32 hi / lo planes (rn_tf32(x), rn_tf32(x - hi)) of the fused q|k projection [B*N, 2C] and of the
-// transposed value projection V^T [C, B*N] (see nets.cu), so every operand tile arrives by TMA ready for the tensor core.
+// Inputs are hi / lo planes of q, k [rows, ld] and of the transposed values V^T [C, B*N] (see nets.cu), so every operand tile arrives
+// by TMA ready for the tensor core.  Default (F16): fp16 planes of x * 2^e, e from the tensor's tracked range (split_rows_h16 /
+// split_transpose_h16 at the end of this file), three kind::f16 MMAs per 16-wide K step; F16 = false: TF32 planes (rn_tf32(x),
+// rn_tf32(x - hi)) written by the projection's epilogue, three kind::tf32 per 8-wide step (the round-1 scheme, --mma 3).
 //
-// One CTA = 128 queries of one (batch, head); keys are walked in blocks of 64.  320 threads:
-//   warp 0    TMA producer: Q planes once (through a staging buffer), then K / V^T hi+lo tiles into two 2-deep rings.
-//   warp 1    MMA issuer.  S_j = Q K_j^T as TS-mode MMAs (Q hi/lo live in TMEM, K tiles in smem): lo*hi + hi*lo + hi*hi,
-//             M=128, N=64, K=d.  O_j = P_j V_j with P hi/lo in TMEM and V^T tiles in smem, M=128, N=round16(d), K=64,
-//             written FRESH into TMEM for every key block.  S is double-buffered so S_{j+1} is computed while the
-//             softmax of block j runs.
-//   warps 2-9 softmax + accumulation, two threads per query row (32 key columns and half of the O columns each; the row
-//             max is exchanged through smem, a first profile showed 4 softmax warps issue-bound at 30 % tensor activity):
-//             tcgen05.ld S -> online max / exp2 / row sum in registers
-//             -> split P into hi/lo -> tcgen05.st into TMEM; O_total = O_total * corr + O_j with round-to-nearest fp32
-//             adds in registers (the tensor core's accumulation truncates, see kernels_tc.cu; accumulating per block in
-//             registers also makes the online-softmax rescale free).  Final O / l -> global.
+// One CTA = 128 queries of one (batch, head); keys are walked in blocks of 64.  128 + 32 * 4 * NSUB threads (640 for d <= 40):
+//   warp 0    TMA producer: Q planes once (through a staging buffer that aliases the last K stage), then K and V^T hi+lo tiles into
+//             3-4 deep rings.
+//   warp 1    MMA issuer of the Q.K^T stream: S_j = Q K_j^T as TS-mode MMAs (Q hi/lo live in TMEM, K tiles in smem):
+//             lo*hi + hi*lo + hi*hi, M=128, N=64, K=d.
+//   warps 2-3 MMA issuers of the P.V stream (even / odd key blocks when there are two P/O buffers): O_j = P_j V_j with P hi/lo in
+//             TMEM and V^T tiles in smem, M=128, N=round16(d), K=64, written FRESH into TMEM for every key block.
+//   warps 4.. softmax + accumulation, NSUB threads per query row (64/NSUB key columns and 1/NSUB of the O columns each; the row max
+//             is exchanged through smem; a first profile showed 4 softmax warps issue-bound at 30 % tensor activity):
+//             tcgen05.ld S -> online max / exp2 / row sum in registers -> split P into hi/lo (F16: fp16(p * 2^10) pairs) ->
+//             tcgen05.st into TMEM; O_total = O_total * corr + O_j with round-to-nearest fp32 adds in registers (the tensor core's
+//             accumulation truncates, see kernels_tc.cu; accumulating per block in registers also makes the online-softmax rescale
+//             free).  Final O / l -> global.
 // TMEM columns (<= 512): [S x SB][P hi|lo x PB][O x PB][Q_hi][Q_lo], see ACfg.
 #include <cuda_fp16.h>
 
