@@ -422,7 +422,9 @@ def run_ours(args):
                        'l2': 'no flush: GBs of weights + >1 GB activations per U-Net call are streamed every call (>> 126 MB L2)',
                        'loop': ('lock-step: one U-Net call per step on [source | target uncond | target cond] (3B samples), recovered noise '
                                 'consumed in the same step' if latent else 'two-phase: source-model encode, target-model decode'),
-                       'unet_calls_per_step': (S if latent else 2 * S - 1), 'unet_ms': unet_ms, 'stage_ms_two_phase': stage_ms},
+                       'unet_calls_per_step': (S if latent else 2 * S - 1), 'unet_ms': unet_ms, 'stage_ms_two_phase': stage_ms,
+                       'launch': ('programmatic dependent launch (GEMM / attention / norm kernels)' if os.environ.get('CDX_PDL', '1') != '0'
+                                  else 'stream-serialised launches (CDX_PDL=0)')},
             'e2e': {'value': round(e2e_value, 4), 'unit': UNIT, 'h2d_bytes_per_step': h2d[0], 'd2h_bytes_per_step': 4 * out_host.numel(),
                     'steps': e2e_steps, 'api': api},
             'gpu_launches': launches, 'clocks': clk, 'roofline': roof, 'kernel_families': families, 'hbm_bound_kernels': norm_probe,
